@@ -1,0 +1,208 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz from the unmodified
+reference (mess42/pyrate at /root/reference, imported through oracle/refshim.py).
+
+Run in the build container:   python oracle/gen_golden.py
+The fixtures are committed; the GPU box never needs /root/reference.
+
+What is dumped (all float64 / complex128 / bool / int64, NumPy .npz):
+  seqtrace_<config>.npz  every RayBundle of every RayPath returned by
+                         OpticalSystem.seqtrace (optical_system.py:73-94):
+                         x, k, valid, rayID (+E for anisotropic segments); for
+                         GRIN bundles only the first and the last two history
+                         rows plus the row count (history is 200+ rows).
+  frames.npz             LocalCoordinates chains (localcoordinates.py:238-307)
+  shapes.npz             getSag/getGrad/getNormal (surface_shape.py:100-237,
+                         :529-555, :785-807)
+  aniso_modes.npz        MaxwellMaterial.sortKnormEField (material.py:122-153)
+  spot.npz               RayBundleAnalysis centroid / rms (ray_analysis.py:44-86)
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+
+import refshim  # noqa: E402
+from pyrate_b200 import configs  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# (config, rings, kdir, efield, splitup, tag)
+DEG = np.pi / 180.0
+TRACES = [
+    ("c1_doublet", 18, (0, 0, 1), (0, 1, 0), False, ""),
+    ("c2_doublegauss", 6, (0, 0, 1), (0, 1, 0), False, ""),
+    ("c2_doublegauss", 4, (0, np.sin(5 * DEG), np.cos(5 * DEG)), (1, 0, 0),
+     False, "_field5"),
+    # E0 not perpendicular to k0: first segment direction follows the
+    # Poynting vector (ray.py:136-152)
+    ("c2_doublegauss", 3, (0, np.sin(3 * DEG), np.cos(3 * DEG)), (0, 1, 0),
+     False, "_obliqueE"),
+    ("c3_asphere", 6, (0, 0, 1), (0, 1, 0), False, ""),
+    ("c4_anisotropic", 3, (0, 0, 1), (0, 1, 0), False, ""),
+    ("c4_anisotropic", 2, (0, 0, 1), (0, 1, 0), True, "_split"),
+    ("c5_grin", 3, (0, 0, 1), (0, 1, 0), False, ""),
+    ("x1_tilted", 8, (0, 0, 1), (0, 1, 0), False, ""),
+    ("x2_xypoly", 6, (0, 0, 1), (0, 1, 0), False, ""),
+    ("x3_vignette", 10, (0, 0, 1), (0, 1, 0), False, ""),
+]
+
+
+def dump_trace(api, name, rings, kdir, efield, splitup, tag):
+    spec = configs.CONFIGS[name]
+    (s, seq) = configs.build_system(spec, api)
+    (x0, k0, e0) = configs.config_bundle(spec, rings, kdir, efield)
+    bundle = api.RayBundle(x0, k0, e0, wave=configs.DLINE)
+    paths = s.seqtrace(bundle, seq, splitup=splitup)
+    out = {"x0": x0, "k0": k0, "E0": e0, "npaths": np.int64(len(paths)),
+           "splitup": np.bool_(splitup)}
+    for (ip, path) in enumerate(paths):
+        out["p%d_nbundles" % ip] = np.int64(len(path.raybundles))
+        for (ib, rb) in enumerate(path.raybundles):
+            pre = "p%d_b%d_" % (ip, ib)
+            rows = rb.x.shape[0]
+            out[pre + "rows"] = np.int64(rows)
+            sel = slice(None) if rows <= 3 else [0, rows - 2, rows - 1]
+            out[pre + "x"] = np.asarray(rb.x)[sel]
+            out[pre + "k"] = np.asarray(rb.k)[sel]
+            out[pre + "valid"] = np.asarray(rb.valid)[sel]
+            out[pre + "rayID"] = np.asarray(rb.rayID, dtype=np.int64)
+            if np.iscomplexobj(rb.Efield) or name.startswith("c4"):
+                out[pre + "E"] = np.asarray(rb.Efield)[sel]
+    fn = os.path.join(OUT, "seqtrace_%s%s.npz" % (name, tag))
+    np.savez_compressed(fn, **out)
+    nlast = paths[0].raybundles[-1].x.shape[2]
+    print("%-32s paths=%d bundles=%d last-width=%d" %
+          (os.path.basename(fn), len(paths), len(paths[0].raybundles), nlast))
+    return paths
+
+
+def dump_frames(api):
+    rng = np.random.default_rng(20260925)
+    n = 24
+    params = np.zeros((n, 3, 7))
+    basis = np.zeros((n, 3, 3, 3))
+    origin = np.zeros((n, 3, 3))
+    for i in range(n):
+        parent = None
+        for lvl in range(3):
+            dec = rng.uniform(-10, 10, 3)
+            tilt = rng.uniform(-np.pi, np.pi, 3)
+            ttd = int(rng.integers(0, 2))
+            params[i, lvl] = (*dec, *tilt, ttd)
+            lc = api.LocalCoordinates.p(name="l%d_%d" % (i, lvl), decx=dec[0],
+                                        decy=dec[1], decz=dec[2],
+                                        tiltx=tilt[0], tilty=tilt[1],
+                                        tiltz=tilt[2], tiltThenDecenter=ttd)
+            if parent is not None:
+                parent.addChild(lc)
+            parent = lc
+            basis[i, lvl] = lc.localbasis
+            origin[i, lvl] = lc.globalcoordinates
+    pts = rng.uniform(-5, 5, (3, 7))
+    lc_last = parent
+    np.savez_compressed(
+        os.path.join(OUT, "frames.npz"), params=params, basis=basis,
+        origin=origin, pts=pts,
+        last_l2g_pts=lc_last.returnLocalToGlobalPoints(pts),
+        last_g2l_pts=lc_last.returnGlobalToLocalPoints(pts),
+        last_l2g_dir=lc_last.returnLocalToGlobalDirections(pts),
+        last_g2l_dir=lc_last.returnGlobalToLocalDirections(pts))
+    print("frames.npz")
+
+
+def dump_shapes(api):
+    rng = np.random.default_rng(7)
+    lc = api.LocalCoordinates.p(name="shapes")
+    x = rng.uniform(-3, 3, 40)
+    y = rng.uniform(-3, 3, 40)
+    out = {"x": x, "y": y}
+    conic_params = [(0.05, 0.0), (-0.08, -1.0), (0.11, 0.7), (0.0, 0.0),
+                    (0.3, 2.0)]   # last one: sag undefined for large r
+    out["conic_params"] = np.array(conic_params)
+    for (i, (curv, cc)) in enumerate(conic_params):
+        sh = api.Conic.p(lc, curv=curv, cc=cc)
+        out["conic%d_sag" % i] = sh.getSag(x.copy(), y.copy())
+        out["conic%d_grad" % i] = sh.getGrad(x.copy(), y.copy())
+        out["conic%d_normal" % i] = sh.getNormal(x.copy(), y.copy())
+    asph = api.Asphere.p(lc, curv=-0.02, cc=-1.0,
+                         coefficients=[1e-3, 1e-5, -1e-7])
+    out["asph_params"] = np.array([-0.02, -1.0, 1e-3, 1e-5, -1e-7])
+    out["asph_sag"] = asph.getSag(x, y)
+    out["asph_grad"] = asph.getGrad(x, y)
+    out["asph_normal"] = asph.getNormal(x, y)
+    coeffs = [(2, 0, -0.9), (0, 2, -1.1), (1, 1, 0.05), (3, 0, 0.02),
+              (1, 2, -0.03), (0, 0, 0.1), (0, 1, 0.02)]
+    xy = api.XYPolynomials.p(lc, normradius=10.0, coefficients=coeffs)
+    out["xy_coeffs"] = np.array(coeffs, dtype=float)
+    out["xy_normradius"] = np.float64(10.0)
+    out["xy_sag"] = xy.getSag(x, y)
+    out["xy_grad"] = xy.getGrad(x, y)
+    out["xy_normal"] = xy.getNormal(x, y)
+    np.savez_compressed(os.path.join(OUT, "shapes.npz"), **out)
+    print("shapes.npz")
+
+
+def dump_aniso(api):
+    rng = np.random.default_rng(11)
+    lc = api.LocalCoordinates.p(name="aniso")
+    npts = 12
+    cases = {
+        "uniaxial_y": np.diag([1.658 ** 2, 1.486 ** 2, 1.658 ** 2]),
+        "biaxial_rot": None,
+    }
+    # rotated biaxial tensor (real symmetric, positive definite)
+    q, _ = np.linalg.qr(rng.normal(size=(3, 3)))
+    cases["biaxial_rot"] = q @ np.diag([2.2, 2.6, 3.1]) @ q.T
+    out = {}
+    for (nm, eps) in cases.items():
+        mat = api.AnisotropicMaterial.p(lc, eps, name=nm)
+        n = rng.normal(size=(3, npts))
+        n[2] = np.abs(n[2]) + 2.0
+        n /= np.linalg.norm(n, axis=0)
+        kin = rng.normal(size=(3, npts)) * 0.3
+        kin[2] += 1.0
+        kpa = kin - np.sum(kin * n, axis=0) * n
+        x = np.zeros((3, npts))
+        (k4, e4) = mat.sortKnormEField(x, n, kpa, n)
+        (xi4, ev4) = mat.calcXiEigenvectorsNorm(x, n, kpa)
+        out[nm + "_eps"] = eps
+        out[nm + "_n"] = n
+        out[nm + "_kpa"] = kpa
+        out[nm + "_k4"] = k4
+        out[nm + "_e4"] = e4
+        out[nm + "_xi4"] = xi4
+    np.savez_compressed(os.path.join(OUT, "aniso_modes.npz"), **out)
+    print("aniso_modes.npz")
+
+
+def dump_spot(api, paths):
+    from pyrateoptics.raytracer.analysis.ray_analysis import RayBundleAnalysis
+    last = paths[0].raybundles[-1]
+    ra = RayBundleAnalysis(last)
+    c = ra.get_centroid_position()
+    np.savez_compressed(os.path.join(OUT, "spot.npz"), x=np.asarray(last.x[-1]),
+                        centroid=c, rms=np.float64(ra.get_rms_spot_size(c)),
+                        rms0=np.float64(ra.get_rms_spot_size(np.zeros(3))))
+    print("spot.npz rms=%r" % ra.get_rms_spot_size(c))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    api = refshim.api()
+    np.random.seed(0)
+    for t in TRACES:
+        paths = dump_trace(api, *t)
+        if t[0] == "c2_doublegauss" and t[5] == "":
+            dump_spot(api, paths)
+    dump_frames(api)
+    dump_shapes(api)
+    dump_aniso(api)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,338 @@
+"""Benchmark / parity configurations of BASELINE.json as plain data.
+
+Every configuration is a *chain* system: each surface frame is the child of the
+previous one (as `build_simple_optical_element` does it, reference
+pyrateoptics/__init__.py:124-211).  `build_system(spec, api)` instantiates a
+spec through any class namespace that follows the pyrateoptics constructor API
+(`X.p(...)`): the reference's own classes (oracle/refshim.py, build container
+only) or this package's (`pyrate_b200.api()`), which is itself a drop-in check
+of the host API mirror.
+
+Sources:
+  C1 demos/demo_doublet.py:48-96
+  C2 demos/data/double_gauss_rudolph_1897_v2.spd:7-40 (Rudolph 1897, d-line indices)
+  C3 demos/demo_asphere.py:47-57 with A4=1e-7, A6=-1e-10
+  C4 geometry of demos/demo_anisotropic_doublet.py:55-116, uniaxial crystals
+  C5 demos/demo_grin.py:52-146
+"""
+import math
+
+import numpy as np
+
+DLINE = 0.5876e-3  # mm, reference globalconstants.py:38
+
+
+def hexapolar(rings):
+    """Hexapolar pupil sampling on the unit disk (defined by us).
+
+    Ring 0 is the centre point, ring j = 1..rings carries 6j points at radius
+    j/rings and angle 2 pi i/(6j).  N = 1 + 3 R (R + 1).
+    """
+    rings = int(rings)
+    if rings <= 0:
+        return np.zeros(1), np.zeros(1)
+    j = np.repeat(np.arange(1, rings + 1), 6 * np.arange(1, rings + 1))
+    start = 3 * (j - 1) * j          # number of ring points before ring j
+    i = np.arange(j.size) - start
+    ang = 2.0 * math.pi * i / (6.0 * j)
+    rad = j / float(rings)
+    px = np.concatenate(([0.0], rad * np.cos(ang)))
+    py = np.concatenate(([0.0], rad * np.sin(ang)))
+    return px, py
+
+
+def hexapolar_count(rings):
+    return 1 + 3 * rings * (rings + 1)
+
+
+def rings_for(nrays):
+    """Smallest ring count with at least `nrays` points."""
+    r = int(math.ceil((-3.0 + math.sqrt(9.0 + 12.0 * (nrays - 1))) / 6.0))
+    while hexapolar_count(r) < nrays:
+        r += 1
+    return max(r, 0)
+
+
+def collimated_bundle(rings, radius, z0, kdir=(0.0, 0.0, 1.0),
+                      efield=(0.0, 1.0, 0.0)):
+    """x0, k0, E0 as (3, N) float64 arrays; |k0| = 1 (background index)."""
+    px, py = hexapolar(rings)
+    n = px.size
+    x0 = np.empty((3, n))
+    x0[0] = radius * px
+    x0[1] = radius * py
+    x0[2] = z0
+    k0 = np.repeat(np.asarray(kdir, dtype=float)[:, None], n, axis=1)
+    e0 = np.repeat(np.asarray(efield, dtype=float)[:, None], n, axis=1)
+    return x0, np.ascontiguousarray(k0), np.ascontiguousarray(e0)
+
+
+def _conic(name, decz, curv=0.0, cc=0.0, mat=None, aperture=None, opt=None,
+           **lckw):
+    lc = {"decz": decz}
+    lc.update(lckw)
+    return {"name": name, "lc": lc,
+            "shape": ("Conic", {"curv": curv, "cc": cc}),
+            "aperture": aperture, "mat": mat, "opt": opt or {}}
+
+
+def _circ(r):
+    return ("CircularAperture", {"maxradius": r})
+
+
+C1_DOUBLET = {
+    "name": "c1_doublet",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", -1.048, curv=1. / 62.8, mat="bk7", aperture=_circ(12.7)),
+        _conic("cement", 4.0, curv=-1. / 45.7, mat="sf5", aperture=_circ(12.7)),
+        _conic("rear", 2.5, curv=-1. / 128.2, mat=None, aperture=_circ(12.7)),
+        _conic("image", 97.2),
+    ],
+    "materials": {"bk7": ("ConstantIndexGlass", {"n": 1.5168}),
+                  "sf5": ("ConstantIndexGlass", {"n": 1.6727})},
+    "bundle": {"rings": 18, "radius": 11.43, "z0": -5.0},
+    "s_counted": 3,
+}
+
+_N1, _N2, _N3 = 1.52345716953278, 1.54813778400421, 1.60341715812683
+_DG = [  # (name, radius, decz_before, material after)
+    ("obj", 0.0, 0.0, None),
+    ("s1", 43.5219015164416, 20.0, "g1"),
+    ("s2", -22.9137468057709, 6.63155126149407, "g2"),
+    ("s3", -54.9830148717816, 5.21926274183504, None),
+    ("s4", -39.5941875735904, 5.86288269028215, "g3"),
+    ("s5", 208.80831176475, 4.91037116991389, None),
+    ("stop", 0.0, 3.65022739559149, None),
+    ("s6", -208.80831176475, 3.65022739559149, "g3"),
+    ("s7", 39.5941875735904, 4.91037116991389, None),
+    ("s8", 54.9830148717816, 5.86288269028215, "g2"),
+    ("s9", 22.9137468057709, 5.21926274183504, "g1"),
+    ("s10", -43.5219015164416, 6.63155126149407, None),
+    ("image", 0.0, 100.0, None),
+]
+
+C2_DOUBLEGAUSS = {
+    "name": "c2_doublegauss",
+    "surfaces": [
+        _conic(nm, dz, curv=(1. / r if abs(r) > 1e-17 else 0.0), mat=mt,
+               opt=({"is_stop": True} if nm == "stop" else {}))
+        for (nm, r, dz, mt) in _DG],
+    "materials": {"g1": ("ConstantIndexGlass", {"n": _N1}),
+                  "g2": ("ConstantIndexGlass", {"n": _N2}),
+                  "g3": ("ConstantIndexGlass", {"n": _N3})},
+    "bundle": {"rings": 1825, "radius": 5.0, "z0": 0.0},
+    "s_counted": 10,
+}
+
+C3_ASPHERE = {
+    "name": "c3_asphere",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 5.0, mat="glass"),
+        {"name": "back", "lc": {"decz": 20.0},
+         "shape": ("Asphere", {"curv": -1. / 50.0, "cc": -1.0,
+                               "coefficients": [0.0, 1e-7, -1e-10]}),
+         "aperture": None, "mat": None, "opt": {}},
+        _conic("image", 100.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.5168})},
+    "bundle": {"rings": 1825, "radius": 11.43, "z0": -5.0},
+    "s_counted": 2,
+}
+
+_EPS1 = np.diag([1.658 ** 2, 1.486 ** 2, 1.658 ** 2]).tolist()  # calcite-like
+_EPS2 = np.diag([1.544 ** 2, 1.553 ** 2, 1.544 ** 2]).tolist()  # quartz-like
+
+C4_ANISOTROPIC = {
+    "name": "c4_anisotropic",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", -1.048, curv=1. / 62.8, mat="crystal1", aperture=_circ(12.7)),
+        _conic("cement", 4.0, curv=-1. / 45.7, mat="crystal2", aperture=_circ(12.7)),
+        _conic("rear", 2.5, curv=-1. / 128.2, mat=None, aperture=_circ(12.7)),
+        _conic("image", 97.2),
+    ],
+    "materials": {"crystal1": ("AnisotropicMaterial", {"epstensor": _EPS1}),
+                  "crystal2": ("AnisotropicMaterial", {"epstensor": _EPS2})},
+    "bundle": {"rings": 577, "radius": 11.43, "z0": -5.0},
+    "s_counted": 3,
+}
+
+GRIN_SOURCE = r"""
+import numpy as np
+
+grin_strength = 0.5
+
+
+def nfunc(x, **kw):
+    return grin_strength*np.exp(-x[0]**2 - 4.*x[1]**2)+1.0
+
+
+def dndx(x, **kw):
+    return -2.*x[0]*grin_strength*np.exp(-x[0]**2 - 4.*x[1]**2)
+
+
+def dndy(x, **kw):
+    return -2.*4.*x[1]*grin_strength*np.exp(-x[0]**2 - 4.*x[1]**2)
+
+
+def dndz(x, **kw):
+    return np.zeros_like(x[0])
+
+
+def bnd(x):
+    return x[0]**2 + x[1]**2 < 10.**2
+"""
+
+C5_GRIN = {
+    "name": "c5_grin",
+    "surfaces": [
+        _conic("object", 0.0, opt={"is_stop": True}),
+        _conic("surf1", 10.0, curv=1. / 24.0, mat="grin", aperture=_circ(5.0),
+               tiltx=5. * math.pi / 180.0),
+        _conic("surf2", 20.0, curv=-1. / 24.0, mat=None, aperture=_circ(5.0),
+               tiltx=10. * math.pi / 180.0),
+        _conic("image", 10.0),
+    ],
+    "materials": {"grin": ("IsotropicGrinMaterial", {
+        "source": GRIN_SOURCE,
+        "names": ("nfunc", "dndx", "dndy", "dndz", "bnd"),
+        "parameterlist": [("n0", 0.5)],
+        "ds": 0.05, "energyviolation": 0.01,
+        # closed-catalogue device profile: n = n0 + g exp(-a x^2 - b y^2),
+        # boundary x^2 + y^2 < r^2  (checked against the Python source at
+        # lowering time, pyrate_b200/lowering.py)
+        "device_profile": {"kind": "gaussian_xy",
+                           "params": [1.0, 0.5, 1.0, 4.0],
+                           "boundary": {"kind": "cylinder", "params": [10.0]}},
+    })},
+    "bundle": {"rings": 5773, "radius": 2.5, "z0": -5.0},
+    "s_counted": 2,
+}
+
+CONFIGS = {c["name"]: c for c in
+           (C1_DOUBLET, C2_DOUBLEGAUSS, C3_ASPHERE, C4_ANISOTROPIC, C5_GRIN)}
+
+
+def build_system(spec, api):
+    """Instantiate `spec` with the classes in `api`; returns (system, seq)."""
+    s = api.OpticalSystem.p(name=spec["name"])
+    lc0 = s.addLocalCoordinateSystem(
+        api.LocalCoordinates.p(name="object_lc0", decz=0.0),
+        refname=s.rootcoordinatesystem.name)
+    elem = api.OpticalElement.p(lc0, name="stdelem")
+    refname = lc0.name
+    lastmat = None
+    seq = []
+    made = set()
+    for surf in spec["surfaces"]:
+        lc = elem.addLocalCoordinateSystem(
+            api.LocalCoordinates.p(name=surf["name"] + "_lc", **surf["lc"]),
+            refname=refname)
+        (shapekind, shapekw) = surf["shape"]
+        shape = getattr(api, shapekind).p(lc, **shapekw)
+        aperture = None
+        if surf["aperture"] is not None:
+            (apkind, apkw) = surf["aperture"]
+            aperture = getattr(api, apkind).p(lc, **apkw)
+        surface = api.Surface.p(lc, shape=shape, aperture=aperture,
+                                name=surf["name"] + "_surf")
+        mat = surf["mat"]
+        if mat is not None and mat not in made:
+            elem.addMaterial(mat, _make_material(api, lc, spec["materials"][mat],
+                                                 mat))
+            made.add(mat)
+        elem.addSurface(surf["name"], surface, (lastmat, mat))
+        lastmat = mat
+        refname = lc.name
+        seq.append((surf["name"], dict(surf["opt"])))
+    s.addElement("stdelem", elem)
+    return s, [("stdelem", seq)]
+
+
+def _make_material(api, lc, matspec, name):
+    (kind, kw) = matspec
+    if kind == "ConstantIndexGlass":
+        return api.ConstantIndexGlass.p(lc, n=kw["n"], name=name)
+    if kind == "ModelGlass":
+        return api.ModelGlass.p(lc, n0_A_B=tuple(kw["n0_A_B"]), name=name)
+    if kind == "AnisotropicMaterial":
+        return api.AnisotropicMaterial.p(lc, np.array(kw["epstensor"]),
+                                         name=name)
+    if kind == "IsotropicGrinMaterial":
+        m = api.IsotropicGrinMaterial.p(lc, kw["source"], *kw["names"],
+                                        parameterlist=list(kw["parameterlist"]),
+                                        name=name)
+        m.annotations["ds"] = kw["ds"]
+        m.annotations["energyviolation"] = kw["energyviolation"]
+        # ignored by the reference; read by pyrate_b200's lowering
+        m.annotations["device_profile"] = kw["device_profile"]
+        return m
+    raise ValueError("unknown material kind %r" % (kind,))
+
+
+def config_bundle(spec, rings=None, kdir=(0.0, 0.0, 1.0),
+                  efield=(0.0, 1.0, 0.0)):
+    b = spec["bundle"]
+    return collimated_bundle(b["rings"] if rings is None else rings,
+                             b["radius"], b["z0"], kdir, efield)
+
+
+# ---------------------------------------------------------------------------
+# Extra parity-only systems (not BASELINE configs): general frames, mirror,
+# rectangular aperture, dispersion model, XY polynomial, vignetting / TIR.
+# ---------------------------------------------------------------------------
+X1_TILTED = {
+    "name": "x1_tilted",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 3.0, curv=1. / 40.0, cc=-0.5, mat="mg",
+               aperture=_circ(9.0), decx=0.3, decy=-0.2,
+               tiltx=2.0 * math.pi / 180.0, tilty=-1.5 * math.pi / 180.0),
+        _conic("back", 5.0, curv=-1. / 55.0, cc=0.3, mat=None,
+               aperture=("RectangularAperture", {"width": 14.0, "height": 12.0}),
+               tiltz=10.0 * math.pi / 180.0, tiltx=-1.0 * math.pi / 180.0,
+               tiltThenDecenter=1, decy=0.25),
+        _conic("mirror", 30.0, curv=-1. / 200.0, mat=None,
+               tiltx=12.0 * math.pi / 180.0, opt={"is_mirror": True}),
+        _conic("image", -25.0, tiltx=12.0 * math.pi / 180.0),
+    ],
+    "materials": {"mg": ("ModelGlass", {"n0_A_B": (1.49749699179,
+                                                   0.0100998734374 * 1e-3,
+                                                   0.000328623343942 * (1e-3) ** 3.5)})},
+    "bundle": {"rings": 8, "radius": 6.0, "z0": -4.0},
+    "s_counted": 3,
+}
+
+X2_XYPOLY = {
+    "name": "x2_xypoly",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 4.0, curv=1. / 80.0, mat="glass"),
+        {"name": "back", "lc": {"decz": 6.0, "tilty": 1.0 * math.pi / 180.0},
+         "shape": ("XYPolynomials", {"normradius": 10.0, "coefficients": [
+             (2, 0, -0.9), (0, 2, -1.1), (1, 1, 0.05), (3, 0, 0.02),
+             (1, 2, -0.03), (4, 0, 0.004), (2, 2, 0.006), (0, 4, -0.005)]}),
+         "aperture": None, "mat": None, "opt": {}},
+        _conic("image", 60.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.62})},
+    "bundle": {"rings": 6, "radius": 7.0, "z0": -3.0},
+    "s_counted": 2,
+}
+
+X3_VIGNETTE = {   # misses, aperture clipping and total internal reflection
+    "name": "x3_vignette",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 2.0, curv=1. / 9.0, mat="dense", aperture=_circ(8.5)),
+        _conic("back", 6.0, curv=-1. / 7.5, mat=None, aperture=_circ(7.0)),
+        _conic("image", 12.0),
+    ],
+    "materials": {"dense": ("ConstantIndexGlass", {"n": 1.9})},
+    "bundle": {"rings": 10, "radius": 9.5, "z0": -2.0},
+    "s_counted": 2,
+}
+
+CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE)})
