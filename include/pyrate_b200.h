@@ -1,0 +1,241 @@
+/*
+ * pyrate_b200 -- C ABI of the B200-native sequential trace engine.
+ *
+ * This is the drop-in boundary for ONE path of mess42/pyrate (pyrateoptics
+ * 0.4.0): OpticalSystem.seqtrace (raytracer/optical_system.py:73-94) ->
+ * OpticalElement.seqtrace (raytracer/optical_element.py:324-379) and the
+ * per-surface step below it.  The reference has no FFI on this path (it is pure
+ * NumPy); its one FFI precedent is the ctypes binding of a user DLL in
+ * raytracer/surface_shape_zmxdll.py:293, and INTEGRATION.md shows the ctypes
+ * stub a pyrate maintainer would add inside OpticalSystem.seqtrace to call
+ * pyr_trace().  Signatures are plain C: pointers, sizes, PODs.  No torch types.
+ *
+ * Conventions
+ *   - all ray arrays are component-major "(3, n)" like the reference's
+ *     RayBundle rows (raytracer/ray.py:40-66): element (c, i) lives at
+ *     base[c * ld + i] with leading dimension ld >= n (ld even and base 16-byte
+ *     aligned enables 128-bit accesses; anything else still works).
+ *   - complex arrays are interleaved (re, im) doubles = numpy/torch complex128;
+ *     element (c, i) at base[2 * (c * ld + i)].
+ *   - every device pointer is caller-owned (the engine allocates nothing
+ *     persistent and frees nothing); calls are asynchronous on `stream`.
+ *   - return value: 0 = ok, < 0 = PYR_E_* (see pyr_strerror), > 0 = cudaError_t.
+ *   - per-ray failures are never errors: they are reported through the flag
+ *     byte (and NaN coordinates), like the reference's `valid` rows.
+ */
+#ifndef PYRATE_B200_H
+#define PYRATE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PYR_ABI_VERSION 1
+
+#define PYR_MAX_COEFF 32        /* asphere coefficients / XY-polynomial terms */
+#define PYR_MAX_GRIN_PARAMS 8
+
+/* error codes */
+#define PYR_OK 0
+#define PYR_E_BADARG (-1)
+#define PYR_E_UNSUPPORTED (-2)
+#define PYR_E_TOOLARGE (-3)
+#define PYR_E_NODEVICE (-4)
+
+/* Shape.intersect variants (raytracer/surface_shape.py) */
+enum PyrShapeKind {
+    PYR_SHAPE_CONIC = 0,        /* Conic.intersect :289-325, closed form          */
+    PYR_SHAPE_ASPHERE = 1,      /* ExplicitShape.intersect :448-465 + Asphere.F   */
+    PYR_SHAPE_XYPOLY = 2        /* ExplicitShape.intersect + XYPolynomials.F :785 */
+};
+
+/* raytracer/aperture.py:71-140 */
+enum PyrApertureKind {
+    PYR_AP_BASE = 0,            /* passes everything                               */
+    PYR_AP_CIRCULAR = 1,        /* p[0] = minradius, p[1] = maxradius              */
+    PYR_AP_RECTANGULAR = 2      /* p[0] = width, p[1] = height                     */
+};
+
+/* what the material on the far side does with the ray (optical_element.py:338-368) */
+enum PyrInteraction {
+    PYR_REFRACT = 0,            /* Material.refract                                */
+    PYR_REFLECT = 1             /* Material.reflect (is_mirror)                    */
+};
+
+/* medium model (raytracer/material/*.py) */
+enum PyrMediumKind {
+    PYR_MEDIUM_ISO_CONST = 0,   /* IsotropicMaterial with position-independent n   */
+    PYR_MEDIUM_ISO_GRIN = 1,    /* IsotropicGrinMaterial (material_grin.py)        */
+    PYR_MEDIUM_ANISO = 2        /* AnisotropicMaterial (material_anisotropic.py)   */
+};
+
+/* closed catalogue of GRIN index profiles, evaluated in the material frame */
+enum PyrGrinProfile {
+    PYR_GRIN_GAUSSIAN_XY = 0,   /* n = p0 + p1 exp(-p2 x^2 - p3 y^2)               */
+    PYR_GRIN_POLY_RZ = 1        /* n = p0 + p1 r^2 + p2 r^4 + p3 r^6
+                                       + p4 z + p5 z^2 + p6 z^3,  r^2 = x^2+y^2    */
+};
+
+enum PyrGrinBoundary {
+    PYR_BND_NONE = 0,
+    PYR_BND_CYLINDER = 1,       /* x^2 + y^2 < b0^2                                */
+    PYR_BND_BOX = 2,            /* |x| < b0 and |y| < b1                           */
+    PYR_BND_SPHERE = 3          /* x^2 + y^2 + z^2 < b0^2                          */
+};
+
+/* which half of the step runs: the fused path always uses PYR_STEP_FULL; the two
+ * partial modes back the reference's stand-alone plugin calls
+ * Material.propagate / Surface.intersect and Material.refract / reflect          */
+enum PyrStepMode {
+    PYR_STEP_FULL = 0,
+    PYR_STEP_PROPAGATE_ONLY = 1, /* intersect + aperture; k, E unchanged            */
+    PYR_STEP_DEFLECT_ONLY = 2    /* x is already the hit point; refract / reflect   */
+};
+
+/* how the ray direction d is obtained from (k, E) before the intersect
+ * (RayBundle.returnKtoD, raytracer/ray.py:136-152) */
+enum PyrDirMode {
+    PYR_DIR_POYNTING = 0,       /* d = S/|S|, S = Re(|E|^2 k - (E.k) conj(E))      */
+    PYR_DIR_K = 1               /* d = Re(k)/|Re(k)|: exact whenever E.k = 0, which
+                                   every isotropic refraction guarantees          */
+};
+
+/* A frame maps local -> global as  x_g = R x_l + o  (R row-major, orthonormal),
+ * global -> local as  x_l = R^T (x_g - o)   (localcoordinates.py:383-413).      */
+typedef struct PyrFrame {
+    double r[9];
+    double o[3];
+} PyrFrame;
+
+typedef struct PyrMedium {
+    int32_t kind;               /* PyrMediumKind                                   */
+    int32_t grin_profile;       /* PyrGrinProfile                                  */
+    int32_t grin_boundary;      /* PyrGrinBoundary                                 */
+    int32_t grin_max_steps;     /* safety cap per ray (0 = default 1000000)        */
+    double n;                   /* ISO_CONST: refractive index at the bundle wave  */
+    double eps[18];             /* ANISO: complex 3x3 (row-major, re/im) in the
+                                   MATERIAL frame (get_epsilon_tensor)             */
+    double grin_p[PYR_MAX_GRIN_PARAMS];
+    double grin_b[4];
+    double grin_ds;             /* annotations["ds"] (material_grin.py:218)        */
+    double grin_energy_tol;     /* annotations["energyviolation"], tested PER RAY  */
+    PyrFrame frame;             /* material frame (material.lc)                    */
+} PyrMedium;
+
+/* One entry of the element sequence = propagate to the surface, intersect,
+ * aperture, then refract/reflect into `after` (optical_element.py:336-375).     */
+typedef struct PyrStep {
+    int32_t shape_kind;         /* PyrShapeKind                                    */
+    int32_t aperture_kind;      /* PyrApertureKind                                 */
+    int32_t interaction;        /* PyrInteraction                                  */
+    int32_t dir_mode;           /* PyrDirMode for the segment ending here          */
+    int32_t n_coeff;            /* used entries of coeff[]                         */
+    int32_t newton_maxit;       /* iteration cap of the explicit-shape solve       */
+    int32_t split;              /* ANISO deflection only: 1 = this step doubles the
+                                   rays (splitup=False, material_anisotropic.py
+                                   :87-100); only allowed on the LAST step of a
+                                   pyr_trace call                                  */
+    int32_t mode;               /* PyrStepMode                                     */
+    double k_norm_hint;         /* > 0: |Re k| on entry is known to be this value
+                                   (index of `before` after an isotropic
+                                   deflection); saves the normalisation in
+                                   PYR_DIR_K mode.  0 = unknown                    */
+    double curv, cc;            /* conic / asphere base conic                      */
+    double normradius;          /* XY polynomial                                   */
+    double newton_tol;          /* |dt| <= tol (1 + |t|) ends the iteration        */
+    double coeff[PYR_MAX_COEFF];        /* asphere: A2, A4, ...; XY: c_mn          */
+    int8_t xpow[PYR_MAX_COEFF];         /* XY polynomial exponents                 */
+    int8_t ypow[PYR_MAX_COEFF];
+    double aperture_p[4];
+    PyrFrame shape_frame;       /* shape.lc                                        */
+    PyrFrame aperture_frame;    /* aperture.lc                                     */
+    PyrMedium before;           /* medium the ray propagates in up to the surface  */
+    PyrMedium after;            /* medium that deflects the ray at the surface     */
+
+    /* where to record this step (device pointers; NULL = do not record).
+     * n = rays of the call, n_out = n, or 2n on a split step.                    */
+    double *out_x;              /* (3, n)      hit point, global frame             */
+    double *out_k;              /* (3, n_out)  wave vector after deflection, global;
+                                   complex if PYR_F_COMPLEX                        */
+    double *out_e;              /* (3, n_out)  E field after deflection, global    */
+    uint8_t *out_flags;         /* (n)         PYR_RAY_* bits                      */
+    int64_t ld_out;             /* leading dimension of out_x / out_k / out_e      */
+} PyrStep;
+
+/* per-ray flag bits written to out_flags */
+#define PYR_RAY_HIT 1u          /* still valid after propagate+intersect+aperture
+                                   (RayBundle.valid[-1] after Surface.intersect)   */
+#define PYR_RAY_ALIVE 2u        /* survives the deflection: contained in the next
+                                   RayBundle (material_isotropic.py:183-199)       */
+
+typedef struct PyrRaysIn {
+    const double *x;            /* (3, n_x)  start points, global frame            */
+    const double *k;            /* (3, n)    wave vectors (complex if flag)        */
+    const double *e;            /* (3, n)    E field (complex if flag); NULL ->
+                                   (0, 1, 0) like ray.py:71-73                     */
+    const uint8_t *alive;       /* (n_x) PYR_RAY_ALIVE bit of the producing step,
+                                   NULL -> all alive                               */
+    int64_t ld;                 /* leading dimension of x, k, e                    */
+    int64_t n_x;                /* width of x/alive; ray i reads column i % n_x
+                                   (n_x = n/2 right after a split step); 0 -> n    */
+} PyrRaysIn;
+
+/* flags of pyr_trace */
+#define PYR_F_COMPLEX 1u        /* k and E are complex128 on input and output      */
+#define PYR_F_RECORD_E 2u       /* maintain E and write out_e                      */
+
+int pyr_version(void);
+const char *pyr_strerror(int code);
+
+/* sizeof(PyrStep) / sizeof(PyrRaysIn) as compiled, so a foreign-language binding
+ * can verify its struct layout before the first call. */
+int64_t pyr_sizeof_step(void);
+int64_t pyr_sizeof_rays_in(void);
+
+/* Number of CUDA devices visible (0 when the driver is missing). */
+int pyr_device_count(void);
+
+/*
+ * Trace `n_rays` rays through steps[0..n_steps): replaces the loop body of
+ * OpticalElement.seqtrace (optical_element.py:336-375) for every ray of the
+ * bundle -- Material.propagate (material_isotropic.py:238-247,
+ * material_grin.py:106-220), Surface.intersect (surface.py:116-135),
+ * Material.refract / reflect (material_isotropic.py:163-236,
+ * material_anisotropic.py:70-155).  `steps` is HOST memory (copied into the
+ * launch), the rays and all outputs are DEVICE memory on the current device.
+ * One persistent kernel launch per call (long sequences are chunked).
+ */
+int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
+              int64_t n_rays, uint32_t flags, void *stream);
+
+/*
+ * Spot statistics of RayBundleAnalysis (analysis/ray_analysis.py:44-86) over
+ * the rays whose `flags & mask` is non-zero (flags NULL = all):
+ *   out[0..2] = sum x, out[3] = count, out[4..6] = sum x^2, out[7] = 0
+ * written to DEVICE memory `out8` (accumulated: caller zeroes it), so partial
+ * sums of several ranks can be all-reduced before centroid / rms are formed.
+ */
+int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
+                  uint32_t mask, int64_t n, double *out8, void *stream);
+
+/*
+ * End-to-end host entry: start points / wave vectors / E in (pinned) HOST
+ * memory, final-surface record back in HOST memory.  Chunks the bundle,
+ * overlaps H2D, trace and D2H on internal streams.  `workspace` is caller-owned
+ * DEVICE memory of at least pyr_trace_host_workspace() bytes.  Only real
+ * (non-complex), non-splitting sequences.  Outputs (host, ld = n_rays):
+ *   x_last (3, n), k_last (3, n), flags_last (n), spot8[8] (sums as above).
+ */
+int64_t pyr_trace_host_workspace(int32_t n_steps, int64_t chunk_rays);
+int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0,
+                   const double *k0, const double *e0, int64_t n_rays,
+                   double *x_last, double *k_last, uint8_t *flags_last,
+                   double *spot8, void *workspace, int64_t workspace_bytes,
+                   int64_t chunk_rays);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYRATE_B200_H */

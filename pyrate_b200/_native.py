@@ -1,0 +1,118 @@
+"""ctypes binding of the C ABI in include/pyrate_b200.h (libpyrate_b200.so).
+
+The same mechanism the reference uses for its only FFI
+(raytracer/surface_shape_zmxdll.py:293, ctypes.CDLL).  There is NO fallback: if
+the library is missing or was built for another ABI, loading raises.
+"""
+import ctypes as C
+import os
+
+MAX_COEFF = 32
+MAX_GRIN_PARAMS = 8
+
+(SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY) = (0, 1, 2)
+(AP_BASE, AP_CIRCULAR, AP_RECTANGULAR) = (0, 1, 2)
+(REFRACT, REFLECT) = (0, 1)
+(MEDIUM_ISO_CONST, MEDIUM_ISO_GRIN, MEDIUM_ANISO) = (0, 1, 2)
+(GRIN_GAUSSIAN_XY, GRIN_POLY_RZ) = (0, 1)
+(BND_NONE, BND_CYLINDER, BND_BOX, BND_SPHERE) = (0, 1, 2, 3)
+(DIR_POYNTING, DIR_K) = (0, 1)
+(STEP_FULL, STEP_PROPAGATE_ONLY, STEP_DEFLECT_ONLY) = (0, 1, 2)
+(RAY_HIT, RAY_ALIVE) = (1, 2)
+(F_COMPLEX, F_RECORD_E) = (1, 2)
+
+
+class PyrFrame(C.Structure):
+    _fields_ = [("r", C.c_double * 9), ("o", C.c_double * 3)]
+
+
+class PyrMedium(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("grin_profile", C.c_int32),
+                ("grin_boundary", C.c_int32), ("grin_max_steps", C.c_int32),
+                ("n", C.c_double), ("eps", C.c_double * 18),
+                ("grin_p", C.c_double * MAX_GRIN_PARAMS),
+                ("grin_b", C.c_double * 4),
+                ("grin_ds", C.c_double), ("grin_energy_tol", C.c_double),
+                ("frame", PyrFrame)]
+
+
+class PyrStep(C.Structure):
+    _fields_ = [("shape_kind", C.c_int32), ("aperture_kind", C.c_int32),
+                ("interaction", C.c_int32), ("dir_mode", C.c_int32),
+                ("n_coeff", C.c_int32), ("newton_maxit", C.c_int32),
+                ("split", C.c_int32), ("mode", C.c_int32),
+                ("k_norm_hint", C.c_double),
+                ("curv", C.c_double), ("cc", C.c_double),
+                ("normradius", C.c_double), ("newton_tol", C.c_double),
+                ("coeff", C.c_double * MAX_COEFF),
+                ("xpow", C.c_int8 * MAX_COEFF), ("ypow", C.c_int8 * MAX_COEFF),
+                ("aperture_p", C.c_double * 4),
+                ("shape_frame", PyrFrame), ("aperture_frame", PyrFrame),
+                ("before", PyrMedium), ("after", PyrMedium),
+                ("out_x", C.c_void_p), ("out_k", C.c_void_p),
+                ("out_e", C.c_void_p), ("out_flags", C.c_void_p),
+                ("ld_out", C.c_int64)]
+
+
+class PyrRaysIn(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("k", C.c_void_p), ("e", C.c_void_p),
+                ("alive", C.c_void_p), ("ld", C.c_int64), ("n_x", C.c_int64)]
+
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
+                        "libpyrate_b200.so")
+
+EXPORTS = ("pyr_version", "pyr_strerror", "pyr_sizeof_step",
+           "pyr_sizeof_rays_in", "pyr_device_count", "pyr_trace",
+           "pyr_spot_sums", "pyr_trace_host_workspace", "pyr_trace_host")
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load():
+    """Load (once) and type the library.  Raises if absent or ABI-mismatched."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            "pyrate_b200: %s not built (run `make` or __graft_entry__.build()); "
+            "there is no CPU fallback" % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.pyr_version.restype = C.c_int
+    lib.pyr_strerror.restype = C.c_char_p
+    lib.pyr_strerror.argtypes = [C.c_int]
+    lib.pyr_sizeof_step.restype = C.c_int64
+    lib.pyr_sizeof_rays_in.restype = C.c_int64
+    lib.pyr_device_count.restype = C.c_int
+    lib.pyr_trace.restype = C.c_int
+    lib.pyr_trace.argtypes = [C.POINTER(PyrStep), C.c_int32,
+                              C.POINTER(PyrRaysIn), C.c_int64, C.c_uint32,
+                              C.c_void_p]
+    lib.pyr_spot_sums.restype = C.c_int
+    lib.pyr_spot_sums.argtypes = [C.c_void_p, C.c_int64, C.c_void_p,
+                                  C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]
+    lib.pyr_trace_host_workspace.restype = C.c_int64
+    lib.pyr_trace_host_workspace.argtypes = [C.c_int32, C.c_int64]
+    lib.pyr_trace_host.restype = C.c_int
+    lib.pyr_trace_host.argtypes = [C.POINTER(PyrStep), C.c_int32, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int64,
+                                   C.c_void_p, C.c_void_p, C.c_void_p,
+                                   C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    if lib.pyr_sizeof_step() != C.sizeof(PyrStep) or \
+            lib.pyr_sizeof_rays_in() != C.sizeof(PyrRaysIn):
+        raise NativeError("pyrate_b200: struct layout mismatch between "
+                          "_native.py and libpyrate_b200.so (%d vs %d)" %
+                          (C.sizeof(PyrStep), lib.pyr_sizeof_step()))
+    _lib = lib
+    return lib
+
+
+def check(code):
+    if code != 0:
+        raise NativeError("pyrate_b200 native call failed (%d): %s" %
+                          (code, load().pyr_strerror(code).decode()))

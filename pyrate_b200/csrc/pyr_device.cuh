@@ -1,0 +1,117 @@
+// Device-side step table and small FP64 helpers of the trace kernels.
+//
+// The public PyrStep (include/pyrate_b200.h) is a fat, self-describing POD.  For
+// the launch it is packed into a compact DStep (hot fields every step needs)
+// plus an optional DAux (polynomial coefficients, second frame, GRIN / crystal
+// payload).  Both tables travel in the kernel parameter block
+// (__grid_constant__, constant bank 0), so per-step constants reach the FP64
+// pipe as constant-cache operands instead of LSU traffic, and the library keeps
+// no global state (re-entrant per stream).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/pyrate_b200.h"
+
+namespace pyr {
+
+constexpr int kMaxSteps = 40;      // per launch (longer sequences are chunked)
+constexpr int kMaxAux = 10;
+
+// DStep.bits
+constexpr uint32_t kRotIdentity = 1u;      // shape frame rotation is the identity
+constexpr uint32_t kApSameFrame = 2u;      // aperture.lc == shape.lc
+constexpr uint32_t kSplit = 4u;            // anisotropic ray doubling on this step
+constexpr uint32_t kSphere = 8u;           // cc == 0: |grad| == 1, no normalisation
+constexpr uint32_t kPlane = 16u;           // curv == 0 (and conic shape)
+
+struct DFrame {
+    double r[9];
+    double o[3];
+};
+
+struct DMedium {
+    int32_t kind, profile, boundary, max_steps;
+    double n;
+    double eps[18];        // rotated into the SHAPE frame of the step at pack time
+    double p[PYR_MAX_GRIN_PARAMS];
+    double b[4];
+    double ds, energy_tol;
+    DFrame frame;          // material frame
+    DFrame to_shape;       // material frame -> shape frame of this step
+};
+
+struct DAux {
+    double coeff[PYR_MAX_COEFF];
+    int8_t xpow[PYR_MAX_COEFF];
+    int8_t ypow[PYR_MAX_COEFF];
+    double normradius, newton_tol;
+    int32_t n_coeff, newton_maxit;
+    DFrame aperture_frame;
+    DMedium before, after;
+};
+
+struct DStep {
+    DFrame frame;                  // shape frame (local -> global)
+    double curv, cc;
+    double ap0, ap1;               // circular: min^2, max^2; rectangular: w/2, h/2
+    double n2sq;                   // (index of the deflecting medium)^2, ISO_CONST
+    double inv_knorm;              // > 0: |k| known on entry (1/n of `before`)
+    double *out_x, *out_k, *out_e;
+    uint8_t *out_flags;
+    int64_t ld_out;
+    uint32_t bits;
+    int8_t shape_kind, aperture_kind, interaction, dir_mode;
+    int8_t before_kind, after_kind, aux, pad0;
+};
+
+struct LaunchParams {
+    const double *x, *k, *e;
+    const uint8_t *alive;
+    int64_t ld_in, n_x, n;
+    int32_t n_steps;
+    uint32_t flags;
+    int32_t in_vec2;               // inputs allow 128-bit loads
+    int32_t pad;
+    DStep steps[kMaxSteps];
+    DAux aux[kMaxAux];
+};
+
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double dot3(const double a[3], const double b[3]) {
+    return fma(a[0], b[0], fma(a[1], b[1], a[2] * b[2]));
+}
+
+// y = R^T v   (global -> local direction)
+__device__ __forceinline__ void rot_t(const double r[9], const double v[3], double y[3]) {
+    y[0] = fma(r[0], v[0], fma(r[3], v[1], r[6] * v[2]));
+    y[1] = fma(r[1], v[0], fma(r[4], v[1], r[7] * v[2]));
+    y[2] = fma(r[2], v[0], fma(r[5], v[1], r[8] * v[2]));
+}
+
+// y = R v     (local -> global direction)
+__device__ __forceinline__ void rot(const double r[9], const double v[3], double y[3]) {
+    y[0] = fma(r[0], v[0], fma(r[1], v[1], r[2] * v[2]));
+    y[1] = fma(r[3], v[0], fma(r[4], v[1], r[5] * v[2]));
+    y[2] = fma(r[6], v[0], fma(r[7], v[1], r[8] * v[2]));
+}
+
+__device__ __forceinline__ void g2l_point(const DFrame &f, const double x[3], double y[3]) {
+    const double t[3] = {x[0] - f.o[0], x[1] - f.o[1], x[2] - f.o[2]};
+    rot_t(f.r, t, y);
+}
+
+__device__ __forceinline__ void l2g_point(const DFrame &f, const double x[3], double y[3]) {
+    y[0] = fma(f.r[0], x[0], fma(f.r[1], x[1], fma(f.r[2], x[2], f.o[0])));
+    y[1] = fma(f.r[3], x[0], fma(f.r[4], x[1], fma(f.r[5], x[2], f.o[1])));
+    y[2] = fma(f.r[6], x[0], fma(f.r[7], x[1], fma(f.r[8], x[2], f.o[2])));
+}
+
+__device__ __forceinline__ bool finite3(const double v[3]) {
+    return isfinite(v[0]) && isfinite(v[1]) && isfinite(v[2]);
+}
+
+__device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
+
+}  // namespace pyr

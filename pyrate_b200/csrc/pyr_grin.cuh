@@ -1,0 +1,105 @@
+// GRIN media: index profiles and the 4th-order symplectic integrator.
+// Mirrors raytracer/material/material_grin.py of the reference:
+//   symplecticintegrator :106-213 (Forest-Ruth coefficients :116-123, drift/kick
+//   loop :139-157, energy test :164-176, "final" test :181-186, boundary :189-193,
+//   freeze rule :195-196, k = p/n :198-199), propagate :215-220.
+// Normalisations (documented in DESIGN.md): the energy test is per ray instead of
+// bundle-summed, and a ray stops stepping once it is final instead of stepping in
+// lock-step with the slowest ray of the bundle.
+#pragma once
+
+#include "pyr_shapes.cuh"
+
+namespace pyr {
+
+// index n and gradient at material-frame position q
+__device__ __forceinline__ double grin_index(const DMedium &m, const double q[3], double g[3],
+                                             bool want_grad) {
+    if (m.profile == PYR_GRIN_GAUSSIAN_XY) {
+        const double ex = m.p[1] * exp(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]));
+        if (want_grad) {
+            g[0] = -2.0 * m.p[2] * q[0] * ex;
+            g[1] = -2.0 * m.p[3] * q[1] * ex;
+            g[2] = 0.0;
+        }
+        return m.p[0] + ex;
+    }
+    // PYR_GRIN_POLY_RZ
+    const double r2 = fma(q[0], q[0], q[1] * q[1]);
+    const double z = q[2];
+    const double nr = fma(fma(fma(m.p[3], r2, m.p[2]), r2, m.p[1]), r2, m.p[0]);
+    const double nz = z * fma(fma(m.p[6], z, m.p[5]), z, m.p[4]);
+    if (want_grad) {
+        const double dr = 2.0 * fma(fma(3.0 * m.p[3], r2, 2.0 * m.p[2]), r2, m.p[1]);
+        g[0] = q[0] * dr;
+        g[1] = q[1] * dr;
+        g[2] = fma(fma(3.0 * m.p[6], z, 2.0 * m.p[5]), z, m.p[4]);
+    }
+    return nr + nz;
+}
+
+__device__ __forceinline__ bool grin_inside(const DMedium &m, const double q[3]) {
+    switch (m.boundary) {
+        case PYR_BND_CYLINDER: return fma(q[0], q[0], q[1] * q[1]) < m.b[0] * m.b[0];
+        case PYR_BND_BOX: return fabs(q[0]) < m.b[0] && fabs(q[1]) < m.b[1];
+        case PYR_BND_SPHERE: return dot3(q, q) < m.b[0] * m.b[0];
+        default: return true;
+    }
+}
+
+// Integrates from global point x along global unit direction d through medium m
+// until the next surface (shape of the current step) is crossed.  On return x is
+// the last position BEFORE the crossing and k = p/n there (both global);
+// returns validity (energy, boundary, step cap).
+__device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind, const DAux *aux,
+                                               double curv, double cc, double x[3],
+                                               const double d[3], double k[3]) {
+    const double c0 = 1.0 / (2.0 * (2.0 - 1.2599210498948732));
+    const double c1 = (1.0 - 1.2599210498948732) / (2.0 * (2.0 - 1.2599210498948732));
+    const double d0 = 1.0 / (2.0 - 1.2599210498948732);
+    const double d1 = -1.2599210498948732 / (2.0 - 1.2599210498948732);
+    const double cs[4] = {c0, c1, c1, c0};
+    const double ds[4] = {d0, d1, d0, 0.0};
+
+    double q[3], p[3], g[3];
+    g2l_point(m.frame, x, q);
+    rot_t(m.frame.r, d, p);
+    const double n0 = grin_index(m, q, g, false);
+    p[0] *= n0; p[1] *= n0; p[2] *= n0;
+    double uq[3] = {q[0], q[1], q[2]}, up[3] = {p[0], p[1], p[2]};
+    const double tau2 = 2.0 * m.ds;
+    const int cap = m.max_steps > 0 ? m.max_steps : 1000000;
+    bool valid = true;
+    for (int it = 0; it < cap; ++it) {
+        double nq = 0.0;
+#pragma unroll
+        for (int s = 0; s < 4; ++s) {
+            q[0] = fma(tau2 * cs[s], p[0], q[0]);
+            q[1] = fma(tau2 * cs[s], p[1], q[1]);
+            q[2] = fma(tau2 * cs[s], p[2], q[2]);
+            nq = grin_index(m, q, g, s < 3);
+            if (s < 3) {
+                const double f = tau2 * ds[s] * nq;
+                p[0] = fma(f, g[0], p[0]);
+                p[1] = fma(f, g[1], p[1]);
+                p[2] = fma(f, g[2], p[2]);
+            }
+        }
+        if (fabs(dot3(p, p) - nq * nq) > m.energy_tol) valid = false;
+        double xs[3];
+        l2g_point(m.to_shape, q, xs);
+        const bool crossed = xs[2] - shape_sag(shape_kind, aux, curv, cc, xs[0], xs[1]) > 0.0;
+        if (!grin_inside(m, q)) valid = false;
+        if (crossed || !valid) break;
+        uq[0] = q[0]; uq[1] = q[1]; uq[2] = q[2];
+        up[0] = p[0]; up[1] = p[1]; up[2] = p[2];
+        if (it == cap - 1) valid = false;
+    }
+    const double inv = 1.0 / grin_index(m, uq, g, false);
+    const double kl[3] = {up[0] * inv, up[1] * inv, up[2] * inv};
+    l2g_point(m.frame, uq, x);
+    rot(m.frame.r, kl, k);
+    return valid;
+}
+
+}  // namespace pyr

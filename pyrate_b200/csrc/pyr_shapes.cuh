@@ -1,0 +1,141 @@
+// Surface shapes: sag, gradient and ray intersection in the shape frame.
+// Mirrors (does not copy) raytracer/surface_shape.py of the reference:
+//   Conic.intersect :289-325, conic_function :206-219, getGrad :221-237
+//   ExplicitShape.intersect :448-465 (root of z0 + t dz - F(x0 + t dx, y0 + t dy))
+//   Asphere.F :529-537, gradF :539-555;  XYPolynomials.F :785-793, gradF :795-807
+#pragma once
+
+#include "pyr_device.cuh"
+
+namespace pyr {
+
+// Closed-form conic hit.  Returns t; `ok` = (F^2 + H G >= 0) as in :321.
+__device__ __forceinline__ double conic_t(double curv, double cc, const double r0[3],
+                                          const double d[3], bool &ok) {
+    const double cc1 = 1.0 + cc;
+    const double F = d[2] - curv * fma(d[0], r0[0], fma(d[1], r0[1], d[2] * r0[2] * cc1));
+    const double G = curv * fma(r0[0], r0[0], fma(r0[1], r0[1], r0[2] * r0[2] * cc1)) - 2.0 * r0[2];
+    const double H = -curv - cc * curv * d[2] * d[2];
+    const double square = fma(F, F, H * G);
+    ok = square >= 0.0;
+    return G / (F + sqrt(square));
+}
+
+// Unit normal of a conic at (x, y) on the vertex branch.
+//   reference: z = sag(x, y); grad = (-c x, -c y, 1 - c z (1 + cc)); n = grad/|grad|
+//   with s = 1 - (1 + cc) c^2 r^2 one has 1 - c z (1 + cc) = sqrt(s) and
+//   |grad|^2 = 1 - cc c^2 r^2, which is what is evaluated here (s <= 0 -> NaN,
+//   like conic_function :214-216).
+__device__ __forceinline__ void conic_normal(double curv, double cc, bool sphere, double x,
+                                             double y, double n[3]) {
+    const double c2r2 = curv * curv * fma(x, x, y * y);
+    const double s = fma(-(1.0 + cc), c2r2, 1.0);
+    double gz = (s > 0.0) ? sqrt(s) : qnan();
+    double gx = -curv * x, gy = -curv * y;
+    if (!sphere) {
+        const double inv = rsqrt(fma(-cc, c2r2, 1.0));
+        gx *= inv; gy *= inv; gz *= inv;
+    }
+    n[0] = gx; n[1] = gy; n[2] = gz;
+}
+
+__device__ __forceinline__ double conic_sag(double curv, double cc, double x, double y) {
+    const double r2 = fma(x, x, y * y);
+    const double s = fma(-(1.0 + cc) * curv * curv, r2, 1.0);
+    if (!(s > 0.0)) return qnan();
+    return curv * r2 / (1.0 + sqrt(s));
+}
+
+// Asphere: value and gradient (gx, gy; gz = 1) of z - F(x, y) in one pass.
+__device__ __forceinline__ void asphere_eval(const DAux &a, double curv, double cc, double x,
+                                             double y, double &F, double &Fx, double &Fy) {
+    const double r2 = fma(x, x, y * y);
+    const double sq = sqrt(fma(-curv * curv * (1.0 + cc), r2, 1.0));   // NaN outside
+    // polynomial part: sum a_n r2^(n+1) and its r2-derivative by Horner
+    double p = 0.0, dp = 0.0;
+    for (int i = a.n_coeff - 1; i >= 0; --i) {
+        dp = fma(dp, r2, p);
+        p = fma(p, r2, a.coeff[i]);
+    }
+    // p(r2) = sum a_i r2^i  ->  poly = r2 p,  d poly / d r2 = p + r2 dp
+    F = curv * r2 / (1.0 + sq) + r2 * p;
+    const double dr = curv / sq + 2.0 * fma(r2, dp, p);                // dF/dx = x * dr
+    Fx = x * dr;
+    Fy = y * dr;
+}
+
+// XY polynomial: F = sum c x^m y^n / R^(m+n)
+__device__ __forceinline__ void xypoly_eval(const DAux &a, double x, double y, double &F,
+                                            double &Fx, double &Fy) {
+    const double ir = 1.0 / a.normradius;
+    const double xs = x * ir, ys = y * ir;
+    double f = 0.0, fx = 0.0, fy = 0.0;
+    for (int i = 0; i < a.n_coeff; ++i) {
+        const int m = a.xpow[i], n = a.ypow[i];
+        double xm1 = 1.0, yn1 = 1.0;                   // xs^(m-1), ys^(n-1)
+        for (int j = 1; j < m; ++j) xm1 *= xs;
+        for (int j = 1; j < n; ++j) yn1 *= ys;
+        const double xm = (m >= 1) ? xm1 * xs : 1.0;
+        const double yn = (n >= 1) ? yn1 * ys : 1.0;
+        const double c = a.coeff[i];
+        f = fma(c, xm * yn, f);
+        if (m >= 1) fx = fma(c * m, xm1 * yn, fx);
+        if (n >= 1) fy = fma(c * n, xm * yn1, fy);
+    }
+    F = f;
+    Fx = fx * ir;
+    Fy = fy * ir;
+}
+
+__device__ __forceinline__ void explicit_eval(int kind, const DAux &a, double curv, double cc,
+                                              double x, double y, double &F, double &Fx,
+                                              double &Fy) {
+    if (kind == PYR_SHAPE_ASPHERE) asphere_eval(a, curv, cc, x, y, F, Fx, Fy);
+    else xypoly_eval(a, x, y, F, Fx, Fy);
+}
+
+__device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv, double cc,
+                                            double x, double y) {
+    if (kind == PYR_SHAPE_CONIC) return conic_sag(curv, cc, x, y);
+    double F, Fx, Fy;
+    explicit_eval(kind, *a, curv, cc, x, y, F, Fx, Fy);
+    return F;
+}
+
+// Newton iteration on f(t) = z0 + t dz - F(x0 + t dx, y0 + t dy), seeded with the
+// base-conic hit (plane for XY polynomials).  The warp leaves the loop together
+// (__all_sync vote on the step size), capped at `maxit`.
+__device__ __forceinline__ double explicit_t(int kind, const DAux &a, double curv, double cc,
+                                             const double r0[3], const double d[3],
+                                             bool active) {
+    bool ok;
+    double t = (kind == PYR_SHAPE_ASPHERE) ? conic_t(curv, cc, r0, d, ok)
+                                           : -r0[2] / d[2];
+    if (!isfinite(t)) t = 0.0;
+    for (int it = 0; it < a.newton_maxit; ++it) {
+        const double x = fma(t, d[0], r0[0]);
+        const double y = fma(t, d[1], r0[1]);
+        double F, Fx, Fy;
+        explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
+        const double res = fma(t, d[2], r0[2]) - F;
+        const double dres = d[2] - fma(Fx, d[0], Fy * d[1]);
+        double step = res / dres;
+        const bool bad = !isfinite(step);
+        if (bad) step = 0.0;
+        t -= step;
+        const bool done = bad || !active || fabs(step) <= a.newton_tol * (1.0 + fabs(t));
+        if (__all_sync(__activemask(), done)) break;
+    }
+    return t;
+}
+
+// unit normal of an explicit shape: grad = (-Fx, -Fy, 1)/|.|  (FreeShape.getGrad :420-423)
+__device__ __forceinline__ void explicit_normal(int kind, const DAux &a, double curv, double cc,
+                                                double x, double y, double n[3]) {
+    double F, Fx, Fy;
+    explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
+    const double inv = rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
+    n[0] = -Fx * inv; n[1] = -Fy * inv; n[2] = inv;
+}
+
+}  // namespace pyr

@@ -1,0 +1,610 @@
+// pyrate_b200 trace kernels (sm_100a) and C ABI (include/pyrate_b200.h).
+//
+// One persistent launch walks every ray of the bundle through the whole element
+// sequence: the ray state (x, k[, E]) lives in registers from the first surface
+// to the last, each thread owns two adjacent rays of the (3, n) component-major
+// arrays so every HBM access is a coalesced 128-bit load/store, the per-step
+// record (hit point, wave vector after deflection, flag byte) is streamed out
+// with evict-first stores, and the step table sits in the kernel parameter block
+// (constant bank).  FP64 throughout: parity with the reference is <= 1e-10.
+// HBM-bound integer/FP64 streaming work; no tensor cores (no dense contraction).
+//
+// Reference path replaced (pyrateoptics/raytracer, file:line):
+//   optical_element.py:336-375   per-surface loop
+//   surface.py:116-135           Surface.intersect (+ aperture.py:71-140)
+//   surface_shape.py:151-155, 289-325, 448-465   Shape.intersect
+//   ray.py:136-161               returnKtoD, getLocalSurfaceNormal
+//   material/material_isotropic.py:137-247   Snell via in-plane k, propagate
+//   material/material_grin.py:106-220        GRIN symplectic propagate
+//   localcoordinates.py:383-413  global <-> local maps
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "pyr_device.cuh"
+#include "pyr_grin.cuh"
+#include "pyr_shapes.cuh"
+
+namespace pyr {
+
+constexpr uint32_t kOutVec2 = 32u;   // DStep.bits: outputs allow 128-bit stores
+constexpr uint32_t kNoDeflect = 64u; // PYR_STEP_PROPAGATE_ONLY
+constexpr uint32_t kNoIntersect = 128u;  // PYR_STEP_DEFLECT_ONLY
+
+template <bool WITH_E>
+struct Ray {
+    double x[3], k[3];
+    double e[WITH_E ? 3 : 1];
+    bool alive;
+};
+
+__device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void store_stream2(double *p, double a, double b) {
+    __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+}
+
+// d from (k, E): ray.py:140-152 for real k, E
+__device__ __forceinline__ void poynting_dir(const double k[3], const double e[3], double d[3]) {
+    const double ee = dot3(e, e), ek = dot3(e, k);
+    double s[3] = {fma(ee, k[0], -ek * e[0]), fma(ee, k[1], -ek * e[1]), fma(ee, k[2], -ek * e[2])};
+    const double inv = rsqrt(dot3(s, s));
+    d[0] = s[0] * inv; d[1] = s[1] * inv; d[2] = s[2] * inv;
+}
+
+// Deterministic E perpendicular to the new k (the reference's choice is an
+// SVD null-space vector, arbitrary in the plane; only |E| = 1, E.k = 0 matter).
+__device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
+    const double kk = dot3(k, k);
+    double c = dot3(e, k) / kk;
+    double t[3] = {fma(-c, k[0], e[0]), fma(-c, k[1], e[1]), fma(-c, k[2], e[2])};
+    double tt = dot3(t, t);
+    if (!(tt > 1e-24 * dot3(e, e))) {
+        // E was parallel to k: restart from the axis least aligned with k
+        const double ax = fabs(k[0]), ay = fabs(k[1]), az = fabs(k[2]);
+        double a[3] = {0.0, 0.0, 0.0};
+        if (ax <= ay && ax <= az) a[0] = 1.0; else if (ay <= az) a[1] = 1.0; else a[2] = 1.0;
+        c = dot3(a, k) / kk;
+        t[0] = fma(-c, k[0], a[0]); t[1] = fma(-c, k[1], a[1]); t[2] = fma(-c, k[2], a[2]);
+        tt = dot3(t, t);
+    }
+    const double inv = rsqrt(tt);
+    e[0] = t[0] * inv; e[1] = t[1] * inv; e[2] = t[2] * inv;
+}
+
+// One sequence entry for one ray (real k, E).  Returns the flag byte.
+template <bool WITH_E, bool GENERAL>
+__device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
+                                              Ray<WITH_E> &r, double hit_g[3]) {
+    const DAux *aux = (GENERAL && st.aux >= 0) ? &P.aux[st.aux] : nullptr;
+    bool ok = r.alive;
+
+    // ---- direction of energy transport (ray.py:136-152) ----
+    double d[3];
+    if (WITH_E && st.dir_mode == PYR_DIR_POYNTING) {
+        poynting_dir(r.k, r.e, d);
+    } else {
+        const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm : rsqrt(dot3(r.k, r.k));
+        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
+    }
+
+    // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
+    if (GENERAL && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
+        const bool v = grin_propagate(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k);
+        ok = ok && v;
+        const double inv = rsqrt(dot3(r.k, r.k));
+        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
+    }
+
+    // ---- into the shape frame (surface_shape.py:151-155) ----
+    double r0[3], dl[3];
+    if (st.bits & kRotIdentity) {
+        r0[0] = r.x[0] - st.frame.o[0]; r0[1] = r.x[1] - st.frame.o[1]; r0[2] = r.x[2] - st.frame.o[2];
+        dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2];
+    } else {
+        g2l_point(st.frame, r.x, r0);
+        rot_t(st.frame.r, d, dl);
+    }
+
+    // ---- intersect ----
+    double t;
+    bool hit_ok = true;
+    if (GENERAL && (st.bits & kNoIntersect)) {
+        t = 0.0;
+    } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
+        t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
+    } else {
+        t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok);
+    }
+    const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
+    if (st.bits & kRotIdentity) {
+        hit_g[0] = h[0] + st.frame.o[0]; hit_g[1] = h[1] + st.frame.o[1]; hit_g[2] = h[2] + st.frame.o[2];
+    } else {
+        l2g_point(st.frame, h, hit_g);
+    }
+
+    // ---- aperture (surface.py:127-135) ----
+    bool ap_ok = true;
+    if (st.aperture_kind != PYR_AP_BASE) {
+        double ax = h[0], ay = h[1];
+        if (GENERAL && !(st.bits & kApSameFrame)) {
+            double a[3];
+            g2l_point(aux->aperture_frame, hit_g, a);
+            ax = a[0]; ay = a[1];
+        }
+        if (st.aperture_kind == PYR_AP_CIRCULAR) {
+            const double rr = fma(ax, ax, ay * ay);
+            ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
+        } else {
+            ap_ok = (ax >= -st.ap0) && (ax <= st.ap0) && (ay >= -st.ap1) && (ay <= st.ap1);
+        }
+    }
+    const bool hit = ok && hit_ok && ap_ok;
+
+    // ---- surface normal in the shape frame (ray.py:156-161) ----
+    double nrm[3];
+    if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
+        conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
+    } else {
+        explicit_normal(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+    }
+
+    // ---- deflection (material_isotropic.py:163-236), done in the shape frame ----
+    double kl[3];
+    if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
+    else rot_t(st.frame.r, r.k, kl);
+    double n2sq = st.n2sq;
+    if (GENERAL && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
+        double q[3], g[3];
+        g2l_point(aux->after.frame, hit_g, q);
+        const double nn = grin_index(aux->after, q, g, false);
+        n2sq = nn * nn;
+    }
+    const double kn = dot3(kl, nrm);
+    // k_inplane = k - (k.n) n ; square = n^2 - k_inplane.k_inplane
+    const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
+    const double square = n2sq - dot3(kin, kin);
+    const double xi = sqrt(square);
+    const bool refr_ok = (square > 0.0) && finite3(nrm);
+    double k2[3];
+    if (st.interaction == PYR_REFLECT) {
+        k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
+    } else {
+        k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
+    }
+    bool alive = hit && refr_ok;
+    if (GENERAL && (st.bits & kNoDeflect)) {
+        alive = hit;                       // k unchanged
+    } else if (st.bits & kRotIdentity) { r.k[0] = k2[0]; r.k[1] = k2[1]; r.k[2] = k2[2]; }
+    else rot(st.frame.r, k2, r.k);
+    r.x[0] = hit_g[0]; r.x[1] = hit_g[1]; r.x[2] = hit_g[2];
+    if (!ok) { hit_g[0] = hit_g[1] = hit_g[2] = qnan(); }
+    if (!alive) {
+        const double q = qnan();
+        r.x[0] = r.x[1] = r.x[2] = q;
+        r.k[0] = r.k[1] = r.k[2] = q;
+    }
+    if (WITH_E) {
+        if (!alive) r.e[0] = r.e[1] = r.e[2] = qnan();
+        else if (!(GENERAL && (st.bits & kNoDeflect))) reproject_e(r.k, r.e);
+    }
+    r.alive = alive;
+    return (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
+}
+
+template <int RPT, bool WITH_E, bool GENERAL>
+__global__ void __launch_bounds__(256)
+trace_real_kernel(const __grid_constant__ LaunchParams P) {
+    const int64_t n = P.n;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * RPT;
+    const bool need_e0 = P.steps[0].dir_mode == PYR_DIR_POYNTING;
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RPT; base < n;
+         base += stride) {
+        // WITH_E == false still needs E for the first segment's Poynting direction
+        Ray<true> in[RPT];
+        bool in_range[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
+
+        if (RPT == 2 && P.in_vec2 && in_range[1]) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const double2 vx = __ldcs(reinterpret_cast<const double2 *>(P.x + c * P.ld_in + base));
+                const double2 vk = __ldcs(reinterpret_cast<const double2 *>(P.k + c * P.ld_in + base));
+                in[0].x[c] = vx.x; in[RPT - 1].x[c] = vx.y;
+                in[0].k[c] = vk.x; in[RPT - 1].k[c] = vk.y;
+                if (WITH_E || need_e0) {
+                    double2 ve = make_double2(c == 1 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0);
+                    if (P.e) ve = __ldcs(reinterpret_cast<const double2 *>(P.e + c * P.ld_in + base));
+                    in[0].e[c] = ve.x; in[RPT - 1].e[c] = ve.y;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                in[j].alive = P.alive ? (P.alive[base + j] & PYR_RAY_ALIVE) != 0 : true;
+        } else {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int64_t i = in_range[j] ? base + j : base;
+                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    in[j].x[c] = P.x[c * P.ld_in + ix];
+                    in[j].k[c] = P.k[c * P.ld_in + i];
+                    in[j].e[c] = P.e ? P.e[c * P.ld_in + i] : (c == 1 ? 1.0 : 0.0);
+                }
+                in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
+            }
+        }
+
+        Ray<WITH_E> ray[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) { ray[j].x[c] = in[j].x[c]; ray[j].k[c] = in[j].k[c]; }
+            if (WITH_E) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) ray[j].e[c] = in[j].e[c];
+            }
+            ray[j].alive = in[j].alive;
+        }
+
+        for (int s = 0; s < P.n_steps; ++s) {
+            const DStep &st = P.steps[s];
+            double hit[RPT][3];
+            uint32_t fl[RPT];
+            if (s == 0 && need_e0) {
+                // first segment: direction from the user's (k, E)
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    Ray<true> tmp;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { tmp.x[c] = ray[j].x[c]; tmp.k[c] = ray[j].k[c]; tmp.e[c] = in[j].e[c]; }
+                    tmp.alive = ray[j].alive;
+                    fl[j] = step_real<true, GENERAL>(P, st, tmp, hit[j]);
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { ray[j].x[c] = tmp.x[c]; ray[j].k[c] = tmp.k[c]; }
+                    if (WITH_E) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) ray[j].e[c] = tmp.e[c];
+                    }
+                    ray[j].alive = tmp.alive;
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) fl[j] = step_real<WITH_E, GENERAL>(P, st, ray[j], hit[j]);
+            }
+
+            // ---- record the step (evict-first streaming stores) ----
+            const int64_t ld = st.ld_out;
+            const bool v2 = RPT == 2 && (st.bits & kOutVec2) && in_range[RPT - 1];
+            if (st.out_x) {
+                if (v2) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_stream2(st.out_x + c * ld + base, hit[0][c], hit[RPT - 1][c]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j)
+                        if (in_range[j]) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) store_stream(st.out_x + c * ld + base + j, hit[j][c]);
+                        }
+                }
+            }
+            if (st.out_k) {
+                if (v2) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_stream2(st.out_k + c * ld + base, ray[0].k[c], ray[RPT - 1].k[c]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j)
+                        if (in_range[j]) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) store_stream(st.out_k + c * ld + base + j, ray[j].k[c]);
+                        }
+                }
+            }
+            if (WITH_E && st.out_e) {
+                if (v2) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) store_stream2(st.out_e + c * ld + base, ray[0].e[c], ray[RPT - 1].e[c]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j)
+                        if (in_range[j]) {
+#pragma unroll
+                            for (int c = 0; c < 3; ++c) store_stream(st.out_e + c * ld + base + j, ray[j].e[c]);
+                        }
+                }
+            }
+            if (st.out_flags) {
+                if (v2) {
+                    __stcs(reinterpret_cast<uchar2 *>(st.out_flags + base),
+                           make_uchar2((unsigned char)fl[0], (unsigned char)fl[RPT - 1]));
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j)
+                        if (in_range[j]) st.out_flags[base + j] = (uint8_t)fl[j];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// spot sums (analysis/ray_analysis.py:44-86): sum x, count, sum x^2
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spot_sums_kernel(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
+                 double *out8) {
+    double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (flags && !(flags[i] & mask)) continue;
+        const double a = x[i], b = x[ld + i], c = x[2 * ld + i];
+        acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += 1.0;
+        acc[4] = fma(a, a, acc[4]); acc[5] = fma(b, b, acc[5]); acc[6] = fma(c, c, acc[6]);
+    }
+    __shared__ double sm[8][7];
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        double v = acc[q];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5][q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += sm[w][threadIdx.x];
+        atomicAdd(out8 + threadIdx.x, v);
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side: pack the public step table into launch parameters
+// ---------------------------------------------------------------------------
+static void pack_frame(const PyrFrame &f, DFrame &d) {
+    for (int i = 0; i < 9; ++i) d.r[i] = f.r[i];
+    for (int i = 0; i < 3; ++i) d.o[i] = f.o[i];
+}
+
+static bool frame_equal(const PyrFrame &a, const PyrFrame &b) {
+    return std::memcmp(&a, &b, sizeof(PyrFrame)) == 0;
+}
+
+static bool rot_is_identity(const PyrFrame &f) {
+    const double id[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i)
+        if (f.r[i] != id[i]) return false;
+    return true;
+}
+
+// frame mapping material-local -> shape-local:  x_s = Rs^T (Rm x_m + om - os)
+static void compose_to_shape(const PyrFrame &m, const PyrFrame &s, DFrame &out) {
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int l = 0; l < 3; ++l) v += s.r[l * 3 + i] * m.r[l * 3 + j];
+            out.r[i * 3 + j] = v;
+        }
+    for (int i = 0; i < 3; ++i) {
+        double v = 0.0;
+        for (int l = 0; l < 3; ++l) v += s.r[l * 3 + i] * (m.o[l] - s.o[l]);
+        out.o[i] = v;
+    }
+}
+
+static void pack_medium(const PyrMedium &m, const PyrFrame &shape, DMedium &d) {
+    d.kind = m.kind; d.profile = m.grin_profile; d.boundary = m.grin_boundary;
+    d.max_steps = m.grin_max_steps;
+    d.n = m.n;
+    for (int i = 0; i < 18; ++i) d.eps[i] = m.eps[i];
+    for (int i = 0; i < PYR_MAX_GRIN_PARAMS; ++i) d.p[i] = m.grin_p[i];
+    for (int i = 0; i < 4; ++i) d.b[i] = m.grin_b[i];
+    d.ds = m.grin_ds; d.energy_tol = m.grin_energy_tol;
+    pack_frame(m.frame, d.frame);
+    compose_to_shape(m.frame, shape, d.to_shape);
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+struct Packed {
+    LaunchParams P;
+    bool general;
+    bool any_aniso;
+};
+
+static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+                uint32_t flags, Packed &out) {
+    if (!steps || !rays || n_steps <= 0 || n_rays < 0) return PYR_E_BADARG;
+    if (n_steps > kMaxSteps) return PYR_E_TOOLARGE;
+    if (!rays->x || !rays->k) return PYR_E_BADARG;
+    LaunchParams &P = out.P;
+    std::memset(&P, 0, sizeof(P));
+    P.x = rays->x; P.k = rays->k; P.e = rays->e; P.alive = rays->alive;
+    P.ld_in = rays->ld > 0 ? rays->ld : n_rays;
+    P.n = n_rays;
+    P.n_x = rays->n_x > 0 ? rays->n_x : n_rays;
+    P.n_steps = n_steps;
+    P.flags = flags;
+    P.in_vec2 = (P.n_x == P.n) && (P.ld_in % 2 == 0) && aligned16(P.x) && aligned16(P.k) &&
+                (!P.e || aligned16(P.e));
+    out.general = false;
+    out.any_aniso = false;
+    int n_aux = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const PyrStep &u = steps[s];
+        DStep &d = P.steps[s];
+        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_XYPOLY) return PYR_E_UNSUPPORTED;
+        if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
+        if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
+        if (u.split && s != n_steps - 1) return PYR_E_BADARG;
+        pack_frame(u.shape_frame, d.frame);
+        d.curv = u.curv; d.cc = u.cc;
+        if (u.aperture_kind == PYR_AP_CIRCULAR) {
+            d.ap0 = u.aperture_p[0] * u.aperture_p[0];
+            d.ap1 = u.aperture_p[1] * u.aperture_p[1];
+        } else if (u.aperture_kind == PYR_AP_RECTANGULAR) {
+            d.ap0 = 0.5 * u.aperture_p[0];
+            d.ap1 = 0.5 * u.aperture_p[1];
+        }
+        d.n2sq = u.after.n * u.after.n;
+        d.inv_knorm = (u.dir_mode == PYR_DIR_K && u.k_norm_hint > 0.0 &&
+                       u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / u.k_norm_hint : 0.0;
+        d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
+        d.ld_out = u.ld_out > 0 ? u.ld_out : n_rays;
+        d.shape_kind = (int8_t)u.shape_kind; d.aperture_kind = (int8_t)u.aperture_kind;
+        d.interaction = (int8_t)u.interaction; d.dir_mode = (int8_t)u.dir_mode;
+        d.before_kind = (int8_t)u.before.kind; d.after_kind = (int8_t)u.after.kind;
+        uint32_t bits = 0;
+        if (rot_is_identity(u.shape_frame)) bits |= kRotIdentity;
+        const bool ap_same = u.aperture_kind == PYR_AP_BASE || frame_equal(u.shape_frame, u.aperture_frame);
+        if (ap_same) bits |= kApSameFrame;
+        if (u.split) bits |= kSplit;
+        if (u.cc == 0.0) bits |= kSphere;
+        if (u.curv == 0.0 && u.shape_kind == PYR_SHAPE_CONIC) bits |= kPlane;
+        if (u.mode == PYR_STEP_PROPAGATE_ONLY) bits |= kNoDeflect;
+        else if (u.mode == PYR_STEP_DEFLECT_ONLY) bits |= kNoIntersect;
+        else if (u.mode != PYR_STEP_FULL) return PYR_E_BADARG;
+        if ((d.ld_out % 2 == 0) && (!d.out_x || aligned16(d.out_x)) && (!d.out_k || aligned16(d.out_k)) &&
+            (!d.out_e || aligned16(d.out_e)) &&
+            (!d.out_flags || (reinterpret_cast<uintptr_t>(d.out_flags) & 1u) == 0))
+            bits |= kOutVec2;
+        d.bits = bits;
+        const bool aniso = u.before.kind == PYR_MEDIUM_ANISO || u.after.kind == PYR_MEDIUM_ANISO;
+        out.any_aniso = out.any_aniso || aniso;
+        const bool need_aux = u.shape_kind != PYR_SHAPE_CONIC || !ap_same || u.mode != PYR_STEP_FULL ||
+                              u.before.kind != PYR_MEDIUM_ISO_CONST ||
+                              u.after.kind != PYR_MEDIUM_ISO_CONST;
+        d.aux = -1;
+        if (need_aux) {
+            if (n_aux >= kMaxAux) return PYR_E_TOOLARGE;
+            DAux &a = P.aux[n_aux];
+            for (int i = 0; i < PYR_MAX_COEFF; ++i) {
+                a.coeff[i] = i < u.n_coeff ? u.coeff[i] : 0.0;
+                a.xpow[i] = u.xpow[i]; a.ypow[i] = u.ypow[i];
+            }
+            a.normradius = u.normradius != 0.0 ? u.normradius : 1.0;
+            a.newton_tol = u.newton_tol > 0.0 ? u.newton_tol : 1e-14;
+            a.n_coeff = u.n_coeff;
+            a.newton_maxit = u.newton_maxit > 0 ? u.newton_maxit : 30;
+            pack_frame(u.aperture_frame, a.aperture_frame);
+            pack_medium(u.before, u.shape_frame, a.before);
+            pack_medium(u.after, u.shape_frame, a.after);
+            d.aux = (int8_t)n_aux++;
+            out.general = true;
+        }
+    }
+    return PYR_OK;
+}
+
+static int g_sm_count = 0;
+
+static int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, sms = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+        g_sm_count = sms > 0 ? sms : 148;
+    }
+    return g_sm_count;
+}
+
+template <typename K>
+static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream) {
+    const int threads = 256;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    const int64_t work = (P.n + (int64_t)threads * rpt - 1) / ((int64_t)threads * rpt);
+    // persistent grid: a whole number of CTAs per SM (148 SMs on B200)
+    int64_t grid = (int64_t)sm_count() * per_sm;
+    if (work < grid) grid = work;
+    if (grid < 1) return PYR_OK;
+    kernel<<<(unsigned)grid, threads, 0, stream>>>(P);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? PYR_OK : (int)e;
+}
+
+int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+                  uint32_t flags, cudaStream_t stream);   // pyr_aniso.cu
+
+static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+                      uint32_t flags, cudaStream_t stream) {
+    if (flags & PYR_F_COMPLEX) return trace_complex(steps, n_steps, rays, n_rays, flags, stream);
+    static thread_local Packed pk;
+    int rc = pack(steps, n_steps, rays, n_rays, flags, pk);
+    if (rc != PYR_OK) return rc;
+    if (pk.any_aniso) return PYR_E_UNSUPPORTED;      // needs PYR_F_COMPLEX
+    if (n_rays == 0) return PYR_OK;
+    bool with_e = (flags & PYR_F_RECORD_E) != 0;
+    // a Poynting-direction step after the first needs E carried along
+    for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
+    if (!pk.general) {
+        return with_e ? launch(trace_real_kernel<2, true, false>, pk.P, 2, stream)
+                      : launch(trace_real_kernel<2, false, false>, pk.P, 2, stream);
+    }
+    return with_e ? launch(trace_real_kernel<2, true, true>, pk.P, 2, stream)
+                  : launch(trace_real_kernel<2, false, true>, pk.P, 2, stream);
+}
+
+int trace_entry(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+                uint32_t flags, cudaStream_t stream) {
+    return trace_impl(steps, n_steps, rays, n_rays, flags, stream);
+}
+
+}  // namespace pyr
+
+// ---------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------
+extern "C" {
+
+int pyr_version(void) { return PYR_ABI_VERSION; }
+int64_t pyr_sizeof_step(void) { return (int64_t)sizeof(PyrStep); }
+int64_t pyr_sizeof_rays_in(void) { return (int64_t)sizeof(PyrRaysIn); }
+
+const char *pyr_strerror(int code) {
+    switch (code) {
+        case PYR_OK: return "ok";
+        case PYR_E_BADARG: return "bad argument";
+        case PYR_E_UNSUPPORTED: return "unsupported shape / medium / flag combination";
+        case PYR_E_TOOLARGE: return "too many steps or auxiliary records for one launch";
+        case PYR_E_NODEVICE: return "no CUDA device";
+        default: break;
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "unknown error";
+}
+
+int pyr_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+              uint32_t flags, void *stream) {
+    return pyr::trace_impl(steps, n_steps, rays, n_rays, flags, (cudaStream_t)stream);
+}
+
+int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
+                  double *out8, void *stream) {
+    if (!x || !out8 || n < 0) return PYR_E_BADARG;
+    if (n == 0) return PYR_OK;
+    if (ld <= 0) ld = n;
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)pyr::sm_count() * 8;
+    if (grid > cap) grid = cap;
+    pyr::spot_sums_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n, out8);
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PYR_OK : (int)e;
+}
+
+}  // extern "C"

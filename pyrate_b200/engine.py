@@ -1,0 +1,581 @@
+"""Host driver of the native trace: allocates the per-step records as torch CUDA
+tensors, fills the output pointers of the PyrStep table, launches pyr_trace()
+(one launch per non-splitting stretch of the sequence) and wraps the records as
+RayBundle / RayPath views with the reference's structure
+(optical_system.py:73-94: path = [b0, b0, b1, ..., bS]).
+
+PyTorch is plumbing here (device memory, streams); all ray arithmetic is in
+libpyrate_b200.so.  No CPU fallback: without a CUDA device every entry point
+raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _native as nat
+from . import lowering
+from .raytracer.ray import RayBundle, RayPath, as_tensor
+
+LD_ALIGN = 16           # doubles: rows start on 128-byte boundaries
+
+
+class DeviceRequired(RuntimeError):
+    pass
+
+
+def require_cuda():
+    if not torch.cuda.is_available():
+        raise DeviceRequired(
+            "pyrate_b200: a CUDA device is required (the trace runs only as "
+            "sm_100a kernels; there is no CPU fallback)")
+    lib = nat.load()
+    return lib
+
+
+def _round_up(v, m):
+    return (v + m - 1) // m * m
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class TraceRecord(object):
+    """Per-step device records of one seqtrace call.
+
+    hit[s]   (3, n_in[s])   global hit point at sequence entry s
+    k[s]     (3, n_out[s])  wave vector after the deflection (real or complex)
+    e[s]     (3, n_out[s])  E field after the deflection, or None
+    flags[s] (n_in[s])      PYR_RAY_HIT | PYR_RAY_ALIVE bits
+    n_out[s] = 2 n_in[s] on a birefringent (splitting) step.
+    """
+
+    def __init__(self):
+        self.x0 = self.k0 = self.e0 = None
+        self.hit = []
+        self.k = []
+        self.e = []
+        self.flags = []
+        self.n_in = []
+        self.n_out = []
+        self.split = []
+        self.lowered = None
+        self.wave = None
+
+
+def _alloc_rows(rows, n, device, complex_=False):
+    ld = _round_up(max(n, 1), LD_ALIGN)
+    if complex_:
+        buf = torch.empty((rows, 3, ld, 2), dtype=torch.float64, device=device)
+    else:
+        buf = torch.empty((rows, 3, ld), dtype=torch.float64, device=device)
+    return buf, ld
+
+
+def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
+    arr = (nat.PyrStep * (hi - lo))()
+    for i in range(lo, hi):
+        C.memmove(C.addressof(arr[i - lo]), C.addressof(steps[i]),
+                  C.sizeof(nat.PyrStep))
+    rin = nat.PyrRaysIn()
+    rin.x = x.data_ptr()
+    rin.k = k.data_ptr()
+    rin.e = e.data_ptr() if e is not None else None
+    rin.alive = alive.data_ptr() if alive is not None else None
+    rin.ld = ld_in
+    rin.n_x = n_x
+    nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
+
+
+def _padded(t, complex_=False):
+    """Copy a (3, n) tensor into a (3, ld[, 2]) buffer with aligned rows."""
+    n = t.shape[1]
+    ld = _round_up(max(n, 1), LD_ALIGN)
+    if complex_:
+        tc = t.to(torch.complex128)
+        buf = torch.zeros((3, ld, 2), dtype=torch.float64, device=t.device)
+        buf[:, :n, :] = torch.view_as_real(tc)
+    else:
+        if n == ld and t.is_contiguous():
+            return t, ld
+        buf = torch.zeros((3, ld), dtype=torch.float64, device=t.device)
+        buf[:, :n] = t
+    return buf, ld
+
+
+def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
+    """Run the lowered sequence on the device.  Returns a TraceRecord."""
+    lib = require_cuda()
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    x0 = as_tensor(x0, device)
+    k0 = as_tensor(k0, device)
+    e0 = None if e0 is None else as_tensor(e0, device)
+    if x0.is_complex():
+        raise ValueError("ray positions must be real")
+    n0 = x0.shape[1]
+    nsteps = len(lowered)
+    rec = TraceRecord()
+    rec.lowered = lowered
+    rec.wave = wave
+    (rec.x0, rec.k0, rec.e0) = (x0, k0, e0)
+    steps = [ls.st for ls in lowered]
+    stream_ptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream
+                            if stream is None else stream)
+
+    # stretches: [lo, hi) with no ray doubling except possibly at hi-1; the
+    # run turns complex at the first anisotropic medium and stays complex
+    # (the reference's dtype behaviour)
+    first_aniso = None
+    for (i, ls) in enumerate(lowered):
+        if ls.st.after.kind == nat.MEDIUM_ANISO or ls.st.before.kind == nat.MEDIUM_ANISO:
+            first_aniso = i
+            break
+    cuts = [0]
+    if first_aniso is not None and first_aniso > 0:
+        cuts.append(first_aniso)
+    for (i, ls) in enumerate(lowered):
+        if ls.st.split and i + 1 < nsteps:
+            cuts.append(i + 1)
+    cuts = sorted(set(cuts)) + [nsteps]
+
+    with torch.cuda.device(device):
+        complex_in = k0.is_complex() or (e0 is not None and e0.is_complex())
+        (cur_x, ld_x) = _padded(x0)
+        (cur_k, ld_k) = _padded(k0, complex_in)
+        cur_e = None
+        if e0 is not None:
+            (cur_e, _) = _padded(e0, complex_in)
+        elif complex_in:
+            tmp = torch.zeros((3, n0), dtype=torch.float64, device=device)
+            tmp[1] = 1.0
+            (cur_e, _) = _padded(tmp, True)
+        cur_alive = None
+        n = n0
+        n_x = n0
+        is_complex = complex_in
+        for ci in range(len(cuts) - 1):
+            (lo, hi) = (cuts[ci], cuts[ci + 1])
+            seg_complex = is_complex or (first_aniso is not None and lo >= first_aniso)
+            if seg_complex and not is_complex:
+                # promote the state handed over from the real stretch
+                (cur_k, ld_k) = _padded(cur_k[:, :n], True)
+                if cur_e is None:
+                    raise RuntimeError("internal: E must be recorded ahead of an "
+                                       "anisotropic medium")
+                (cur_e, _) = _padded(cur_e[:, :n], True)
+                is_complex = True
+            want_e = record_e or seg_complex or \
+                (first_aniso is not None and hi == first_aniso)
+            rows = hi - lo
+            last_split = bool(steps[hi - 1].split)
+            (xbuf, ld) = _alloc_rows(rows, n, device)
+            fbuf = torch.empty((rows, ld), dtype=torch.uint8, device=device)
+            if last_split:
+                (kbuf, _) = _alloc_rows(max(rows - 1, 1), n, device, seg_complex)
+                ld2 = _round_up(2 * n, LD_ALIGN)
+                klast = torch.empty((3, ld2, 2), dtype=torch.float64, device=device)
+                elast = torch.empty((3, ld2, 2), dtype=torch.float64, device=device)
+            else:
+                (kbuf, _) = _alloc_rows(rows, n, device, seg_complex)
+            ebuf = None
+            if want_e:
+                (ebuf, _) = _alloc_rows(rows, n, device, seg_complex)
+            for i in range(lo, hi):
+                st = steps[i]
+                r = i - lo
+                st.out_x = xbuf[r].data_ptr()
+                st.out_flags = fbuf[r].data_ptr()
+                st.ld_out = ld
+                if last_split and i == hi - 1:
+                    st.out_k = klast.data_ptr()
+                    st.out_e = elast.data_ptr()
+                    st.ld_out = ld        # out_x/flags use ld; k/e of a split step use 2n rows
+                else:
+                    st.out_k = kbuf[r].data_ptr()
+                    st.out_e = ebuf[r].data_ptr() if ebuf is not None else None
+            flags = 0
+            if seg_complex:
+                flags |= nat.F_COMPLEX | nat.F_RECORD_E
+            elif want_e:
+                flags |= nat.F_RECORD_E
+            if lo == 0 and cur_e is None and not seg_complex:
+                cur_e_arg = None            # engine substitutes (0, 1, 0)
+            else:
+                cur_e_arg = cur_e
+            _launch(lib, steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
+                    ld_k, flags, stream_ptr)
+            for i in range(lo, hi):
+                r = i - lo
+                rec.hit.append(xbuf[r, :, :n])
+                rec.flags.append(fbuf[r, :n])
+                rec.n_in.append(n)
+                if last_split and i == hi - 1:
+                    rec.k.append(torch.view_as_complex(klast)[:, :2 * n])
+                    rec.e.append(torch.view_as_complex(elast)[:, :2 * n])
+                    rec.n_out.append(2 * n)
+                    rec.split.append(True)
+                else:
+                    if seg_complex:
+                        rec.k.append(torch.view_as_complex(kbuf[r])[:, :n])
+                        rec.e.append(torch.view_as_complex(ebuf[r])[:, :n])
+                    else:
+                        rec.k.append(kbuf[r, :, :n])
+                        rec.e.append(ebuf[r, :, :n] if ebuf is not None else None)
+                    rec.n_out.append(n)
+                    rec.split.append(False)
+            # state handed to the next stretch
+            if hi < nsteps:
+                r = hi - 1 - lo
+                cur_x = xbuf[r]
+                ld_x = ld
+                cur_alive = fbuf[r]
+                if last_split:
+                    (cur_k, cur_e) = (klast, elast)
+                    ld_k = _round_up(2 * n, LD_ALIGN)
+                    n_x = n
+                    n = 2 * n
+                    if ld_k != ld_x:
+                        # x / alive are read with column i % n_x from rows of
+                        # leading dimension ld_k: re-pad to the common ld
+                        nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
+                        nx[:, :n_x] = cur_x[:, :n_x]
+                        cur_x = nx
+                else:
+                    cur_k = kbuf[r]
+                    cur_e = ebuf[r] if ebuf is not None else None
+                    ld_k = ld
+                    n_x = n
+    return rec
+
+
+# ---------------------------------------------------------------------------
+# TraceRecord -> RayPath views
+# ---------------------------------------------------------------------------
+def _hit_mask(flags):
+    return (flags & nat.RAY_HIT) != 0
+
+
+def _alive_mask(flags):
+    return (flags & nat.RAY_ALIVE) != 0
+
+
+def _lazy_efield(k):
+    """A unit E perpendicular to k (any such vector satisfies the reference's
+    contract: its own choice is an arbitrary SVD null vector)."""
+    kr = k.real if k.is_complex() else k
+    a = torch.zeros_like(kr)
+    idx = kr.abs().argmin(dim=-2, keepdim=True)
+    a.scatter_(-2, idx, 1.0)
+    t = a - (a * kr).sum(-2, keepdim=True) / (kr * kr).sum(-2, keepdim=True) * kr
+    t = t / torch.sqrt((t * t).sum(-2, keepdim=True))
+    return t.to(k.dtype)
+
+
+class _BundleBuilder(object):
+    """Materialises one RayBundle of a traced path on first field access.
+
+    start_*: state right after the deflection that opens the bundle (full
+    width, before compaction); `mask` marks the rays the reference keeps
+    (material_isotropic.py:194-199); hit / hitmask: record of the next
+    intersect (None for the last bundle, which has a single row).
+    """
+
+    def __init__(self, start_x, start_k, start_e, mask, ids, hit, hitmask):
+        (self.start_x, self.start_k, self.start_e) = (start_x, start_k, start_e)
+        (self.mask, self.ids, self.hit, self.hitmask) = (mask, ids, hit, hitmask)
+        self.cache = None
+
+    def build(self):
+        if self.cache is not None:
+            return self.cache
+        mask = self.mask
+        if mask is None or bool(mask.all()):
+            def take(t):
+                return t
+        else:
+            def take(t):
+                return t[..., mask]
+        x0 = take(self.start_x)
+        k0 = take(self.start_k)
+        e_full = self.start_e if self.start_e is not None else _lazy_efield(self.start_k)
+        e0 = take(e_full)
+        ids = take(self.ids)
+        ones = torch.ones(x0.shape[-1], dtype=torch.bool, device=x0.device)
+        if self.hit is None:
+            out = {"x": x0.unsqueeze(0), "k": k0.unsqueeze(0),
+                   "Efield": e0.unsqueeze(0), "valid": ones.unsqueeze(0),
+                   "rayID": ids}
+        else:
+            x = torch.stack((x0, take(self.hit)))
+            out = {"x": x, "k": k0.unsqueeze(0).expand(2, -1, -1),
+                   "Efield": e0.unsqueeze(0).expand(2, -1, -1),
+                   "valid": torch.stack((ones, take(self.hitmask))),
+                   "rayID": ids}
+        self.cache = out
+        return out
+
+    def field(self, name):
+        return lambda: self.build()[name]
+
+
+def paths_from_record(rec, splitup=False):
+    """list[RayPath] with the reference's structure: path = [b0, b0, b1..bS]
+    (optical_system.py:74-91); with splitup=True every birefringent interface
+    forks the path (2^m paths of n0 rays), otherwise it doubles the rays
+    (one path, hstack order, material_anisotropic.py:87-113)."""
+    nsteps = len(rec.hit)
+    n0 = rec.x0.shape[1]
+    dev = rec.x0.device
+    nsplit = sum(1 for s in rec.split if s)
+    npaths = (2 ** nsplit) if splitup else 1
+    e0 = rec.e0
+    if e0 is None:
+        e0 = torch.zeros_like(rec.x0)
+        e0[1] = 1.0
+    paths = []
+    for p in range(npaths):
+        def block(width):
+            # after q splits the device bundle has 2^q blocks of n0 columns;
+            # path p lives in block p mod 2^q
+            if not splitup:
+                return slice(0, width)
+            b = p % (width // n0)
+            return slice(b * n0, (b + 1) * n0)
+
+        (sx, sk, se) = (rec.x0, rec.k0, e0)
+        mask = None
+        ids = torch.arange(n0, device=dev)
+        bundles = []
+        for s in range(nsteps):
+            blk_in = block(rec.n_in[s])
+            hit = rec.hit[s][:, blk_in]
+            fl = rec.flags[s][blk_in]
+            bb = _BundleBuilder(sx, sk, se, mask, ids, hit, _hit_mask(fl))
+            splitted = bool(s >= 1 and rec.split[s - 1] and not splitup)
+            bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
+                                     wave=rec.wave, splitted=splitted))
+            blk_out = block(rec.n_out[s])
+            sk = rec.k[s][:, blk_out]
+            se = rec.e[s][:, blk_out] if rec.e[s] is not None else None
+            # survivors: the device ALIVE bit is cumulative; an anisotropic
+            # deflection keeps every ray it was handed (material_anisotropic.py
+            # :87-100 has no validity filter), which the kernel mirrors
+            mask = _alive_mask(fl)
+            if rec.split[s] and not splitup:
+                sx = torch.cat((hit, hit), dim=1)
+                mask = torch.cat((mask, mask))
+                ids = torch.cat((ids, ids))
+            else:
+                sx = hit
+        bb = _BundleBuilder(sx, sk, se, mask, ids, None, None)
+        splitted = bool(nsteps >= 1 and rec.split[nsteps - 1] and not splitup)
+        bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
+                                 wave=rec.wave, splitted=splitted))
+        path = RayPath(bundles[0])
+        path.appendRayBundle(bundles[0])          # path[0] is path[1]
+        for rb in bundles[1:]:
+            path.appendRayBundle(rb)
+        paths.append(path)
+    return paths
+
+
+# ---------------------------------------------------------------------------
+# entry used by OpticalSystem.seqtrace
+# ---------------------------------------------------------------------------
+def seqtrace(system, initialbundle, elementsequence, splitup=False,
+             record_e=False):
+    lowered = lowering.lower(system, elementsequence, initialbundle.wave,
+                             splitup=splitup)
+    if initialbundle.x.shape[0] != 1:
+        x0 = initialbundle.x[-1]
+        k0 = initialbundle.k[-1]
+        e0 = initialbundle.Efield[-1]
+    else:
+        (x0, k0, e0) = (initialbundle.x[0], initialbundle.k[0],
+                        initialbundle.Efield[0])
+    rec = trace(lowered, x0, k0, e0, initialbundle.wave, record_e=record_e)
+    paths = paths_from_record(rec, splitup=splitup)
+    for p in paths:
+        p.record = rec
+    return paths
+
+
+# ---------------------------------------------------------------------------
+# stand-alone plugin calls (Material.propagate / refract, Surface.intersect)
+# ---------------------------------------------------------------------------
+def _single_step(st, bundle, mode, record_e=True):
+    lib = require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    x = as_tensor(bundle.x[-1], dev).contiguous()
+    k = as_tensor(bundle.k[-1], dev).contiguous()
+    e = as_tensor(bundle.Efield[-1], dev).contiguous()
+    if k.is_complex() or e.is_complex() or st.after.kind == nat.MEDIUM_ANISO or \
+            st.before.kind == nat.MEDIUM_ANISO:
+        raise NotImplementedError("stand-alone plugin calls with complex fields: "
+                                  "use OpticalSystem.seqtrace")
+    n = x.shape[1]
+    st.mode = mode
+    (xb, ld) = _padded(x)
+    (kb, _) = _padded(k)
+    (eb, _) = _padded(e)
+    ox = torch.empty((3, ld), dtype=torch.float64, device=dev)
+    ok = torch.empty((3, ld), dtype=torch.float64, device=dev)
+    oe = torch.empty((3, ld), dtype=torch.float64, device=dev)
+    of = torch.empty((ld,), dtype=torch.uint8, device=dev)
+    (st.out_x, st.out_k, st.out_e, st.out_flags) = (ox.data_ptr(), ok.data_ptr(),
+                                                    oe.data_ptr(), of.data_ptr())
+    st.ld_out = ld
+    alive = (bundle.valid[-1].to(dev).to(torch.uint8) * nat.RAY_ALIVE).contiguous()
+    alive_p = torch.zeros((ld,), dtype=torch.uint8, device=dev)
+    alive_p[:n] = alive
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        _launch(lib, [st], 0, 1, xb, kb, eb, alive_p, n, n, ld,
+                nat.F_RECORD_E, stream)
+    return (ox[:, :n], ok[:, :n], oe[:, :n], of[:n])
+
+
+def _surface_step(surface, before_mat, after_mat, wave, mirror=False):
+    st = nat.PyrStep()
+    lowering.lower_surface(surface, st)
+    st.before = lowering.lower_medium(before_mat, wave)
+    st.after = lowering.lower_medium(after_mat, wave)
+    st.interaction = nat.REFLECT if mirror else nat.REFRACT
+    st.dir_mode = nat.DIR_POYNTING
+    return st
+
+
+def _probe_medium():
+    m = nat.PyrMedium()
+    m.kind = nat.MEDIUM_ISO_CONST
+    m.n = 1.0
+    for i in range(3):
+        m.frame.r[i * 4] = 1.0
+    return m
+
+
+def surface_intersect(surface, bundle, remove_rays_outside_aperture=True,
+                      medium=None):
+    st = nat.PyrStep()
+    lowering.lower_surface(surface, st)
+    if not remove_rays_outside_aperture:
+        st.aperture_kind = nat.AP_BASE
+    st.before = _probe_medium() if medium is None else \
+        lowering.lower_medium(medium, bundle.wave)
+    st.after = _probe_medium()
+    st.dir_mode = nat.DIR_POYNTING
+    (ox, ok, oe, of) = _single_step(st, bundle, nat.STEP_PROPAGATE_ONLY)
+    valid = _hit_mask(of) | ~bundle.valid[-1].to(of.device)
+    # RayBundle.append ANDs with the previous row itself (ray.py:100)
+    bundle.append(ox, ok if medium is not None else bundle.k[-1].to(ox.device),
+                  bundle.Efield[-1].to(ox.device), valid)
+
+
+def shape_intersect(shape, bundle):
+    class _S(object):
+        pass
+    from .raytracer.aperture import BaseAperture
+    s = _S()
+    s.shape = shape
+    s.aperture = BaseAperture.p(shape.lc)
+    surface_intersect(s, bundle, remove_rays_outside_aperture=False)
+
+
+def material_propagate(material, bundle, next_surface):
+    surface_intersect(next_surface, bundle, True, medium=material)
+
+
+def material_deflect(material, bundle, surface, mirror=False, splitup=False):
+    st = nat.PyrStep()
+    lowering.lower_surface(surface, st)
+    st.aperture_kind = nat.AP_BASE
+    st.before = _probe_medium()
+    st.after = lowering.lower_medium(material, bundle.wave)
+    st.interaction = nat.REFLECT if mirror else nat.REFRACT
+    st.dir_mode = nat.DIR_K
+    (ox, ok, oe, of) = _single_step(st, bundle, nat.STEP_DEFLECT_ONLY)
+    alive = _alive_mask(of)
+    ids = bundle.rayID.to(ox.device)
+    return (RayBundle(ox[:, alive], ok[:, alive], oe[:, alive], ids[alive],
+                      wave=bundle.wave),)
+
+
+# ---------------------------------------------------------------------------
+# end-to-end host entry (pyr_trace_host): host bundle in, final record out
+# ---------------------------------------------------------------------------
+class HostTracer(object):
+    """Reusable binding of pyr_trace_host for one lowered (real, non-splitting)
+    sequence: owns the device workspace and pinned result buffers."""
+
+    def __init__(self, lowered, n_rays, chunk_rays=1 << 20, device=None):
+        self.lib = require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) \
+            if device is None else torch.device(device)
+        self.lowered = lowered
+        self.steps = lowering.step_array(lowered)
+        self.n = int(n_rays)
+        self.chunk = int(min(chunk_rays, max(self.n, 1)))
+        nbytes = self.lib.pyr_trace_host_workspace(len(lowered), self.chunk)
+        self.workspace = torch.empty((nbytes + 256,), dtype=torch.uint8,
+                                     device=self.device)
+        off = (-self.workspace.data_ptr()) % 256
+        self.ws_ptr = self.workspace.data_ptr() + off
+        self.ws_bytes = nbytes
+        self.x_last = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
+        self.k_last = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
+        self.flags_last = torch.empty((self.n,), dtype=torch.uint8).pin_memory()
+        self.spot8 = torch.zeros((8,), dtype=torch.float64).pin_memory()
+
+    @property
+    def h2d_bytes(self):
+        return 72 * self.n
+
+    @property
+    def d2h_bytes(self):
+        return 49 * self.n + 64
+
+    def __call__(self, x0, k0, e0):
+        """x0, k0, e0: contiguous (3, n) float64 CPU tensors (pinned for
+        overlap).  Returns (x_last, k_last, flags_last, spot8) host tensors."""
+        for t in (x0, k0, e0):
+            assert t.device.type == "cpu" and t.dtype == torch.float64 and \
+                t.is_contiguous() and t.shape == (3, self.n)
+        with torch.cuda.device(self.device):
+            nat.check(self.lib.pyr_trace_host(
+                self.steps, len(self.lowered), x0.data_ptr(), k0.data_ptr(),
+                e0.data_ptr(), self.n, self.x_last.data_ptr(),
+                self.k_last.data_ptr(), self.flags_last.data_ptr(),
+                self.spot8.data_ptr(), self.ws_ptr, self.ws_bytes, self.chunk))
+        return (self.x_last, self.k_last, self.flags_last, self.spot8)
+
+
+def spot_sums(x, flags=None, mask=nat.RAY_ALIVE, out=None):
+    """Device partial sums of RayBundleAnalysis (ray_analysis.py:44-86):
+    out[0:3] = sum x, out[3] = count, out[4:7] = sum x^2 (float64 CUDA tensor).
+    Sums of several ranks can be all-reduced before `spot_from_sums`."""
+    lib = require_cuda()
+    dev = x.device
+    if out is None:
+        out = torch.zeros((8,), dtype=torch.float64, device=dev)
+    assert x.dim() == 2 and x.shape[0] == 3 and x.stride(1) == 1
+    ld = x.stride(0)
+    n = x.shape[1]
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        nat.check(lib.pyr_spot_sums(x.data_ptr(), ld,
+                                    flags.data_ptr() if flags is not None else None,
+                                    mask, n, out.data_ptr(), stream))
+    return out
+
+
+def spot_from_sums(s):
+    """(centroid[3], rms about the centroid) with the reference's
+    normalisations: centroid = sum/(N + 1e-17), rms = sqrt(sum|x-c|^2 /
+    (N - 1 + 1e-17))."""
+    s = [float(v) for v in s]
+    n = s[3]
+    c = [s[i] / (n + 1e-17) for i in range(3)]
+    ss = sum(s[4 + i] - 2.0 * c[i] * s[i] + n * c[i] * c[i] for i in range(3))
+    return c, (max(ss, 0.0) / (n - 1 + 1e-17)) ** 0.5

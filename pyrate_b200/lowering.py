@@ -1,0 +1,257 @@
+"""Lowering: (OpticalSystem, elementsequence) -> flat table of PyrStep records.
+
+Walks the object graph exactly as the reference's per-surface loop does
+(raytracer/optical_element.py:324-375): material look-up with background
+substitution (:344-346), toggle by object identity (:109-126, :353-356),
+mirrors keep the current material (:357-358), every element starts in the
+background medium (:328).  Every parameter is re-read here on each trace
+(`v()` / `.evaluate()`), because optimisers mutate variables between traces
+(optimize/optimize.py:73-91).
+
+Objects are inspected by duck typing (class names along the MRO, attribute
+names of the reference), so the *reference's own* object graph lowers too --
+that is how identical systems are fed to both engines in the parity tests.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+from .raytracer.material.material_grin import (BOUNDARY_KINDS, PROFILE_KINDS,
+                                               profile_functions)
+
+
+class LoweringError(Exception):
+    pass
+
+
+def _mro_names(obj):
+    return {c.__name__ for c in type(obj).__mro__}
+
+
+def _frame(lc):
+    f = nat.PyrFrame()
+    b = np.asarray(lc.localbasis, dtype=float)
+    o = np.asarray(lc.globalcoordinates, dtype=float)
+    for i in range(3):
+        for j in range(3):
+            f.r[i * 3 + j] = b[i, j]
+        f.o[i] = o[i]
+    return f
+
+
+def _value(v):
+    return float(v() if callable(v) else v)
+
+
+# ---------------------------------------------------------------------------
+# media
+# ---------------------------------------------------------------------------
+def _verify_grin_profile(mat, profile, samples=64):
+    """Compare user Python index functions with the declared device profile."""
+    user = None
+    if hasattr(mat, "user_functions"):
+        user = mat.user_functions()
+    elif hasattr(mat, "nfunc"):             # reference object
+        kw = getattr(mat, "params", {})
+        user = tuple((lambda x, f=f: f(x, **kw)) for f in
+                     (mat.nfunc, mat.dndx, mat.dndy, mat.dndz)) + \
+            (mat.boundaryfunction,)
+    if user is None:
+        return
+    ours = profile_functions(profile)
+    rng = np.random.default_rng(12345)
+    pts = rng.uniform(-3.0, 3.0, (3, samples))
+    for (i, (fu, fo)) in enumerate(zip(user[:4], ours[:4])):
+        (a, b) = (np.asarray(fu(pts), dtype=float), np.asarray(fo(pts), dtype=float))
+        if not np.allclose(a, b, rtol=1e-12, atol=1e-13):
+            raise LoweringError(
+                "GRIN material %r: annotations['device_profile'] disagrees with the "
+                "Python source (function #%d, max |diff| = %.3e); refusing to trace a "
+                "different medium" % (getattr(mat, "name", "?"), i,
+                                      float(np.max(np.abs(a - b)))))
+    far = rng.uniform(-30.0, 30.0, (3, samples))
+    if not np.array_equal(np.asarray(user[4](far), dtype=bool),
+                          np.asarray(ours[4](far), dtype=bool)):
+        raise LoweringError("GRIN material %r: boundary function disagrees with the "
+                            "declared device boundary" % (getattr(mat, "name", "?"),))
+
+
+def lower_medium(mat, wave):
+    m = nat.PyrMedium()
+    names = _mro_names(mat)
+    m.frame = _frame(mat.lc)
+    if "AnisotropicMaterial" in names:
+        m.kind = nat.MEDIUM_ANISO
+        eps = np.asarray(mat.epstensor, dtype=complex)
+        if eps.shape != (3, 3):
+            raise LoweringError("epsilon tensor must be 3x3")
+        flat = eps.reshape(-1)
+        for i in range(9):
+            m.eps[2 * i] = flat[i].real
+            m.eps[2 * i + 1] = flat[i].imag
+        m.n = 0.0
+    elif "IsotropicGrinMaterial" in names:
+        m.kind = nat.MEDIUM_ISO_GRIN
+        prof = mat.annotations.get("device_profile")
+        if prof is None:
+            raise LoweringError(
+                "GRIN material %r needs annotations['device_profile'] "
+                "(catalogue: %s)" % (getattr(mat, "name", "?"),
+                                     ", ".join(sorted(PROFILE_KINDS))))
+        _verify_grin_profile(mat, prof)
+        m.grin_profile = PROFILE_KINDS[prof["kind"]]
+        for (i, v) in enumerate(prof["params"]):
+            m.grin_p[i] = float(v)
+        bspec = prof.get("boundary", {"kind": "none", "params": []})
+        m.grin_boundary = BOUNDARY_KINDS[bspec["kind"]]
+        for (i, v) in enumerate(bspec.get("params", [])):
+            m.grin_b[i] = float(v)
+        m.grin_ds = float(mat.annotations["ds"])
+        m.grin_energy_tol = float(mat.annotations["energyviolation"])
+        m.grin_max_steps = int(mat.annotations.get("max_steps", 0))
+        m.n = 0.0
+    elif "IsotropicMaterial" in names:
+        m.kind = nat.MEDIUM_ISO_CONST
+        m.n = float(mat.get_optical_index(None, wave))
+    else:
+        raise LoweringError("unsupported material class %s" % type(mat).__name__)
+    return m
+
+
+# ---------------------------------------------------------------------------
+# surfaces
+# ---------------------------------------------------------------------------
+def _xy_terms(shape):
+    terms = []
+    for (key, var) in shape.params.items():
+        if key[0] == "C":
+            (xp, yp) = key[2:].split("Y")
+            terms.append((int(xp), int(yp), _value(var)))
+    return terms
+
+
+def lower_surface(surface, st):
+    """Fill shape / aperture fields of PyrStep `st`."""
+    shape = surface.shape
+    names = _mro_names(shape)
+    st.shape_frame = _frame(shape.lc)
+    if "Cylinder" in names:
+        raise LoweringError("Cylinder is dead code in the reference "
+                            "(surface_shape.py:367-388) and not supported")
+    if "Conic" in names:
+        st.shape_kind = nat.SHAPE_CONIC
+        st.curv = _value(shape.curvature)
+        st.cc = _value(shape.conic)
+    elif "Asphere" in names:
+        st.shape_kind = nat.SHAPE_ASPHERE
+        st.curv = _value(shape.params["curv"])
+        st.cc = _value(shape.params["cc"])
+        ncoef = int(shape.annotations["numcoefficients"])
+        if ncoef > nat.MAX_COEFF:
+            raise LoweringError("too many asphere coefficients")
+        st.n_coeff = ncoef
+        for i in range(ncoef):
+            st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
+    elif "XYPolynomials" in names:
+        st.shape_kind = nat.SHAPE_XYPOLY
+        terms = _xy_terms(shape)
+        if len(terms) > nat.MAX_COEFF:
+            raise LoweringError("too many XY polynomial terms")
+        st.normradius = _value(shape.params["normradius"])
+        st.n_coeff = len(terms)
+        for (i, (xp, yp, c)) in enumerate(terms):
+            if not (0 <= xp < 64 and 0 <= yp < 64):
+                raise LoweringError("XY exponent out of range")
+            (st.xpow[i], st.ypow[i], st.coeff[i]) = (xp, yp, c)
+    else:
+        raise LoweringError("unsupported shape class %s" % type(shape).__name__)
+    if st.shape_kind != nat.SHAPE_CONIC:
+        ann = getattr(shape, "annotations", {})
+        # The reference's fsolve stops at xtol = annotations["tol"] (1e-6) but
+        # lands at ~1e-15 residual; Newton is run to machine precision and
+        # `iterations` is only used as a (generous) cap.
+        st.newton_tol = 1e-14
+        st.newton_maxit = max(30, 3 * int(ann.get("iterations", 10)))
+    ap = surface.aperture
+    apn = _mro_names(ap)
+    st.aperture_frame = _frame(ap.lc)
+    if "CircularAperture" in apn:
+        st.aperture_kind = nat.AP_CIRCULAR
+        st.aperture_p[0] = float(ap.annotations["minradius"])
+        st.aperture_p[1] = float(ap.annotations["maxradius"])
+    elif "RectangularAperture" in apn:
+        st.aperture_kind = nat.AP_RECTANGULAR
+        st.aperture_p[0] = float(ap.annotations["width"])
+        st.aperture_p[1] = float(ap.annotations["height"])
+    elif "BaseAperture" in apn:
+        st.aperture_kind = nat.AP_BASE
+    else:
+        raise LoweringError("unsupported aperture class %s" % type(ap).__name__)
+
+
+class LoweredStep(object):
+    """One PyrStep plus the bookkeeping the host needs."""
+    __slots__ = ("st", "elemkey", "surfkey", "before_obj", "after_obj",
+                 "is_aniso_deflect", "is_stop")
+
+    def __init__(self):
+        self.st = nat.PyrStep()
+
+
+def lower(system, elementsequence, wave, splitup=False):
+    """Returns list[LoweredStep] for `elementsequence`
+    = [(elemkey, [(surfkey, {"is_mirror": .., "is_stop": ..}), ...]), ...]."""
+    background = system.material_background
+    out = []
+    last_deflector = None          # medium object that set |k| last
+    for (elemkey, subseq) in elementsequence:
+        if elemkey not in system.elements:
+            raise LoweringError("unknown element %r" % (elemkey,))
+        elem = system.elements[elemkey]
+        current = background                                    # :328
+        conn = elem.annotations["surf_mat_connection"]
+        for (surfkey, surfoptions) in subseq:
+            mirror = bool(surfoptions.get("is_mirror", False))
+            surface = elem.surfaces[surfkey]
+            (mnkey, pnkey) = conn[surfkey]
+            mnmat = elem.materials.get(mnkey, background)       # :345-346
+            pnmat = elem.materials.get(pnkey, background)
+            before = current
+            if not mirror:                                       # :353-358
+                current = pnmat if (mnmat is current) else mnmat
+            after = current
+            ls = LoweredStep()
+            st = ls.st
+            lower_surface(surface, st)
+            st.interaction = nat.REFLECT if mirror else nat.REFRACT
+            st.before = lower_medium(before, wave)
+            st.after = lower_medium(after, wave)
+            first = len(out) == 0
+            if first or st.before.kind == nat.MEDIUM_ANISO:
+                st.dir_mode = nat.DIR_POYNTING
+            else:
+                st.dir_mode = nat.DIR_K
+            st.k_norm_hint = 0.0
+            if (not first and last_deflector is not None and
+                    last_deflector is before and
+                    st.before.kind == nat.MEDIUM_ISO_CONST):
+                st.k_norm_hint = st.before.n
+            ls.is_aniso_deflect = st.after.kind == nat.MEDIUM_ANISO
+            st.split = 1 if (ls.is_aniso_deflect) else 0
+            st.mode = nat.STEP_FULL
+            ls.elemkey = elemkey
+            ls.surfkey = surfkey
+            ls.before_obj = before
+            ls.after_obj = after
+            ls.is_stop = bool(surfoptions.get("is_stop", False))
+            out.append(ls)
+            last_deflector = after
+    return out
+
+
+def step_array(lowered):
+    arr = (nat.PyrStep * len(lowered))()
+    for (i, ls) in enumerate(lowered):
+        C.memmove(C.addressof(arr[i]), C.addressof(ls.st), C.sizeof(nat.PyrStep))
+    return arr

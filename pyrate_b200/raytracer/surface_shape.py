@@ -1,0 +1,249 @@
+"""Surface shapes (host API mirror of reference raytracer/surface_shape.py).
+
+`Conic` :158-325, `Asphere` :520-606, `XYPolynomials` :780-858 with the same
+`.p(...)` signatures, parameter containers (`curvature` / `conic` variables,
+`params` dict with keys "curv", "cc", "A2", ..., "CX{m}Y{n}", "normradius") and
+annotations ("tol", "iterations", "numcoefficients").  `getSag` / `getGrad` /
+`getNormal` / `getHessian` evaluate on NumPy arrays or torch tensors (plotting and
+analysis helpers).  `intersect(raybundle)` is the device path: one
+PYR_STEP_PROPAGATE_ONLY launch of the native engine (no host arithmetic on rays).
+"""
+import numpy as np
+
+from ..core import ClassWithOptimizableVariables, FloatOptimizableVariable
+
+try:
+    import torch
+except Exception:          # pragma: no cover
+    torch = None
+
+
+def _lib(a):
+    return torch if (torch is not None and isinstance(a, torch.Tensor)) else np
+
+
+class Shape(ClassWithOptimizableVariables):
+
+    def setKind(self):
+        self.kind = "shape"
+
+    def getSag(self, x, y):
+        raise NotImplementedError()
+
+    def getGrad(self, x, y):
+        raise NotImplementedError()
+
+    def getHessian(self, x, y):
+        raise NotImplementedError()
+
+    def getCentralCurvature(self):
+        raise NotImplementedError()
+
+    def getNormal(self, x, y):
+        xp = _lib(x)
+        g = self.getGrad(x, y)
+        return g / xp.sqrt((g * g).sum(0))
+
+    def intersect(self, raybundle):
+        """Appends the intersection row to `raybundle` (device)."""
+        from .. import engine
+        engine.shape_intersect(self, raybundle)
+
+
+class Conic(Shape):
+
+    @classmethod
+    def p(cls, lc, curv=0.0, cc=0.0, name=""):
+        return cls({}, {"curvature": FloatOptimizableVariable(curv, name="curvature"),
+                        "conic": FloatOptimizableVariable(cc, name="conic constant"),
+                        "lc": lc}, name)
+
+    def setKind(self):
+        self.kind = "shape_Conic"
+
+    def getCentralCurvature(self):
+        return self.curvature()
+
+    def conic_function(self, rsquared):
+        xp = _lib(rsquared)
+        (curv, cc) = (self.curvature(), self.conic())
+        s = 1 - (1 + cc) * curv ** 2 * rsquared
+        bad = s <= 0
+        nan = float("nan")
+        r2 = xp.where(bad, xp.full_like(rsquared, nan), rsquared)
+        s = xp.where(bad, xp.zeros_like(s), s)
+        return curv * r2 / (1 + xp.sqrt(s))
+
+    def getSag(self, x, y):
+        return self.conic_function(x * x + y * y)
+
+    def getGrad(self, x, y):
+        xp = _lib(x)
+        (curv, cc) = (self.curvature(), self.conic())
+        z = self.getSag(x, y)
+        return xp.stack((-curv * x, -curv * y, 1. - curv * z * (1 + cc)))
+
+    def getHessian(self, x, y):
+        xp = _lib(x)
+        (curv, cc) = (self.curvature(), self.conic())
+        h = xp.zeros((3, 3) + tuple(x.shape), dtype=x.dtype)
+        h[0, 0] = curv
+        h[1, 1] = curv
+        h[2, 2] = curv * (1 + cc)
+        return h
+
+
+class FreeShape(Shape):
+
+    @staticmethod
+    def createAnnotationsAndStructure(lc, paramlist=(), tol=1e-6, iterations=10):
+        params = {}
+        for (name, value) in paramlist:
+            params[name] = FloatOptimizableVariable(value, name=name)
+        return ({"tol": tol, "iterations": iterations},
+                {"lc": lc, "params": params})
+
+    def getGrad(self, x, y):
+        return self.gradF(x, y, self.getSag(x, y))
+
+    def getHessian(self, x, y):
+        return self.hessF(x, y, self.getSag(x, y))
+
+
+class ExplicitShape(FreeShape):
+    """z = F(x, y); the reference solves the ray equation with fsolve
+    (:448-465); here the native engine runs a per-ray Newton iteration."""
+
+    def getSag(self, x, y):
+        return self.F(x, y)
+
+
+class Asphere(ExplicitShape):
+
+    @classmethod
+    def p(cls, lc, curv=0, cc=0, coefficients=None, name=""):
+        coefficients = [] if coefficients is None else list(coefficients)
+        plist = [("curv", curv), ("cc", cc)] + \
+                [("A" + str(2 * i + 2), v) for (i, v) in enumerate(coefficients)]
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc, plist)
+        ann["numcoefficients"] = len(coefficients)
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_Asphere"
+
+    def getAsphereParameters(self):
+        return (self.params["curv"](), self.params["cc"](),
+                [self.params["A" + str(2 * i + 2)]()
+                 for i in range(self.annotations["numcoefficients"])])
+
+    def getCentralCurvature(self):
+        return self.params["curv"]()
+
+    def sqrtfun(self, r2):
+        (curv, cc, _) = self.getAsphereParameters()
+        return _lib(r2).sqrt(1 - curv ** 2 * (1 + cc) * r2)
+
+    def F(self, x, y):
+        (curv, cc, acoeffs) = self.getAsphereParameters()
+        r2 = x * x + y * y
+        res = curv * r2 / (1 + self.sqrtfun(r2))
+        for (n, an) in enumerate(acoeffs):
+            res = res + an * r2 ** (n + 1)
+        return res
+
+    def gradF(self, x, y, z):
+        xp = _lib(x)
+        (curv, cc, acoeffs) = self.getAsphereParameters()
+        r2 = x * x + y * y
+        radial = curv / self.sqrtfun(r2)
+        for (n, an) in enumerate(acoeffs):
+            radial = radial + 2. * (n + 1) * an * r2 ** n
+        return xp.stack((-x * radial, -y * radial, xp.ones_like(x)))
+
+    def hessF(self, x, y, z):
+        xp = _lib(x)
+        (curv, cc, acoeffs) = self.getAsphereParameters()
+        r2 = x * x + y * y
+        sq = self.sqrtfun(r2)
+        main1 = -curv / (2. * sq)
+        main2 = -curv ** 3 * (1 + cc) / (4. * sq)
+        for (n, an) in enumerate(acoeffs):
+            main1 = main1 - an * (n + 1) * r2 ** n
+            if n >= 1:
+                main2 = main2 - an * (n + 1) * n * r2 ** (n - 1)
+        h = xp.zeros((3, 3) + tuple(x.shape), dtype=x.dtype)
+        h[0, 0] = 2 * (2 * main2 * x * x + main1)
+        h[1, 1] = 2 * (2 * main2 * y * y + main1)
+        h[0, 1] = h[1, 0] = 4 * main2 * x * y
+        return h
+
+
+class XYPolynomials(ExplicitShape):
+
+    @classmethod
+    def p(cls, lc, normradius=1.0, coefficients=None, name=""):
+        coefficients = [] if coefficients is None else list(coefficients)
+        plist = [("normradius", normradius)] + \
+                [("CX" + str(xp_) + "Y" + str(yp_), c)
+                 for (xp_, yp_, c) in coefficients]
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc, plist)
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_XYPolynomials"
+
+    def getXYParameters(self):
+        terms = []
+        for (key, var) in self.params.items():
+            if key[0] == "C":
+                (xpow, ypow) = key[2:].split("Y")
+                terms.append([int(xpow), int(ypow), var()])
+        return (self.params["normradius"](), terms)
+
+    def getCentralCurvature(self):
+        (nr, terms) = self.getXYParameters()
+        c = 0.0
+        for (xpow, ypow, coeff) in terms:
+            if (xpow, ypow) in ((2, 0), (0, 2)):
+                c += coeff / nr ** 2
+        return c
+
+    def F(self, x, y):
+        (nr, terms) = self.getXYParameters()
+        res = _lib(x).zeros_like(x)
+        for (xpow, ypow, c) in terms:
+            res = res + x ** xpow * y ** ypow * (c / nr ** (xpow + ypow))
+        return res
+
+    def gradF(self, x, y, z):
+        xp = _lib(x)
+        (nr, terms) = self.getXYParameters()
+        gx = xp.zeros_like(x)
+        gy = xp.zeros_like(x)
+        for (xpow, ypow, c) in terms:
+            c = c / nr ** (xpow + ypow)
+            if xpow >= 1:
+                gx = gx - xpow * x ** (xpow - 1) * y ** ypow * c
+            if ypow >= 1:
+                gy = gy - ypow * x ** xpow * y ** (ypow - 1) * c
+        return xp.stack((gx, gy, xp.ones_like(x)))
+
+    def hessF(self, x, y, z):
+        xp = _lib(x)
+        (nr, terms) = self.getXYParameters()
+        h = xp.zeros((3, 3) + tuple(x.shape), dtype=x.dtype)
+        for (xpow, ypow, c) in terms:
+            c = c / nr ** (xpow + ypow)
+            if xpow >= 2:
+                h[0, 0] -= xpow * (xpow - 1) * x ** (xpow - 2) * y ** ypow * c
+            if xpow >= 1 and ypow >= 1:
+                h[0, 1] -= xpow * ypow * x ** (xpow - 1) * y ** (ypow - 1) * c
+            if ypow >= 2:
+                h[1, 1] -= ypow * (ypow - 1) * x ** xpow * y ** (ypow - 2) * c
+        h[1, 0] = h[0, 1]
+        return h
+
+
+accessible_shapes = {"shape_Conic": Conic, "shape_Asphere": Asphere,
+                     "shape_XYPolynomials": XYPolynomials}

@@ -1,0 +1,116 @@
+"""GPU: the native sm_100a path (through OpticalSystem.seqtrace -> lowering ->
+C ABI pyr_trace) against (a) the committed reference fixtures and (b) the NumPy
+oracle on seeded bundles.  Tolerances are BASELINE.json's: <= 1e-10 relative for
+closed-form isotropic conics, <= 1e-6 for iterated asphere / XY / GRIN."""
+import numpy as np
+import pytest
+
+import pyrate_b200 as pb
+from pyrate_b200 import configs
+
+import util
+
+pytestmark = pytest.mark.gpu
+
+REAL_TAGS = [t for t in util.golden_traces() if not t.startswith("c4")]
+
+
+def _device_paths(name, x0, k0, e0, splitup=False, record_efield=False):
+    (s, seq) = configs.build_system(configs.CONFIGS[name], pb.api())
+    bundle = pb.RayBundle(x0, k0, e0, wave=configs.DLINE)
+    return s.seqtrace(bundle, seq, splitup=splitup, record_efield=record_efield)
+
+
+@pytest.mark.parametrize("tag", REAL_TAGS)
+def test_matches_reference_fixture(tag):
+    g = util.load_golden(tag)
+    name = util.config_of(tag)
+    paths = _device_paths(name, g["x0"], g["k0"], g["E0"])
+    ref_paths = util.golden_paths(g)
+    assert len(paths) == len(ref_paths) == 1
+    tol = util.tolerance_of(name)
+    (path, rpath) = (paths[0].raybundles, ref_paths[0])
+    assert len(path) == len(rpath)
+    assert path[0] is path[1]
+    worst = 0.0
+    for (ib, (b, rb)) in enumerate(zip(path, rpath)):
+        grin_bundle = rb["rows"] > 3
+        worst = max(worst, util.compare_bundle(
+            b.numpy(), rb, tol, "%s b%d" % (tag, ib), first_last_only=grin_bundle,
+            check_k_last=not grin_bundle))
+    print("%s worst rel err %.3e" % (tag, worst))
+
+
+@pytest.mark.parametrize("name,rings", [("c1_doublet", 30), ("c2_doublegauss", 40),
+                                        ("x1_tilted", 25), ("x3_vignette", 30),
+                                        ("c3_asphere", 12), ("x2_xypoly", 12)])
+def test_matches_oracle_on_larger_bundles(name, rings):
+    import pyrate_np as onp
+    spec = configs.CONFIGS[name]
+    deg = np.pi / 180.0
+    (x0, k0, e0) = configs.config_bundle(spec, rings, (np.sin(1.5 * deg) * 0.6,
+                                                       np.sin(1.5 * deg) * 0.8,
+                                                       np.cos(1.5 * deg)), (0., 1., 0.))
+    paths = _device_paths(name, x0, k0, e0)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    tol = util.tolerance_of(name)
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                        "rayID": rb["rayID"]}, tol, "%s b%d" % (name, ib))
+
+
+def test_efield_invariants_and_input_untouched():
+    spec = configs.CONFIGS["c2_doublegauss"]
+    (x0, k0, e0) = configs.config_bundle(spec, 12)
+    (x0c, k0c, e0c) = (x0.copy(), k0.copy(), e0.copy())
+    for rec_e in (False, True):
+        paths = _device_paths("c2_doublegauss", x0, k0, e0, record_efield=rec_e)
+        for b in paths[0].raybundles[2:]:
+            d = b.numpy()
+            (k, e) = (d["k"][0], d["Efield"][0])
+            assert np.allclose(np.sum(e * e, axis=0), 1.0, atol=1e-12)
+            assert np.max(np.abs(np.sum(e * k, axis=0))) < 1e-12
+    assert np.array_equal(x0, x0c) and np.array_equal(k0, k0c) and np.array_equal(e0, e0c)
+
+
+def test_empty_and_tiny_bundles():
+    spec = configs.CONFIGS["c1_doublet"]
+    for n in (0, 1, 2, 3, 31, 33):
+        (x0, k0, e0) = configs.config_bundle(spec, 4)
+        (x0, k0, e0) = (x0[:, :n].copy(), k0[:, :n].copy(), e0[:, :n].copy())
+        paths = _device_paths("c1_doublet", x0, k0, e0)
+        last = paths[0].raybundles[-1].numpy()
+        assert last["x"].shape == (1, 3, n)
+        if n:
+            import pyrate_np as onp
+            ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0)[0][-1]
+            assert util.relerr(last["x"], ref["x"]) < 1e-10
+            assert util.relerr(last["k"], ref["k"]) < 1e-10
+
+
+def test_full_size_properties_double_gauss():
+    """BASELINE size (1e7 rays): size-independent checks -- |k| = n after every
+    surface, all hit points on their surface, symmetry of the on-axis bundle,
+    and agreement of a strided subsample with the oracle."""
+    import torch
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c2_doublegauss"]
+    (x0, k0, e0) = configs.config_bundle(spec)          # 9 997 351 rays
+    paths = _device_paths("c2_doublegauss", x0, k0, e0)
+    rec = paths[0].record
+    nidx = [1.0] + [ls.st.after.n for ls in rec.lowered]
+    for (s, k) in enumerate(rec.k):
+        alive = (rec.flags[s] & 2) != 0
+        kn = torch.sqrt((k * k).sum(0))[alive]
+        assert float((kn - nidx[s + 1]).abs().max()) < 1e-12
+        assert bool(alive.all())
+    # centroid of an on-axis hexapolar bundle stays on the axis
+    last = rec.hit[-1]
+    assert abs(float(last[0].mean())) < 1e-9 and abs(float(last[1].mean())) < 1e-9
+    sub = np.arange(0, x0.shape[1], 9973)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0[:, sub], k0[:, sub], e0[:, sub])
+    for s in range(len(rec.hit)):
+        got_x = rec.hit[s][:, sub].cpu().numpy()
+        got_k = rec.k[s][:, sub].cpu().numpy()
+        assert util.relerr(got_x, ref[0][s + 1]["x"][-1]) < 1e-10
+        assert util.relerr(got_k, ref[0][s + 2]["k"][0]) < 1e-10

@@ -1,0 +1,108 @@
+"""CPU: the NumPy restatement (oracle/pyrate_np.py) against the fixtures dumped
+from the unmodified reference (oracle/gen_golden.py) -- this is what pins the
+oracle.  Bit-level agreement is expected wherever the arithmetic is the same
+NumPy expression; the Newton-vs-fsolve and eig-ordering cases get tolerances."""
+import numpy as np
+import pytest
+
+import pyrate_np as onp
+from pyrate_b200 import configs
+
+import util
+
+
+@pytest.mark.parametrize("tag", util.golden_traces())
+def test_seqtrace_matches_reference(tag):
+    g = util.load_golden(tag)
+    name = util.config_of(tag)
+    system = onp.system_from_spec(configs.CONFIGS[name])
+    paths = onp.seqtrace(system, g["x0"], g["k0"], g["E0"], wave=configs.DLINE,
+                         splitup=bool(g["splitup"]))
+    ref_paths = util.golden_paths(g)
+    assert len(paths) == len(ref_paths)
+    tol = 1e-11 if util.tolerance_of(name) == util.TOL_ITERATED else 1e-13
+    for (ip, (path, rpath)) in enumerate(zip(paths, ref_paths)):
+        assert len(path) == len(rpath)
+        assert path[0] is path[1]
+        for (ib, (b, rb)) in enumerate(zip(path, rpath)):
+            assert b["x"].shape[0] == rb["rows"]
+            got = {"x": b["x"], "k": b["k"], "valid": b["valid"], "rayID": b["rayID"]}
+            if rb["rows"] > 3:
+                sel = [0, rb["rows"] - 2, rb["rows"] - 1]
+                got = {"x": b["x"][sel], "k": b["k"][sel], "valid": b["valid"][sel],
+                       "rayID": b["rayID"]}
+            util.compare_bundle(got, rb, tol, "%s p%d b%d" % (tag, ip, ib))
+
+
+def test_frames_match_reference():
+    g = np.load(util.GOLDEN + "/frames.npz")
+    for i in range(g["params"].shape[0]):
+        frame = onp.ROOT_FRAME
+        for lvl in range(3):
+            (dx, dy, dz, tx, ty, tz, ttd) = g["params"][i, lvl]
+            frame = onp.child_frame(frame, decx=dx, decy=dy, decz=dz, tiltx=tx,
+                                    tilty=ty, tiltz=tz, tiltThenDecenter=int(ttd))
+            assert np.allclose(frame[0], g["basis"][i, lvl], rtol=0, atol=1e-14)
+            assert np.allclose(frame[1], g["origin"][i, lvl], rtol=0, atol=1e-13)
+    pts = g["pts"]
+    assert np.allclose(onp.l2g_pts(frame, pts), g["last_l2g_pts"], atol=1e-13)
+    assert np.allclose(onp.g2l_pts(frame, pts), g["last_g2l_pts"], atol=1e-13)
+    assert np.allclose(onp.l2g_dir(frame, pts), g["last_l2g_dir"], atol=1e-13)
+    assert np.allclose(onp.g2l_dir(frame, pts), g["last_g2l_dir"], atol=1e-13)
+
+
+def test_shapes_match_reference():
+    g = np.load(util.GOLDEN + "/shapes.npz")
+    (x, y) = (g["x"], g["y"])
+    for (i, (curv, cc)) in enumerate(g["conic_params"]):
+        sh = {"kind": "Conic", "curv": curv, "cc": cc}
+        assert np.allclose(onp.shape_sag(sh, x, y), g["conic%d_sag" % i],
+                           rtol=1e-14, atol=0, equal_nan=True)
+        assert np.allclose(onp.shape_grad(sh, x, y), g["conic%d_grad" % i],
+                           rtol=1e-14, atol=1e-16, equal_nan=True)
+        assert np.allclose(onp.shape_normal(sh, x, y), g["conic%d_normal" % i],
+                           rtol=1e-14, atol=1e-16, equal_nan=True)
+    ap = g["asph_params"]
+    sh = {"kind": "Asphere", "curv": ap[0], "cc": ap[1], "coefficients": list(ap[2:])}
+    assert np.allclose(onp.shape_sag(sh, x, y), g["asph_sag"], rtol=1e-14)
+    assert np.allclose(onp.shape_grad(sh, x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
+    sh = {"kind": "XYPolynomials", "normradius": float(g["xy_normradius"]),
+          "coefficients": [tuple(c) for c in g["xy_coeffs"]]}
+    assert np.allclose(onp.shape_sag(sh, x, y), g["xy_sag"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(onp.shape_grad(sh, x, y), g["xy_grad"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(onp.shape_normal(sh, x, y), g["xy_normal"], rtol=1e-13, atol=1e-16)
+
+
+def test_aniso_modes_match_reference():
+    g = np.load(util.GOLDEN + "/aniso_modes.npz")
+    for nm in ("uniaxial_y", "biaxial_rot"):
+        (k4, e4) = onp.aniso_modes_sorted(g[nm + "_eps"], g[nm + "_n"], g[nm + "_kpa"])
+        assert np.allclose(k4, g[nm + "_k4"], rtol=1e-10, atol=1e-12)
+        # eigenvectors are defined up to a complex scalar: compare directions
+        ref = g[nm + "_e4"]
+        num = np.abs(np.sum(np.conj(e4) * ref, axis=1))
+        den = np.sqrt(np.sum(np.abs(e4) ** 2, axis=1) * np.sum(np.abs(ref) ** 2, axis=1))
+        assert np.all(num / den > 1 - 1e-9)
+
+
+def test_spot_matches_reference():
+    g = np.load(util.GOLDEN + "/spot.npz")
+    c = onp.centroid(g["x"])
+    assert np.allclose(c, g["centroid"], rtol=1e-15, atol=1e-18)
+    assert np.isclose(onp.rms_spot(g["x"], c), float(g["rms"]), rtol=1e-14)
+    assert np.isclose(onp.rms_spot(g["x"], np.zeros(3)), float(g["rms0"]), rtol=1e-14)
+
+
+def test_known_answer_seed_vector():
+    """double-Gauss ray 0 at the image plane."""
+    system = onp.system_from_spec(configs.CONFIGS["c2_doublegauss"])
+    x0 = np.array([[0.0], [5.0], [0.0]])
+    k0 = np.array([[0.0], [0.0], [1.0]])
+    e0 = np.array([[1.0], [0.0], [0.0]])
+    path = onp.seqtrace(system, x0, k0, e0)[0]
+    assert np.allclose(path[-1]["x"][0][:, 0],
+                       [0.0, -0.5212471710809123, 172.54859051823328], rtol=1e-13)
+    assert np.allclose(path[-1]["k"][0][:, 0],
+                       [0.0, -0.04314208775168256, 0.9990689467020913], rtol=1e-13)
+    assert np.allclose(path[3]["k"][0][:, 0],
+                       [0.0, -0.06039952118111261, 1.522259388291602], rtol=1e-13)
