@@ -162,6 +162,10 @@ typedef struct PyrStep {
     double *out_e;              /* (3, n_out)  E field after deflection, global    */
     uint8_t *out_flags;         /* (n)         PYR_RAY_* bits                      */
     int64_t ld_out;             /* leading dimension of out_x / out_k / out_e      */
+    int64_t ld_out2;            /* split step only: leading dimension of out_k /
+                                   out_e (width 2n: mode a of ray i in column i,
+                                   mode b in column n + i, the reference's hstack
+                                   order, material_anisotropic.py:89-100)          */
 } PyrStep;
 
 /* per-ray flag bits written to out_flags */

@@ -335,4 +335,30 @@ X3_VIGNETTE = {   # misses, aperture clipping and total internal reflection
     "s_counted": 2,
 }
 
-CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE)})
+def _rotated_biaxial():
+    # real symmetric positive-definite tensor with principal values
+    # (2.2, 2.6, 3.1) in a frame rotated about a skew axis
+    (a, b, c) = (0.4, -0.3, 0.25)
+    rx = np.array([[1, 0, 0], [0, math.cos(a), -math.sin(a)], [0, math.sin(a), math.cos(a)]])
+    ry = np.array([[math.cos(b), 0, math.sin(b)], [0, 1, 0], [-math.sin(b), 0, math.cos(b)]])
+    rz = np.array([[math.cos(c), -math.sin(c), 0], [math.sin(c), math.cos(c), 0], [0, 0, 1]])
+    q = rz @ ry @ rx
+    return (q @ np.diag([2.2, 2.6, 3.1]) @ q.T).tolist()
+
+
+X4_BIAXIAL = {   # biaxial crystal lens, tilted material frame, into air
+    "name": "x4_biaxial",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 3.0, curv=1. / 50.0, mat="biax", aperture=_circ(8.0),
+               tiltx=3.0 * math.pi / 180.0, tilty=-2.0 * math.pi / 180.0),
+        _conic("back", 5.0, curv=-1. / 60.0, cc=-0.4, mat=None,
+               tiltx=-3.0 * math.pi / 180.0),
+        _conic("image", 40.0),
+    ],
+    "materials": {"biax": ("AnisotropicMaterial", {"epstensor": _rotated_biaxial()})},
+    "bundle": {"rings": 3, "radius": 5.0, "z0": -2.0},
+    "s_counted": 2,
+}
+
+CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL)})

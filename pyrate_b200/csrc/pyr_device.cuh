@@ -60,7 +60,7 @@ struct DStep {
     double inv_knorm;              // > 0: |k| known on entry (1/n of `before`)
     double *out_x, *out_k, *out_e;
     uint8_t *out_flags;
-    int64_t ld_out;
+    int64_t ld_out, ld_out2;
     uint32_t bits;
     int8_t shape_kind, aperture_kind, interaction, dir_mode;
     int8_t before_kind, after_kind, aux, pad0;
@@ -77,6 +77,8 @@ struct LaunchParams {
     DStep steps[kMaxSteps];
     DAux aux[kMaxAux];
 };
+
+static_assert(sizeof(LaunchParams) <= 32000, "kernel parameter block is limited to 32 KB");
 
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double dot3(const double a[3], const double b[3]) {

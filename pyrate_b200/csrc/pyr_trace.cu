@@ -400,12 +400,28 @@ static void pack_medium(const PyrMedium &m, const PyrFrame &shape, DMedium &d) {
     d.kind = m.kind; d.profile = m.grin_profile; d.boundary = m.grin_boundary;
     d.max_steps = m.grin_max_steps;
     d.n = m.n;
-    for (int i = 0; i < 18; ++i) d.eps[i] = m.eps[i];
+    compose_to_shape(m.frame, shape, d.to_shape);
+    // eps (complex, material frame) -> shape frame: Q eps Q^T with the real rotation
+    // Q = Rs^T Rm, so the whole deflection can run in the shape frame
+    {
+        const double *q = d.to_shape.r;
+        for (int part = 0; part < 2; ++part) {
+            double t[9], o[9];
+            for (int i = 0; i < 9; ++i) t[i] = m.eps[2 * i + part];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double v = 0.0;
+                    for (int a = 0; a < 3; ++a)
+                        for (int b = 0; b < 3; ++b) v += q[i * 3 + a] * t[a * 3 + b] * q[j * 3 + b];
+                    o[i * 3 + j] = v;
+                }
+            for (int i = 0; i < 9; ++i) d.eps[2 * i + part] = o[i];
+        }
+    }
     for (int i = 0; i < PYR_MAX_GRIN_PARAMS; ++i) d.p[i] = m.grin_p[i];
     for (int i = 0; i < 4; ++i) d.b[i] = m.grin_b[i];
     d.ds = m.grin_ds; d.energy_tol = m.grin_energy_tol;
     pack_frame(m.frame, d.frame);
-    compose_to_shape(m.frame, shape, d.to_shape);
 }
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -455,6 +471,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                        u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / u.k_norm_hint : 0.0;
         d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
         d.ld_out = u.ld_out > 0 ? u.ld_out : n_rays;
+        d.ld_out2 = u.ld_out2 > 0 ? u.ld_out2 : 2 * d.ld_out;
         d.shape_kind = (int8_t)u.shape_kind; d.aperture_kind = (int8_t)u.aperture_kind;
         d.interaction = (int8_t)u.interaction; d.dir_mode = (int8_t)u.dir_mode;
         d.before_kind = (int8_t)u.before.kind; d.after_kind = (int8_t)u.after.kind;
@@ -500,9 +517,20 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
     return PYR_OK;
 }
 
+int pack_steps(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+               uint32_t flags, LaunchParams &P, bool &general, bool &any_aniso) {
+    static thread_local Packed pk;
+    const int rc = pack(steps, n_steps, rays, n_rays, flags, pk);
+    if (rc != PYR_OK) return rc;
+    std::memcpy(&P, &pk.P, sizeof(LaunchParams));
+    general = pk.general;
+    any_aniso = pk.any_aniso;
+    return PYR_OK;
+}
+
 static int g_sm_count = 0;
 
-static int sm_count() {
+int sm_count() {
     if (g_sm_count == 0) {
         int dev = 0, sms = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 148;

@@ -147,10 +147,10 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
         cur_e = None
         if e0 is not None:
             (cur_e, _) = _padded(e0, complex_in)
-        elif complex_in:
+        elif complex_in or first_aniso is not None:
             tmp = torch.zeros((3, n0), dtype=torch.float64, device=device)
-            tmp[1] = 1.0
-            (cur_e, _) = _padded(tmp, True)
+            tmp[1] = 1.0                      # ray.py:71-73 default
+            (cur_e, _) = _padded(tmp, complex_in)
         cur_alive = None
         n = n0
         n_x = n0
@@ -191,7 +191,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
                 if last_split and i == hi - 1:
                     st.out_k = klast.data_ptr()
                     st.out_e = elast.data_ptr()
-                    st.ld_out = ld        # out_x/flags use ld; k/e of a split step use 2n rows
+                    st.ld_out2 = ld2      # k / e of a split step are 2n wide
                 else:
                     st.out_k = kbuf[r].data_ptr()
                     st.out_e = ebuf[r].data_ptr() if ebuf is not None else None

@@ -12,7 +12,7 @@ import util
 
 pytestmark = pytest.mark.gpu
 
-REAL_TAGS = [t for t in util.golden_traces() if not t.startswith("c4")]
+REAL_TAGS = [t for t in util.golden_traces() if not t.startswith(("c4", "x4"))]
 
 
 def _device_paths(name, x0, k0, e0, splitup=False, record_efield=False):
@@ -139,3 +139,56 @@ def test_host_entry_matches_device_path():
     assert np.allclose(dev_sums[:3], ref.sum(axis=1), rtol=1e-12, atol=1e-9)
     assert dev_sums[3] == n
     assert np.allclose(dev_sums[4:7], (ref ** 2).sum(axis=1), rtol=1e-12)
+
+
+ANISO_TAGS = ["c4_anisotropic", "c4_anisotropic_split", "x4_biaxial"]
+
+
+@pytest.mark.parametrize("tag", ANISO_TAGS)
+def test_birefringent_matches_reference_fixture(tag):
+    """Anisotropic doublet / biaxial lens: o/e ray split (ray doubling or path
+    forking), complex k and E, Poynting-vector propagation inside the crystal."""
+    g = util.load_golden(tag)
+    name = util.config_of(tag)
+    splitup = bool(g["splitup"])
+    paths = _device_paths(name, g["x0"], g["k0"], g["E0"], splitup=splitup)
+    ref_paths = util.golden_paths(g)
+    assert len(paths) == len(ref_paths)
+    # forked paths: the reference's path order depends on the same arbitrary
+    # mode order, so match whole paths by their final k
+    remaining = list(range(len(ref_paths)))
+    for (ip, path) in enumerate(paths):
+        bundles = path.raybundles
+        last = bundles[-1].numpy()
+        cost = [np.nanmax(np.abs(last["k"] - ref_paths[j][-1]["k"])) +
+                np.nanmax(np.abs(last["x"] - ref_paths[j][-1]["x"])) for j in remaining]
+        j = remaining.pop(int(np.argmin(cost)))
+        rpath = ref_paths[j]
+        assert len(bundles) == len(rpath)
+        for (ib, (b, rb)) in enumerate(zip(bundles, rpath)):
+            d = b.numpy()
+            d["E"] = d["Efield"]
+            iscomplex = np.iscomplexobj(rb["k"])
+            assert np.iscomplexobj(d["k"]) == iscomplex, "dtype of k, bundle %d" % ib
+            if iscomplex:
+                util.compare_birefringent_bundle(d, rb, 1e-9, "%s p%d b%d" % (tag, ip, ib))
+            else:
+                util.compare_bundle(d, rb, 1e-10, "%s p%d b%d" % (tag, ip, ib))
+
+
+def test_birefringent_larger_bundle_against_oracle():
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c4_anisotropic"]
+    (x0, k0, e0) = configs.config_bundle(spec, 7, (0.0, np.sin(0.02), np.cos(0.02)),
+                                         (1.0, 0.0, 0.0))
+    paths = _device_paths("c4_anisotropic", x0, k0, e0)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        d = b.numpy()
+        d["E"] = d["Efield"]
+        rbd = {"x": rb["x"], "k": rb["k"], "valid": rb["valid"], "rayID": rb["rayID"],
+               "E": rb["E"]}
+        if np.iscomplexobj(rb["k"]):
+            util.compare_birefringent_bundle(d, rbd, 1e-9, "c4 b%d" % ib)
+        else:
+            util.compare_bundle(d, rbd, 1e-10, "c4 b%d" % ib)

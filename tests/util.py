@@ -85,3 +85,42 @@ def compare_bundle(got, ref, tol, what, first_last_only=False, check_k_last=True
     assert ex <= tol, "%s: x rel err %.3e > %.1e" % (what, ex, tol)
     assert ek <= tol, "%s: k rel err %.3e > %.1e" % (what, ek, tol)
     return max(ex, ek)
+
+
+def compare_birefringent_bundle(got, ref, tol, what):
+    """Bundles downstream of a birefringent interface.  Children of one parent
+    ray share its rayID; the order of the two forward modes depends on LAPACK's
+    eigenvector normalisation in the reference (material.py:148 sorts S.n of
+    un-normalised fields), so children are matched as an unordered set per
+    rayID; E is compared up to a complex scalar."""
+    gid, rid = np.asarray(got["rayID"]), np.asarray(ref["rayID"])
+    assert np.array_equal(np.sort(gid), np.sort(rid)), "%s: rayID multiset differs" % what
+    gx, rx = np.asarray(got["x"]), np.asarray(ref["x"])
+    gk, rk = np.asarray(got["k"]), np.asarray(ref["k"])
+    assert gx.shape == rx.shape and gk.shape == rk.shape, (what, gx.shape, rx.shape)
+    gv, rv = np.asarray(got["valid"]), np.asarray(ref["valid"])
+    ge = np.asarray(got["E"]) if "E" in got else None
+    re_ = np.asarray(ref["E"]) if "E" in ref else None
+    scale_x = max(1e-300, np.nanmax(np.abs(rx)))
+    scale_k = max(1e-300, np.nanmax(np.abs(rk)))
+    worst = 0.0
+    for ray in np.unique(rid):
+        gc = np.where(gid == ray)[0]
+        rc = list(np.where(rid == ray)[0])
+        assert len(gc) == len(rc)
+        for g in gc:
+            feats = [np.max(np.abs(gk[0][:, g] - rk[0][:, r])) / scale_k +
+                     np.max(np.abs(gx[-1][:, g] - rx[-1][:, r])) / scale_x for r in rc]
+            j = int(np.argmin(feats))
+            r = rc.pop(j)
+            ex = np.max(np.abs(gx[:, :, g] - rx[:, :, r])) / scale_x
+            ek = np.max(np.abs(gk[:, :, g] - rk[:, :, r])) / scale_k
+            assert ex <= tol and ek <= tol, "%s ray %d: x %.3e k %.3e" % (what, ray, ex, ek)
+            assert np.array_equal(gv[:, g], rv[:, r]), "%s ray %d: valid differs" % (what, ray)
+            worst = max(worst, ex, ek)
+            if ge is not None and re_ is not None:
+                (a, b) = (ge[0][:, g], re_[0][:, r])
+                col = np.abs(np.sum(np.conj(a) * b)) / np.sqrt(
+                    np.sum(np.abs(a) ** 2) * np.sum(np.abs(b) ** 2))
+                assert col > 1 - 1e-7, "%s ray %d: E not colinear (%.3e)" % (what, ray, 1 - col)
+    return worst
