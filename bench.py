@@ -189,9 +189,10 @@ def run_gpu(args):
     k0 = torch.from_numpy(k0h).to(dev)
     e0 = torch.from_numpy(e0h).to(dev)
     spot = torch.zeros(8, dtype=torch.float64, device=dev)
+    pool = engine.RecordPool()      # record buffers allocated once, reused per step
 
     def step():
-        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev)
+        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool)
         spot.zero_()
         engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot)
         if world > 1:
@@ -217,7 +218,7 @@ def run_gpu(args):
         t0.record()
         for i in range(args.steps):
             ev[i][0].record()
-            rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev)
+            rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool)
             ev[i][1].record()
             spot.zero_()
             engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot)

@@ -64,13 +64,16 @@ class TraceRecord(object):
         self.wave = None
 
 
-def _alloc_rows(rows, n, device, complex_=False):
+def _empty(shape, dtype, device, pool):
+    if pool is not None:
+        return pool.get(shape, dtype, device)
+    return torch.empty(shape, dtype=dtype, device=device)
+
+
+def _alloc_rows(rows, n, device, complex_=False, pool=None):
     ld = _round_up(max(n, 1), LD_ALIGN)
-    if complex_:
-        buf = torch.empty((rows, 3, ld, 2), dtype=torch.float64, device=device)
-    else:
-        buf = torch.empty((rows, 3, ld), dtype=torch.float64, device=device)
-    return buf, ld
+    shape = (rows, 3, ld, 2) if complex_ else (rows, 3, ld)
+    return _empty(shape, torch.float64, device, pool), ld
 
 
 def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
@@ -88,30 +91,64 @@ def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
     nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
 
 
-def _padded(t, complex_=False):
-    """Copy a (3, n) tensor into a (3, ld[, 2]) buffer with aligned rows."""
+def _padded(t, complex_=False, pad=True):
+    """(3, n) tensor -> buffer the kernels can read, and its leading dimension.
+
+    pad=False hands a contiguous tensor through unchanged (ld = n; the kernels
+    fall back to 64-bit loads when rows are not 16-byte aligned) -- used for
+    the caller's input bundle, which is never copied needlessly."""
     n = t.shape[1]
-    ld = _round_up(max(n, 1), LD_ALIGN)
     if complex_:
         tc = t.to(torch.complex128)
+        if not pad and tc.is_contiguous():
+            return torch.view_as_real(tc), max(n, 1)
+        ld = _round_up(max(n, 1), LD_ALIGN)
         buf = torch.zeros((3, ld, 2), dtype=torch.float64, device=t.device)
         buf[:, :n, :] = torch.view_as_real(tc)
-    else:
-        if n == ld and t.is_contiguous():
-            return t, ld
-        buf = torch.zeros((3, ld), dtype=torch.float64, device=t.device)
-        buf[:, :n] = t
+        return buf, ld
+    if t.is_complex():
+        raise ValueError("complex data in a real-valued stretch")
+    if not pad and t.is_contiguous():
+        return t, max(n, 1)
+    ld = _round_up(max(n, 1), LD_ALIGN)
+    if n == ld and t.is_contiguous():
+        return t, ld
+    buf = torch.zeros((3, ld), dtype=torch.float64, device=t.device)
+    buf[:, :n] = t
     return buf, ld
 
 
-def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
+class RecordPool(object):
+    """Opt-in reuse of the per-step record buffers across calls with identical
+    shapes (optimisation loops, benchmarks): a TraceRecord returned with a pool
+    is overwritten by the next trace that uses the same pool."""
+
+    def __init__(self):
+        self.bufs = {}
+        self.cursor = 0
+
+    def begin(self):
+        self.cursor = 0
+
+    def get(self, shape, dtype, device):
+        key = (self.cursor, tuple(shape), dtype, str(device))
+        self.cursor += 1
+        t = self.bufs.get(key)
+        if t is None:
+            t = torch.empty(shape, dtype=dtype, device=device)
+            self.bufs[key] = t
+        return t
+
+
+def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
+          pool=None):
     """Run the lowered sequence on the device.  Returns a TraceRecord."""
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
-    x0 = as_tensor(x0, device)
-    k0 = as_tensor(k0, device)
-    e0 = None if e0 is None else as_tensor(e0, device)
+    x0 = as_tensor(x0, device).contiguous()
+    k0 = as_tensor(k0, device).contiguous()
+    e0 = None if e0 is None else as_tensor(e0, device).contiguous()
     if x0.is_complex():
         raise ValueError("ray positions must be real")
     n0 = x0.shape[1]
@@ -140,17 +177,19 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
             cuts.append(i + 1)
     cuts = sorted(set(cuts)) + [nsteps]
 
+    if pool is not None:
+        pool.begin()
     with torch.cuda.device(device):
         complex_in = k0.is_complex() or (e0 is not None and e0.is_complex())
-        (cur_x, ld_x) = _padded(x0)
-        (cur_k, ld_k) = _padded(k0, complex_in)
+        (cur_x, ld_x) = _padded(x0, pad=False)
+        (cur_k, ld_k) = _padded(k0, complex_in, pad=False)
         cur_e = None
         if e0 is not None:
-            (cur_e, _) = _padded(e0, complex_in)
+            (cur_e, _) = _padded(e0, complex_in, pad=False)
         elif complex_in or first_aniso is not None:
             tmp = torch.zeros((3, n0), dtype=torch.float64, device=device)
             tmp[1] = 1.0                      # ray.py:71-73 default
-            (cur_e, _) = _padded(tmp, complex_in)
+            (cur_e, _) = _padded(tmp, complex_in, pad=False)
         cur_alive = None
         n = n0
         n_x = n0
@@ -166,22 +205,26 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
                                        "anisotropic medium")
                 (cur_e, _) = _padded(cur_e[:, :n], True)
                 is_complex = True
+                if ld_k != ld_x:
+                    nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
+                    nx[:, :n_x] = cur_x[:, :n_x]
+                    (cur_x, ld_x) = (nx, ld_k)
             want_e = record_e or seg_complex or \
                 (first_aniso is not None and hi == first_aniso)
             rows = hi - lo
             last_split = bool(steps[hi - 1].split)
-            (xbuf, ld) = _alloc_rows(rows, n, device)
-            fbuf = torch.empty((rows, ld), dtype=torch.uint8, device=device)
+            (xbuf, ld) = _alloc_rows(rows, n, device, pool=pool)
+            fbuf = _empty((rows, ld), torch.uint8, device, pool)
             if last_split:
-                (kbuf, _) = _alloc_rows(max(rows - 1, 1), n, device, seg_complex)
+                (kbuf, _) = _alloc_rows(max(rows - 1, 1), n, device, seg_complex, pool=pool)
                 ld2 = _round_up(2 * n, LD_ALIGN)
-                klast = torch.empty((3, ld2, 2), dtype=torch.float64, device=device)
-                elast = torch.empty((3, ld2, 2), dtype=torch.float64, device=device)
+                klast = _empty((3, ld2, 2), torch.float64, device, pool)
+                elast = _empty((3, ld2, 2), torch.float64, device, pool)
             else:
-                (kbuf, _) = _alloc_rows(rows, n, device, seg_complex)
+                (kbuf, _) = _alloc_rows(rows, n, device, seg_complex, pool=pool)
             ebuf = None
             if want_e:
-                (ebuf, _) = _alloc_rows(rows, n, device, seg_complex)
+                (ebuf, _) = _alloc_rows(rows, n, device, seg_complex, pool=pool)
             for i in range(lo, hi):
                 st = steps[i]
                 r = i - lo
@@ -241,7 +284,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None):
                         # leading dimension ld_k: re-pad to the common ld
                         nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
                         nx[:, :n_x] = cur_x[:, :n_x]
-                        cur_x = nx
+                        (cur_x, ld_x) = (nx, ld_k)
                 else:
                     cur_k = kbuf[r]
                     cur_e = ebuf[r] if ebuf is not None else None
