@@ -116,4 +116,48 @@ __device__ __forceinline__ bool finite3(const double v[3]) {
 
 __device__ __forceinline__ double qnan() { return __longlong_as_double(0x7ff8000000000000LL); }
 
+// ---------------------------------------------------------------------------
+// Branch-free FP64 sqrt / rsqrt / reciprocal for the hot path.
+// MUFU seed (~2^-22 relative) + one third-order / two second-order Newton steps
+// -> ~1 ulp.  No slow-path subroutine (CUDA's sqrt()/division carry a range check
+// and a CALL): arguments here are O(1) geometric quantities, never denormal.
+// Contract: a < 0 or NaN -> NaN; a == 0 -> NaN (reference: tangent ray / TIR
+// boundary, invalid there as well); +-inf not expected.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double e = fma(-a, y * y, 1.0);            // 1 - a y^2
+    return fma(fma(e, 0.375, 0.5), y * e, y);        // y (1 + e/2 + 3 e^2/8)
+}
+
+__device__ __forceinline__ double fast_sqrt(double a) {
+    const double y = fast_rsqrt(a);
+    const double s = a * y;
+    return fma(fma(-s, s, a), 0.5 * y, s);           // one Heron correction
+}
+
+// sqrt(a) and 1/sqrt(a) together
+__device__ __forceinline__ double fast_sqrt_r(double a, double &rs) {
+    rs = fast_rsqrt(a);
+    const double s = a * rs;
+    return fma(fma(-s, s, a), 0.5 * rs, s);
+}
+
+__device__ __forceinline__ double fast_rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+}
+
+// a / b with one residual correction (~1 ulp)
+__device__ __forceinline__ double fast_div(double a, double b) {
+    const double y = fast_rcp(b);
+    const double q = a * y;
+    return fma(fma(-q, b, a), y, q);
+}
+
 }  // namespace pyr

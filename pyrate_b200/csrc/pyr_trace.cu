@@ -21,6 +21,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "pyr_device.cuh"
@@ -193,8 +194,104 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     return (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
 }
 
-template <int RPT, bool WITH_E, bool GENERAL>
-__global__ void __launch_bounds__(256)
+// Tuned step for the common case (conic shape, homogeneous isotropic media,
+// aperture in the shape frame): same arithmetic as step_real, but
+//   * plane surfaces (curv == 0) take a closed form without the conic machinery,
+//   * sqrt / division run branch-free (fast_sqrt / fast_div, ~1 ulp),
+//   * validity rides on NaN propagation: a ray that dies gets k = NaN once, every
+//     later hit point and wave vector is NaN by arithmetic, and `square > 0`
+//     already rejects NaN normals (no separate finite check).
+template <bool WITH_E>
+__device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, double hit_g[3]) {
+    const bool ok = r.alive;
+    double d[3];
+    if (WITH_E && st.dir_mode == PYR_DIR_POYNTING) {
+        poynting_dir(r.k, r.e, d);
+    } else {
+        const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm : fast_rsqrt(dot3(r.k, r.k));
+        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
+    }
+    const bool ident = (st.bits & kRotIdentity) != 0;
+    double r0[3], dl[3], kl[3];
+    if (ident) {
+        r0[0] = r.x[0] - st.frame.o[0]; r0[1] = r.x[1] - st.frame.o[1]; r0[2] = r.x[2] - st.frame.o[2];
+        dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2];
+        kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2];
+    } else {
+        g2l_point(st.frame, r.x, r0);
+        rot_t(st.frame.r, d, dl);
+        rot_t(st.frame.r, r.k, kl);
+    }
+    const double curv = st.curv, cc = st.cc;
+    double t, nrm[3];
+    bool hit_ok = true;
+    double h[3];
+    const bool plane = (st.bits & kPlane) != 0;
+    if (plane && dl[2] > 0.0) {
+        // F = d_z, G = -2 z0, H = 0  ->  t = -z0 / d_z  (surface_shape.py:305-318)
+        t = -r0[2] * fast_rcp(dl[2]);
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
+        nrm[0] = 0.0; nrm[1] = 0.0; nrm[2] = 1.0;
+    } else {
+        const double cc1 = 1.0 + cc;
+        const double F = dl[2] - curv * fma(dl[0], r0[0], fma(dl[1], r0[1], dl[2] * r0[2] * cc1));
+        const double G = curv * fma(r0[0], r0[0], fma(r0[1], r0[1], r0[2] * r0[2] * cc1)) - 2.0 * r0[2];
+        const double H = -curv - cc * curv * dl[2] * dl[2];
+        const double square = fma(F, F, H * G);
+        hit_ok = square >= 0.0;
+        t = fast_div(G, F + fast_sqrt(square));
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
+        // unit normal: (-c x, -c y, sqrt(1 - (1+cc) c^2 r^2)) / sqrt(1 - cc c^2 r^2)
+        const double c2r2 = curv * curv * fma(h[0], h[0], h[1] * h[1]);
+        const double s = fma(-cc1, c2r2, 1.0);
+        double gz = fast_sqrt(s);                       // s <= 0 -> NaN (conic_function :214-216)
+        double gx = -curv * h[0], gy = -curv * h[1];
+        if (!(st.bits & kSphere)) {
+            const double inv = fast_rsqrt(fma(-cc, c2r2, 1.0));
+            gx *= inv; gy *= inv; gz *= inv;
+        }
+        nrm[0] = gx; nrm[1] = gy; nrm[2] = gz;
+    }
+    if (ident) {
+        hit_g[0] = h[0] + st.frame.o[0]; hit_g[1] = h[1] + st.frame.o[1]; hit_g[2] = h[2] + st.frame.o[2];
+    } else {
+        l2g_point(st.frame, h, hit_g);
+    }
+    bool ap_ok = true;
+    if (st.aperture_kind == PYR_AP_CIRCULAR) {
+        const double rr = fma(h[0], h[0], h[1] * h[1]);
+        ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
+    } else if (st.aperture_kind == PYR_AP_RECTANGULAR) {
+        ap_ok = (fabs(h[0]) <= st.ap0) && (fabs(h[1]) <= st.ap1);
+    }
+    const bool hit = ok && hit_ok && ap_ok;
+
+    // Snell via in-plane k (material_isotropic.py:175-185 / :224)
+    const double kn = dot3(kl, nrm);
+    const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
+    const double square2 = st.n2sq - dot3(kin, kin);
+    const double xi = fast_sqrt(square2);
+    const bool alive = hit && (square2 > 0.0);
+    double k2[3];
+    if (st.interaction == PYR_REFLECT) {
+        k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
+    } else {
+        k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
+    }
+    if (ident) { r.k[0] = k2[0]; r.k[1] = k2[1]; r.k[2] = k2[2]; }
+    else rot(st.frame.r, k2, r.k);
+    r.x[0] = hit_g[0]; r.x[1] = hit_g[1]; r.x[2] = hit_g[2];
+    if (!alive) { const double q = qnan(); r.k[0] = q; r.k[1] = q; r.k[2] = q; }
+    if (WITH_E) {
+        if (alive) reproject_e(r.k, r.e);
+        else r.e[0] = r.e[1] = r.e[2] = qnan();
+    }
+    r.alive = alive;
+    return (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
+}
+
+template <int RPT, bool WITH_E, bool GENERAL, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
     const int64_t n = P.n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * RPT;
@@ -248,6 +345,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 for (int c = 0; c < 3; ++c) ray[j].e[c] = in[j].e[c];
             }
             ray[j].alive = in[j].alive;
+            if (!in[j].alive) { ray[j].k[0] = ray[j].k[1] = ray[j].k[2] = qnan(); }
         }
 
         for (int s = 0; s < P.n_steps; ++s) {
@@ -262,7 +360,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { tmp.x[c] = ray[j].x[c]; tmp.k[c] = ray[j].k[c]; tmp.e[c] = in[j].e[c]; }
                     tmp.alive = ray[j].alive;
-                    fl[j] = step_real<true, GENERAL>(P, st, tmp, hit[j]);
+                    fl[j] = GENERAL ? step_real<true, true>(P, st, tmp, hit[j]) : step_lean<true>(st, tmp, hit[j]);
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { ray[j].x[c] = tmp.x[c]; ray[j].k[c] = tmp.k[c]; }
                     if (WITH_E) {
@@ -273,7 +371,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) fl[j] = step_real<WITH_E, GENERAL>(P, st, ray[j], hit[j]);
+                for (int j = 0; j < RPT; ++j) fl[j] = GENERAL ? step_real<WITH_E, true>(P, st, ray[j], hit[j]) : step_lean<WITH_E>(st, ray[j], hit[j]);
             }
 
             // ---- record the step (evict-first streaming stores) ----
@@ -572,8 +670,21 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
     if (!pk.general) {
-        return with_e ? launch(trace_real_kernel<2, true, false>, pk.P, 2, stream)
-                      : launch(trace_real_kernel<2, false, false>, pk.P, 2, stream);
+        if (with_e) return launch(trace_real_kernel<2, true, false>, pk.P, 2, stream);
+        // tuning knob (not part of the ABI): resident CTAs per SM the lean kernel is
+        // compiled for; PYR_LEAN_VARIANT = 1 (free), 3, 4, or 11 (one ray per thread)
+        static const int variant = [] {
+            const char *e = std::getenv("PYR_LEAN_VARIANT");
+            return e ? std::atoi(e) : 0;
+        }();
+        switch (variant) {
+            case 1: return launch(trace_real_kernel<2, false, false, 1>, pk.P, 2, stream);
+            case 3: return launch(trace_real_kernel<2, false, false, 3>, pk.P, 2, stream);
+            case 4: return launch(trace_real_kernel<2, false, false, 4>, pk.P, 2, stream);
+            case 11: return launch(trace_real_kernel<1, false, false, 4>, pk.P, 1, stream);
+            case 12: return launch(trace_real_kernel<1, false, false, 6>, pk.P, 1, stream);
+            default: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream);
+        }
     }
     return with_e ? launch(trace_real_kernel<2, true, true>, pk.P, 2, stream)
                   : launch(trace_real_kernel<2, false, true>, pk.P, 2, stream);
@@ -619,6 +730,7 @@ int pyr_device_count(void) {
 
 int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
               uint32_t flags, void *stream) {
+    if (n_rays == 0 && steps && rays && n_steps > 0) return PYR_OK;
     return pyr::trace_impl(steps, n_steps, rays, n_rays, flags, (cudaStream_t)stream);
 }
 

@@ -77,6 +77,8 @@ def _alloc_rows(rows, n, device, complex_=False, pool=None):
 
 
 def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
+    if n == 0:
+        return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
     for i in range(lo, hi):
         C.memmove(C.addressof(arr[i - lo]), C.addressof(steps[i]),
