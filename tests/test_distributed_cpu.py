@@ -1,0 +1,65 @@
+"""CPU (gloo, world_size 2): the multi-rank host logic -- ray sharding, the
+8-double all-reduce of the spot sums and the reference's centroid / RMS
+normalisations.  The per-rank partial sums are formed with torch on the CPU
+here (on the GPU box they come from pyr_spot_sums)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, xfile, out):
+    sys.path.insert(0, ROOT)
+    from pyrate_b200 import distributed as pd
+    from pyrate_b200 import engine
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    x = torch.from_numpy(np.load(xfile))
+    (xs, _, _, (lo, hi)) = pd.shard_bundle(x, x, None)
+    sums = torch.zeros(8, dtype=torch.float64)
+    sums[0:3] = xs.sum(1)
+    sums[3] = xs.shape[1]
+    sums[4:7] = (xs * xs).sum(1)
+    pd.allreduce_spot_sums(sums)
+    (c, rms) = engine.spot_from_sums(sums)
+    np.save(out % rank, np.array(list(c) + [rms, sums[3].item(), lo, hi]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_sharded_spot_matches_reference_statistic(tmp_path):
+    g = np.load(os.path.join(ROOT, "tests", "golden", "spot.npz"))
+    xfile = str(tmp_path / "x.npy")
+    np.save(xfile, g["x"])
+    out = str(tmp_path / "r%d.npy")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(2, port, xfile, out), nprocs=2, join=True)
+    n = g["x"].shape[1]
+    for r in range(2):
+        v = np.load(out % r)
+        assert np.allclose(v[:3], g["centroid"], rtol=1e-12, atol=1e-14)
+        assert np.isclose(v[3], float(g["rms"]), rtol=1e-9)
+        assert v[4] == n
+    (lo0, hi0) = np.load(out % 0)[5:7]
+    (lo1, hi1) = np.load(out % 1)[5:7]
+    assert (lo0, hi0, hi1) == (0, n // 2, n) and lo1 == hi0
+
+
+def test_shard_range_partitions():
+    from pyrate_b200 import distributed as pd
+    for n in (0, 1, 7, 9997351):
+        for w in (1, 2, 3, 8):
+            ranges = [pd.shard_range(n, r, w) for r in range(w)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            for (a, b) in zip(ranges[:-1], ranges[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for (lo, hi) in ranges]
+            assert max(sizes) - min(sizes) <= 1

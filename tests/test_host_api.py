@@ -1,0 +1,160 @@
+"""CPU: the host API mirror (frames, shapes, builders, lowering) against the
+reference fixtures, and -- when the reference tree is present (build container)
+-- the lowering of the reference's OWN object graph against ours."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+import pyrate_b200 as pb
+from pyrate_b200 import _native as nat
+from pyrate_b200 import configs, lowering
+
+import util
+
+
+def test_frames_match_reference_fixture():
+    g = np.load(util.GOLDEN + "/frames.npz")
+    for i in range(g["params"].shape[0]):
+        parent = None
+        for lvl in range(3):
+            (dx, dy, dz, tx, ty, tz, ttd) = g["params"][i, lvl]
+            lc = pb.LocalCoordinates.p(name="l%d_%d" % (i, lvl), decx=dx, decy=dy, decz=dz,
+                                       tiltx=tx, tilty=ty, tiltz=tz, tiltThenDecenter=int(ttd))
+            if parent is not None:
+                parent.addChild(lc)
+            parent = lc
+            assert np.allclose(lc.localbasis, g["basis"][i, lvl], atol=1e-14)
+            assert np.allclose(lc.globalcoordinates, g["origin"][i, lvl], atol=1e-13)
+    pts = g["pts"]
+    assert np.allclose(parent.returnLocalToGlobalPoints(pts), g["last_l2g_pts"], atol=1e-13)
+    assert np.allclose(parent.returnGlobalToLocalPoints(pts), g["last_g2l_pts"], atol=1e-13)
+    assert np.allclose(parent.returnLocalToGlobalDirections(pts), g["last_l2g_dir"], atol=1e-13)
+    assert np.allclose(parent.returnGlobalToLocalDirections(pts), g["last_g2l_dir"], atol=1e-13)
+
+
+def test_frame_round_trips_and_invariants():
+    """Same properties the reference pins with hypothesis
+    (tests/test_localcoordinates.py:63-183): round trips, scalar products and
+    tensor contractions are frame independent."""
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        kw = dict(zip(("decx", "decy", "decz", "tiltx", "tilty", "tiltz"),
+                      rng.uniform(-3, 3, 6)))
+        root = pb.LocalCoordinates.p(name="root", **kw)
+        lc = root.addChild(pb.LocalCoordinates.p(name="child", tiltThenDecenter=1,
+                                                 **dict(zip(kw, rng.uniform(-3, 3, 6)))))
+        (a, b) = (rng.normal(size=(3, 5)), rng.normal(size=(3, 5)))
+        t = rng.normal(size=(3, 3, 5))
+        assert np.allclose(lc.returnGlobalToLocalPoints(lc.returnLocalToGlobalPoints(a)), a)
+        assert np.allclose(lc.returnLocalToGlobalDirections(lc.returnGlobalToLocalDirections(a)), a)
+        assert np.allclose(lc.returnGlobalToLocalTensors(lc.returnLocalToGlobalTensors(t)), t)
+        (ag, bg) = (lc.returnLocalToGlobalDirections(a), lc.returnLocalToGlobalDirections(b))
+        assert np.allclose(np.sum(ag * bg, axis=0), np.sum(a * b, axis=0))
+        tg = lc.returnLocalToGlobalTensors(t)
+        assert np.allclose(np.einsum("in,ijn,jn->n", ag, tg, bg),
+                           np.einsum("in,ijn,jn->n", a, t, b))
+        assert np.allclose(root.returnOtherToActualPoints(
+            root.returnActualToOtherPoints(a, lc), lc), a)
+
+
+def test_shapes_match_reference_fixture():
+    g = np.load(util.GOLDEN + "/shapes.npz")
+    lc = pb.LocalCoordinates.p(name="s")
+    (x, y) = (g["x"], g["y"])
+    for (i, (curv, cc)) in enumerate(g["conic_params"]):
+        sh = pb.Conic.p(lc, curv=curv, cc=cc)
+        assert np.allclose(sh.getSag(x, y), g["conic%d_sag" % i], rtol=1e-14, equal_nan=True)
+        assert np.allclose(sh.getGrad(x, y), g["conic%d_grad" % i], rtol=1e-14, atol=1e-16,
+                           equal_nan=True)
+        assert np.allclose(sh.getNormal(x, y), g["conic%d_normal" % i], rtol=1e-14, atol=1e-16,
+                           equal_nan=True)
+    ap = g["asph_params"]
+    sh = pb.Asphere.p(lc, curv=ap[0], cc=ap[1], coefficients=list(ap[2:]))
+    assert np.allclose(sh.getSag(x, y), g["asph_sag"], rtol=1e-14)
+    assert np.allclose(sh.getGrad(x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(sh.getNormal(x, y), g["asph_normal"], rtol=1e-13, atol=1e-16)
+    sh = pb.XYPolynomials.p(lc, normradius=float(g["xy_normradius"]),
+                            coefficients=[(int(a), int(b), c) for (a, b, c) in g["xy_coeffs"]])
+    assert np.allclose(sh.getSag(x, y), g["xy_sag"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(sh.getGrad(x, y), g["xy_grad"], rtol=1e-13, atol=1e-16)
+    # same evaluators on torch tensors
+    import torch
+    (xt, yt) = (torch.from_numpy(x), torch.from_numpy(y))
+    assert np.allclose(sh.getNormal(xt, yt).numpy(), g["xy_normal"], rtol=1e-13, atol=1e-16)
+
+
+def test_structural_errors_like_the_reference():
+    s = pb.OpticalSystem.p()
+    lc0 = s.addLocalCoordinateSystem(pb.LocalCoordinates.p(name="obj"),
+                                     refname=s.rootcoordinatesystem.name)
+    elem = pb.OpticalElement.p(lc0, name="e")
+    stray = pb.LocalCoordinates.p(name="stray")
+    with pytest.raises(Exception):       # optical_element.py:76
+        elem.addSurface("s", pb.Surface.p(stray), (None, None))
+    with pytest.raises(Exception):       # optical_element.py:107
+        elem.addMaterial("m", pb.ConstantIndexGlass.p(stray, 1.5))
+    with pytest.raises(Exception):       # optical_system.py:227
+        s.addElement("e2", pb.OpticalElement.p(stray))
+    with pytest.raises(lowering.LoweringError):
+        lowering.lower(s, [("nope", [])], configs.DLINE)
+
+
+def test_lowering_follows_material_toggle_and_mirror_rules():
+    (s, seq) = configs.build_system(configs.CONFIGS["x1_tilted"], pb.api())
+    low = lowering.lower(s, seq, configs.DLINE)
+    kinds = [(l.surfkey, round(l.st.before.n, 4), round(l.st.after.n, 4), l.st.interaction)
+             for l in low]
+    n_mg = round(pb.ModelGlass.p(pb.LocalCoordinates.p()).get_optical_index(None, configs.DLINE), 4)
+    assert kinds == [("stop", 1.0, 1.0, 0), ("front", 1.0, n_mg, 0), ("back", n_mg, 1.0, 0),
+                     ("mirror", 1.0, 1.0, 1), ("image", 1.0, 1.0, 0)]
+    assert low[0].st.dir_mode == nat.DIR_POYNTING and low[1].st.dir_mode == nat.DIR_K
+    assert low[2].st.k_norm_hint == pytest.approx(low[2].st.before.n)
+
+
+def test_grin_profile_is_verified_against_python_source():
+    spec = configs.CONFIGS["c5_grin"]
+    (s, seq) = configs.build_system(spec, pb.api())
+    lowering.lower(s, seq, configs.DLINE)                       # consistent: passes
+    grin = s.elements["stdelem"].materials["grin"]
+    grin.annotations["device_profile"] = dict(grin.annotations["device_profile"],
+                                              params=[1.0, 0.4, 1.0, 4.0])
+    with pytest.raises(lowering.LoweringError):
+        lowering.lower(s, seq, configs.DLINE)
+    del grin.annotations["device_profile"]
+    with pytest.raises(lowering.LoweringError):
+        lowering.lower(s, seq, configs.DLINE)
+
+
+def _step_bytes(ls):
+    st = nat.PyrStep()
+    ctypes.memmove(ctypes.addressof(st), ctypes.addressof(ls.st), ctypes.sizeof(nat.PyrStep))
+    (st.out_x, st.out_k, st.out_e, st.out_flags) = (None, None, None, None)
+    return bytes(st)
+
+
+@pytest.mark.parametrize("name", sorted(configs.CONFIGS))
+def test_reference_object_graph_lowers_like_ours(name):
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference tree not present (GPU box)")
+    (rs, rseq) = configs.build_system(configs.CONFIGS[name], refshim.api())
+    (s, seq) = configs.build_system(configs.CONFIGS[name], pb.api())
+    a = lowering.lower(rs, rseq, configs.DLINE)
+    b = lowering.lower(s, seq, configs.DLINE)
+    assert len(a) == len(b)
+    for (la, lb) in zip(a, b):
+        (sa, sb) = (la.st, lb.st)
+        for f in ("shape_kind", "aperture_kind", "interaction", "dir_mode", "n_coeff", "split"):
+            assert getattr(sa, f) == getattr(sb, f), f
+        for f in ("curv", "cc", "normradius", "k_norm_hint"):
+            assert getattr(sa, f) == pytest.approx(getattr(sb, f), rel=1e-15, abs=0)
+        for fr in ("shape_frame", "aperture_frame"):
+            assert np.allclose(list(getattr(sa, fr).r), list(getattr(sb, fr).r), atol=1e-15)
+            assert np.allclose(list(getattr(sa, fr).o), list(getattr(sb, fr).o), atol=1e-13)
+        for m in ("before", "after"):
+            (ma, mb) = (getattr(sa, m), getattr(sb, m))
+            assert ma.kind == mb.kind and ma.n == pytest.approx(mb.n, rel=1e-15)
+            assert list(ma.eps) == list(mb.eps) and list(ma.grin_p) == list(mb.grin_p)
+        assert sorted(zip(sa.xpow, sa.ypow, sa.coeff)) == sorted(zip(sb.xpow, sb.ypow, sb.coeff))
