@@ -189,12 +189,13 @@ def run_gpu(args):
     k0 = torch.from_numpy(k0h).to(dev)
     e0 = torch.from_numpy(e0h).to(dev)
     spot = torch.zeros(8, dtype=torch.float64, device=dev)
+    origin = engine.last_surface_origin(lowered)
     pool = engine.RecordPool()      # record buffers allocated once, reused per step
 
     def step():
         rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool)
         spot.zero_()
-        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot)
+        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
         if world > 1:
             dist.all_reduce(spot)
         return rec
@@ -221,7 +222,7 @@ def run_gpu(args):
             rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool)
             ev[i][1].record()
             spot.zero_()
-            engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot)
+            engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
             if world > 1:
                 dist.all_reduce(spot)
         t1.record()
@@ -234,7 +235,7 @@ def run_gpu(args):
     total_ms = float(tmax.item())
     ms_step = total_ms / args.steps
     value = world * n * S_COUNTED / (ms_step * 1e-3)
-    (centroid, rms) = engine.spot_from_sums(spot.cpu())
+    (centroid, rms) = engine.spot_from_sums(spot.cpu(), origin)
 
     # ---- end to end through the C ABI with host buffers (rank-local) ----
     e2e = None
@@ -258,7 +259,7 @@ def run_gpu(args):
                "ms_per_step": 1e3 * float(dt.item()),
                "what": "pyr_trace_host: pinned host x0,k0,E0 -> H2D -> trace -> D2H of the "
                        "image-plane record (x, k, flags) + 8 spot sums, 3-slot pipeline"}
-        (c2, rms2) = engine.spot_from_sums(ht.spot8)
+        (c2, rms2) = engine.spot_from_sums(ht.spot8, origin)
         e2e["spot_rms"] = rms2
         e2e["spot_count"] = float(ht.spot8[3])
 

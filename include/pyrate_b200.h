@@ -216,13 +216,16 @@ int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
 
 /*
  * Spot statistics of RayBundleAnalysis (analysis/ray_analysis.py:44-86) over
- * the rays whose `flags & mask` is non-zero (flags NULL = all):
- *   out[0..2] = sum x, out[3] = count, out[4..6] = sum x^2, out[7] = 0
- * written to DEVICE memory `out8` (accumulated: caller zeroes it), so partial
- * sums of several ranks can be all-reduced before centroid / rms are formed.
+ * the rays whose `flags & mask` is non-zero (flags NULL = all), about a
+ * reference point `shift` (HOST pointer to 3 doubles, NULL = origin; pass e.g.
+ * the vertex of the image surface so the sums do not cancel catastrophically):
+ *   out[0..2] = sum (x - shift), out[3] = count, out[4..6] = sum (x - shift)^2
+ * ACCUMULATED into DEVICE memory `out8` (caller zeroes it), so partial sums of
+ * several ranks (same shift) can be all-reduced before centroid / rms are formed.
  */
 int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
-                  uint32_t mask, int64_t n, double *out8, void *stream);
+                  uint32_t mask, int64_t n, const double *shift, double *out8,
+                  void *stream);
 
 /*
  * End-to-end host entry: start points / wave vectors / E in (pinned) HOST
@@ -230,7 +233,8 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
  * overlaps H2D, trace and D2H on internal streams.  `workspace` is caller-owned
  * DEVICE memory of at least pyr_trace_host_workspace() bytes.  Only real
  * (non-complex), non-splitting sequences.  Outputs (host, ld = n_rays):
- *   x_last (3, n), k_last (3, n), flags_last (n), spot8[8] (sums as above).
+ *   x_last (3, n), k_last (3, n), flags_last (n), spot8[8] (sums as above, about
+ *   the origin of the last step's shape frame).
  */
 int64_t pyr_trace_host_workspace(int32_t n_steps, int64_t chunk_rays);
 int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0,

@@ -95,7 +95,8 @@ def load():
                               C.c_void_p]
     lib.pyr_spot_sums.restype = C.c_int
     lib.pyr_spot_sums.argtypes = [C.c_void_p, C.c_int64, C.c_void_p,
-                                  C.c_uint32, C.c_int64, C.c_void_p, C.c_void_p]
+                                  C.c_uint32, C.c_int64, C.POINTER(C.c_double),
+                                  C.c_void_p, C.c_void_p]
     lib.pyr_trace_host_workspace.restype = C.c_int64
     lib.pyr_trace_host_workspace.argtypes = [C.c_int32, C.c_int64]
     lib.pyr_trace_host.restype = C.c_int

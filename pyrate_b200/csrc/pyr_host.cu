@@ -100,7 +100,8 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0, cons
         rc = pyr::trace_entry(local.data(), n_steps, &in, cn, 0u, s);
         if (rc != PYR_OK) break;
         if (spot8) {
-            rc = pyr_spot_sums(ox, L.ld, of, PYR_RAY_ALIVE, cn, spot_dev, s);
+            rc = pyr_spot_sums(ox, L.ld, of, PYR_RAY_ALIVE, cn, steps[n_steps - 1].shape_frame.o,
+                               spot_dev, s);
             if (rc != PYR_OK) break;
         }
         if (x_last)

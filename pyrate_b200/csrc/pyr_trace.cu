@@ -435,12 +435,12 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 spot_sums_kernel(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
-                 double *out8) {
+                 double sx, double sy, double sz, double *out8) {
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         if (flags && !(flags[i] & mask)) continue;
-        const double a = x[i], b = x[ld + i], c = x[2 * ld + i];
+        const double a = x[i] - sx, b = x[ld + i] - sy, c = x[2 * ld + i] - sz;
         acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += 1.0;
         acc[4] = fma(a, a, acc[4]); acc[5] = fma(b, b, acc[5]); acc[6] = fma(c, c, acc[6]);
     }
@@ -735,14 +735,16 @@ int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int6
 }
 
 int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
-                  double *out8, void *stream) {
+                  const double *shift, double *out8, void *stream) {
     if (!x || !out8 || n < 0) return PYR_E_BADARG;
     if (n == 0) return PYR_OK;
     if (ld <= 0) ld = n;
     int64_t grid = (n + 255) / 256;
     const int64_t cap = (int64_t)pyr::sm_count() * 8;
     if (grid > cap) grid = cap;
-    pyr::spot_sums_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n, out8);
+    const double sx = shift ? shift[0] : 0.0, sy = shift ? shift[1] : 0.0, sz = shift ? shift[2] : 0.0;
+    pyr::spot_sums_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n, sx, sy,
+                                                                          sz, out8);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? PYR_OK : (int)e;
 }

@@ -38,16 +38,17 @@ def allreduce_spot_sums(sums):
     return sums
 
 
-def global_spot(x_last, flags_last=None):
+def global_spot(x_last, flags_last=None, shift=None):
     """Centroid and RMS spot radius of the surviving rays of ALL ranks.
 
     x_last: (3, n_local) CUDA tensor (rows may be strided), flags_last: (n_local)
-    uint8 PYR_RAY_* flags or None.  Returns (centroid[3], rms, count)."""
+    uint8 PYR_RAY_* flags or None, shift: common reference point of the sums
+    (e.g. engine.last_surface_origin).  Returns (centroid[3], rms, count)."""
     from . import engine
-    sums = engine.spot_sums(x_last, flags_last)
+    sums = engine.spot_sums(x_last, flags_last, shift=shift)
     allreduce_spot_sums(sums)
     host = sums.cpu()
-    (c, rms) = engine.spot_from_sums(host)
+    (c, rms) = engine.spot_from_sums(host, shift)
     return c, rms, float(host[3])
 
 

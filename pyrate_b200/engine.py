@@ -596,10 +596,12 @@ class HostTracer(object):
         return (self.x_last, self.k_last, self.flags_last, self.spot8)
 
 
-def spot_sums(x, flags=None, mask=nat.RAY_ALIVE, out=None):
-    """Device partial sums of RayBundleAnalysis (ray_analysis.py:44-86):
-    out[0:3] = sum x, out[3] = count, out[4:7] = sum x^2 (float64 CUDA tensor).
-    Sums of several ranks can be all-reduced before `spot_from_sums`."""
+def spot_sums(x, flags=None, mask=nat.RAY_ALIVE, out=None, shift=None):
+    """Device partial sums of RayBundleAnalysis (ray_analysis.py:44-86) about
+    the reference point `shift` (3 floats, default origin): out[0:3] =
+    sum (x - shift), out[3] = count, out[4:7] = sum (x - shift)^2 (float64 CUDA
+    tensor, accumulated).  Sums of several ranks (same shift) can be all-reduced
+    before `spot_from_sums`."""
     lib = require_cuda()
     dev = x.device
     if out is None:
@@ -608,19 +610,28 @@ def spot_sums(x, flags=None, mask=nat.RAY_ALIVE, out=None):
     ld = x.stride(0)
     n = x.shape[1]
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    sh = None if shift is None else (C.c_double * 3)(*[float(v) for v in shift])
     with torch.cuda.device(dev):
         nat.check(lib.pyr_spot_sums(x.data_ptr(), ld,
                                     flags.data_ptr() if flags is not None else None,
-                                    mask, n, out.data_ptr(), stream))
+                                    mask, n, sh, out.data_ptr(), stream))
     return out
 
 
-def spot_from_sums(s):
+def spot_from_sums(s, shift=None):
     """(centroid[3], rms about the centroid) with the reference's
     normalisations: centroid = sum/(N + 1e-17), rms = sqrt(sum|x-c|^2 /
-    (N - 1 + 1e-17))."""
+    (N - 1 + 1e-17)); `shift` = the reference point the sums were taken about."""
     s = [float(v) for v in s]
     n = s[3]
     c = [s[i] / (n + 1e-17) for i in range(3)]
     ss = sum(s[4 + i] - 2.0 * c[i] * s[i] + n * c[i] * c[i] for i in range(3))
+    if shift is not None:
+        c = [c[i] + float(shift[i]) for i in range(3)]
     return c, (max(ss, 0.0) / (n - 1 + 1e-17)) ** 0.5
+
+
+def last_surface_origin(lowered):
+    """Global vertex of the last sequence entry: the natural reference point
+    of the spot sums."""
+    return [float(v) for v in lowered[-1].st.shape_frame.o]
