@@ -77,18 +77,9 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 // One sequence entry for one ray (real k, E).  Returns the flag byte.
 template <bool WITH_E, bool GENERAL>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
-                                              Ray<WITH_E> &r, double hit_g[3]) {
+                                              Ray<WITH_E> &r, double d[3], double hit_g[3]) {
     const DAux *aux = (GENERAL && st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
-
-    // ---- direction of energy transport (ray.py:136-152) ----
-    double d[3];
-    if (WITH_E && st.dir_mode == PYR_DIR_POYNTING) {
-        poynting_dir(r.k, r.e, d);
-    } else {
-        const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm : rsqrt(dot3(r.k, r.k));
-        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
-    }
 
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
     if (GENERAL && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
@@ -202,15 +193,9 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
 //     later hit point and wave vector is NaN by arithmetic, and `square > 0`
 //     already rejects NaN normals (no separate finite check).
 template <bool WITH_E>
-__device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, double hit_g[3]) {
+__device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, const double d[3],
+                                              double hit_g[3]) {
     const bool ok = r.alive;
-    double d[3];
-    if (WITH_E && st.dir_mode == PYR_DIR_POYNTING) {
-        poynting_dir(r.k, r.e, d);
-    } else {
-        const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm : fast_rsqrt(dot3(r.k, r.k));
-        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
-    }
     const bool ident = (st.bits & kRotIdentity) != 0;
     double r0[3], dl[3], kl[3];
     if (ident) {
@@ -352,26 +337,21 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             const DStep &st = P.steps[s];
             double hit[RPT][3];
             uint32_t fl[RPT];
-            if (s == 0 && need_e0) {
-                // first segment: direction from the user's (k, E)
 #pragma unroll
-                for (int j = 0; j < RPT; ++j) {
-                    Ray<true> tmp;
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { tmp.x[c] = ray[j].x[c]; tmp.k[c] = ray[j].k[c]; tmp.e[c] = in[j].e[c]; }
-                    tmp.alive = ray[j].alive;
-                    fl[j] = GENERAL ? step_real<true, true>(P, st, tmp, hit[j]) : step_lean<true>(st, tmp, hit[j]);
-#pragma unroll
-                    for (int c = 0; c < 3; ++c) { ray[j].x[c] = tmp.x[c]; ray[j].k[c] = tmp.k[c]; }
-                    if (WITH_E) {
-#pragma unroll
-                        for (int c = 0; c < 3; ++c) ray[j].e[c] = tmp.e[c];
-                    }
-                    ray[j].alive = tmp.alive;
+            for (int j = 0; j < RPT; ++j) {
+                // direction of energy transport (ray.py:136-152): Poynting vector of the
+                // user's (k, E) on the first segment, k/|k| wherever E.k = 0 is guaranteed
+                double d[3];
+                if (st.dir_mode == PYR_DIR_POYNTING && (WITH_E || s == 0)) {
+                    if (WITH_E) poynting_dir(ray[j].k, ray[j].e, d);
+                    else poynting_dir(ray[j].k, in[j].e, d);
+                } else {
+                    const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm
+                                                            : fast_rsqrt(dot3(ray[j].k, ray[j].k));
+                    d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
                 }
-            } else {
-#pragma unroll
-                for (int j = 0; j < RPT; ++j) fl[j] = GENERAL ? step_real<WITH_E, true>(P, st, ray[j], hit[j]) : step_lean<WITH_E>(st, ray[j], hit[j]);
+                fl[j] = GENERAL ? step_real<WITH_E, true>(P, st, ray[j], d, hit[j])
+                                : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
             // ---- record the step (evict-first streaming stores) ----
@@ -639,8 +619,7 @@ int sm_count() {
 }
 
 template <typename K>
-static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream) {
-    const int threads = 256;
+static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, int threads = 256) {
     int per_sm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
     if (e != cudaSuccess) return (int)e;
@@ -683,6 +662,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             case 4: return launch(trace_real_kernel<2, false, false, 4>, pk.P, 2, stream);
             case 11: return launch(trace_real_kernel<1, false, false, 4>, pk.P, 1, stream);
             case 12: return launch(trace_real_kernel<1, false, false, 6>, pk.P, 1, stream);
+            case 21: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 128);
+            case 22: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 64);
+            case 23: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 192);
             default: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream);
         }
     }

@@ -1,8 +1,6 @@
 #!/bin/bash
-for v in 0 1 3 4 11 12; do PYR_LEAN_VARIANT=$v python tools/time_kernel.py c2_doublegauss 0 20; done
-python tools/time_kernel.py c2_doublegauss 0 10 1
-python tools/time_kernel.py c1_doublet 1000000 10
-python tools/time_kernel.py x1_tilted 4000000 10
-python tools/time_kernel.py c3_asphere 0 10
-python tools/time_kernel.py c5_grin 1000000 5
-python tools/time_kernel.py c4_anisotropic 1000000 5
+for v in 0 3 21 22 23 11; do PYR_LEAN_VARIANT=$v timeout 300 python tools/time_kernel.py c2_doublegauss 0 20; done
+timeout 300 python tools/time_kernel.py c2_doublegauss 0 10 1
+timeout 300 python tools/time_kernel.py c1_doublet 1000000 10
+timeout 300 python tools/time_kernel.py x1_tilted 4000000 10
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:trace_real -s 2 -c 1 -f -o gpurun_out/prof_v1 python tools/profile_target.py c2_doublegauss 0 4 > gpurun_out/ncu_full.log 2>&1; tail -2 gpurun_out/ncu_full.log
