@@ -26,6 +26,7 @@ S_SEQ = 13            # sequence entries (bytes move for every one of them)
 S_COUNTED = 10        # refracting surfaces with a real shape (headline count)
 BYTES_PER_RAY_ENTRY = 49.0 + 72.0 / S_SEQ      # 54.54 B
 METRIC = "ray-surface intersections/sec"
+CPU_BLOCK = 1000
 
 
 def measured_peaks():
@@ -99,58 +100,79 @@ def _cpu_worker(args):
         pass
     system = onp.system_from_spec(configs.CONFIGS[CONFIG])
     t = time.perf_counter()
-    onp.seqtrace(system, x0[:, lo:hi], k0[:, lo:hi], e0[:, lo:hi],
-                 wave=configs.DLINE)
+    # cache-blocked: 1000-ray pieces keep every NumPy temporary below the
+    # malloc mmap threshold (no page-fault storm when all cores run) -- the
+    # fastest way we found to run the reference algorithm on the host
+    for a in range(lo, hi, CPU_BLOCK):
+        b = min(a + CPU_BLOCK, hi)
+        onp.seqtrace(system, x0[:, a:b], k0[:, a:b], e0[:, a:b], wave=configs.DLINE)
     return time.perf_counter() - t
 
 
-def cpu_pass(nrays, procs):
-    """One pass of `nrays` rays through the oracle port on `procs` processes."""
-    import multiprocessing as mp
+def cpu_pass(nrays, procs, pool=None):
+    """One pass of `nrays` rays through the oracle port on `procs` processes
+    (ray-sharded, one single-threaded NumPy process per core)."""
+    import numpy as np
     from pyrate_b200 import configs
     spec = configs.CONFIGS[CONFIG]
     (x0, k0, e0) = configs.config_bundle(spec, configs.rings_for(nrays))
     n = x0.shape[1]
     bounds = [(i * n) // procs for i in range(procs + 1)]
-    jobs = [(0, bounds[i], bounds[i + 1], x0, k0, e0) for i in range(procs)]
+    jobs = [(0, 0, bounds[i + 1] - bounds[i],
+             np.ascontiguousarray(x0[:, bounds[i]:bounds[i + 1]]),
+             np.ascontiguousarray(k0[:, bounds[i]:bounds[i + 1]]),
+             np.ascontiguousarray(e0[:, bounds[i]:bounds[i + 1]])) for i in range(procs)]
     t = time.perf_counter()
-    if procs == 1:
-        _cpu_worker(jobs[0])
+    if procs == 1 or pool is None:
+        for j in jobs:
+            _cpu_worker(j)
     else:
-        with mp.get_context("fork").Pool(procs) as pool:
-            pool.map(_cpu_worker, jobs)
+        pool.map(_cpu_worker, jobs, chunksize=1)
     return n, time.perf_counter() - t
 
 
 def run_reference(args):
+    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    nrays = int(args.cpu_rays) if args.cpu_rays else 25000 * cores
-    for _ in range(max(args.warmup, 0)):
-        cpu_pass(min(nrays, 20000), cores)
-    total_t = 0.0
-    n = 0
-    for _ in range(args.steps):
-        (n, dt) = cpu_pass(nrays, cores)
-        total_t += dt
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    nrays = int(args.cpu_rays) if args.cpu_rays else min(50000 * cores, 4000000)
+    pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
+    try:
+        for _ in range(max(args.warmup, 1)):
+            cpu_pass(max(2000 * cores, 2000), cores, pool)
+        total_t = 0.0
+        n = 0
+        for _ in range(args.steps):
+            (n, dt) = cpu_pass(nrays, cores, pool)
+            total_t += dt
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
     ms = 1e3 * total_t / args.steps
     val = n * S_COUNTED / (ms * 1e-3)
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "ray-surfaces/s",
-            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": "double-Gauss (Rudolph 1897) 10 refracting conic "
                        "surfaces / 13 sequence entries, hexapolar bundle, single "
-                       "wavelength; CPU sample of %d rays" % n,
-                       "rays_per_step": n, "s_counted": S_COUNTED, "s_seq": S_SEQ},
+                       "wavelength; CPU sample of %d rays per step" % n,
+                       "rays_per_step": n, "s_counted": S_COUNTED, "s_seq": S_SEQ,
+                       "value_all_entries": n * S_SEQ / (ms * 1e-3)},
             "cpu_baseline": {"value": val, "unit": "ray-surfaces/s", "cores": cores,
                              "kind": "port",
-                             "sample": "%d rays x %d steps, oracle/pyrate_np.py (NumPy "
-                                       "restatement incl. the per-refraction 3x3 SVD for "
-                                       "E), ray-sharded over %d processes" %
-                                       (n, args.steps, cores)},
+                             "sample": "%d rays x %d steps through oracle/pyrate_np.py (NumPy "
+                                       "restatement of the reference seqtrace incl. its "
+                                       "per-refraction 3x3 SVD for E), ray-sharded over %d "
+                                       "single-threaded processes; the Python reference itself "
+                                       "cannot travel to the GPU box" % (n, args.steps, cores)},
             "e2e": {"value": val, "unit": "ray-surfaces/s", "h2d_bytes_per_step": 0,
                     "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -278,6 +300,7 @@ def run_gpu(args):
         cpu = None
         if world == 1 and not args.no_cpu:
             (cn, cdt) = cpu_pass(int(args.cpu_rays) if args.cpu_rays else 200000, 1)
+            # (single process; `--impl reference` times the all-cores variant)
             cpu = {"value": cn * S_COUNTED / cdt, "unit": "ray-surfaces/s", "cores": 1,
                    "kind": "port",
                    "sample": "%d rays of the same workload, one pass, oracle/pyrate_np.py "
