@@ -158,3 +158,21 @@ def test_reference_object_graph_lowers_like_ours(name):
             assert ma.kind == mb.kind and ma.n == pytest.approx(mb.n, rel=1e-15)
             assert list(ma.eps) == list(mb.eps) and list(ma.grin_p) == list(mb.grin_p)
         assert sorted(zip(sa.xpow, sa.ypow, sa.coeff)) == sorted(zip(sb.xpow, sb.ypow, sb.coeff))
+
+
+def test_convenience_builders_match_spec_builder():
+    """build_rotationally_symmetric_optical_system (reference __init__.py:83-121)
+    lowers to the same step table as the explicit construction of C2."""
+    from pyrate_b200.configs import _DG, _N1, _N2, _N3
+    idx = {"g1": _N1, "g2": _N2, "g3": _N3, None: None}
+    rows = [(r, 0.0, dz, idx[mt], nm, {"is_stop": True} if nm == "stop" else {})
+            for (nm, r, dz, mt) in _DG]
+    (s1, seq1) = pb.build_rotationally_symmetric_optical_system(rows)
+    (s2, seq2) = configs.build_system(configs.CONFIGS["c2_doublegauss"], pb.api())
+    a = lowering.lower(s1, seq1, configs.DLINE)
+    b = lowering.lower(s2, seq2, configs.DLINE)
+    assert [l.surfkey for l in a] == [l.surfkey for l in b]
+    for (la, lb) in zip(a, b):
+        assert _step_bytes(la) == _step_bytes(lb)
+    with pytest.raises(NotImplementedError):
+        pb.build_rotationally_symmetric_optical_system([(10.0, 0, 1.0, "N-BK7", "s", {})])
