@@ -232,17 +232,15 @@ def run_gpu(args):
     sync()
     # kernel-only timing of the trace launch (CUDA events on the launch stream)
     kern_ms = []
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-          for _ in range(args.steps)]
+    ev = []          # (start, end) CUDA events recorded around each native trace launch
     with ClockSampler(local) as clocks:
         sync()
         t0 = torch.cuda.Event(enable_timing=True)
         t1 = torch.cuda.Event(enable_timing=True)
         t0.record()
         for i in range(args.steps):
-            ev[i][0].record()
-            rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool)
-            ev[i][1].record()
+            rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool,
+                               events=ev)
             spot.zero_()
             engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
             if world > 1:

@@ -217,25 +217,36 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
         t = -r0[2] * fast_rcp(dl[2]);
         h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
         nrm[0] = 0.0; nrm[1] = 0.0; nrm[2] = 1.0;
+    } else if (st.bits & kSphere) {
+        // cc = 0:  F = d_z - c (d.r0),  G = c (r0.r0) - 2 z0,  H = -c
+        const double F = fma(-curv, dot3(dl, r0), dl[2]);
+        const double G = fma(curv, dot3(r0, r0), -2.0 * r0[2]);
+        const double square = fma(F, F, -curv * G);
+        hit_ok = square >= 0.0;
+        t = fast_div(G, F + fast_sqrt(square));
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
+        // unit normal (-c x, -c y, sqrt(1 - c^2 r^2)); on the vertex branch of the sphere
+        // sqrt(1 - c^2 r^2) == 1 - c z exactly (surface equation), which saves the sqrt.
+        // The far branch (1 - c z <= 0) keeps the reference's sag-based value.
+        double gz = fma(-curv, h[2], 1.0);
+        if (!(gz > 0.0)) gz = fast_sqrt(fma(-curv * curv, fma(h[0], h[0], h[1] * h[1]), 1.0));
+        nrm[0] = -curv * h[0]; nrm[1] = -curv * h[1]; nrm[2] = gz;
     } else {
         const double cc1 = 1.0 + cc;
         const double F = dl[2] - curv * fma(dl[0], r0[0], fma(dl[1], r0[1], dl[2] * r0[2] * cc1));
         const double G = curv * fma(r0[0], r0[0], fma(r0[1], r0[1], r0[2] * r0[2] * cc1)) - 2.0 * r0[2];
-        const double H = -curv - cc * curv * dl[2] * dl[2];
+        const double H = fma(-cc * curv * dl[2], dl[2], -curv);
         const double square = fma(F, F, H * G);
         hit_ok = square >= 0.0;
         t = fast_div(G, F + fast_sqrt(square));
         h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
-        // unit normal: (-c x, -c y, sqrt(1 - (1+cc) c^2 r^2)) / sqrt(1 - cc c^2 r^2)
-        const double c2r2 = curv * curv * fma(h[0], h[0], h[1] * h[1]);
-        const double s = fma(-cc1, c2r2, 1.0);
-        double gz = fast_sqrt(s);                       // s <= 0 -> NaN (conic_function :214-216)
+        // grad = (-c x, -c y, sqrt(1 - (1+cc) c^2 r^2)); the z component equals
+        // 1 - c (1+cc) z on the vertex branch (see the sphere case)
         double gx = -curv * h[0], gy = -curv * h[1];
-        if (!(st.bits & kSphere)) {
-            const double inv = fast_rsqrt(fma(-cc, c2r2, 1.0));
-            gx *= inv; gy *= inv; gz *= inv;
-        }
-        nrm[0] = gx; nrm[1] = gy; nrm[2] = gz;
+        double gz = fma(-curv * cc1, h[2], 1.0);
+        if (!(gz > 0.0)) gz = fast_sqrt(fma(-cc1 * curv * curv, fma(h[0], h[0], h[1] * h[1]), 1.0));
+        const double inv = fast_rsqrt(fma(gx, gx, fma(gy, gy, gz * gz)));
+        nrm[0] = gx * inv; nrm[1] = gy * inv; nrm[2] = gz * inv;
     }
     if (ident) {
         hit_g[0] = h[0] + st.frame.o[0]; hit_g[1] = h[1] + st.frame.o[1]; hit_g[2] = h[2] + st.frame.o[2];

@@ -76,7 +76,8 @@ def _alloc_rows(rows, n, device, complex_=False, pool=None):
     return _empty(shape, torch.float64, device, pool), ld
 
 
-def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
+def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
+            events=None):
     if n == 0:
         return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
@@ -90,6 +91,17 @@ def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream):
     rin.alive = alive.data_ptr() if alive is not None else None
     rin.ld = ld_in
     rin.n_x = n_x
+    if events is not None:
+        # CUDA events recorded back to back with the launch on the launch stream:
+        # the pair brackets the kernel itself, not the host-side packing
+        ext = torch.cuda.ExternalStream(stream.value) if stream.value else \
+            torch.cuda.current_stream()
+        (a, b) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        a.record(ext)
+        nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
+        b.record(ext)
+        events.append((a, b))
+        return
     nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
 
 
@@ -143,8 +155,11 @@ class RecordPool(object):
 
 
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
-          pool=None):
-    """Run the lowered sequence on the device.  Returns a TraceRecord."""
+          pool=None, events=None):
+    """Run the lowered sequence on the device.  Returns a TraceRecord.
+
+    events: optional list; a (start, end) pair of CUDA timing events is appended
+    per native launch (kernel-only timing for benchmarks)."""
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
@@ -250,7 +265,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
             else:
                 cur_e_arg = cur_e
             _launch(lib, steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
-                    ld_k, flags, stream_ptr)
+                    ld_k, flags, stream_ptr, events)
             for i in range(lo, hi):
                 r = i - lo
                 rec.hit.append(xbuf[r, :, :n])
