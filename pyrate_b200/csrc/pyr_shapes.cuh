@@ -50,7 +50,8 @@ __device__ __forceinline__ double conic_sag(double curv, double cc, double x, do
 __device__ __forceinline__ void asphere_eval(const DAux &a, double curv, double cc, double x,
                                              double y, double &F, double &Fx, double &Fy) {
     const double r2 = fma(x, x, y * y);
-    const double sq = sqrt(fma(-curv * curv * (1.0 + cc), r2, 1.0));   // NaN outside
+    double rsq;
+    const double sq = fast_sqrt_r(fma(-curv * curv * (1.0 + cc), r2, 1.0), rsq);   // NaN outside
     // polynomial part: sum a_n r2^(n+1) and its r2-derivative by Horner
     double p = 0.0, dp = 0.0;
     for (int i = a.n_coeff - 1; i >= 0; --i) {
@@ -58,8 +59,8 @@ __device__ __forceinline__ void asphere_eval(const DAux &a, double curv, double 
         p = fma(p, r2, a.coeff[i]);
     }
     // p(r2) = sum a_i r2^i  ->  poly = r2 p,  d poly / d r2 = p + r2 dp
-    F = curv * r2 / (1.0 + sq) + r2 * p;
-    const double dr = curv / sq + 2.0 * fma(r2, dp, p);                // dF/dx = x * dr
+    F = fma(curv * r2, fast_rcp(1.0 + sq), r2 * p);
+    const double dr = fma(curv, rsq, 2.0 * fma(r2, dp, p));            // dF/dx = x * dr
     Fx = x * dr;
     Fy = y * dr;
 }
@@ -119,7 +120,7 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
         explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
         const double res = fma(t, d[2], r0[2]) - F;
         const double dres = d[2] - fma(Fx, d[0], Fy * d[1]);
-        double step = res / dres;
+        double step = fast_div(res, dres);
         const bool bad = !isfinite(step);
         if (bad) step = 0.0;
         t -= step;
@@ -134,7 +135,7 @@ __device__ __forceinline__ void explicit_normal(int kind, const DAux &a, double 
                                                 double x, double y, double n[3]) {
     double F, Fx, Fy;
     explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
-    const double inv = rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
+    const double inv = fast_rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
     n[0] = -Fx * inv; n[1] = -Fy * inv; n[2] = inv;
 }
 

@@ -361,8 +361,10 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                                                             : fast_rsqrt(dot3(ray[j].k, ray[j].k));
                     d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
                 }
-                fl[j] = GENERAL ? step_real<WITH_E, true>(P, st, ray[j], d, hit[j])
-                                : step_lean<WITH_E>(st, ray[j], d, hit[j]);
+                // steps without an auxiliary record (conic shape, homogeneous isotropic
+                // media, aperture in the shape frame) always take the tuned path
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, true>(P, st, ray[j], d, hit[j])
+                                                 : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
             // ---- record the step (evict-first streaming stores) ----
