@@ -206,3 +206,41 @@ def test_birefringent_larger_bundle_against_oracle():
                                              check_e=ib >= 2 and low[ib - 2].is_aniso_deflect)
         else:
             util.compare_bundle(d, rbd, 1e-10, "c4 b%d" % ib)
+
+
+@pytest.mark.parametrize("name", ["c1_doublet", "x1_tilted", "x3_vignette", "c5_grin"])
+def test_plugin_calls_reproduce_the_fused_trace(name):
+    """The reference's plugin-level calls -- Material.propagate(bundle, surface)
+    (mutates), Material.refract / reflect(bundle, surface) (fresh bundle) --
+    driven by a hand-written copy of the per-surface loop
+    (optical_element.py:336-375) must give the same rays as the fused launch."""
+    spec = configs.CONFIGS[name]
+    (s, seq) = configs.build_system(spec, pb.api())
+    (x0, k0, e0) = configs.config_bundle(spec, 6)
+    fused = s.seqtrace(pb.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)[0].raybundles
+    elem = s.elements["stdelem"]
+    background = s.material_background
+    current = background
+    bundle = pb.RayBundle(x0, k0, e0, wave=configs.DLINE)
+    stepwise = [bundle]
+    for (surfkey, opts) in seq[0][1]:
+        surface = elem.surfaces[surfkey]
+        (mn, pn) = elem.annotations["surf_mat_connection"][surfkey]
+        mnmat = elem.materials.get(mn, background)
+        pnmat = elem.materials.get(pn, background)
+        current.propagate(bundle, surface)
+        mirror = opts.get("is_mirror", False)
+        if not mirror:
+            current = elem.findoutWhichMaterial(mnmat, pnmat, current)
+        (bundle,) = (current.reflect if mirror else current.refract)(bundle, surface)
+        stepwise.append(bundle)
+    tol = util.tolerance_of(name)
+    assert len(stepwise) == len(fused) - 1
+    for (ib, (a, b)) in enumerate(zip(stepwise, fused[1:])):
+        (da, db) = (a.numpy(), b.numpy())
+        assert np.array_equal(da["rayID"], db["rayID"]), ib
+        assert np.array_equal(da["valid"][-1], db["valid"][-1]), ib
+        v = db["valid"][-1]
+        assert util.relerr(da["x"][-1][:, v], db["x"][-1][:, v]) <= tol, ib
+        assert util.relerr(da["x"][0], db["x"][0]) <= tol, ib
+        assert util.relerr(da["k"][0], db["k"][0]) <= tol, ib
