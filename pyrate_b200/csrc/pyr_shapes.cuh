@@ -18,7 +18,7 @@ __device__ __forceinline__ double conic_t(double curv, double cc, const double r
     const double H = -curv - cc * curv * d[2] * d[2];
     const double square = fma(F, F, H * G);
     ok = square >= 0.0;
-    return G / (F + sqrt(square));
+    return fast_div(G, F + fast_sqrt(square));
 }
 
 // Unit normal of a conic at (x, y) on the vertex branch.
@@ -30,10 +30,10 @@ __device__ __forceinline__ void conic_normal(double curv, double cc, bool sphere
                                              double y, double n[3]) {
     const double c2r2 = curv * curv * fma(x, x, y * y);
     const double s = fma(-(1.0 + cc), c2r2, 1.0);
-    double gz = (s > 0.0) ? sqrt(s) : qnan();
+    double gz = fast_sqrt(s);                           // s <= 0 -> NaN
     double gx = -curv * x, gy = -curv * y;
     if (!sphere) {
-        const double inv = rsqrt(fma(-cc, c2r2, 1.0));
+        const double inv = fast_rsqrt(fma(-cc, c2r2, 1.0));
         gx *= inv; gy *= inv; gz *= inv;
     }
     n[0] = gx; n[1] = gy; n[2] = gz;
@@ -42,8 +42,7 @@ __device__ __forceinline__ void conic_normal(double curv, double cc, bool sphere
 __device__ __forceinline__ double conic_sag(double curv, double cc, double x, double y) {
     const double r2 = fma(x, x, y * y);
     const double s = fma(-(1.0 + cc) * curv * curv, r2, 1.0);
-    if (!(s > 0.0)) return qnan();
-    return curv * r2 / (1.0 + sqrt(s));
+    return curv * r2 * fast_rcp(1.0 + fast_sqrt(s));    // s <= 0 -> NaN
 }
 
 // Asphere: value and gradient (gx, gy; gz = 1) of z - F(x, y) in one pass.
@@ -111,7 +110,7 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
                                              bool active) {
     bool ok;
     double t = (kind == PYR_SHAPE_ASPHERE) ? conic_t(curv, cc, r0, d, ok)
-                                           : -r0[2] / d[2];
+                                           : -r0[2] * fast_rcp(d[2]);
     if (!isfinite(t)) t = 0.0;
     for (int it = 0; it < a.newton_maxit; ++it) {
         const double x = fma(t, d[0], r0[0]);

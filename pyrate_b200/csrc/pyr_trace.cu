@@ -75,17 +75,18 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 }
 
 // One sequence entry for one ray (real k, E).  Returns the flag byte.
-template <bool WITH_E, bool GENERAL>
+template <bool WITH_E, bool HAS_GRIN>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
                                               Ray<WITH_E> &r, double d[3], double hit_g[3]) {
-    const DAux *aux = (GENERAL && st.aux >= 0) ? &P.aux[st.aux] : nullptr;
+    constexpr bool GENERAL = true;
+    const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
 
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
-    if (GENERAL && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
+    if (HAS_GRIN && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
         const bool v = grin_propagate(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k);
         ok = ok && v;
-        const double inv = rsqrt(dot3(r.k, r.k));
+        const double inv = fast_rsqrt(dot3(r.k, r.k));
         d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
     }
 
@@ -147,7 +148,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
     else rot_t(st.frame.r, r.k, kl);
     double n2sq = st.n2sq;
-    if (GENERAL && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
+    if (HAS_GRIN && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
         double q[3], g[3];
         g2l_point(aux->after.frame, hit_g, q);
         const double nn = grin_index(aux->after, q, g, false);
@@ -157,7 +158,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     // k_inplane = k - (k.n) n ; square = n^2 - k_inplane.k_inplane
     const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
     const double square = n2sq - dot3(kin, kin);
-    const double xi = sqrt(square);
+    const double xi = fast_sqrt(square);
     const bool refr_ok = (square > 0.0) && finite3(nrm);
     double k2[3];
     if (st.interaction == PYR_REFLECT) {
@@ -286,9 +287,13 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
     return (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
 }
 
-template <int RPT, bool WITH_E, bool GENERAL, int MINB = 1>
+// FEAT: 0 = lean steps only; 1 = + explicit shapes / own-frame apertures / partial
+// step modes; 3 = + GRIN media (separate instantiations keep the register budget of
+// the common cases small)
+template <int RPT, bool WITH_E, int FEAT, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
+    constexpr bool GENERAL = FEAT != 0;
     const int64_t n = P.n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * RPT;
     const bool need_e0 = P.steps[0].dir_mode == PYR_DIR_POYNTING;
@@ -363,7 +368,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, true>(P, st, ray[j], d, hit[j])
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j])
                                                  : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
@@ -662,7 +667,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
     if (!pk.general) {
-        if (with_e) return launch(trace_real_kernel<2, true, false>, pk.P, 2, stream);
+        if (with_e) return launch(trace_real_kernel<2, true, 0>, pk.P, 2, stream);
         // tuning knob (not part of the ABI): resident CTAs per SM the lean kernel is
         // compiled for; PYR_LEAN_VARIANT = 1 (free), 3, 4, or 11 (one ray per thread)
         static const int variant = [] {
@@ -670,19 +675,27 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             return e ? std::atoi(e) : 0;
         }();
         switch (variant) {
-            case 1: return launch(trace_real_kernel<2, false, false, 1>, pk.P, 2, stream);
-            case 3: return launch(trace_real_kernel<2, false, false, 3>, pk.P, 2, stream);
-            case 4: return launch(trace_real_kernel<2, false, false, 4>, pk.P, 2, stream);
-            case 11: return launch(trace_real_kernel<1, false, false, 4>, pk.P, 1, stream);
-            case 12: return launch(trace_real_kernel<1, false, false, 6>, pk.P, 1, stream);
-            case 21: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 128);
-            case 22: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 64);
-            case 23: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream, 192);
-            default: return launch(trace_real_kernel<2, false, false, 2>, pk.P, 2, stream);
+            case 1: return launch(trace_real_kernel<2, false, 0, 1>, pk.P, 2, stream);
+            case 3: return launch(trace_real_kernel<2, false, 0, 3>, pk.P, 2, stream);
+            case 4: return launch(trace_real_kernel<2, false, 0, 4>, pk.P, 2, stream);
+            case 11: return launch(trace_real_kernel<1, false, 0, 4>, pk.P, 1, stream);
+            case 12: return launch(trace_real_kernel<1, false, 0, 6>, pk.P, 1, stream);
+            case 21: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 128);
+            case 22: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 64);
+            case 23: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 192);
+            default: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
         }
     }
-    return with_e ? launch(trace_real_kernel<2, true, true>, pk.P, 2, stream)
-                  : launch(trace_real_kernel<2, false, true>, pk.P, 2, stream);
+    bool has_grin = false;
+    for (int s = 0; s < n_steps; ++s)
+        has_grin = has_grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN ||
+                   steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
+    if (has_grin)   // integrator loops do not interleave across rays: one ray per thread,
+                    // more resident warps
+        return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
+                      : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
+    return with_e ? launch(trace_real_kernel<2, true, 1>, pk.P, 2, stream)
+                  : launch(trace_real_kernel<2, false, 1, 2>, pk.P, 2, stream);
 }
 
 int trace_entry(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
