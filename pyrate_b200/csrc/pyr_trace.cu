@@ -41,6 +41,13 @@ struct Ray {
     bool alive;
 };
 
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
 __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
     __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
@@ -296,44 +303,71 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr bool GENERAL = FEAT != 0;
     const int64_t n = P.n;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x * RPT;
-    const bool need_e0 = P.steps[0].dir_mode == PYR_DIR_POYNTING;
-    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RPT; base < n;
-         base += stride) {
+
+    // Step table: one cooperative copy from the parameter block into shared memory;
+    // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
+    // register-indexed constant loads.
+    __shared__ DStep sst[kMaxSteps];
+    {
+        const uint64_t *src = reinterpret_cast<const uint64_t *>(P.steps);
+        uint64_t *dst = reinterpret_cast<uint64_t *>(sst);
+        const int words = P.n_steps * (int)(sizeof(DStep) / 8);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const bool need_e0 = sst[0].dir_mode == PYR_DIR_POYNTING;
+    const bool load_e = (WITH_E || need_e0) && P.e != nullptr;
+
+    // Input staging: the bundle of the NEXT ray pair is fetched with cp.async into a
+    // private shared-memory slot while the current pair walks through the sequence, so
+    // the HBM read latency never sits on the critical path.  Layout
+    // [stage][ray][component 0..8][thread] keeps every warp access conflict-free; a
+    // thread only ever reads the slots it filled itself (no block synchronisation).
+    extern __shared__ double stage_buf[];
+    constexpr int bdim = 256;                     // fixed CTA size (see launch())
+    auto slot = [&](int stage, int j, int c) -> double * {
+        return stage_buf + ((size_t)((stage * RPT + j) * 9 + c)) * bdim + threadIdx.x;
+    };
+    auto prefetch = [&](int64_t pbase, int stage) {
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int64_t i = pbase + j;
+            if (i < n) {
+                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    cp_async8(slot(stage, j, c), P.x + c * P.ld_in + ix);
+                    cp_async8(slot(stage, j, 3 + c), P.k + c * P.ld_in + i);
+                    if (load_e) cp_async8(slot(stage, j, 6 + c), P.e + c * P.ld_in + i);
+                }
+            }
+        }
+        cp_async_commit();
+    };
+
+    int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RPT;
+    int stage = 0;
+    if (base < n) prefetch(base, 0);
+    for (; base < n; base += stride, stage ^= 1) {
+        if (base + stride < n) prefetch(base + stride, stage ^ 1);
+        else cp_async_commit();                    // keep the group count uniform
+        cp_async_wait_prev();                      // this pair's data has landed
+
         // WITH_E == false still needs E for the first segment's Poynting direction
         Ray<true> in[RPT];
         bool in_range[RPT];
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
-
-        if (RPT == 2 && P.in_vec2 && in_range[1]) {
+        for (int j = 0; j < RPT; ++j) {
+            in_range[j] = base + j < n;
+            const int64_t i = in_range[j] ? base + j : base;
+            const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                const double2 vx = __ldcs(reinterpret_cast<const double2 *>(P.x + c * P.ld_in + base));
-                const double2 vk = __ldcs(reinterpret_cast<const double2 *>(P.k + c * P.ld_in + base));
-                in[0].x[c] = vx.x; in[RPT - 1].x[c] = vx.y;
-                in[0].k[c] = vk.x; in[RPT - 1].k[c] = vk.y;
-                if (WITH_E || need_e0) {
-                    double2 ve = make_double2(c == 1 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0);
-                    if (P.e) ve = __ldcs(reinterpret_cast<const double2 *>(P.e + c * P.ld_in + base));
-                    in[0].e[c] = ve.x; in[RPT - 1].e[c] = ve.y;
-                }
+                in[j].x[c] = in_range[j] ? *slot(stage, j, c) : 0.0;
+                in[j].k[c] = in_range[j] ? *slot(stage, j, 3 + c) : 0.0;
+                in[j].e[c] = (load_e && in_range[j]) ? *slot(stage, j, 6 + c) : (c == 1 ? 1.0 : 0.0);
             }
-#pragma unroll
-            for (int j = 0; j < RPT; ++j)
-                in[j].alive = P.alive ? (P.alive[base + j] & PYR_RAY_ALIVE) != 0 : true;
-        } else {
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                const int64_t i = in_range[j] ? base + j : base;
-                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    in[j].x[c] = P.x[c * P.ld_in + ix];
-                    in[j].k[c] = P.k[c * P.ld_in + i];
-                    in[j].e[c] = P.e ? P.e[c * P.ld_in + i] : (c == 1 ? 1.0 : 0.0);
-                }
-                in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
-            }
+            in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
         }
 
         Ray<WITH_E> ray[RPT];
@@ -350,7 +384,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
         }
 
         for (int s = 0; s < P.n_steps; ++s) {
-            const DStep &st = P.steps[s];
+            const DStep &st = sst[s];
             double hit[RPT][3];
             uint32_t fl[RPT];
 #pragma unroll
@@ -637,9 +671,14 @@ int sm_count() {
 }
 
 template <typename K>
-static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, int threads = 256) {
+static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream) {
+    const int threads = 256;                     // the kernels index their staging slots with it
+    // dynamic shared memory: two input stages x rpt rays x 9 doubles per thread
+    const size_t smem = (size_t)2 * rpt * 9 * sizeof(double) * threads;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
     if (e != cudaSuccess) return (int)e;
     if (per_sm < 1) per_sm = 1;
     const int64_t work = (P.n + (int64_t)threads * rpt - 1) / ((int64_t)threads * rpt);
@@ -647,7 +686,7 @@ static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream,
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (work < grid) grid = work;
     if (grid < 1) return PYR_OK;
-    kernel<<<(unsigned)grid, threads, 0, stream>>>(P);
+    kernel<<<(unsigned)grid, threads, smem, stream>>>(P);
     e = cudaGetLastError();
     return e == cudaSuccess ? PYR_OK : (int)e;
 }
@@ -680,9 +719,6 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             case 4: return launch(trace_real_kernel<2, false, 0, 4>, pk.P, 2, stream);
             case 11: return launch(trace_real_kernel<1, false, 0, 4>, pk.P, 1, stream);
             case 12: return launch(trace_real_kernel<1, false, 0, 6>, pk.P, 1, stream);
-            case 21: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 128);
-            case 22: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 64);
-            case 23: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream, 192);
             default: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
         }
     }
