@@ -50,6 +50,7 @@ TRACES = [
     ("x2_xypoly", 6, (0, 0, 1), (0, 1, 0), False, ""),
     ("x3_vignette", 10, (0, 0, 1), (0, 1, 0), False, ""),
     ("x4_biaxial", 3, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
+    ("x5_degenerate", 2, (0, 0, 1), (0, 1, 0), False, ""),
 ]
 
 
@@ -72,7 +73,7 @@ def dump_trace(api, name, rings, kdir, efield, splitup, tag):
             out[pre + "k"] = np.asarray(rb.k)[sel]
             out[pre + "valid"] = np.asarray(rb.valid)[sel]
             out[pre + "rayID"] = np.asarray(rb.rayID, dtype=np.int64)
-            if np.iscomplexobj(rb.Efield) or name.startswith(("c4", "x4")):
+            if np.iscomplexobj(rb.Efield) or name.startswith(("c4", "x4", "x5")):
                 out[pre + "E"] = np.asarray(rb.Efield)[sel]
     fn = os.path.join(OUT, "seqtrace_%s%s.npz" % (name, tag))
     np.savez_compressed(fn, **out)

@@ -361,4 +361,17 @@ X4_BIAXIAL = {   # biaxial crystal lens, tilted material frame, into air
     "s_counted": 2,
 }
 
-CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL)})
+X5_DEGENERATE = {   # the demo's own choice (demos/demo_anisotropic_doublet.py:92-93):
+    # "crystals" with isotropic tensors -> every mode pair is degenerate
+    "name": "x5_degenerate",
+    "surfaces": C4_ANISOTROPIC["surfaces"],
+    "materials": {"crystal1": ("AnisotropicMaterial",
+                               {"epstensor": (1.5168 ** 2 * np.eye(3)).tolist()}),
+                  "crystal2": ("AnisotropicMaterial",
+                               {"epstensor": (1.6727 ** 2 * np.eye(3)).tolist()})},
+    "bundle": {"rings": 3, "radius": 11.43, "z0": -5.0},
+    "s_counted": 3,
+}
+
+CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
+                                       X5_DEGENERATE)})

@@ -129,45 +129,38 @@ __device__ __forceinline__ cplx poly_eval(const cplx c[5], cplx z, cplx &dp) {
     return p;
 }
 
-// roots of c[4] z^4 + ... + c[0]; returns false if the iteration met non-finite data
-__device__ __forceinline__ bool quartic_roots(const cplx c[5], cplx z[4]) {
-    // Cauchy-type radius for the start circle
-    const double a4 = sqrt(abs2(c[4]));
-    double rad = 0.0;
-    for (int i = 0; i < 4; ++i) rad = fmax(rad, pow(sqrt(abs2(c[i])) / a4, 1.0 / (4 - i)));
-    if (!isfinite(rad) || !(a4 > 0.0)) return false;
-    rad = fmax(rad, 1e-300);
-    const cplx centre = (-0.25) * (c[3] / c[4]);
-    const double ang0 = 0.7;                                  // avoids symmetric stalls
-    for (int i = 0; i < 4; ++i) {
-        double sn, cs;
-        sincos(ang0 + 1.5707963267948966 * i, &sn, &cs);
-        z[i] = centre + cplx{rad * cs, rad * sn};
-    }
-    for (int it = 0; it < 80; ++it) {
+// roots of c[4] z^4 + ... + c[0]; returns false if the iteration met non-finite data.
+// Aberth-Ehrlich sweeps (cubic convergence) from the four starts z0[]; once every
+// correction is below 1e-9 relative, exactly one more sweep lands on the rounding
+// floor -- no tolerance at the 1e-16 level that rounding noise could keep missing.
+__device__ __forceinline__ bool quartic_roots(const cplx c[5], const cplx z0[4], double scale,
+                                              cplx z[4]) {
+    if (!(abs2(c[4]) > 0.0) || !isfinite(scale)) return false;
+    for (int i = 0; i < 4; ++i) z[i] = z0[i];
+    bool last = false;
+    for (int it = 0; it < 60; ++it) {
         double worst = 0.0;
         for (int i = 0; i < 4; ++i) {
             cplx dp;
             const cplx p = poly_eval(c, z[i], dp);
             if (abs2(p) == 0.0) continue;
             cplx w = p / dp;                                  // Newton correction
-            if (!cfinite(w)) { w = cplx{1e-8 * rad, 1e-8 * rad}; }
+            if (!cfinite(w)) { w = cplx{1e-8 * scale, 1e-8 * scale}; }
             cplx rep = C(0.0);
             for (int j = 0; j < 4; ++j)
                 if (j != i) {
                     cplx dz = z[i] - z[j];
-                    if (abs2(dz) == 0.0) dz = cplx{1e-16 * rad, 1e-16 * rad};
+                    if (abs2(dz) == 0.0) dz = cplx{1e-16 * scale, 1e-16 * scale};
                     rep = rep + C(1.0) / dz;
                 }
-            cplx den = C(1.0) - w * rep;
-            cplx step = w / den;
+            cplx step = w / (C(1.0) - w * rep);
             if (!cfinite(step)) step = w;
             z[i] = z[i] - step;
-            const double rel = sqrt(abs2(step)) / (sqrt(abs2(z[i])) + 1e-300 + 1e-3 * rad);
-            worst = fmax(worst, rel);
+            worst = fmax(worst, abs2(step) / (abs2(z[i]) + 1e-6 * scale * scale));
         }
         if (!(worst == worst)) return false;                  // NaN
-        if (worst < 4e-16) break;
+        if (last) break;
+        if (worst < 1e-18) last = true;                       // |step| < 1e-9 |z|: one more sweep
     }
     return true;
 }
@@ -238,7 +231,16 @@ __device__ __forceinline__ void aniso_modes(const EpsInv &ei, const cplx kl[3], 
         c[2] = s0 * q2 + s1 * q1 + s2 * q0 - ei.c2 * s2 + a2;
         c[1] = s0 * q1 + s1 * q0 - ei.c2 * s1 + a1;
         c[0] = s0 * q0 - ei.c2 * s0 + a0 + ei.det;
-        ok = quartic_roots(c, xi);
+        // starts: the roots of the isotropic medium with the mean permittivity,
+        // xi = +-sqrt(tr(eps)/3 - p.p), split by a few per cent off the real axis
+        const cplx third = {1.0 / 3.0, 0.0};
+        const cplx xi2 = third * (ei.eps[0] + ei.eps[4] + ei.eps[8]) - s0;
+        cplx r = csqrt_(xi2);
+        double scale = sqrt(abs2(r));
+        if (!(scale > 1e-3)) { scale = 1.0; r = C(1.0); }
+        const cplx z0[4] = {r * cplx{1.03, 0.02}, r * cplx{0.97, -0.02},
+                            r * cplx{-1.03, 0.02}, r * cplx{-0.97, -0.02}};
+        ok = quartic_roots(c, z0, scale, xi);
     }
     if (!ok) {
         const cplx q = {qnan(), qnan()};

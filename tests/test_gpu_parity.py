@@ -148,7 +148,7 @@ def test_host_entry_matches_device_path():
     assert np.isclose(rms, onp.rms_spot(full, onp.centroid(full)), rtol=1e-10)
 
 
-ANISO_TAGS = ["c4_anisotropic", "c4_anisotropic_split", "x4_biaxial"]
+ANISO_TAGS = ["c4_anisotropic", "c4_anisotropic_split", "x4_biaxial", "x5_degenerate"]
 
 
 @pytest.mark.parametrize("tag", ANISO_TAGS)
@@ -181,9 +181,13 @@ def test_birefringent_matches_reference_fixture(tag):
             # after an isotropic one it is an arbitrary null vector in the reference
             low = path.record.lowered
             from_crystal = ib >= 2 and low[ib - 2].is_aniso_deflect
+            # isotropic tensors make every mode a double root of the quartic:
+            # both engines are then limited to ~sqrt(eps) and E is arbitrary
+            degenerate = tag.startswith("x5")
             if iscomplex:
-                util.compare_birefringent_bundle(d, rb, 1e-9, "%s p%d b%d" % (tag, ip, ib),
-                                                 check_e=from_crystal)
+                util.compare_birefringent_bundle(d, rb, 1e-6 if degenerate else 1e-9,
+                                                 "%s p%d b%d" % (tag, ip, ib),
+                                                 check_e=from_crystal and not degenerate)
             else:
                 util.compare_bundle(d, rb, 1e-10, "%s p%d b%d" % (tag, ip, ib))
 
