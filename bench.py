@@ -207,9 +207,9 @@ def run_gpu(args):
     n = x0h.shape[1]
     (s, seq) = configs.build_system(spec, pb.api())
     lowered = lowering.lower(s, seq, configs.DLINE)
-    x0 = torch.from_numpy(x0h).to(dev)
-    k0 = torch.from_numpy(k0h).to(dev)
-    e0 = torch.from_numpy(e0h).to(dev)
+    # resident inputs in the engine's row-aligned layout (what any host upload
+    # through the public API produces)
+    (x0, k0, e0) = engine.device_bundle(x0h, k0h, e0h, dev)
     spot = torch.zeros(8, dtype=torch.float64, device=dev)
     origin = engine.last_surface_origin(lowered)
     pool = engine.RecordPool()      # record buffers allocated once, reused per step

@@ -41,12 +41,40 @@ struct Ray {
     bool alive;
 };
 
-__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gsrc) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(gsrc) : "memory");
+// ---- mbarrier + 1-D TMA bulk copy (global -> shared), sm_90+/sm_100a ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_prev() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(double *smem_dst, const double *gsrc, unsigned bytes,
+                                            unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 
 __device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
 __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
@@ -302,8 +330,6 @@ __global__ void __launch_bounds__(256, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr bool GENERAL = FEAT != 0;
     const int64_t n = P.n;
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x * RPT;
-
     // Step table: one cooperative copy from the parameter block into shared memory;
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
     // register-indexed constant loads.
@@ -318,55 +344,87 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     const bool need_e0 = sst[0].dir_mode == PYR_DIR_POYNTING;
     const bool load_e = (WITH_E || need_e0) && P.e != nullptr;
 
-    // Input staging: the bundle of the NEXT ray pair is fetched with cp.async into a
-    // private shared-memory slot while the current pair walks through the sequence, so
-    // the HBM read latency never sits on the critical path.  Layout
-    // [stage][ray][component 0..8][thread] keeps every warp access conflict-free; a
-    // thread only ever reads the slots it filled itself (no block synchronisation).
-    extern __shared__ double stage_buf[];
-    constexpr int bdim = 256;                     // fixed CTA size (see launch())
-    auto slot = [&](int stage, int j, int c) -> double * {
-        return stage_buf + ((size_t)((stage * RPT + j) * 9 + c)) * bdim + threadIdx.x;
-    };
-    auto prefetch = [&](int64_t pbase, int stage) {
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-            const int64_t i = pbase + j;
-            if (i < n) {
-                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
-#pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    cp_async8(slot(stage, j, c), P.x + c * P.ld_in + ix);
-                    cp_async8(slot(stage, j, 3 + c), P.k + c * P.ld_in + i);
-                    if (load_e) cp_async8(slot(stage, j, 6 + c), P.e + c * P.ld_in + i);
-                }
-            }
+    // Input staging (aligned bundles): a CTA owns tiles of TILE consecutive rays; the
+    // rows of the tile two iterations ahead are pulled into shared memory by the TMA
+    // (cp.async.bulk, one elected thread, mbarrier completion), so the HBM read latency
+    // never sits on any warp's critical path and costs no registers or scoreboards.
+    // Bundles whose rows are not 16-byte aligned are read with plain coalesced loads.
+    constexpr int TILE = 256 * RPT;
+    extern __shared__ __align__(128) double stage_buf[];          // [2][9][TILE]
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    const bool staged = P.in_vec2 != 0;
+    const int rows = load_e ? 9 : 6;
+    auto issue_tile = [&](int64_t tile, int stage) {
+        const int64_t t0 = tile * TILE;
+        const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
+        const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
+        mbar_expect_tx(&full_bar[stage], bytes * rows);
+        double *dst = stage_buf + (size_t)stage * 9 * TILE;
+        for (int c = 0; c < 3; ++c) {
+            tma_load_1d(dst + c * TILE, P.x + c * P.ld_in + t0, bytes, &full_bar[stage]);
+            tma_load_1d(dst + (3 + c) * TILE, P.k + c * P.ld_in + t0, bytes, &full_bar[stage]);
+            if (load_e) tma_load_1d(dst + (6 + c) * TILE, P.e + c * P.ld_in + t0, bytes, &full_bar[stage]);
         }
-        cp_async_commit();
     };
+    if (staged && threadIdx.x == 0) {
+        mbar_init(&full_bar[0], 1);
+        mbar_init(&full_bar[1], 1);
+        fence_mbar_init();
+        if ((int64_t)blockIdx.x * TILE < n) issue_tile(blockIdx.x, 0);
+        if (((int64_t)blockIdx.x + gridDim.x) * TILE < n) issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
+    }
+    __syncthreads();
 
-    int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * RPT;
-    int stage = 0;
-    if (base < n) prefetch(base, 0);
-    for (; base < n; base += stride, stage ^= 1) {
-        if (base + stride < n) prefetch(base + stride, stage ^ 1);
-        else cp_async_commit();                    // keep the group count uniform
-        cp_async_wait_prev();                      // this pair's data has landed
-
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
+        const int64_t base = tile * TILE + (int64_t)threadIdx.x * RPT;
+        const int stage = it & 1;
         // WITH_E == false still needs E for the first segment's Poynting direction
         Ray<true> in[RPT];
         bool in_range[RPT];
 #pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-            in_range[j] = base + j < n;
-            const int64_t i = in_range[j] ? base + j : base;
-            const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
+        for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
+        if (staged) {
+            mbar_wait(&full_bar[stage], (it >> 1) & 1);
+            const double *src = stage_buf + (size_t)stage * 9 * TILE + threadIdx.x * RPT;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                in[j].x[c] = in_range[j] ? *slot(stage, j, c) : 0.0;
-                in[j].k[c] = in_range[j] ? *slot(stage, j, 3 + c) : 0.0;
-                in[j].e[c] = (load_e && in_range[j]) ? *slot(stage, j, 6 + c) : (c == 1 ? 1.0 : 0.0);
+                if (RPT == 2) {
+                    const double2 vx = *reinterpret_cast<const double2 *>(src + c * TILE);
+                    const double2 vk = *reinterpret_cast<const double2 *>(src + (3 + c) * TILE);
+                    in[0].x[c] = vx.x; in[RPT - 1].x[c] = vx.y;
+                    in[0].k[c] = vk.x; in[RPT - 1].k[c] = vk.y;
+                    double2 ve = make_double2(c == 1 ? 1.0 : 0.0, c == 1 ? 1.0 : 0.0);
+                    if (load_e) ve = *reinterpret_cast<const double2 *>(src + (6 + c) * TILE);
+                    in[0].e[c] = ve.x; in[RPT - 1].e[c] = ve.y;
+                } else {
+                    in[0].x[c] = src[c * TILE];
+                    in[0].k[c] = src[(3 + c) * TILE];
+                    in[0].e[c] = load_e ? src[(6 + c) * TILE] : (c == 1 ? 1.0 : 0.0);
+                }
             }
+            __syncthreads();                       // every thread has drained this stage
+            if (threadIdx.x == 0) {
+                const int64_t next = tile + 2 * (int64_t)gridDim.x;
+                if (next * TILE < n) issue_tile(next, stage);
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
+                const int64_t i = in_range[j] ? base + j : 0;
+                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    in[j].x[c] = __ldcs(P.x + c * P.ld_in + ix);
+                    in[j].k[c] = __ldcs(P.k + c * P.ld_in + i);
+                    in[j].e[c] = load_e ? __ldcs(P.e + c * P.ld_in + i) : (c == 1 ? 1.0 : 0.0);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            const int64_t i = in_range[j] ? base + j : 0;
+            const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
             in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
         }
 

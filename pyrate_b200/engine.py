@@ -132,6 +132,47 @@ def _padded(t, complex_=False, pad=True):
     return buf, ld
 
 
+def device_bundle(x0, k0, e0, device=None, complex_=False, like_ld=None):
+    """Bundle rows as the kernels want them: float64 (complex128 if `complex_`) CUDA
+    tensors of shape (3, n) with unit column stride and ONE common leading dimension.
+
+    Host data (NumPy / CPU tensors) is uploaded straight into row-padded buffers
+    (ld a multiple of 16 doubles, rows 128-byte aligned: the layout that enables the
+    TMA-staged input path) -- no extra pass.  Device tensors that already have a
+    common row stride are used in place (the kernels fall back to plain loads
+    when the rows are not 16-byte aligned); anything else is copied once."""
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None \
+        else torch.device(device)
+    ts = [None if t is None else as_tensor(t) for t in (x0, k0, e0)]
+    n = ts[0].shape[1]
+
+    def usable(t, want_complex):
+        return (t.device == device and t.dim() == 2 and t.shape[0] == 3 and
+                (t.stride(1) == 1 or n <= 1) and t.is_complex() == want_complex)
+
+    wants = [False, complex_, complex_]
+    strides = {t.stride(0) for (t, w) in zip(ts, wants) if t is not None and usable(t, w)}
+    all_ok = all(t is None or usable(t, w) for (t, w) in zip(ts, wants))
+    if all_ok and len(strides) == 1 and (like_ld is None or like_ld in strides) and n > 1:
+        return tuple(ts)
+    ld = like_ld if like_ld is not None else _round_up(max(n, 1), LD_ALIGN)
+    out = []
+    for (t, w) in zip(ts, wants):
+        if t is None:
+            out.append(None)
+            continue
+        if usable(t, w) and t.stride(0) == ld:
+            out.append(t)
+            continue
+        buf = torch.empty((3, ld), dtype=torch.complex128 if w else torch.float64,
+                          device=device)
+        buf[:, n:] = 0
+        src = t.to(torch.complex128) if w else t
+        buf[:, :n].copy_(src, non_blocking=True)
+        out.append(buf[:, :n])
+    return tuple(out)
+
+
 class RecordPool(object):
     """Opt-in reuse of the per-step record buffers across calls with identical
     shapes (optimisation loops, benchmarks): a TraceRecord returned with a pool
@@ -163,9 +204,9 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
-    x0 = as_tensor(x0, device).contiguous()
-    k0 = as_tensor(k0, device).contiguous()
-    e0 = None if e0 is None else as_tensor(e0, device).contiguous()
+    complex_in = bool(as_tensor(k0).is_complex() or
+                      (e0 is not None and as_tensor(e0).is_complex()))
+    (x0, k0, e0) = device_bundle(x0, k0, e0, device, complex_in)
     if x0.is_complex():
         raise ValueError("ray positions must be real")
     n0 = x0.shape[1]
@@ -197,16 +238,21 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     if pool is not None:
         pool.begin()
     with torch.cuda.device(device):
-        complex_in = k0.is_complex() or (e0 is not None and e0.is_complex())
-        (cur_x, ld_x) = _padded(x0, pad=False)
-        (cur_k, ld_k) = _padded(k0, complex_in, pad=False)
+        # device_bundle() guarantees unit column stride and ONE leading dimension
+        (cur_x, ld_x) = (x0, max(x0.stride(0), 1))
+        if complex_in:
+            (cur_k, ld_k) = (torch.view_as_real(k0), ld_x)
+        else:
+            (cur_k, ld_k) = (k0, ld_x)
         cur_e = None
         if e0 is not None:
-            (cur_e, _) = _padded(e0, complex_in, pad=False)
+            cur_e = torch.view_as_real(e0) if complex_in else e0
         elif complex_in or first_aniso is not None:
             tmp = torch.zeros((3, n0), dtype=torch.float64, device=device)
             tmp[1] = 1.0                      # ray.py:71-73 default
-            (cur_e, _) = _padded(tmp, complex_in, pad=False)
+            (_, _, cur_e) = device_bundle(x0, x0, tmp, device, complex_in, like_ld=ld_x)
+            e0 = cur_e
+            cur_e = torch.view_as_real(cur_e) if complex_in else cur_e
         cur_alive = None
         n = n0
         n_x = n0

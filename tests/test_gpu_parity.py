@@ -248,3 +248,25 @@ def test_plugin_calls_reproduce_the_fused_trace(name):
         assert util.relerr(da["x"][-1][:, v], db["x"][-1][:, v]) <= tol, ib
         assert util.relerr(da["x"][0], db["x"][0]) <= tol, ib
         assert util.relerr(da["k"][0], db["k"][0]) <= tol, ib
+
+
+def test_device_resident_unaligned_bundle_uses_plain_loads():
+    """Caller-owned CUDA tensors with an odd ray count (rows not 16-byte aligned)
+    are traced in place through the plain-load path; host arrays go through the
+    row-padded TMA-staged path.  Both must agree bit for bit."""
+    import torch
+    from pyrate_b200 import engine, lowering
+    spec = configs.CONFIGS["x1_tilted"]
+    (x0, k0, e0) = configs.config_bundle(spec, 20)              # 1261 rays (odd)
+    (s, seq) = configs.build_system(spec, pb.api())
+    lowered = lowering.lower(s, seq, configs.DLINE)
+    rec_host = engine.trace(lowered, x0, k0, e0, configs.DLINE)
+    dev = rec_host.hit[0].device
+    (xd, kd, ed) = (torch.from_numpy(a).to(dev) for a in (x0, k0, e0))
+    assert xd.stride(0) % 2 == 1
+    rec_dev = engine.trace(lowered, xd, kd, ed, configs.DLINE)
+    assert rec_dev.x0.data_ptr() == xd.data_ptr()               # used in place
+    for s_ in range(len(lowered)):
+        assert torch.equal(rec_host.flags[s_], rec_dev.flags[s_])
+        assert torch.equal(torch.nan_to_num(rec_host.hit[s_]), torch.nan_to_num(rec_dev.hit[s_]))
+        assert torch.equal(torch.nan_to_num(rec_host.k[s_]), torch.nan_to_num(rec_dev.k[s_]))

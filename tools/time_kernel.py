@@ -21,7 +21,7 @@ rings = configs.rings_for(rays) if rays else spec["bundle"]["rings"]
 (s, seq) = configs.build_system(spec, pb.api())
 lowered = lowering.lower(s, seq, configs.DLINE)
 dev = torch.device("cuda", 0)
-(x0, k0, e0) = (torch.from_numpy(a).to(dev) for a in (x0, k0, e0))
+(x0, k0, e0) = engine.device_bundle(x0, k0, e0, dev)
 pool = engine.RecordPool()
 for _ in range(3):
     engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool, record_e=record_e)
