@@ -270,3 +270,28 @@ def test_device_resident_unaligned_bundle_uses_plain_loads():
         assert torch.equal(rec_host.flags[s_], rec_dev.flags[s_])
         assert torch.equal(torch.nan_to_num(rec_host.hit[s_]), torch.nan_to_num(rec_dev.hit[s_]))
         assert torch.equal(torch.nan_to_num(rec_host.k[s_]), torch.nan_to_num(rec_dev.k[s_]))
+
+
+def test_ray_bundle_analysis_on_device_bundles():
+    """RayBundleAnalysis (reference analysis/ray_analysis.py:44-170) on traced
+    CUDA bundles: native spot sums and torch path integrals against NumPy."""
+    import pyrate_np as onp
+    from pyrate_b200.raytracer.analysis.ray_analysis import RayBundleAnalysis
+    spec = configs.CONFIGS["x3_vignette"]            # some rays are dropped on the way
+    (x0, k0, e0) = configs.config_bundle(spec, 25)
+    paths = _device_paths("x3_vignette", x0, k0, e0)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0)[0]
+    last = paths[0].raybundles[-1]
+    ra = RayBundleAnalysis(last)
+    xr = ref[-1]["x"][-1]
+    assert xr.shape[1] > 10 and last.x.shape[2] == xr.shape[1]
+    c = ra.get_centroid_position().numpy()
+    assert np.allclose(c, onp.centroid(xr), rtol=1e-11, atol=1e-12)
+    assert np.isclose(ra.get_rms_spot_size_centroid(), onp.rms_spot(xr, onp.centroid(xr)),
+                      rtol=1e-10)
+    mid = paths[0].raybundles[3]
+    got = RayBundleAnalysis(mid).get_arc_length().cpu().numpy()
+    xm = ref[3]["x"]
+    want = np.sqrt(((xm[1:] - xm[:-1]) ** 2).sum(axis=1)).sum(axis=0)
+    v = ref[3]["valid"][-1]
+    assert np.allclose(got[v], want[v], rtol=1e-10)
