@@ -76,9 +76,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
         : "memory");
 }
 
-__device__ __forceinline__ void store_stream(double *p, double v) { __stcs(p, v); }
+// Record stores.  POLICY 0: evict-first (st.global.cs) -- the records are written once
+// and never re-read by the kernel; 1: default write-back; 2: cache-global (st.global.cg).
+template <int POLICY>
+__device__ __forceinline__ void store_stream(double *p, double v) {
+    if (POLICY == 0) __stcs(p, v); else if (POLICY == 2) __stcg(p, v); else *p = v;
+}
+template <int POLICY>
 __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
-    __stcs(reinterpret_cast<double2 *>(p), make_double2(a, b));
+    double2 *q = reinterpret_cast<double2 *>(p);
+    const double2 v = make_double2(a, b);
+    if (POLICY == 0) __stcs(q, v); else if (POLICY == 2) __stcg(q, v); else *q = v;
 }
 
 // d from (k, E): ray.py:140-152 for real k, E
@@ -325,7 +333,7 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
 // FEAT: 0 = lean steps only; 1 = + explicit shapes / own-frame apertures / partial
 // step modes; 3 = + GRIN media (separate instantiations keep the register budget of
 // the common cases small)
-template <int RPT, bool WITH_E, int FEAT, int MINB = 1>
+template <int RPT, bool WITH_E, int FEAT, int MINB = 1, int POLICY = 0>
 __global__ void __launch_bounds__(256, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr bool GENERAL = FEAT != 0;
@@ -470,39 +478,39 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             if (st.out_x) {
                 if (v2) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) store_stream2(st.out_x + c * ld + base, hit[0][c], hit[RPT - 1][c]);
+                    for (int c = 0; c < 3; ++c) store_stream2<POLICY>(st.out_x + c * ld + base, hit[0][c], hit[RPT - 1][c]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < RPT; ++j)
                         if (in_range[j]) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) store_stream(st.out_x + c * ld + base + j, hit[j][c]);
+                            for (int c = 0; c < 3; ++c) store_stream<POLICY>(st.out_x + c * ld + base + j, hit[j][c]);
                         }
                 }
             }
             if (st.out_k) {
                 if (v2) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) store_stream2(st.out_k + c * ld + base, ray[0].k[c], ray[RPT - 1].k[c]);
+                    for (int c = 0; c < 3; ++c) store_stream2<POLICY>(st.out_k + c * ld + base, ray[0].k[c], ray[RPT - 1].k[c]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < RPT; ++j)
                         if (in_range[j]) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) store_stream(st.out_k + c * ld + base + j, ray[j].k[c]);
+                            for (int c = 0; c < 3; ++c) store_stream<POLICY>(st.out_k + c * ld + base + j, ray[j].k[c]);
                         }
                 }
             }
             if (WITH_E && st.out_e) {
                 if (v2) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) store_stream2(st.out_e + c * ld + base, ray[0].e[c], ray[RPT - 1].e[c]);
+                    for (int c = 0; c < 3; ++c) store_stream2<POLICY>(st.out_e + c * ld + base, ray[0].e[c], ray[RPT - 1].e[c]);
                 } else {
 #pragma unroll
                     for (int j = 0; j < RPT; ++j)
                         if (in_range[j]) {
 #pragma unroll
-                            for (int c = 0; c < 3; ++c) store_stream(st.out_e + c * ld + base + j, ray[j].e[c]);
+                            for (int c = 0; c < 3; ++c) store_stream<POLICY>(st.out_e + c * ld + base + j, ray[j].e[c]);
                         }
                 }
             }
@@ -777,6 +785,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             case 4: return launch(trace_real_kernel<2, false, 0, 4>, pk.P, 2, stream);
             case 11: return launch(trace_real_kernel<1, false, 0, 4>, pk.P, 1, stream);
             case 12: return launch(trace_real_kernel<1, false, 0, 6>, pk.P, 1, stream);
+            case 31: return launch(trace_real_kernel<2, false, 0, 2, 1>, pk.P, 2, stream);
+            case 32: return launch(trace_real_kernel<2, false, 0, 2, 2>, pk.P, 2, stream);
+            case 33: return launch(trace_real_kernel<2, false, 0, 3, 1>, pk.P, 2, stream);
             default: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
         }
     }

@@ -12,7 +12,7 @@ import util
 
 pytestmark = pytest.mark.gpu
 
-REAL_TAGS = [t for t in util.golden_traces() if not t.startswith(("c4", "x4"))]
+REAL_TAGS = [t for t in util.golden_traces() if not t.startswith(("c4", "x4", "x5"))]
 
 
 def _device_paths(name, x0, k0, e0, splitup=False, record_efield=False):
