@@ -62,6 +62,19 @@ __device__ __forceinline__ void tma_load_1d(double *smem_dst, const double *gsrc
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void tma_store_1d(void *gdst, const void *smem_src, unsigned bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
+                 "r"(smem_u32(smem_src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
     asm volatile(
         "{\n"
@@ -80,13 +93,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // and never re-read by the kernel; 1: default write-back; 2: cache-global (st.global.cg).
 template <int POLICY>
 __device__ __forceinline__ void store_stream(double *p, double v) {
-    if (POLICY == 0) __stcs(p, v); else if (POLICY == 2) __stcg(p, v); else *p = v;
+    if (POLICY == 0 || POLICY == 3) __stcs(p, v); else if (POLICY == 2) __stcg(p, v); else *p = v;
 }
 template <int POLICY>
 __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
     double2 *q = reinterpret_cast<double2 *>(p);
     const double2 v = make_double2(a, b);
-    if (POLICY == 0) __stcs(q, v); else if (POLICY == 2) __stcg(q, v); else *q = v;
+    if (POLICY == 0 || POLICY == 3) __stcs(q, v); else if (POLICY == 2) __stcg(q, v); else *q = v;
 }
 
 // d from (k, E): ray.py:140-152 for real k, E
@@ -358,8 +371,15 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // never sits on any warp's critical path and costs no registers or scoreboards.
     // Bundles whose rows are not 16-byte aligned are read with plain coalesced loads.
     constexpr int TILE = 256 * RPT;
-    extern __shared__ __align__(128) double stage_buf[];          // [2][9][TILE]
+    // POLICY 3 (TMA record stores) stages the outputs in shared memory as well and
+    // therefore keeps a single input stage (prefetch distance: one tile = 13 steps)
+    constexpr bool TMA_OUT = POLICY == 3 && RPT == 2 && !WITH_E;
+    constexpr int IN_STAGES = TMA_OUT ? 1 : 2;
+    extern __shared__ __align__(128) double stage_buf[];          // [IN_STAGES][9][TILE] (+ out)
     __shared__ __align__(8) unsigned long long full_bar[2];
+    double *out_buf = stage_buf + (size_t)IN_STAGES * 9 * TILE;   // [2][6][TILE] doubles
+    unsigned char *out_fl = reinterpret_cast<unsigned char *>(out_buf + 2 * 6 * TILE);   // [2][TILE]
+    unsigned store_count = 0;
     const bool staged = P.in_vec2 != 0;
     const int rows = load_e ? 9 : 6;
     auto issue_tile = [&](int64_t tile, int stage) {
@@ -379,21 +399,22 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
         mbar_init(&full_bar[1], 1);
         fence_mbar_init();
         if ((int64_t)blockIdx.x * TILE < n) issue_tile(blockIdx.x, 0);
-        if (((int64_t)blockIdx.x + gridDim.x) * TILE < n) issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
+        if (IN_STAGES == 2 && ((int64_t)blockIdx.x + gridDim.x) * TILE < n)
+            issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
     }
     __syncthreads();
 
     int it = 0;
     for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
         const int64_t base = tile * TILE + (int64_t)threadIdx.x * RPT;
-        const int stage = it & 1;
+        const int stage = it % IN_STAGES;
         // WITH_E == false still needs E for the first segment's Poynting direction
         Ray<true> in[RPT];
         bool in_range[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
         if (staged) {
-            mbar_wait(&full_bar[stage], (it >> 1) & 1);
+            mbar_wait(&full_bar[stage], (it / IN_STAGES) & 1);
             const double *src = stage_buf + (size_t)stage * 9 * TILE + threadIdx.x * RPT;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -413,7 +434,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             }
             __syncthreads();                       // every thread has drained this stage
             if (threadIdx.x == 0) {
-                const int64_t next = tile + 2 * (int64_t)gridDim.x;
+                const int64_t next = tile + IN_STAGES * (int64_t)gridDim.x;
                 if (next * TILE < n) issue_tile(next, stage);
             }
         } else {
@@ -472,8 +493,42 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                                                  : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
-            // ---- record the step (evict-first streaming stores) ----
+            // ---- record the step ----
             const int64_t ld = st.ld_out;
+            if (TMA_OUT && (st.bits & kOutVec2)) {
+                // The CTA's slice of the record goes through shared memory and leaves
+                // as TMA bulk stores issued by one thread: no per-thread global stores,
+                // no store back-pressure on the warps that do the arithmetic.
+                const int b = store_count & 1;
+                ++store_count;
+                if (threadIdx.x == 0) tma_store_wait_read<1>();     // buffer b is free again
+                __syncthreads();
+                double *ob = out_buf + (size_t)b * 6 * TILE + threadIdx.x * 2;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    *reinterpret_cast<double2 *>(ob + c * TILE) = make_double2(hit[0][c], hit[RPT - 1][c]);
+                    *reinterpret_cast<double2 *>(ob + (3 + c) * TILE) =
+                        make_double2(ray[0].k[c], ray[RPT - 1].k[c]);
+                }
+                *reinterpret_cast<uchar2 *>(out_fl + b * TILE + threadIdx.x * 2) =
+                    make_uchar2((unsigned char)fl[0], (unsigned char)fl[RPT - 1]);
+                fence_proxy_async_smem();
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int64_t t0 = tile * TILE;
+                    const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
+                    const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
+                    const double *sb = out_buf + (size_t)b * 6 * TILE;
+                    for (int c = 0; c < 3; ++c) {
+                        if (st.out_x) tma_store_1d(st.out_x + c * ld + t0, sb + c * TILE, bytes);
+                        if (st.out_k) tma_store_1d(st.out_k + c * ld + t0, sb + (3 + c) * TILE, bytes);
+                    }
+                    if (st.out_flags)
+                        tma_store_1d(st.out_flags + t0, out_fl + b * TILE, (unsigned)((cnt + 15) & ~(int64_t)15));
+                    tma_store_commit();
+                }
+                continue;
+            }
             const bool v2 = RPT == 2 && (st.bits & kOutVec2) && in_range[RPT - 1];
             if (st.out_x) {
                 if (v2) {
@@ -526,6 +581,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             }
         }
     }
+    if (TMA_OUT && threadIdx.x == 0) tma_store_wait_read<0>();      // smem must outlive the reads
 }
 
 // ---------------------------------------------------------------------------
@@ -737,10 +793,13 @@ int sm_count() {
 }
 
 template <typename K>
-static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream) {
+static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, bool tma_out = false) {
     const int threads = 256;                     // the kernels index their staging slots with it
-    // dynamic shared memory: two input stages x rpt rays x 9 doubles per thread
-    const size_t smem = (size_t)2 * rpt * 9 * sizeof(double) * threads;
+    // dynamic shared memory: input stages of rpt x 9 doubles per thread (two, or one plus
+    // two output stages of rpt x 6 doubles + flag bytes when records leave through the TMA)
+    const size_t tile = (size_t)threads * rpt;
+    const size_t smem = tma_out ? tile * 9 * 8 + 2 * tile * 6 * 8 + 2 * tile
+                                : 2 * tile * 9 * 8;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -788,6 +847,8 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             case 31: return launch(trace_real_kernel<2, false, 0, 2, 1>, pk.P, 2, stream);
             case 32: return launch(trace_real_kernel<2, false, 0, 2, 2>, pk.P, 2, stream);
             case 33: return launch(trace_real_kernel<2, false, 0, 3, 1>, pk.P, 2, stream);
+            case 41: return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
+            case 43: return launch(trace_real_kernel<2, false, 0, 3, 3>, pk.P, 2, stream, true);
             default: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
         }
     }
