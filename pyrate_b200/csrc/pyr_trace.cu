@@ -832,8 +832,8 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
     if (!pk.general) {
         if (with_e) return launch(trace_real_kernel<2, true, 0>, pk.P, 2, stream);
-        // tuning knob (not part of the ABI): resident CTAs per SM the lean kernel is
-        // compiled for; PYR_LEAN_VARIANT = 1 (free), 3, 4, or 11 (one ray per thread)
+        // tuning knob (not part of the ABI), used by tools/gpu_variants.sh to A/B kernel
+        // configurations: launch bounds, rays per thread, record-store policy
         static const int variant = [] {
             const char *e = std::getenv("PYR_LEAN_VARIANT");
             return e ? std::atoi(e) : 0;
@@ -847,9 +847,8 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             case 31: return launch(trace_real_kernel<2, false, 0, 2, 1>, pk.P, 2, stream);
             case 32: return launch(trace_real_kernel<2, false, 0, 2, 2>, pk.P, 2, stream);
             case 33: return launch(trace_real_kernel<2, false, 0, 3, 1>, pk.P, 2, stream);
-            case 41: return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
-            case 43: return launch(trace_real_kernel<2, false, 0, 3, 3>, pk.P, 2, stream, true);
-            default: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
+            case 50: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);   // STG records
+            default: return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
         }
     }
     bool has_grin = false;
@@ -861,7 +860,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
     return with_e ? launch(trace_real_kernel<2, true, 1>, pk.P, 2, stream)
-                  : launch(trace_real_kernel<2, false, 1, 2>, pk.P, 2, stream);
+                  : launch(trace_real_kernel<2, false, 1, 2, 3>, pk.P, 2, stream, true);
 }
 
 int trace_entry(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
