@@ -13,8 +13,11 @@
  * Conventions
  *   - all ray arrays are component-major "(3, n)" like the reference's
  *     RayBundle rows (raytracer/ray.py:40-66): element (c, i) lives at
- *     base[c * ld + i] with leading dimension ld >= n (ld even and base 16-byte
- *     aligned enables 128-bit accesses; anything else still works).
+ *     base[c * ld + i] with leading dimension ld >= n.  Inputs with ld even and
+ *     16-byte aligned rows are staged by the TMA (reads may touch one pad element
+ *     past n); outputs with ld a multiple of 16 and 16-byte aligned rows leave as
+ *     TMA bulk stores (writes may touch the row pad up to the next multiple of 16
+ *     elements).  Anything else still works through plain loads / stores.
  *   - complex arrays are interleaved (re, im) doubles = numpy/torch complex128;
  *     element (c, i) at base[2 * (c * ld + i)].
  *   - every device pointer is caller-owned (the engine allocates nothing

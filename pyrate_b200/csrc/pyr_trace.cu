@@ -737,9 +737,11 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         if (u.mode == PYR_STEP_PROPAGATE_ONLY) bits |= kNoDeflect;
         else if (u.mode == PYR_STEP_DEFLECT_ONLY) bits |= kNoIntersect;
         else if (u.mode != PYR_STEP_FULL) return PYR_E_BADARG;
-        if ((d.ld_out % 2 == 0) && (!d.out_x || aligned16(d.out_x)) && (!d.out_k || aligned16(d.out_k)) &&
+        // rows padded to 16 elements: the vector / TMA record path may write up to the
+        // next multiple of 2 doubles (16 flag bytes) past the last ray of a row
+        if ((d.ld_out % 16 == 0) && (!d.out_x || aligned16(d.out_x)) && (!d.out_k || aligned16(d.out_k)) &&
             (!d.out_e || aligned16(d.out_e)) &&
-            (!d.out_flags || (reinterpret_cast<uintptr_t>(d.out_flags) & 1u) == 0))
+            (!d.out_flags || aligned16(d.out_flags)))
             bits |= kOutVec2;
         d.bits = bits;
         const bool aniso = u.before.kind == PYR_MEDIUM_ANISO || u.after.kind == PYR_MEDIUM_ANISO;

@@ -18,6 +18,17 @@ from . import lowering
 from .raytracer.ray import RayBundle, RayPath, as_tensor
 
 LD_ALIGN = 16           # doubles: rows start on 128-byte boundaries
+MAX_STEPS_PER_LAUNCH = 40       # kMaxSteps
+MAX_AUX_PER_LAUNCH = 10         # kMaxAux
+
+
+def _needs_aux(st):
+    """Mirror of pack() in csrc/pyr_trace.cu: does this entry need a DAux record?"""
+    same_frame = st.aperture_kind == nat.AP_BASE or \
+        bytes(st.shape_frame) == bytes(st.aperture_frame)
+    return (st.shape_kind != nat.SHAPE_CONIC or not same_frame or
+            st.mode != nat.STEP_FULL or st.before.kind != nat.MEDIUM_ISO_CONST or
+            st.after.kind != nat.MEDIUM_ISO_CONST)
 
 
 class DeviceRequired(RuntimeError):
@@ -233,7 +244,23 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     for (i, ls) in enumerate(lowered):
         if ls.st.split and i + 1 < nsteps:
             cuts.append(i + 1)
+    # one launch carries at most MAX_STEPS_PER_LAUNCH entries and MAX_AUX_PER_LAUNCH
+    # entries with an auxiliary record (kernel parameter block, csrc/pyr_device.cuh);
+    # longer sequences continue from the last recorded state in a further launch
     cuts = sorted(set(cuts)) + [nsteps]
+    bounded = [0]
+    for hi in cuts[1:]:
+        lo = bounded[-1]
+        (count, aux) = (0, 0)
+        for i in range(lo, hi):
+            a = 1 if _needs_aux(lowered[i].st) else 0
+            if count + 1 > MAX_STEPS_PER_LAUNCH or aux + a > MAX_AUX_PER_LAUNCH:
+                bounded.append(i)
+                (count, aux) = (0, 0)
+            count += 1
+            aux += a
+        bounded.append(hi)
+    cuts = bounded
 
     if pool is not None:
         pool.begin()

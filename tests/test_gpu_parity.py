@@ -295,3 +295,34 @@ def test_ray_bundle_analysis_on_device_bundles():
     want = np.sqrt(((xm[1:] - xm[:-1]) ** 2).sum(axis=1)).sum(axis=0)
     v = ref[3]["valid"][-1]
     assert np.allclose(got[v], want[v], rtol=1e-10)
+
+
+def test_long_sequences_are_chunked_across_launches():
+    """More sequence entries than one kernel parameter block holds (40) and more
+    aspheres than auxiliary records (10): the engine continues from the last
+    recorded state in further launches; results equal the oracle."""
+    import pyrate_np as onp
+    surfaces = [configs._conic("stop", 0.0, opt={"is_stop": True})]
+    for i in range(30):
+        if i % 2 == 0:
+            surfaces.append({"name": "a%d" % i, "lc": {"decz": 1.5},
+                             "shape": ("Asphere", {"curv": 0.01 * (1 if i % 4 == 0 else -1),
+                                                   "cc": -0.5, "coefficients": [0.0, 1e-6]}),
+                             "aperture": None, "mat": "g" if i % 4 == 0 else None, "opt": {}})
+        else:
+            surfaces.append(configs._conic("c%d" % i, 1.0, curv=0.004 * (-1) ** i,
+                                           mat=None if i % 4 == 1 else "g"))
+    for i in range(24):
+        surfaces.append(configs._conic("p%d" % i, 0.5))
+    spec = {"name": "long", "surfaces": surfaces,
+            "materials": {"g": ("ConstantIndexGlass", {"n": 1.5})},
+            "bundle": {"rings": 6, "radius": 3.0, "z0": -1.0}}
+    (x0, k0, e0) = configs.config_bundle(spec)
+    (s, seq) = configs.build_system(spec, pb.api())
+    assert len(seq[0][1]) == 55
+    paths = s.seqtrace(pb.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    assert len(paths[0].raybundles) == len(ref[0]) == 57
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                        "rayID": rb["rayID"]}, 1e-6, "long b%d" % ib)
