@@ -51,7 +51,11 @@ extern "C" {
 enum PyrShapeKind {
     PYR_SHAPE_CONIC = 0,        /* Conic.intersect :289-325, closed form          */
     PYR_SHAPE_ASPHERE = 1,      /* ExplicitShape.intersect :448-465 + Asphere.F   */
-    PYR_SHAPE_XYPOLY = 2        /* ExplicitShape.intersect + XYPolynomials.F :785 */
+    PYR_SHAPE_XYPOLY = 2,       /* ExplicitShape.intersect + XYPolynomials.F :785 */
+    PYR_SHAPE_BICONIC = 3       /* ExplicitShape.intersect + Biconic.F :618-629:
+                                   curv/cc = x section, curv2/cc2 = y section,
+                                   coeff[i] = A_(2i+2), coeff[16 + i] = B_(2i+2),
+                                   n_coeff <= 16 pairs                             */
 };
 
 /* raytracer/aperture.py:71-140 */
@@ -145,7 +149,8 @@ typedef struct PyrStep {
                                    (index of `before` after an isotropic
                                    deflection); saves the normalisation in
                                    PYR_DIR_K mode.  0 = unknown                    */
-    double curv, cc;            /* conic / asphere base conic                      */
+    double curv, cc;            /* conic / asphere base conic; biconic x section   */
+    double curv2, cc2;          /* biconic y section                               */
     double normradius;          /* XY polynomial                                   */
     double newton_tol;          /* |dt| <= tol (1 + |t|) ends the iteration        */
     double coeff[PYR_MAX_COEFF];        /* asphere: A2, A4, ...; XY: c_mn          */

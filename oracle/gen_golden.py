@@ -51,6 +51,7 @@ TRACES = [
     ("x3_vignette", 10, (0, 0, 1), (0, 1, 0), False, ""),
     ("x4_biaxial", 3, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
     ("x5_degenerate", 2, (0, 0, 1), (0, 1, 0), False, ""),
+    ("x6_biconic", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
 ]
 
 
@@ -145,6 +146,12 @@ def dump_shapes(api):
     out["xy_sag"] = xy.getSag(x, y)
     out["xy_grad"] = xy.getGrad(x, y)
     out["xy_normal"] = xy.getNormal(x, y)
+    bic = api.Biconic.p(lc, curvx=0.03, ccx=-0.6, curvy=-0.02, ccy=0.4,
+                        coefficients=[(1e-3, 0.3), (-2e-5, -0.2)])
+    out["bic_params"] = np.array([0.03, -0.6, -0.02, 0.4, 1e-3, 0.3, -2e-5, -0.2])
+    out["bic_sag"] = bic.getSag(x, y)
+    out["bic_grad"] = bic.getGrad(x, y)
+    out["bic_normal"] = bic.getNormal(x, y)
     np.savez_compressed(os.path.join(OUT, "shapes.npz"), **out)
     print("shapes.npz")
 

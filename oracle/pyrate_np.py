@@ -150,8 +150,37 @@ def xypoly_grad(normradius, coeffs, x, y):
     return np.vstack((gx, gy, np.ones_like(x)))
 
 
+def biconic_sag(cx, cy, ccx, ccy, coeffs, x, y):
+    """Biconic.F surface_shape.py:618-629; coeffs = [(a_n, b_n), ...]."""
+    r2 = x * x + y * y
+    ast2 = x * x - y * y
+    with np.errstate(invalid="ignore"):
+        sq = np.sqrt(1 - cx ** 2 * (1 + ccx) * x ** 2 - cy ** 2 * (1 + ccy) * y ** 2)
+    res = (cx * x ** 2 + cy * y ** 2) / (1 + sq)
+    for (n, (an, bn)) in enumerate(coeffs):
+        res = res + an * (r2 - bn * ast2) ** (n + 1)
+    return res
+
+
+def biconic_grad(cx, cy, ccx, ccy, coeffs, x, y):
+    """Biconic.gradF surface_shape.py:631-649."""
+    r2 = x * x + y * y
+    ast2 = x * x - y * y
+    with np.errstate(invalid="ignore", divide="ignore"):
+        sq = np.sqrt(1 - cx ** 2 * (1 + ccx) * x ** 2 - cy ** 2 * (1 + ccy) * y ** 2)
+        gx = -cx * x * (cx * (ccx + 1) * (cx * x ** 2 + cy * y ** 2) + 2 * (sq + 1) * sq) / ((sq + 1) ** 2 * sq)
+        gy = -cy * y * (cy * (ccy + 1) * (cx * x ** 2 + cy * y ** 2) + 2 * (sq + 1) * sq) / ((sq + 1) ** 2 * sq)
+    for (n, (an, bn)) in enumerate(coeffs):
+        gx = gx + 2 * an * (n + 1) * x * (bn - 1) * (-bn * ast2 + r2) ** n
+        gy = gy - 2 * an * (n + 1) * y * (bn + 1) * (-bn * ast2 + r2) ** n
+    return np.vstack((gx, gy, np.ones_like(x)))
+
+
 def shape_sag(shape, x, y):
     kind = shape["kind"]
+    if kind == "Biconic":
+        return biconic_sag(shape["curvx"], shape["curvy"], shape["ccx"], shape["ccy"],
+                           shape["coefficients"], x, y)
     if kind == "Conic":
         return conic_sag(shape["curv"], shape["cc"], x, y)
     if kind == "Asphere":
@@ -163,6 +192,9 @@ def shape_sag(shape, x, y):
 
 def shape_grad(shape, x, y):
     kind = shape["kind"]
+    if kind == "Biconic":
+        return biconic_grad(shape["curvx"], shape["curvy"], shape["ccx"], shape["ccy"],
+                            shape["coefficients"], x, y)
     if kind == "Conic":
         return conic_grad(shape["curv"], shape["cc"], x, y)
     if kind == "Asphere":
@@ -559,7 +591,7 @@ def system_from_spec(spec):
         shape = dict(skw)
         shape["kind"] = skind
         shape["frame"] = frame
-        if skind == "Asphere":
+        if skind in ("Asphere", "Biconic"):
             shape.setdefault("coefficients", [])
         if surf["aperture"] is None:
             ap = {"kind": "Base"}

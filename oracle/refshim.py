@@ -49,7 +49,7 @@ def api():
     from pyrateoptics.raytracer.optical_element import OpticalElement
     from pyrateoptics.raytracer.localcoordinates import LocalCoordinates
     from pyrateoptics.raytracer.surface import Surface
-    from pyrateoptics.raytracer.surface_shape import (Conic, Asphere,
+    from pyrateoptics.raytracer.surface_shape import (Conic, Asphere, Biconic,
                                                       XYPolynomials)
     from pyrateoptics.raytracer.aperture import (BaseAperture,
                                                  CircularAperture,

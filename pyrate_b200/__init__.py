@@ -20,7 +20,7 @@ from .raytracer.optical_element import OpticalElement  # noqa: F401
 from .raytracer.optical_system import OpticalSystem  # noqa: F401
 from .raytracer.ray import RayBundle, RayPath  # noqa: F401
 from .raytracer.surface import Surface  # noqa: F401
-from .raytracer.surface_shape import (Asphere, Conic, XYPolynomials,  # noqa: F401
+from .raytracer.surface_shape import (Asphere, Biconic, Conic, XYPolynomials,  # noqa: F401
                                       accessible_shapes)
 
 __version__ = "0.1.0"
@@ -31,7 +31,8 @@ def api():
     return types.SimpleNamespace(
         OpticalSystem=OpticalSystem, OpticalElement=OpticalElement,
         LocalCoordinates=LocalCoordinates, Surface=Surface, Conic=Conic,
-        Asphere=Asphere, XYPolynomials=XYPolynomials, BaseAperture=BaseAperture,
+        Asphere=Asphere, Biconic=Biconic, XYPolynomials=XYPolynomials,
+        BaseAperture=BaseAperture,
         CircularAperture=CircularAperture, RectangularAperture=RectangularAperture,
         ConstantIndexGlass=ConstantIndexGlass, ModelGlass=ModelGlass,
         AnisotropicMaterial=AnisotropicMaterial,

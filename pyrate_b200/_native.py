@@ -10,7 +10,7 @@ import os
 MAX_COEFF = 32
 MAX_GRIN_PARAMS = 8
 
-(SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY) = (0, 1, 2)
+(SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY, SHAPE_BICONIC) = (0, 1, 2, 3)
 (AP_BASE, AP_CIRCULAR, AP_RECTANGULAR) = (0, 1, 2)
 (REFRACT, REFLECT) = (0, 1)
 (MEDIUM_ISO_CONST, MEDIUM_ISO_GRIN, MEDIUM_ANISO) = (0, 1, 2)
@@ -43,6 +43,7 @@ class PyrStep(C.Structure):
                 ("split", C.c_int32), ("mode", C.c_int32),
                 ("k_norm_hint", C.c_double),
                 ("curv", C.c_double), ("cc", C.c_double),
+                ("curv2", C.c_double), ("cc2", C.c_double),
                 ("normradius", C.c_double), ("newton_tol", C.c_double),
                 ("coeff", C.c_double * MAX_COEFF),
                 ("xpow", C.c_int8 * MAX_COEFF), ("ypow", C.c_int8 * MAX_COEFF),

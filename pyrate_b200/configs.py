@@ -373,5 +373,21 @@ X5_DEGENERATE = {   # the demo's own choice (demos/demo_anisotropic_doublet.py:9
     "s_counted": 3,
 }
 
+X6_BICONIC = {
+    "name": "x6_biconic",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        {"name": "front", "lc": {"decz": 3.0, "tiltz": 20.0 * math.pi / 180.0},
+         "shape": ("Biconic", {"curvx": 1. / 35.0, "ccx": -0.6, "curvy": 1. / 60.0,
+                               "ccy": 0.4, "coefficients": [(1e-5, 0.3), (-2e-8, -0.2)]}),
+         "aperture": _circ(9.0), "mat": "glass", "opt": {}},
+        _conic("back", 5.0, curv=-1. / 70.0, mat=None),
+        _conic("image", 50.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.58})},
+    "bundle": {"rings": 6, "radius": 7.0, "z0": -2.0},
+    "s_counted": 2,
+}
+
 CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
-                                       X5_DEGENERATE)})
+                                       X5_DEGENERATE, X6_BICONIC)})

@@ -47,6 +47,7 @@ struct DAux {
     int8_t xpow[PYR_MAX_COEFF];
     int8_t ypow[PYR_MAX_COEFF];
     double normradius, newton_tol;
+    double curv2, cc2;             // biconic y section
     int32_t n_coeff, newton_maxit;
     DFrame aperture_frame;
     DMedium before, after;

@@ -87,10 +87,40 @@ __device__ __forceinline__ void xypoly_eval(const DAux &a, double x, double y, d
     Fy = fy * ir;
 }
 
+// Biconic (surface_shape.py:609-706): F = (cx x^2 + cy y^2) / (1 + sq) + sum a_n u_n^(n+1),
+// sq = sqrt(1 - cx^2 (1+kx) x^2 - cy^2 (1+ky) y^2), u_n = r^2 - b_n (x^2 - y^2)
+__device__ __forceinline__ void biconic_eval(const DAux &a, double cx, double kx, double x, double y,
+                                             double &F, double &Fx, double &Fy) {
+    const double cy = a.curv2, ky = a.cc2;
+    const double x2 = x * x, y2 = y * y;
+    const double N = fma(cx, x2, cy * y2);
+    double rsq;
+    const double sq = fast_sqrt_r(fma(-cx * cx * (1.0 + kx), x2, fma(-cy * cy * (1.0 + ky), y2, 1.0)), rsq);
+    const double inv1 = fast_rcp(1.0 + sq);
+    const double common = inv1 * inv1 * rsq;
+    const double two = 2.0 * (sq + 1.0) * sq;
+    double f = N * inv1;
+    double fx = cx * x * fma(cx * (kx + 1.0), N, two) * common;
+    double fy = cy * y * fma(cy * (ky + 1.0), N, two) * common;
+    const double r2 = x2 + y2, ast2 = x2 - y2;
+    for (int i = 0; i < a.n_coeff; ++i) {
+        const double an = a.coeff[i], bn = a.coeff[16 + i];
+        const double u = fma(-bn, ast2, r2);
+        double un = 1.0;                                   // u^i
+        for (int j = 0; j < i; ++j) un *= u;
+        f = fma(an * un, u, f);
+        const double g = 2.0 * an * (i + 1) * un;
+        fx = fma(g * (1.0 - bn), x, fx);
+        fy = fma(g * (1.0 + bn), y, fy);
+    }
+    F = f; Fx = fx; Fy = fy;
+}
+
 __device__ __forceinline__ void explicit_eval(int kind, const DAux &a, double curv, double cc,
                                               double x, double y, double &F, double &Fx,
                                               double &Fy) {
     if (kind == PYR_SHAPE_ASPHERE) asphere_eval(a, curv, cc, x, y, F, Fx, Fy);
+    else if (kind == PYR_SHAPE_BICONIC) biconic_eval(a, curv, cc, x, y, F, Fx, Fy);
     else xypoly_eval(a, x, y, F, Fx, Fy);
 }
 
@@ -109,8 +139,10 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
                                              const double r0[3], const double d[3],
                                              bool active) {
     bool ok;
-    double t = (kind == PYR_SHAPE_ASPHERE) ? conic_t(curv, cc, r0, d, ok)
-                                           : -r0[2] * fast_rcp(d[2]);
+    double t;
+    if (kind == PYR_SHAPE_ASPHERE) t = conic_t(curv, cc, r0, d, ok);
+    else if (kind == PYR_SHAPE_BICONIC) t = conic_t(0.5 * (curv + a.curv2), 0.5 * (cc + a.cc2), r0, d, ok);
+    else t = -r0[2] * fast_rcp(d[2]);
     if (!isfinite(t)) t = 0.0;
     for (int it = 0; it < a.newton_maxit; ++it) {
         const double x = fma(t, d[0], r0[0]);

@@ -712,7 +712,8 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
     for (int s = 0; s < n_steps; ++s) {
         const PyrStep &u = steps[s];
         DStep &d = P.steps[s];
-        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_XYPOLY) return PYR_E_UNSUPPORTED;
+        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_BICONIC) return PYR_E_UNSUPPORTED;
+        if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > PYR_MAX_COEFF / 2) return PYR_E_BADARG;
         if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
         if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
         if (u.split && s != n_steps - 1) return PYR_E_BADARG;
@@ -760,10 +761,13 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         if (need_aux) {
             if (n_aux >= kMaxAux) return PYR_E_TOOLARGE;
             DAux &a = P.aux[n_aux];
+            const bool bic = u.shape_kind == PYR_SHAPE_BICONIC;
             for (int i = 0; i < PYR_MAX_COEFF; ++i) {
-                a.coeff[i] = i < u.n_coeff ? u.coeff[i] : 0.0;
+                const bool used = bic ? (i % 16) < u.n_coeff : i < u.n_coeff;
+                a.coeff[i] = used ? u.coeff[i] : 0.0;
                 a.xpow[i] = u.xpow[i]; a.ypow[i] = u.ypow[i];
             }
+            a.curv2 = u.curv2; a.cc2 = u.cc2;
             a.normradius = u.normradius != 0.0 ? u.normradius : 1.0;
             a.newton_tol = u.newton_tol > 0.0 ? u.newton_tol : 1e-14;
             a.n_coeff = u.n_coeff;

@@ -153,6 +153,17 @@ def lower_surface(surface, st):
         st.n_coeff = ncoef
         for i in range(ncoef):
             st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
+    elif "Biconic" in names:
+        st.shape_kind = nat.SHAPE_BICONIC
+        (st.curv, st.cc) = (_value(shape.params["curvx"]), _value(shape.params["ccx"]))
+        (st.curv2, st.cc2) = (_value(shape.params["curvy"]), _value(shape.params["ccy"]))
+        ncoef = int(shape.annotations["numcoefficients"])
+        if ncoef > nat.MAX_COEFF // 2:
+            raise LoweringError("too many biconic coefficient pairs")
+        st.n_coeff = ncoef
+        for i in range(ncoef):
+            st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
+            st.coeff[16 + i] = _value(shape.params["B" + str(2 * i + 2)])
     elif "XYPolynomials" in names:
         st.shape_kind = nat.SHAPE_XYPOLY
         terms = _xy_terms(shape)

@@ -179,6 +179,59 @@ class Asphere(ExplicitShape):
         return h
 
 
+class Biconic(ExplicitShape):
+    """Polynomial biconic (reference surface_shape.py:609-706)."""
+
+    @classmethod
+    def p(cls, lc, curvx=0, ccx=0, curvy=0, ccy=0, coefficients=None, name=""):
+        coefficients = [] if coefficients is None else list(coefficients)
+        plist = [("curvx", curvx), ("curvy", curvy), ("ccx", ccx), ("ccy", ccy)] + \
+                [("A" + str(2 * i + 2), a) for (i, (a, b)) in enumerate(coefficients)] + \
+                [("B" + str(2 * i + 2), b) for (i, (a, b)) in enumerate(coefficients)]
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc, plist)
+        ann["numcoefficients"] = len(coefficients)
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_Biconic"
+
+    def getBiconicParameters(self):
+        return (self.params["curvx"](), self.params["curvy"](), self.params["ccx"](),
+                self.params["ccy"](),
+                [(self.params["A" + str(2 * i + 2)](), self.params["B" + str(2 * i + 2)]())
+                 for i in range(self.annotations["numcoefficients"])])
+
+    def getCentralCurvature(self):
+        return 0.5 * (self.params["curvx"]() + self.params["curvy"]())
+
+    def sqrtfun(self, x, y):
+        (cx, cy, kx, ky, _) = self.getBiconicParameters()
+        return _lib(x).sqrt(1 - cx ** 2 * (1 + kx) * x * x - cy ** 2 * (1 + ky) * y * y)
+
+    def F(self, x, y):
+        (cx, cy, kx, ky, coeffs) = self.getBiconicParameters()
+        (r2, ast2) = (x * x + y * y, x * x - y * y)
+        res = (cx * x * x + cy * y * y) / (1 + self.sqrtfun(x, y))
+        for (n, (an, bn)) in enumerate(coeffs):
+            res = res + an * (r2 - bn * ast2) ** (n + 1)
+        return res
+
+    def gradF(self, x, y, z):
+        xp = _lib(x)
+        (cx, cy, kx, ky, coeffs) = self.getBiconicParameters()
+        (r2, ast2) = (x * x + y * y, x * x - y * y)
+        sq = self.sqrtfun(x, y)
+        base = cx * x * x + cy * y * y
+        den = (sq + 1) ** 2 * sq
+        gx = -cx * x * (cx * (kx + 1) * base + 2 * (sq + 1) * sq) / den
+        gy = -cy * y * (cy * (ky + 1) * base + 2 * (sq + 1) * sq) / den
+        for (n, (an, bn)) in enumerate(coeffs):
+            u = r2 - bn * ast2
+            gx = gx + 2 * an * (n + 1) * x * (bn - 1) * u ** n
+            gy = gy - 2 * an * (n + 1) * y * (bn + 1) * u ** n
+        return xp.stack((gx, gy, xp.ones_like(x)))
+
+
 class XYPolynomials(ExplicitShape):
 
     @classmethod
@@ -246,4 +299,4 @@ class XYPolynomials(ExplicitShape):
 
 
 accessible_shapes = {"shape_Conic": Conic, "shape_Asphere": Asphere,
-                     "shape_XYPolynomials": XYPolynomials}
+                     "shape_Biconic": Biconic, "shape_XYPolynomials": XYPolynomials}

@@ -75,6 +75,12 @@ def test_shapes_match_reference_fixture():
     assert np.allclose(sh.getSag(x, y), g["asph_sag"], rtol=1e-14)
     assert np.allclose(sh.getGrad(x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
     assert np.allclose(sh.getNormal(x, y), g["asph_normal"], rtol=1e-13, atol=1e-16)
+    bp = g["bic_params"]
+    sh = pb.Biconic.p(lc, curvx=bp[0], ccx=bp[1], curvy=bp[2], ccy=bp[3],
+                      coefficients=[(bp[4], bp[5]), (bp[6], bp[7])])
+    assert np.allclose(sh.getSag(x, y), g["bic_sag"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(sh.getGrad(x, y), g["bic_grad"], rtol=1e-12, atol=1e-15)
+    assert np.allclose(sh.getNormal(x, y), g["bic_normal"], rtol=1e-12, atol=1e-15)
     sh = pb.XYPolynomials.p(lc, normradius=float(g["xy_normradius"]),
                             coefficients=[(int(a), int(b), c) for (a, b, c) in g["xy_coeffs"]])
     assert np.allclose(sh.getSag(x, y), g["xy_sag"], rtol=1e-13, atol=1e-16)
@@ -148,7 +154,7 @@ def test_reference_object_graph_lowers_like_ours(name):
         (sa, sb) = (la.st, lb.st)
         for f in ("shape_kind", "aperture_kind", "interaction", "dir_mode", "n_coeff", "split"):
             assert getattr(sa, f) == getattr(sb, f), f
-        for f in ("curv", "cc", "normradius", "k_norm_hint"):
+        for f in ("curv", "cc", "curv2", "cc2", "normradius", "k_norm_hint"):
             assert getattr(sa, f) == pytest.approx(getattr(sb, f), rel=1e-15, abs=0)
         for fr in ("shape_frame", "aperture_frame"):
             assert np.allclose(list(getattr(sa, fr).r), list(getattr(sb, fr).r), atol=1e-15)

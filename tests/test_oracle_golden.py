@@ -66,6 +66,11 @@ def test_shapes_match_reference():
     sh = {"kind": "Asphere", "curv": ap[0], "cc": ap[1], "coefficients": list(ap[2:])}
     assert np.allclose(onp.shape_sag(sh, x, y), g["asph_sag"], rtol=1e-14)
     assert np.allclose(onp.shape_grad(sh, x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
+    bp = g["bic_params"]
+    sh = {"kind": "Biconic", "curvx": bp[0], "ccx": bp[1], "curvy": bp[2], "ccy": bp[3],
+          "coefficients": [(bp[4], bp[5]), (bp[6], bp[7])]}
+    assert np.allclose(onp.shape_sag(sh, x, y), g["bic_sag"], rtol=1e-14, atol=1e-18)
+    assert np.allclose(onp.shape_grad(sh, x, y), g["bic_grad"], rtol=1e-13, atol=1e-16)
     sh = {"kind": "XYPolynomials", "normradius": float(g["xy_normradius"]),
           "coefficients": [tuple(c) for c in g["xy_coeffs"]]}
     assert np.allclose(onp.shape_sag(sh, x, y), g["xy_sag"], rtol=1e-13, atol=1e-16)

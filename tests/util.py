@@ -30,7 +30,7 @@ def config_of(tag):
 
 
 def tolerance_of(name):
-    return TOL_ITERATED if name in ("c3_asphere", "c5_grin", "x2_xypoly") \
+    return TOL_ITERATED if name in ("c3_asphere", "c5_grin", "x2_xypoly", "x6_biconic") \
         else TOL_CLOSED_FORM
 
 
