@@ -215,3 +215,62 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def dump_glasscat():
+    """A handful of refractiveindex.info pages (one per dispersion formula that
+    occurs in the glass shelves) with the reference's indices at F, d, C."""
+    import glob
+    import json
+    import yaml
+    from pyrateoptics.raytracer.material.material_glasscat import CatalogMaterial
+    from pyrateoptics.raytracer.localcoordinates import LocalCoordinates
+    base = os.path.join(refshim.REFERENCE_ROOT, "pyrateoptics",
+                        "refractiveindex.info-database", "database", "data")
+    picks = ["glass/schott/N-BK7.yml", "glass/schott/SF5.yml", "glass/ohara/S-LAH64.yml",
+             "glass/hoya/FCD1.yml", "main/SiO2/Malitson.yml", "main/CaF2/Li.yml",
+             "main/H2O/Daimon-20.0C.yml", "main/Ar/Bideau-Mehu.yml", "main/Si/Edwards.yml",
+             "organic/C3H8O3 - glycerol/Rheims.yml",
+             "organic/C8H5KO4 - potassium hydrogen phthalate/Moutzouris-beta.yml",
+             "organic/C4H10O - butanol/El-Kashef.yml", "other/mixed gases/air/Ciddor.yml"]
+    extra = glob.glob(os.path.join(base, "**", "*.yml"), recursive=True)
+    for typ in ("formula 7", "tabulated n"):
+        for fn in sorted(extra):
+            try:
+                txt = open(fn).read()
+            except Exception:
+                continue
+            if ("type: " + typ + "\n") in txt and os.path.relpath(fn, base) not in picks:
+                picks.append(os.path.relpath(fn, base))
+                if sum(1 for p_ in picks if typ in open(os.path.join(base, p_)).read()) >= 3:
+                    break
+    lc = LocalCoordinates.p(name="gc")
+    out = []
+    waves = [0.4861e-3, 0.5876e-3, 0.6563e-3]
+    for rel in picks:
+        fn = os.path.join(base, rel)
+        if not os.path.exists(fn):
+            continue
+        d = yaml.safe_load(open(fn))
+        data = [e for e in d["DATA"]]
+        if any(e["type"].startswith("tabulated") and len(e["data"]) > 1500 for e in data):
+            continue
+        try:
+            mat = CatalogMaterial.p(lc, {"DATA": data})
+            (lo, hi) = (max(t.waverange[0] for t in mat.nk_table),
+                        min(t.waverange[1] for t in mat.nk_table))
+            use = waves
+            if lo > 1e3 * waves[0] or hi < 1e3 * waves[-1]:
+                use = [1e-3 * (lo + f * (hi - lo)) for f in (0.2, 0.5, 0.8)]
+            ns = [complex(mat.get_optical_index(None, w)) for w in use]
+        except Exception as exc:        # unsupported formula etc.
+            continue
+        out.append({"page": rel, "DATA": data, "waves_mm": use,
+                    "n_real": [v.real for v in ns], "n_imag": [v.imag for v in ns]})
+    json.dump(out, open(os.path.join(OUT, "glasscat.json"), "w"), indent=1)
+    print("glasscat.json", [(o["page"], o["DATA"][0]["type"]) for o in out])
+
+
+if __name__ == "__main__" and "--glasscat" in sys.argv:
+    refshim.install()
+    dump_glasscat()

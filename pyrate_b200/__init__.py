@@ -13,6 +13,7 @@ from .raytracer.globalconstants import (degree, numerical_tolerance,  # noqa: F4
                                         standard_wavelength)
 from .raytracer.localcoordinates import LocalCoordinates  # noqa: F401
 from .raytracer.material.material_anisotropic import AnisotropicMaterial  # noqa: F401
+from .raytracer.material.material_glasscat import CatalogMaterial  # noqa: F401
 from .raytracer.material.material_grin import IsotropicGrinMaterial  # noqa: F401
 from .raytracer.material.material_isotropic import (ConstantIndexGlass,  # noqa: F401
                                                     ModelGlass)
