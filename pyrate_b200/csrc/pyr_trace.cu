@@ -496,15 +496,13 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             // ---- record the step ----
             const int64_t ld = st.ld_out;
             if (TMA_OUT && (st.bits & kOutVec2)) {
-                // The warp's slice of the record (64 rays: 6 rows x 512 B + 64 flag bytes)
-                // goes through its own shared-memory stage and leaves as TMA bulk stores
-                // issued by lane 0: no per-thread global stores, no store back-pressure on
-                // the arithmetic, and only warp-level synchronisation in the step loop.
+                // The CTA's slice of the record goes through shared memory and leaves
+                // as TMA bulk stores issued by one thread: no per-thread global stores,
+                // no store back-pressure on the warps that do the arithmetic.
                 const int b = store_count & 1;
                 ++store_count;
-                const int lane = threadIdx.x & 31;
-                if (lane == 0) tma_store_wait_read<1>();            // stage b is free again
-                __syncwarp();
+                if (threadIdx.x == 0) tma_store_wait_read<1>();     // buffer b is free again
+                __syncthreads();
                 double *ob = out_buf + (size_t)b * 6 * TILE + threadIdx.x * 2;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -515,23 +513,18 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 *reinterpret_cast<uchar2 *>(out_fl + b * TILE + threadIdx.x * 2) =
                     make_uchar2((unsigned char)fl[0], (unsigned char)fl[RPT - 1]);
                 fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    const int w0 = (threadIdx.x >> 5) * 64;                 // first ray of the warp in the tile
-                    const int64_t g0 = tile * TILE + w0;
-                    const int64_t left = n - g0;
-                    if (left > 0) {
-                        const int64_t cnt = left < 64 ? left : 64;
-                        const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
-                        const double *sb = out_buf + (size_t)b * 6 * TILE + w0;
-                        for (int c = 0; c < 3; ++c) {
-                            if (st.out_x) tma_store_1d(st.out_x + c * ld + g0, sb + c * TILE, bytes);
-                            if (st.out_k) tma_store_1d(st.out_k + c * ld + g0, sb + (3 + c) * TILE, bytes);
-                        }
-                        if (st.out_flags)
-                            tma_store_1d(st.out_flags + g0, out_fl + b * TILE + w0,
-                                         (unsigned)((cnt + 15) & ~(int64_t)15));
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int64_t t0 = tile * TILE;
+                    const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
+                    const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
+                    const double *sb = out_buf + (size_t)b * 6 * TILE;
+                    for (int c = 0; c < 3; ++c) {
+                        if (st.out_x) tma_store_1d(st.out_x + c * ld + t0, sb + c * TILE, bytes);
+                        if (st.out_k) tma_store_1d(st.out_k + c * ld + t0, sb + (3 + c) * TILE, bytes);
                     }
+                    if (st.out_flags)
+                        tma_store_1d(st.out_flags + t0, out_fl + b * TILE, (unsigned)((cnt + 15) & ~(int64_t)15));
                     tma_store_commit();
                 }
                 continue;
@@ -588,7 +581,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             }
         }
     }
-    if (TMA_OUT && (threadIdx.x & 31) == 0) tma_store_wait_read<0>();   // smem must outlive the reads
+    if (TMA_OUT && threadIdx.x == 0) tma_store_wait_read<0>();      // smem must outlive the reads
 }
 
 // ---------------------------------------------------------------------------
