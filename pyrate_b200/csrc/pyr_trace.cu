@@ -499,10 +499,10 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 // The CTA's slice of the record goes through shared memory and leaves
                 // as TMA bulk stores issued by one thread: no per-thread global stores,
                 // no store back-pressure on the warps that do the arithmetic.
-                // One CTA barrier per entry: stage b was drained by the bulk group issued two
-                // entries ago, which thread 0 waited for BEFORE the previous barrier.
                 const int b = store_count & 1;
                 ++store_count;
+                if (threadIdx.x == 0) tma_store_wait_read<1>();     // stage b is drained
+                __syncthreads();
                 double *ob = out_buf + (size_t)b * 6 * TILE + threadIdx.x * 2;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
@@ -513,7 +513,6 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 *reinterpret_cast<uchar2 *>(out_fl + b * TILE + threadIdx.x * 2) =
                     make_uchar2((unsigned char)fl[0], (unsigned char)fl[RPT - 1]);
                 fence_proxy_async_smem();
-                if (threadIdx.x == 0) tma_store_wait_read<0>();     // the other stage is drained
                 __syncthreads();
                 if (threadIdx.x == 0) {
                     const int64_t t0 = tile * TILE;
