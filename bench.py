@@ -320,7 +320,7 @@ def run_gpu(args):
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                              "frac": achieved / peak, "traffic": traffic,
                              "peak_source": peak_kind + " (MEASURED_PEAKS.json hbm_gbs)",
-                             "kernel": "trace_real_kernel<2,false,false>",
+                             "kernel": "trace_real_kernel<2,false,0,2,3> (lean, TMA in/out)",
                              "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": algo_bytes},
                 "cpu_baseline": cpu, "e2e": e2e,
