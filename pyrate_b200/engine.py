@@ -10,7 +10,6 @@ raises.
 """
 import ctypes as C
 
-import numpy as np
 import torch
 
 from . import _native as nat
@@ -46,10 +45,6 @@ def require_cuda():
 
 def _round_up(v, m):
     return (v + m - 1) // m * m
-
-
-def _ptr(t):
-    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
 class TraceRecord(object):
@@ -568,16 +563,6 @@ def _single_step(st, bundle, mode, record_e=True):
         _launch(lib, [st], 0, 1, xb, kb, eb, alive_p, n, n, ld,
                 nat.F_RECORD_E, stream)
     return (ox[:, :n], ok[:, :n], oe[:, :n], of[:n])
-
-
-def _surface_step(surface, before_mat, after_mat, wave, mirror=False):
-    st = nat.PyrStep()
-    lowering.lower_surface(surface, st)
-    st.before = lowering.lower_medium(before_mat, wave)
-    st.after = lowering.lower_medium(after_mat, wave)
-    st.interaction = nat.REFLECT if mirror else nat.REFRACT
-    st.dir_mode = nat.DIR_POYNTING
-    return st
 
 
 def _probe_medium():

@@ -2,7 +2,6 @@
 reference fixtures, and -- when the reference tree is present (build container)
 -- the lowering of the reference's OWN object graph against ours."""
 import ctypes
-import os
 
 import numpy as np
 import pytest
