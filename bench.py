@@ -88,8 +88,11 @@ class ClockSampler(object):
 # ---------------------------------------------------------------------------
 # CPU arm: the oracle port (NumPy restatement of the reference's seqtrace)
 # ---------------------------------------------------------------------------
+_SHARED = {}        # bundle arrays inherited by forked workers (copy-on-write, no pickling)
+
+
 def _cpu_worker(args):
-    (rings_unused, lo, hi, x0, k0, e0) = args
+    (lo, hi) = args
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyrate_np as onp
     from pyrate_b200 import configs
@@ -98,6 +101,7 @@ def _cpu_worker(args):
         threadpoolctl.threadpool_limits(1)
     except Exception:
         pass
+    (x0, k0, e0) = (_SHARED["x0"], _SHARED["k0"], _SHARED["e0"])
     system = onp.system_from_spec(configs.CONFIGS[CONFIG])
     t = time.perf_counter()
     # cache-blocked: 1000-ray pieces keep every NumPy temporary below the
@@ -109,19 +113,21 @@ def _cpu_worker(args):
     return time.perf_counter() - t
 
 
-def cpu_pass(nrays, procs, pool=None):
-    """One pass of `nrays` rays through the oracle port on `procs` processes
-    (ray-sharded, one single-threaded NumPy process per core)."""
-    import numpy as np
+def cpu_bundle(nrays):
     from pyrate_b200 import configs
     spec = configs.CONFIGS[CONFIG]
     (x0, k0, e0) = configs.config_bundle(spec, configs.rings_for(nrays))
-    n = x0.shape[1]
-    bounds = [(i * n) // procs for i in range(procs + 1)]
-    jobs = [(0, 0, bounds[i + 1] - bounds[i],
-             np.ascontiguousarray(x0[:, bounds[i]:bounds[i + 1]]),
-             np.ascontiguousarray(k0[:, bounds[i]:bounds[i + 1]]),
-             np.ascontiguousarray(e0[:, bounds[i]:bounds[i + 1]])) for i in range(procs)]
+    _SHARED.update(x0=x0, k0=k0, e0=e0)
+    return x0.shape[1]
+
+
+def cpu_pass(n, procs, pool=None):
+    """One pass of the shared bundle through the oracle port on `procs` processes
+    (ray-sharded, one single-threaded NumPy process per core)."""
+    # many small jobs: dynamic load balance across the cores
+    njobs = procs if procs == 1 else min(max(procs * 4, 1), max(n // CPU_BLOCK, 1))
+    bounds = [(i * n) // njobs for i in range(njobs + 1)]
+    jobs = [(bounds[i], bounds[i + 1]) for i in range(njobs)]
     t = time.perf_counter()
     if procs == 1 or pool is None:
         for j in jobs:
@@ -142,14 +148,14 @@ def run_reference(args):
     except Exception:
         pass
     nrays = int(args.cpu_rays) if args.cpu_rays else min(50000 * cores, 4000000)
+    n = cpu_bundle(nrays)                       # BEFORE the fork: workers inherit the arrays
     pool = mp.get_context("fork").Pool(cores) if cores > 1 else None
     try:
         for _ in range(max(args.warmup, 1)):
-            cpu_pass(max(2000 * cores, 2000), cores, pool)
+            cpu_pass(min(n, max(2000 * cores, 2000)), cores, pool)
         total_t = 0.0
-        n = 0
         for _ in range(args.steps):
-            (n, dt) = cpu_pass(nrays, cores, pool)
+            (n, dt) = cpu_pass(n, cores, pool)
             total_t += dt
     finally:
         if pool is not None:
@@ -297,7 +303,7 @@ def run_gpu(args):
                 traffic = None
         cpu = None
         if world == 1 and not args.no_cpu:
-            (cn, cdt) = cpu_pass(int(args.cpu_rays) if args.cpu_rays else 200000, 1)
+            (cn, cdt) = cpu_pass(cpu_bundle(int(args.cpu_rays) if args.cpu_rays else 200000), 1)
             # (single process; `--impl reference` times the all-cores variant)
             cpu = {"value": cn * S_COUNTED / cdt, "unit": "ray-surfaces/s", "cores": 1,
                    "kind": "port",
