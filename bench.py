@@ -40,29 +40,70 @@ def measured_peaks():
 
 
 class ClockSampler(object):
+    """SM clock and throttle reasons sampled DURING the timed region: NVML in a
+    background thread (sub-millisecond period; nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown",
+            0x4: "sw_power_cap"}
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.sm = []
+        self.max_mhz = None
+        self.reasons = set()
         self.stop = False
         self.thread = None
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nvml = None
+
+    def _sample_nvml(self):
+        nv = self.nvml
+        self.sm.append(int(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+        try:
+            mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        except Exception:
+            mask = 0
+        for (bit, name) in self.BITS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(
+            ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+             "--format=csv,noheader,nounits"], capture_output=True, text=True,
+            timeout=5).stdout.strip().splitlines()
+        if not out:
+            return
+        c = [v.strip() for v in out[0].split(",")]
+        if c[0].isdigit():
+            self.sm.append(int(c[0]))
+        if len(c) > 1 and c[1].isdigit():
+            self.max_mhz = int(c[1])
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for i in range(4):
+            if len(c) >= 6 and c[2 + i].lower().startswith("active"):
+                self.reasons.add(names[i])
 
     def _run(self):
         while not self.stop:
             try:
-                out = subprocess.run(
-                    ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                     "--format=csv,noheader,nounits"], capture_output=True,
-                    text=True, timeout=5).stdout.strip().splitlines()
-                if out:
-                    self.samples.append([c.strip() for c in out[0].split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.0005 if self.nvml is not None else 0.05)
 
     def __enter__(self):
         self.thread = threading.Thread(target=self._run, daemon=True)
@@ -74,15 +115,10 @@ class ClockSampler(object):
         self.thread.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(s[0]) for s in self.samples if s and s[0].isdigit())
-        mx = [int(s[1]) for s in self.samples if len(s) > 1 and s[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                 "sw_power_cap"]
-        reasons = sorted({names[i] for s in self.samples if len(s) >= 6
-                          for i in range(4) if s[2 + i].lower().startswith("active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
-                "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(sm),
+                "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 # ---------------------------------------------------------------------------
