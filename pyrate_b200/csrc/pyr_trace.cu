@@ -495,6 +495,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 
             // ---- record the step ----
             const int64_t ld = st.ld_out;
+            if (!st.out_x && !st.out_k && !st.out_flags && !(WITH_E && st.out_e)) continue;   // not recorded
             if (TMA_OUT && (st.bits & kOutVec2)) {
                 // The CTA's slice of the record goes through shared memory and leaves
                 // as TMA bulk stores issued by one thread: no per-thread global stores,
@@ -653,6 +654,7 @@ trace_real_ws_kernel(const __grid_constant__ LaunchParams P) {
             for (int s = 0; s < P.n_steps; ++s) {
                 const DStep &st = sst[s];
                 if (!(st.bits & kOutVec2)) continue;      // recorded with plain stores
+                if (!st.out_x && !st.out_k && !st.out_flags) continue;   // not recorded
                 const int b = c & 1;
                 mbar_wait(&out_full[b], (c >> 1) & 1);    // all warps have filled stage b
                 const double *sb = out_buf + (size_t)b * 6 * TILE;
@@ -724,6 +726,7 @@ trace_real_ws_kernel(const __grid_constant__ LaunchParams P) {
                                                  : step_lean<false>(st, ray[j], d, hit[j]);
             }
             const int64_t ld = st.ld_out;
+            if (!st.out_x && !st.out_k && !st.out_flags) continue;      // not recorded
             if (st.bits & kOutVec2) {
                 const int b = c & 1;
                 const unsigned u = c >> 1;
