@@ -52,6 +52,7 @@ TRACES = [
     ("x4_biaxial", 3, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
     ("x5_degenerate", 2, (0, 0, 1), (0, 1, 0), False, ""),
     ("x6_biconic", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
+    ("x7_two_elements", 5, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
 ]
 
 

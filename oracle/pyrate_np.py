@@ -534,7 +534,17 @@ def seqtrace(system, x0, k0, e0, wave=0.5876e-3, splitup=False, **grin_kw):
     background = system["background"]
     current = background
     paths = [[first]]
+    prev_elem = None
     for step in system["steps"]:
+        elem = step.get("elem", 0)
+        if elem != prev_elem:
+            # a new element: its seqtrace starts in the background medium
+            # (optical_element.py:328) with a path holding the bundle it was handed
+            # (:331), which the system appends to its own path (optical_system.py:91)
+            current = background
+            for p in paths:
+                p.append(p[-1])
+            prev_elem = elem
         mirror = bool(step.get("is_mirror", False))
         mn = step["mat_minus"] if step["mat_minus"] is not None else background
         pn = step["mat_plus"] if step["mat_plus"] is not None else background
@@ -546,15 +556,14 @@ def seqtrace(system, x0, k0, e0, wave=0.5876e-3, splitup=False, **grin_kw):
         for p in paths:
             res = material_deflect(current, p[-1], step, wave, mirror, splitup)
             for rb in res[1:]:
-                q = [_copy_bundle(b) for b in p]
+                memo = {}                  # deepcopy keeps "same object twice"
+                q = [memo.setdefault(id(b), _copy_bundle(b)) for b in p]
                 q.append(rb)
                 new_paths.append(q)
             p.append(res[0])
         paths = paths + new_paths
-    # optical_system.py:74,83-91: the system-level path starts with the copied
-    # input bundle and then appends the element-level path (which starts with
-    # the very same object) -> path[0] is path[1]
-    return [[p[0]] + p for p in paths]
+    # (the very first hand-over is the copied input bundle: path[0] is path[1])
+    return paths
 
 
 # ---------------------------------------------------------------------------
@@ -620,8 +629,10 @@ def system_from_spec(spec):
             else:
                 raise NotImplementedError(mkind)
             mats[key] = m
+        split = spec.get("split_after")
         steps.append({"name": surf["name"], "shape": shape, "aperture": ap,
                       "mat_minus": mats.get(last), "mat_plus": mats.get(key),
-                      "is_mirror": bool(surf["opt"].get("is_mirror", False))})
+                      "is_mirror": bool(surf["opt"].get("is_mirror", False)),
+                      "elem": 0 if (split is None or len(steps) < split) else 1})
         last = key
     return {"background": background, "steps": steps}

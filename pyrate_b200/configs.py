@@ -216,17 +216,27 @@ CONFIGS = {c["name"]: c for c in
 
 
 def build_system(spec, api):
-    """Instantiate `spec` with the classes in `api`; returns (system, seq)."""
+    """Instantiate `spec` with the classes in `api`; returns (system, seq).
+
+    spec["split_after"] = i puts surfaces[:i] into element "stdelem" and the rest
+    into "elem2" (the ray must be in the background medium at the cut)."""
     s = api.OpticalSystem.p(name=spec["name"])
     lc0 = s.addLocalCoordinateSystem(
         api.LocalCoordinates.p(name="object_lc0", decz=0.0),
         refname=s.rootcoordinatesystem.name)
+    split = spec.get("split_after")
     elem = api.OpticalElement.p(lc0, name="stdelem")
+    elems = [("stdelem", elem, [])]
     refname = lc0.name
     lastmat = None
-    seq = []
     made = set()
-    for surf in spec["surfaces"]:
+    for (isurf, surf) in enumerate(spec["surfaces"]):
+        if split is not None and isurf == split:
+            if lastmat is not None:
+                raise ValueError("split_after must cut in the background medium")
+            elem = api.OpticalElement.p(lc0, name="elem2")
+            elems.append(("elem2", elem, []))
+            made = set()
         lc = elem.addLocalCoordinateSystem(
             api.LocalCoordinates.p(name=surf["name"] + "_lc", **surf["lc"]),
             refname=refname)
@@ -246,9 +256,10 @@ def build_system(spec, api):
         elem.addSurface(surf["name"], surface, (lastmat, mat))
         lastmat = mat
         refname = lc.name
-        seq.append((surf["name"], dict(surf["opt"])))
-    s.addElement("stdelem", elem)
-    return s, [("stdelem", seq)]
+        elems[-1][2].append((surf["name"], dict(surf["opt"])))
+    for (key, el, _) in elems:
+        s.addElement(key, el)
+    return s, [(key, seq) for (key, _, seq) in elems]
 
 
 def _make_material(api, lc, matspec, name):
@@ -389,5 +400,11 @@ X6_BICONIC = {
     "s_counted": 2,
 }
 
+X7_TWO_ELEMENTS = dict(C2_DOUBLEGAUSS, name="x7_two_elements", split_after=6,
+                       bundle={"rings": 5, "radius": 5.0, "z0": 0.0})
+# the double-Gauss cut into two OpticalElements in the air gap after s5: the element
+# sequence has two entries, each element starts again in the background medium
+# (optical_element.py:328) and the hand-over bundle appears twice in the path
+
 CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
-                                       X5_DEGENERATE, X6_BICONIC)})
+                                       X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS)})

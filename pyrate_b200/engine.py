@@ -501,10 +501,14 @@ def paths_from_record(rec, splitup=False):
         splitted = bool(nsteps >= 1 and rec.split[nsteps - 1] and not splitup)
         bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
                                  wave=rec.wave, splitted=splitted))
+        # every element's seqtrace starts its path with the bundle it was handed
+        # (optical_element.py:331) and the system appends that path to its own
+        # (optical_system.py:83-91): the hand-over bundle appears twice
         path = RayPath(bundles[0])
-        path.appendRayBundle(bundles[0])          # path[0] is path[1]
-        for rb in bundles[1:]:
-            path.appendRayBundle(rb)
+        for s in range(nsteps):
+            if s == 0 or rec.lowered[s].elem_index != rec.lowered[s - 1].elem_index:
+                path.appendRayBundle(path.raybundles[-1])
+            path.appendRayBundle(bundles[s + 1])
         paths.append(path)
     return paths
 

@@ -203,7 +203,7 @@ def lower_surface(surface, st):
 
 class LoweredStep(object):
     """One PyrStep plus the bookkeeping the host needs."""
-    __slots__ = ("st", "elemkey", "surfkey", "before_obj", "after_obj",
+    __slots__ = ("st", "elemkey", "elem_index", "surfkey", "before_obj", "after_obj",
                  "is_aniso_deflect", "is_stop")
 
     def __init__(self):
@@ -216,7 +216,7 @@ def lower(system, elementsequence, wave, splitup=False):
     background = system.material_background
     out = []
     last_deflector = None          # medium object that set |k| last
-    for (elemkey, subseq) in elementsequence:
+    for (elem_index, (elemkey, subseq)) in enumerate(elementsequence):
         if elemkey not in system.elements:
             raise LoweringError("unknown element %r" % (elemkey,))
         elem = system.elements[elemkey]
@@ -252,6 +252,7 @@ def lower(system, elementsequence, wave, splitup=False):
             st.split = 1 if (ls.is_aniso_deflect) else 0
             st.mode = nat.STEP_FULL
             ls.elemkey = elemkey
+            ls.elem_index = elem_index
             ls.surfkey = surfkey
             ls.before_obj = before
             ls.after_obj = after
