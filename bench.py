@@ -174,10 +174,15 @@ def cpu_pass(n, procs, pool=None):
 
 
 def run_reference(args):
-    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # one process per core: BLAS/OpenMP pools must not spawn (and spin) a thread
+    # per core inside every worker -- set before NumPy is first imported
+    for var in ("OPENBLAS_NUM_THREADS", "OMP_NUM_THREADS", "MKL_NUM_THREADS",
+                "NUMEXPR_NUM_THREADS"):
+        os.environ[var] = "1"
+    import multiprocessing as mp
     cores = os.cpu_count() or 1
     try:
         cores = len(os.sched_getaffinity(0))

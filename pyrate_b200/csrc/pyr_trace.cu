@@ -586,180 +586,6 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 }
 
 // ---------------------------------------------------------------------------
-// Warp-specialised variant of the real-valued kernel (two rays per thread, no E
-// record): 8 arithmetic warps + 1 I/O warp per CTA.  The I/O warp's lane 0 owns every
-// TMA operation (input tiles, record stages); arithmetic warps hand stages over through
-// mbarriers only, so they never wait for each other at a CTA barrier -- only for a free
-// record stage.
-// ---------------------------------------------------------------------------
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
-template <int FEAT>
-__global__ void __launch_bounds__(288, 2)
-trace_real_ws_kernel(const __grid_constant__ LaunchParams P) {
-    constexpr int RPT = 2, NCOMP = 256, TILE = NCOMP * RPT;
-    constexpr bool GENERAL = FEAT != 0;
-    const int64_t n = P.n;
-    __shared__ DStep sst[kMaxSteps];
-    __shared__ __align__(8) unsigned long long in_full, in_empty, out_full[2], out_empty[2];
-    extern __shared__ __align__(128) double stage_buf[];          // [9][TILE] in, [2][6][TILE] out
-    double *out_buf = stage_buf + (size_t)9 * TILE;
-    unsigned char *out_fl = reinterpret_cast<unsigned char *>(out_buf + 2 * 6 * TILE);
-    {
-        const uint64_t *src = reinterpret_cast<const uint64_t *>(P.steps);
-        uint64_t *dst = reinterpret_cast<uint64_t *>(sst);
-        const int words = P.n_steps * (int)(sizeof(DStep) / 8);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
-    const bool io_thread = threadIdx.x == NCOMP;
-    if (io_thread) {
-        mbar_init(&in_full, 1);
-        mbar_init(&in_empty, NCOMP / 32);
-        for (int b = 0; b < 2; ++b) { mbar_init(&out_full[b], NCOMP / 32); mbar_init(&out_empty[b], 1); }
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const bool need_e0 = sst[0].dir_mode == PYR_DIR_POYNTING;
-    const bool load_e = need_e0 && P.e != nullptr;
-    const int rows = load_e ? 9 : 6;
-    auto issue_tile = [&](int64_t tile) {
-        const int64_t t0 = tile * TILE;
-        const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
-        const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
-        mbar_expect_tx(&in_full, bytes * rows);
-        for (int c = 0; c < 3; ++c) {
-            tma_load_1d(stage_buf + c * TILE, P.x + c * P.ld_in + t0, bytes, &in_full);
-            tma_load_1d(stage_buf + (3 + c) * TILE, P.k + c * P.ld_in + t0, bytes, &in_full);
-            if (load_e) tma_load_1d(stage_buf + (6 + c) * TILE, P.e + c * P.ld_in + t0, bytes, &in_full);
-        }
-    };
-
-    if (threadIdx.x >= NCOMP) {
-        // ---------------- I/O warp ----------------
-        if (!io_thread) return;
-        unsigned c = 0;                                   // record groups issued so far
-        int it = 0;
-        if ((int64_t)blockIdx.x * TILE < n) issue_tile(blockIdx.x);
-        for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
-            const int64_t next = tile + gridDim.x;
-            if (next * TILE < n) {
-                mbar_wait(&in_empty, it & 1);             // every warp has drained the input stage
-                issue_tile(next);
-            }
-            const int64_t t0 = tile * TILE;
-            const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
-            const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
-            for (int s = 0; s < P.n_steps; ++s) {
-                const DStep &st = sst[s];
-                if (!(st.bits & kOutVec2)) continue;      // recorded with plain stores
-                if (!st.out_x && !st.out_k && !st.out_flags) continue;   // not recorded
-                const int b = c & 1;
-                mbar_wait(&out_full[b], (c >> 1) & 1);    // all warps have filled stage b
-                const double *sb = out_buf + (size_t)b * 6 * TILE;
-                for (int q = 0; q < 3; ++q) {
-                    if (st.out_x) tma_store_1d(st.out_x + q * st.ld_out + t0, sb + q * TILE, bytes);
-                    if (st.out_k) tma_store_1d(st.out_k + q * st.ld_out + t0, sb + (3 + q) * TILE, bytes);
-                }
-                if (st.out_flags)
-                    tma_store_1d(st.out_flags + t0, out_fl + b * TILE, (unsigned)((cnt + 15) & ~(int64_t)15));
-                tma_store_commit();
-                tma_store_wait_read<0>();                 // stage b drained
-                mbar_arrive(&out_empty[b]);
-                ++c;
-            }
-        }
-        return;
-    }
-
-    // ---------------- arithmetic warps ----------------
-    const int lane = threadIdx.x & 31;
-    unsigned c = 0;
-    int it = 0;
-    for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
-        const int64_t base = tile * TILE + (int64_t)threadIdx.x * RPT;
-        Ray<true> in[RPT];
-        bool in_range[RPT];
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
-        mbar_wait(&in_full, it & 1);
-        {
-            const double *src = stage_buf + threadIdx.x * RPT;
-#pragma unroll
-            for (int q = 0; q < 3; ++q) {
-                const double2 vx = *reinterpret_cast<const double2 *>(src + q * TILE);
-                const double2 vk = *reinterpret_cast<const double2 *>(src + (3 + q) * TILE);
-                in[0].x[q] = vx.x; in[1].x[q] = vx.y;
-                in[0].k[q] = vk.x; in[1].k[q] = vk.y;
-                double2 ve = make_double2(q == 1 ? 1.0 : 0.0, q == 1 ? 1.0 : 0.0);
-                if (load_e) ve = *reinterpret_cast<const double2 *>(src + (6 + q) * TILE);
-                in[0].e[q] = ve.x; in[1].e[q] = ve.y;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&in_empty);
-        Ray<false> ray[RPT];
-#pragma unroll
-        for (int j = 0; j < RPT; ++j) {
-#pragma unroll
-            for (int q = 0; q < 3; ++q) { ray[j].x[q] = in[j].x[q]; ray[j].k[q] = in[j].k[q]; }
-            const int64_t i = in_range[j] ? base + j : 0;
-            ray[j].alive = in_range[j] && (P.alive ? (P.alive[i] & PYR_RAY_ALIVE) != 0 : true);
-            if (!ray[j].alive) { ray[j].k[0] = ray[j].k[1] = ray[j].k[2] = qnan(); }
-        }
-        for (int s = 0; s < P.n_steps; ++s) {
-            const DStep &st = sst[s];
-            double hit[RPT][3];
-            uint32_t fl[RPT];
-#pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                double d[3];
-                if (st.dir_mode == PYR_DIR_POYNTING && s == 0) {
-                    poynting_dir(ray[j].k, in[j].e, d);
-                } else {
-                    const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm
-                                                            : fast_rsqrt(dot3(ray[j].k, ray[j].k));
-                    d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
-                }
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<false, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j])
-                                                 : step_lean<false>(st, ray[j], d, hit[j]);
-            }
-            const int64_t ld = st.ld_out;
-            if (!st.out_x && !st.out_k && !st.out_flags) continue;      // not recorded
-            if (st.bits & kOutVec2) {
-                const int b = c & 1;
-                const unsigned u = c >> 1;
-                ++c;
-                if (u > 0) mbar_wait(&out_empty[b], (u - 1) & 1);      // previous use of stage b drained
-                double *ob = out_buf + (size_t)b * 6 * TILE + threadIdx.x * 2;
-#pragma unroll
-                for (int q = 0; q < 3; ++q) {
-                    *reinterpret_cast<double2 *>(ob + q * TILE) = make_double2(hit[0][q], hit[1][q]);
-                    *reinterpret_cast<double2 *>(ob + (3 + q) * TILE) = make_double2(ray[0].k[q], ray[1].k[q]);
-                }
-                *reinterpret_cast<uchar2 *>(out_fl + b * TILE + threadIdx.x * 2) =
-                    make_uchar2((unsigned char)fl[0], (unsigned char)fl[1]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&out_full[b]);
-            } else {
-#pragma unroll
-                for (int j = 0; j < RPT; ++j)
-                    if (in_range[j]) {
-#pragma unroll
-                        for (int q = 0; q < 3; ++q) {
-                            if (st.out_x) store_stream<0>(st.out_x + q * ld + base + j, hit[j][q]);
-                            if (st.out_k) store_stream<0>(st.out_k + q * ld + base + j, ray[j].k[q]);
-                        }
-                        if (st.out_flags) st.out_flags[base + j] = (uint8_t)fl[j];
-                    }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------
 // spot sums (analysis/ray_analysis.py:44-86): sum x, count, sum x^2
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -997,26 +823,6 @@ static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream,
     return e == cudaSuccess ? PYR_OK : (int)e;
 }
 
-template <typename K>
-static int launch_ws(K kernel, const LaunchParams &P, cudaStream_t stream) {
-    const int threads = 288;
-    const size_t tile = 512;
-    const size_t smem = tile * 9 * 8 + 2 * tile * 6 * 8 + 2 * tile;
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    const int64_t work = (P.n + (int64_t)tile - 1) / (int64_t)tile;
-    int64_t grid = (int64_t)sm_count() * per_sm;
-    if (work < grid) grid = work;
-    if (grid < 1) return PYR_OK;
-    kernel<<<(unsigned)grid, threads, smem, stream>>>(P);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? PYR_OK : (int)e;
-}
-
 int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                   uint32_t flags, cudaStream_t stream);   // pyr_aniso.cu
 
@@ -1033,30 +839,15 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
     if (!pk.general) {
         if (with_e) return launch(trace_real_kernel<2, true, 0>, pk.P, 2, stream);
-        // tuning knob (not part of the ABI), used by tools/gpu_variants.sh to A/B kernel
-        // configurations: launch bounds, rays per thread, record-store policy
+        // PYR_LEAN_VARIANT=50 selects per-thread STG records instead of the TMA record
+        // path (A/B knob for tools/; not part of the ABI).  Other configurations that
+        // were measured and rejected are listed in profiles/r01_final_kernels.md.
         static const int variant = [] {
             const char *e = std::getenv("PYR_LEAN_VARIANT");
             return e ? std::atoi(e) : 0;
         }();
-        switch (variant) {
-            case 1: return launch(trace_real_kernel<2, false, 0, 1>, pk.P, 2, stream);
-            case 3: return launch(trace_real_kernel<2, false, 0, 3>, pk.P, 2, stream);
-            case 4: return launch(trace_real_kernel<2, false, 0, 4>, pk.P, 2, stream);
-            case 11: return launch(trace_real_kernel<1, false, 0, 4>, pk.P, 1, stream);
-            case 12: return launch(trace_real_kernel<1, false, 0, 6>, pk.P, 1, stream);
-            case 31: return launch(trace_real_kernel<2, false, 0, 2, 1>, pk.P, 2, stream);
-            case 32: return launch(trace_real_kernel<2, false, 0, 2, 2>, pk.P, 2, stream);
-            case 33: return launch(trace_real_kernel<2, false, 0, 3, 1>, pk.P, 2, stream);
-            case 50: return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);   // STG records
-            case 70:    // warp-specialised I/O (needs the aligned, 1:1 input layout)
-                if (pk.P.in_vec2 && !pk.P.alive) return launch_ws(trace_real_ws_kernel<0>, pk.P, stream);
-                return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
-            case 61: return launch(trace_real_kernel<2, false, 0, 4, 3, 128>, pk.P, 2, stream, true, 128);
-            case 62: return launch(trace_real_kernel<2, false, 0, 5, 3, 96>, pk.P, 2, stream, true, 96);
-            case 63: return launch(trace_real_kernel<2, false, 0, 1, 3, 512>, pk.P, 2, stream, true, 512);
-            default: return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
-        }
+        if (variant == 50) return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
+        return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
     }
     bool has_grin = false;
     for (int s = 0; s < n_steps; ++s)
