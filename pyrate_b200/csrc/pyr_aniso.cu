@@ -321,7 +321,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             double t;
             bool hit_ok = true;
             if (st.shape_kind == PYR_SHAPE_CONIC) t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
-            else t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok);
+            else { double gfx, gfy; bool gok; t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
             const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
             double hit_g[3];
             l2g_point(st.frame, h, hit_g);

@@ -134,28 +134,35 @@ __device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv
 
 // Newton iteration on f(t) = z0 + t dz - F(x0 + t dx, y0 + t dy), seeded with the
 // base-conic hit (plane for XY polynomials).  The warp leaves the loop together
-// (__all_sync vote on the step size), capped at `maxit`.
+// (__all_sync vote on the step size), capped at `maxit`.  On return (gx, gy) hold
+// dF/dx, dF/dy of the last evaluation and `grad_ok` tells whether that evaluation
+// was within the convergence tolerance of the returned point -- then the surface
+// normal can reuse it instead of evaluating the shape once more.
 __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double curv, double cc,
                                              const double r0[3], const double d[3],
-                                             bool active) {
+                                             bool active, double &gx, double &gy, bool &grad_ok) {
     bool ok;
     double t;
     if (kind == PYR_SHAPE_ASPHERE) t = conic_t(curv, cc, r0, d, ok);
     else if (kind == PYR_SHAPE_BICONIC) t = conic_t(0.5 * (curv + a.curv2), 0.5 * (cc + a.cc2), r0, d, ok);
     else t = -r0[2] * fast_rcp(d[2]);
     if (!isfinite(t)) t = 0.0;
+    grad_ok = false;
+    gx = gy = 0.0;
     for (int it = 0; it < a.newton_maxit; ++it) {
         const double x = fma(t, d[0], r0[0]);
         const double y = fma(t, d[1], r0[1]);
-        double F, Fx, Fy;
-        explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
+        double F;
+        explicit_eval(kind, a, curv, cc, x, y, F, gx, gy);
         const double res = fma(t, d[2], r0[2]) - F;
-        const double dres = d[2] - fma(Fx, d[0], Fy * d[1]);
+        const double dres = d[2] - fma(gx, d[0], gy * d[1]);
         double step = fast_div(res, dres);
         const bool bad = !isfinite(step);
         if (bad) step = 0.0;
         t -= step;
-        const bool done = bad || !active || fabs(step) <= a.newton_tol * (1.0 + fabs(t));
+        const bool conv = fabs(step) <= a.newton_tol * (1.0 + fabs(t));
+        grad_ok = conv && !bad;
+        const bool done = bad || !active || conv;
         if (__all_sync(__activemask(), done)) break;
     }
     return t;
@@ -166,6 +173,11 @@ __device__ __forceinline__ void explicit_normal(int kind, const DAux &a, double 
                                                 double x, double y, double n[3]) {
     double F, Fx, Fy;
     explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
+    const double inv = fast_rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
+    n[0] = -Fx * inv; n[1] = -Fy * inv; n[2] = inv;
+}
+
+__device__ __forceinline__ void normal_from_gradient(double Fx, double Fy, double n[3]) {
     const double inv = fast_rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
     n[0] = -Fx * inv; n[1] = -Fy * inv; n[2] = inv;
 }

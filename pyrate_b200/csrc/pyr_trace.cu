@@ -159,12 +159,14 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     // ---- intersect ----
     double t;
     bool hit_ok = true;
+    double gfx = 0.0, gfy = 0.0;
+    bool grad_ok = false;
     if (GENERAL && (st.bits & kNoIntersect)) {
         t = 0.0;
     } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
     } else {
-        t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok);
+        t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
     }
     const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
     if (st.bits & kRotIdentity) {
@@ -195,6 +197,9 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     double nrm[3];
     if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
+    } else if (grad_ok) {
+        // gradient of the converged Newton iterate: within tol of the hit point
+        normal_from_gradient(gfx, gfy, nrm);
     } else {
         explicit_normal(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
     }
@@ -373,12 +378,15 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int TILE = BLOCK * RPT;
     // POLICY 3 (TMA record stores) stages the outputs in shared memory as well and
     // therefore keeps a single input stage (prefetch distance: one tile = 13 steps)
-    constexpr bool TMA_OUT = POLICY == 3 && RPT == 2 && !WITH_E;
+    constexpr bool TMA_OUT = POLICY == 3 && RPT == 2;
     constexpr int IN_STAGES = TMA_OUT ? 1 : 2;
+    // record stages: x, k (and E) rows; E recording has room for one stage only
+    constexpr int OUT_ROWS = WITH_E ? 9 : 6;
+    constexpr int OUT_STAGES = WITH_E ? 1 : 2;
     extern __shared__ __align__(128) double stage_buf[];          // [IN_STAGES][9][TILE] (+ out)
     __shared__ __align__(8) unsigned long long full_bar[2];
-    double *out_buf = stage_buf + (size_t)IN_STAGES * 9 * TILE;   // [2][6][TILE] doubles
-    unsigned char *out_fl = reinterpret_cast<unsigned char *>(out_buf + 2 * 6 * TILE);   // [2][TILE]
+    double *out_buf = stage_buf + (size_t)IN_STAGES * 9 * TILE;   // [OUT_STAGES][OUT_ROWS][TILE]
+    unsigned char *out_fl = reinterpret_cast<unsigned char *>(out_buf + OUT_STAGES * OUT_ROWS * TILE);
     unsigned store_count = 0;
     const bool staged = P.in_vec2 != 0;
     const int rows = load_e ? 9 : 6;
@@ -500,16 +508,19 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 // The CTA's slice of the record goes through shared memory and leaves
                 // as TMA bulk stores issued by one thread: no per-thread global stores,
                 // no store back-pressure on the warps that do the arithmetic.
-                const int b = store_count & 1;
+                const int b = store_count % OUT_STAGES;
                 ++store_count;
-                if (threadIdx.x == 0) tma_store_wait_read<1>();     // stage b is drained
+                if (threadIdx.x == 0) tma_store_wait_read<OUT_STAGES - 1>();   // stage b is drained
                 __syncthreads();
-                double *ob = out_buf + (size_t)b * 6 * TILE + threadIdx.x * 2;
+                double *ob = out_buf + (size_t)b * OUT_ROWS * TILE + threadIdx.x * 2;
 #pragma unroll
                 for (int c = 0; c < 3; ++c) {
                     *reinterpret_cast<double2 *>(ob + c * TILE) = make_double2(hit[0][c], hit[RPT - 1][c]);
                     *reinterpret_cast<double2 *>(ob + (3 + c) * TILE) =
                         make_double2(ray[0].k[c], ray[RPT - 1].k[c]);
+                    if (WITH_E)
+                        *reinterpret_cast<double2 *>(ob + (6 + c) * TILE) =
+                            make_double2(ray[0].e[c], ray[RPT - 1].e[c]);
                 }
                 *reinterpret_cast<uchar2 *>(out_fl + b * TILE + threadIdx.x * 2) =
                     make_uchar2((unsigned char)fl[0], (unsigned char)fl[RPT - 1]);
@@ -519,10 +530,11 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                     const int64_t t0 = tile * TILE;
                     const int64_t cnt = (n - t0 < TILE) ? n - t0 : TILE;
                     const unsigned bytes = (unsigned)(((cnt + 1) & ~(int64_t)1) * 8);
-                    const double *sb = out_buf + (size_t)b * 6 * TILE;
+                    const double *sb = out_buf + (size_t)b * OUT_ROWS * TILE;
                     for (int c = 0; c < 3; ++c) {
                         if (st.out_x) tma_store_1d(st.out_x + c * ld + t0, sb + c * TILE, bytes);
                         if (st.out_k) tma_store_1d(st.out_k + c * ld + t0, sb + (3 + c) * TILE, bytes);
+                        if (WITH_E && st.out_e) tma_store_1d(st.out_e + c * ld + t0, sb + (6 + c) * TILE, bytes);
                     }
                     if (st.out_flags)
                         tma_store_1d(st.out_flags + t0, out_fl + b * TILE, (unsigned)((cnt + 15) & ~(int64_t)15));
@@ -801,11 +813,12 @@ int sm_count() {
 
 template <typename K>
 static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, bool tma_out = false,
-                  int threads = 256) {          // must equal the kernel's BLOCK template argument
+                  bool with_e = false, int threads = 256) {   // threads == kernel's BLOCK argument
     // dynamic shared memory: input stages of rpt x 9 doubles per thread (two, or one plus
     // two output stages of rpt x 6 doubles + flag bytes when records leave through the TMA)
     const size_t tile = (size_t)threads * rpt;
-    const size_t smem = tma_out ? tile * 9 * 8 + 2 * tile * 6 * 8 + 2 * tile
+    const size_t out_stages = with_e ? 1 : 2, out_rows = with_e ? 9 : 6;
+    const size_t smem = tma_out ? tile * 9 * 8 + out_stages * out_rows * tile * 8 + out_stages * tile
                                 : 2 * tile * 9 * 8;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
@@ -838,7 +851,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
     if (!pk.general) {
-        if (with_e) return launch(trace_real_kernel<2, true, 0>, pk.P, 2, stream);
+        if (with_e) return launch(trace_real_kernel<2, true, 0, 2, 3>, pk.P, 2, stream, true, true);
         // PYR_LEAN_VARIANT=50 selects per-thread STG records instead of the TMA record
         // path (A/B knob for tools/; not part of the ABI).  Other configurations that
         // were measured and rejected are listed in profiles/r01_final_kernels.md.
@@ -857,7 +870,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
                     // more resident warps
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
-    return with_e ? launch(trace_real_kernel<2, true, 1>, pk.P, 2, stream)
+    return with_e ? launch(trace_real_kernel<2, true, 1, 2, 3>, pk.P, 2, stream, true, true)
                   : launch(trace_real_kernel<2, false, 1, 2, 3>, pk.P, 2, stream, true);
 }
 
