@@ -53,6 +53,7 @@ TRACES = [
     ("x5_degenerate", 2, (0, 0, 1), (0, 1, 0), False, ""),
     ("x6_biconic", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
     ("x7_two_elements", 5, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
+    ("x8_crystal_mirror", 2, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
 ]
 
 
@@ -75,7 +76,7 @@ def dump_trace(api, name, rings, kdir, efield, splitup, tag):
             out[pre + "k"] = np.asarray(rb.k)[sel]
             out[pre + "valid"] = np.asarray(rb.valid)[sel]
             out[pre + "rayID"] = np.asarray(rb.rayID, dtype=np.int64)
-            if np.iscomplexobj(rb.Efield) or name.startswith(("c4", "x4", "x5")):
+            if np.iscomplexobj(rb.Efield) or name.startswith(("c4", "x4", "x5", "x8")):
                 out[pre + "E"] = np.asarray(rb.Efield)[sel]
     fn = os.path.join(OUT, "seqtrace_%s%s.npz" % (name, tag))
     np.savez_compressed(fn, **out)

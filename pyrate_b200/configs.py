@@ -406,5 +406,22 @@ X7_TWO_ELEMENTS = dict(C2_DOUBLEGAUSS, name="x7_two_elements", split_after=6,
 # sequence has two entries, each element starts again in the background medium
 # (optical_element.py:328) and the hand-over bundle appears twice in the path
 
+X8_CRYSTAL_MIRROR = {   # reflection inside a birefringent medium
+    # (material_anisotropic.py:115-155: modes [0], [1] of the Poynting sort, negated)
+    "name": "x8_crystal_mirror",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 2.0, curv=1. / 45.0, mat="crystal", aperture=_circ(9.0)),
+        _conic("mirror", 5.0, curv=-1. / 80.0, mat="crystal", opt={"is_mirror": True},
+               tiltx=4.0 * math.pi / 180.0),
+        _conic("exit", 6.0, curv=0.0, mat=None),
+        _conic("image", 20.0),
+    ],
+    "materials": {"crystal": ("AnisotropicMaterial", {"epstensor": _EPS1})},
+    "bundle": {"rings": 2, "radius": 5.0, "z0": -2.0},
+    "s_counted": 3,
+}
+
 CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
-                                       X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS)})
+                                       X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
+                                       X8_CRYSTAL_MIRROR)})

@@ -12,7 +12,7 @@ import util
 
 pytestmark = pytest.mark.gpu
 
-REAL_TAGS = [t for t in util.golden_traces() if not t.startswith(("c4", "x4", "x5"))]
+REAL_TAGS = [t for t in util.golden_traces() if not t.startswith(("c4", "x4", "x5", "x8"))]
 
 
 def _device_paths(name, x0, k0, e0, splitup=False, record_efield=False):
@@ -149,7 +149,8 @@ def test_host_entry_matches_device_path():
     assert np.isclose(rms, onp.rms_spot(full, onp.centroid(full)), rtol=1e-10)
 
 
-ANISO_TAGS = ["c4_anisotropic", "c4_anisotropic_split", "x4_biaxial", "x5_degenerate"]
+ANISO_TAGS = ["c4_anisotropic", "c4_anisotropic_split", "x4_biaxial", "x5_degenerate",
+              "x8_crystal_mirror"]
 
 
 @pytest.mark.parametrize("tag", ANISO_TAGS)
