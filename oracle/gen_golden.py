@@ -215,7 +215,7 @@ def main():
     dump_aniso(api)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not ({"--rasters", "--glasscat"} & set(sys.argv)):
     main()
 
 
@@ -271,6 +271,37 @@ def dump_glasscat():
                     "n_real": [v.real for v in ns], "n_imag": [v.imag for v in ns]})
     json.dump(out, open(os.path.join(OUT, "glasscat.json"), "w"), indent=1)
     print("glasscat.json", [(o["page"], o["DATA"][0]["type"]) for o in out])
+
+
+def dump_rasters():
+    """sampling2d rasters and OpticalSystemAnalysis bundle generators of the
+    reference (sampling2d/raster.py, analysis/optical_system_analysis.py:83-165)."""
+    from pyrateoptics.sampling2d import raster
+    from pyrateoptics.raytracer.analysis.optical_system_analysis import OpticalSystemAnalysis
+    out = {}
+    for (nm, n) in (("RectGrid", 60), ("HexGrid", 60), ("MeridionalFan", 11), ("SagitalFan", 7),
+                    ("ChiefAndComa", 6), ("Single", 1), ("CircularGrid", 49)):
+        (x, y) = getattr(raster, nm)().getGrid(n)
+        out[nm + "_x"] = x
+        out[nm + "_y"] = y
+        out[nm + "_n"] = np.int64(n)
+    api = refshim.api()
+    (s, seq) = configs.build_system(configs.CONFIGS["c1_doublet"], api)
+    osa = OpticalSystemAnalysis(s, seq)
+    props = {"radius": 11.43, "startz": -5.0, "starty": 0.3, "anglex": 0.02, "angley": -0.01,
+             "raster": raster.RectGrid()}
+    (o, k, e) = osa.collimated_bundle(40, props, wave=configs.DLINE)
+    (out["coll_o"], out["coll_k"], out["coll_e"]) = (o, k, e)
+    props = {"radius": 0.2, "startz": -50.0, "anglex": 0.01, "raster": raster.HexGrid()}
+    (o, k, e) = osa.divergent_bundle(40, props, wave=configs.DLINE)
+    (out["div_o"], out["div_k"], out["div_e"]) = (o, k, e)
+    np.savez_compressed(os.path.join(OUT, "rasters.npz"), **out)
+    print("rasters.npz")
+
+
+if __name__ == "__main__" and "--rasters" in sys.argv:
+    refshim.install()
+    dump_rasters()
 
 
 if __name__ == "__main__" and "--glasscat" in sys.argv:

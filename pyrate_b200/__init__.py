@@ -106,3 +106,7 @@ def build_simple_optical_system(builduplist, material_db_path="", name=""):
     s.addElement("stdelem", elem)
     s.material_background.set_name("background")
     return (s, [elem_seq])
+
+from .raytracer.analysis.optical_system_analysis import (OpticalSystemAnalysis,  # noqa: E402,F401
+                                                         raytrace)
+from .raytracer.analysis.ray_analysis import RayBundleAnalysis  # noqa: E402,F401

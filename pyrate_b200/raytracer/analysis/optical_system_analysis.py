@@ -1,0 +1,136 @@
+"""Bundle generation and trace wrappers (host API mirror of reference
+raytracer/analysis/optical_system_analysis.py:43-320): the callers right above
+`seqtrace`.  Bundles are built on the host in O(N) NumPy -- the reference runs a
+3x3 generalised eigen-solve PER RAY for this even in vacuum
+(material/material.py:476-497) -- and every trace goes through the native engine.
+"""
+import numpy as np
+
+from ...sampling2d.raster import RectGrid
+from ..globalconstants import degree, standard_wavelength
+from ..ray import RayBundle
+from .ray_analysis import RayBundleAnalysis
+
+
+def _perpendicular_unit(direction):
+    """Some unit E with E.d = 0 per column (the reference's choice comes out of an
+    eigen-solver and is arbitrary in the plane)."""
+    d = np.asarray(direction, dtype=float)
+    axis = np.zeros_like(d)
+    axis[np.argmin(np.abs(d), axis=0), np.arange(d.shape[1])] = 1.0
+    e = axis - np.sum(axis * d, axis=0) / np.sum(d * d, axis=0) * d
+    return e / np.sqrt(np.sum(e * e, axis=0))
+
+
+class OpticalSystemAnalysis(object):
+
+    def __init__(self, os, seq, name=""):
+        self.opticalsystem = os
+        self.sequence = seq
+        self.name = name
+        self.field_raster = RectGrid()
+        self.pupil_raster = RectGrid()
+        self.initial_bundles = None
+
+    # ---- bundle generation (reference :83-165) ----
+    def _background_index(self, wave):
+        mat = self.opticalsystem.material_background
+        names = {c.__name__ for c in type(mat).__mro__}
+        if "IsotropicMaterial" not in names or "IsotropicGrinMaterial" in names:
+            raise NotImplementedError("bundle generation needs a homogeneous isotropic "
+                                      "background medium")
+        return float(mat.get_optical_index(None, wave))
+
+    def _bundle(self, origin, unit, wave):
+        n = self._background_index(wave)
+        return (origin, n * unit, _perpendicular_unit(unit))
+
+    def collimated_bundle(self, nrays, properties_dict=None, wave=standard_wavelength):
+        p = properties_dict or {}
+        raster = p.get("raster", RectGrid())
+        radius = p.get("radius", 1.0)
+        (ay, ax) = (p.get("angley", 0.0), p.get("anglex", 0.0))
+        (px, py) = raster.getGrid(nrays)
+        origin = np.vstack((radius * px + p.get("startx", 0.),
+                            radius * py + p.get("starty", 0.),
+                            p.get("startz", 0.) * np.ones_like(px)))
+        unit = np.empty_like(origin)
+        unit[0] = np.sin(ay) * np.cos(ax)
+        unit[1] = np.sin(ax)
+        unit[2] = np.cos(ay) * np.cos(ax)
+        return self._bundle(origin, unit, wave)
+
+    def divergent_bundle(self, nrays, properties_dict=None, wave=standard_wavelength):
+        p = properties_dict or {}
+        raster = p.get("raster", RectGrid())
+        radius = p.get("radius", 45.0 * degree)
+        (ay, ax) = (p.get("angley", 0.0), p.get("anglex", 0.0))
+        (gx, gy) = raster.getGrid(nrays)
+        origin = np.vstack((p.get("startx", 0.) * np.ones_like(gx),
+                            p.get("starty", 0.) * np.ones_like(gx),
+                            p.get("startz", 0.) * np.ones_like(gx)))
+        unit = np.empty_like(origin)
+        unit[0] = np.sin(ay + radius * gx) * np.cos(ax + radius * gy)
+        unit[1] = np.sin(ax + radius * gy)
+        unit[2] = np.cos(ay + radius * gx) * np.cos(ax + radius * gy)
+        return self._bundle(origin, unit, wave)
+
+    def aim(self, numrays, rays_dict, bundletype="collimated", wave=standard_wavelength):
+        make = {"collimated": self.collimated_bundle,
+                "divergent": self.divergent_bundle}[bundletype]
+        (org, kvec, evec) = make(numrays, rays_dict, wave=wave)
+        self.initial_bundles = [RayBundle(x0=org, k0=kvec, Efield0=evec, wave=wave)]
+
+    # ---- traces (reference :184-260) ----
+    def trace(self, **kwargs):
+        return [self.opticalsystem.seqtrace(ib, self.sequence, **kwargs)
+                for ib in self.initial_bundles]
+
+    def trace_3d_global(self, x0, k0, wave=standard_wavelength, **kwargs):
+        n = np.shape(x0)[1]
+        e0 = np.zeros((3, n))
+        e0[1] = 1.0                                   # canonical_ey, reference :205-207
+        self.initial_bundles = [RayBundle(x0, k0, e0, wave=wave)]
+        return [[[(rb.x[0], rb.k[0]) for rb in rp.raybundles] for rp in fp]
+                for fp in self.trace(**kwargs)]
+
+    def _flat_sequence(self):
+        return [(elem, surf) for (elem, elemseq) in self.sequence for (surf, _) in elemseq]
+
+    def trace_3d_local(self, **kwargs):
+        res = self.trace_3d_global(**kwargs)
+        flat = self._flat_sequence()
+        out = []
+        for fp in res:
+            fp_out = []
+            for rp in fp:
+                items = []
+                for ((elem, surf), (x, k)) in zip(flat, rp):
+                    lc = self.opticalsystem.elements[elem].surfaces[surf].rootcoordinatesystem
+                    items.append((lc.returnGlobalToLocalPoints(x),
+                                  lc.returnGlobalToLocalDirections(k)))
+                fp_out.append(items)
+            out.append(fp_out)
+        return out
+
+    def trace_2d_local(self, **kwargs):
+        return [[[(x[:2], k[:2]) for (x, k) in rp] for rp in fp]
+                for fp in self.trace_3d_local(**kwargs)]
+
+    def get_spot(self, raypath):
+        """(x, y of the last bundle in the last surface's frame, RMS spot radius
+        about the centroid) -- reference :283-303."""
+        (last_elem, last_seq) = self.sequence[-1]
+        (last_surf, _) = last_seq[-1]
+        lc = self.opticalsystem.elements[last_elem].surfaces[last_surf].rootcoordinatesystem
+        last = raypath.raybundles[-1]
+        xs = lc.returnGlobalToLocalPoints(last.x[-1])
+        return (xs[0:2, :], RayBundleAnalysis(last).get_rms_spot_size_centroid())
+
+
+def raytrace(s, seq, numrays, rays_dict, bundletype="collimated", traceoptions=None,
+             wave=standard_wavelength):
+    """Convenience function of the reference (pyrateoptics/__init__.py:457-465)."""
+    osa = OpticalSystemAnalysis(s, seq)
+    osa.aim(numrays, rays_dict, bundletype=bundletype, wave=wave)
+    return osa.trace(**(traceoptions or {}))

@@ -1,0 +1,40 @@
+"""CPU: rasters and OpticalSystemAnalysis bundle generators against outputs of the
+reference (tests/golden/rasters.npz, oracle/gen_golden.py --rasters)."""
+import os
+
+import numpy as np
+
+import pyrate_b200 as pb
+from pyrate_b200 import configs
+from pyrate_b200.sampling2d import raster
+
+G = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rasters.npz"))
+
+
+def test_rasters_match_reference():
+    for nm in ("RectGrid", "HexGrid", "MeridionalFan", "SagitalFan", "ChiefAndComa", "Single",
+               "CircularGrid"):
+        (x, y) = getattr(raster, nm)().getGrid(int(G[nm + "_n"]))
+        assert np.allclose(x, G[nm + "_x"], atol=1e-15) and np.allclose(y, G[nm + "_y"], atol=1e-15)
+
+
+def test_hexapolar_raster():
+    (x, y) = raster.HexapolarGrid().getGrid(1000)
+    assert x.size == 1027 and np.max(x * x + y * y) <= 1 + 1e-15
+    assert np.isclose(np.hypot(x[-1], y[-1]), 1.0)
+
+
+def test_bundle_generators_match_reference():
+    (s, seq) = configs.build_system(configs.CONFIGS["c1_doublet"], pb.api())
+    osa = pb.OpticalSystemAnalysis(s, seq)
+    props = {"radius": 11.43, "startz": -5.0, "starty": 0.3, "anglex": 0.02, "angley": -0.01,
+             "raster": raster.RectGrid()}
+    (o, k, e) = osa.collimated_bundle(40, props, wave=configs.DLINE)
+    assert np.allclose(o, G["coll_o"], atol=1e-14) and np.allclose(k, np.real(G["coll_k"]), atol=1e-13)
+    assert np.allclose(np.sum(e * k, axis=0), 0, atol=1e-15) and np.allclose(np.sum(e * e, axis=0), 1)
+    props = {"radius": 0.2, "startz": -50.0, "anglex": 0.01, "raster": raster.HexGrid()}
+    (o, k, e) = osa.divergent_bundle(40, props, wave=configs.DLINE)
+    assert np.allclose(o, G["div_o"], atol=1e-14) and np.allclose(k, np.real(G["div_k"]), atol=1e-13)
+    assert np.allclose(np.sum(e * k, axis=0), 0, atol=1e-15)
+    osa.aim(40, props, bundletype="divergent", wave=configs.DLINE)
+    assert osa.initial_bundles[0].x.shape == (1, 3, o.shape[1])

@@ -328,3 +328,24 @@ def test_long_sequences_are_chunked_across_launches():
     for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
         util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
                                         "rayID": rb["rayID"]}, 1e-6, "long b%d" % ib)
+
+
+def test_raytrace_convenience_function():
+    """pyrateoptics.raytrace (reference __init__.py:457-465): aim a collimated
+    bundle with a raster, trace it, read the spot -- against the oracle."""
+    import pyrate_np as onp
+    from pyrate_b200.sampling2d import raster
+    spec = configs.CONFIGS["c1_doublet"]
+    (s, seq) = configs.build_system(spec, pb.api())
+    props = {"radius": 11.43, "startz": -5.0, "raster": raster.HexGrid(), "anglex": 0.01}
+    res = pb.raytrace(s, seq, 200, props, wave=configs.DLINE)
+    path = res[0][0]
+    osa = pb.OpticalSystemAnalysis(s, seq)
+    (o, k, e) = osa.collimated_bundle(200, props, wave=configs.DLINE)
+    ref = onp.seqtrace(onp.system_from_spec(spec), o, k, e, wave=configs.DLINE)[0]
+    last = path.raybundles[-1].numpy()
+    assert util.relerr(last["x"], ref[-1]["x"]) < 1e-10
+    (xy, rms) = osa.get_spot(path)
+    assert np.isclose(rms, onp.rms_spot(ref[-1]["x"][-1], onp.centroid(ref[-1]["x"][-1])),
+                      rtol=1e-9)
+    assert xy.shape[0] == 2
