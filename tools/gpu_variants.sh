@@ -1,4 +1,7 @@
 #!/bin/bash
-PYR_LEAN_VARIANT=0 timeout 200 python tools/compare_variants.py save
-for v in 70 61 62 63; do PYR_LEAN_VARIANT=$v timeout 200 python tools/compare_variants.py check | tail -1; done
-for v in 0 70 61 62 63; do PYR_LEAN_VARIANT=$v timeout 200 python tools/time_kernel.py c2_doublegauss 0 20; done
+timeout 300 python tools/time_kernel.py c2_doublegauss 0 20
+timeout 300 python tools/time_kernel.py c2_doublegauss 0 10 1
+timeout 300 python tools/time_kernel.py c3_asphere 0 10
+timeout 300 python tools/time_kernel.py x2_xypoly 4000000 10
+timeout 300 python tools/time_kernel.py x6_biconic 4000000 10
+timeout 300 python tools/time_kernel.py c5_grin 1000000 5
