@@ -41,6 +41,37 @@ def hexapolar(rings):
     return px, py
 
 
+def hexapolar_range(rings, lo, hi):
+    """Points lo..hi-1 of hexapolar(rings) without building the whole raster
+    (ray shards of a rank in a multi-GPU run)."""
+    i = np.arange(lo, hi, dtype=np.int64)
+    j = np.floor((3.0 + np.sqrt(np.maximum(9.0 + 12.0 * (i - 1), 0.0))) / 6.0).astype(np.int64)
+    j = np.maximum(j, 0)
+    # correct rounding at ring boundaries: ring j holds indices [1+3(j-1)j, 1+3j(j+1))
+    j = np.where(i < 1 + 3 * (j - 1) * j, j - 1, j)
+    j = np.where(i >= 1 + 3 * j * (j + 1), j + 1, j)
+    j = np.where(i == 0, 0, j)
+    idx = i - (1 + 3 * (j - 1) * j)
+    jj = np.maximum(j, 1)
+    ang = 2.0 * math.pi * idx / (6.0 * jj)
+    rad = j / float(max(rings, 1))
+    return np.where(i == 0, 0.0, rad * np.cos(ang)), np.where(i == 0, 0.0, rad * np.sin(ang))
+
+
+def collimated_shard(rings, radius, z0, lo, hi, kdir=(0.0, 0.0, 1.0),
+                     efield=(0.0, 1.0, 0.0)):
+    """Rays lo..hi-1 of collimated_bundle(rings, ...)."""
+    (px, py) = hexapolar_range(rings, lo, hi)
+    n = px.size
+    x0 = np.empty((3, n))
+    x0[0] = radius * px
+    x0[1] = radius * py
+    x0[2] = z0
+    k0 = np.ascontiguousarray(np.repeat(np.asarray(kdir, dtype=float)[:, None], n, axis=1))
+    e0 = np.ascontiguousarray(np.repeat(np.asarray(efield, dtype=float)[:, None], n, axis=1))
+    return x0, k0, e0
+
+
 def hexapolar_count(rings):
     return 1 + 3 * rings * (rings + 1)
 

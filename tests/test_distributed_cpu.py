@@ -63,3 +63,14 @@ def test_shard_range_partitions():
                 assert a[1] == b[0]
             sizes = [hi - lo for (lo, hi) in ranges]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_hexapolar_shards_concatenate_to_the_full_raster():
+    from pyrate_b200 import configs
+    from pyrate_b200 import distributed as pd
+    for rings in (1, 3, 40):
+        (px, py) = configs.hexapolar(rings)
+        n = px.size
+        parts = [configs.hexapolar_range(rings, *pd.shard_range(n, r, 8)) for r in range(8)]
+        assert np.allclose(np.concatenate([p[0] for p in parts]), px, atol=1e-15)
+        assert np.allclose(np.concatenate([p[1] for p in parts]), py, atol=1e-15)
