@@ -51,3 +51,47 @@ def test_no_cpu_fallback():
     with pytest.raises(engine.DeviceRequired):
         s.seqtrace(pb.RayBundle(x0, k0, e0), seq)
     assert np.array_equal(x0[2], np.full(x0.shape[1], -5.0))
+
+
+def _one_step():
+    st = nat.PyrStep()
+    for i in range(3):
+        st.shape_frame.r[i * 4] = 1.0
+        st.aperture_frame.r[i * 4] = 1.0
+        st.before.frame.r[i * 4] = 1.0
+        st.after.frame.r[i * 4] = 1.0
+    st.before.n = 1.0
+    st.after.n = 1.5
+    return st
+
+
+def test_argument_validation_happens_before_any_device_work():
+    """Structural errors come back as PYR_E_* codes (never exceptions across the
+    boundary, never a launch) -- checked here without a GPU."""
+    lib = nat.load()
+    rays = nat.PyrRaysIn()
+    dummy = (ctypes.c_double * 8)()
+    rays.x = ctypes.addressof(dummy)
+    rays.k = ctypes.addressof(dummy)
+    steps = (nat.PyrStep * 1)(_one_step())
+    assert lib.pyr_trace(steps, 0, ctypes.byref(rays), 1, 0, None) == -1          # BADARG
+    assert lib.pyr_trace(None, 1, ctypes.byref(rays), 1, 0, None) == -1
+    bad = (nat.PyrStep * 1)(_one_step())
+    bad[0].shape_kind = 99
+    assert lib.pyr_trace(bad, 1, ctypes.byref(rays), 1, 0, None) == -2            # UNSUPPORTED
+    bad = (nat.PyrStep * 1)(_one_step())
+    bad[0].n_coeff = 1000
+    assert lib.pyr_trace(bad, 1, ctypes.byref(rays), 1, 0, None) == -1
+    many = (nat.PyrStep * 41)(*[_one_step() for _ in range(41)])
+    assert lib.pyr_trace(many, 41, ctypes.byref(rays), 1, 0, None) == -3          # TOOLARGE
+    split_mid = (nat.PyrStep * 2)(_one_step(), _one_step())
+    split_mid[0].split = 1
+    assert lib.pyr_trace(split_mid, 2, ctypes.byref(rays), 1, 0, None) == -1
+    aniso = (nat.PyrStep * 1)(_one_step())
+    aniso[0].after.kind = nat.MEDIUM_ANISO
+    assert lib.pyr_trace(aniso, 1, ctypes.byref(rays), 1, 0, None) == -2          # needs PYR_F_COMPLEX
+    rays.x = None
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 1, 0, None) == -1
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 0, 0, None) == 0           # empty bundle
+    assert lib.pyr_spot_sums(None, 0, None, 2, 1, None, None, None) == -1
+    assert lib.pyr_trace_host(steps, 1, None, None, None, 1, None, None, None, None, None, 0, 1) == -1
