@@ -59,7 +59,6 @@ struct DStep {
     double ap0, ap1;               // circular: min^2, max^2; rectangular: w/2, h/2
     double n2sq;                   // (index of the deflecting medium)^2, ISO_CONST
     double inv_knorm;              // > 0: |k| known on entry (1/n of `before`)
-    double knorm2;                 // > 0: |k|^2 known on entry
     double *out_x, *out_k, *out_e;
     uint8_t *out_flags;
     int64_t ld_out, ld_out2;

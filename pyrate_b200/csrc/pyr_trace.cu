@@ -102,12 +102,6 @@ __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
     if (POLICY == 0 || POLICY == 3) __stcs(q, v); else if (POLICY == 2) __stcg(q, v); else *q = v;
 }
 
-// S = |E|^2 k - (E.k) E for real k, E (ray.py:140-147), not normalised
-__device__ __forceinline__ void poynting_vec3(const double k[3], const double e[3], double s[3]) {
-    const double ee = dot3(e, e), ek = dot3(e, k);
-    s[0] = fma(ee, k[0], -ek * e[0]); s[1] = fma(ee, k[1], -ek * e[1]); s[2] = fma(ee, k[2], -ek * e[2]);
-}
-
 // d from (k, E): ray.py:140-152 for real k, E
 __device__ __forceinline__ void poynting_dir(const double k[3], const double e[3], double d[3]) {
     const double ee = dot3(e, e), ek = dot3(e, k);
@@ -261,42 +255,38 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
 //     later hit point and wave vector is NaN by arithmetic, and `square > 0`
 //     already rejects NaN normals (no separate finite check).
 template <bool WITH_E>
-__device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, const double u[3],
-                                              double uu, bool u_is_k, double hit_g[3]) {
-    // u: direction of energy transport, NOT normalised (uu = u.u): the conic
-    // intersection is homogeneous in it (F' = |u| F, H' = |u|^2 H, t' = t / |u|), so the
-    // normalisation of ray.py:152 would only be multiplied out again.
+__device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, const double d[3],
+                                              double hit_g[3]) {
     const bool ok = r.alive;
     const bool ident = (st.bits & kRotIdentity) != 0;
-    double r0[3], ul[3], kl[3];
+    double r0[3], dl[3], kl[3];
     if (ident) {
         r0[0] = r.x[0] - st.frame.o[0]; r0[1] = r.x[1] - st.frame.o[1]; r0[2] = r.x[2] - st.frame.o[2];
-        ul[0] = u[0]; ul[1] = u[1]; ul[2] = u[2];
+        dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2];
         kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2];
     } else {
         g2l_point(st.frame, r.x, r0);
-        rot_t(st.frame.r, u, ul);
-        if (u_is_k) { kl[0] = ul[0]; kl[1] = ul[1]; kl[2] = ul[2]; }
-        else rot_t(st.frame.r, r.k, kl);
+        rot_t(st.frame.r, d, dl);
+        rot_t(st.frame.r, r.k, kl);
     }
     const double curv = st.curv, cc = st.cc;
     double t, nrm[3];
     bool hit_ok = true;
     double h[3];
     const bool plane = (st.bits & kPlane) != 0;
-    if (plane && ul[2] > 0.0) {
+    if (plane && dl[2] > 0.0) {
         // F = d_z, G = -2 z0, H = 0  ->  t = -z0 / d_z  (surface_shape.py:305-318)
-        t = -r0[2] * fast_rcp(ul[2]);
-        h[0] = fma(ul[0], t, r0[0]); h[1] = fma(ul[1], t, r0[1]); h[2] = fma(ul[2], t, r0[2]);
+        t = -r0[2] * fast_rcp(dl[2]);
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
         nrm[0] = 0.0; nrm[1] = 0.0; nrm[2] = 1.0;
     } else if (st.bits & kSphere) {
         // cc = 0:  F = d_z - c (d.r0),  G = c (r0.r0) - 2 z0,  H = -c
-        const double F = fma(-curv, dot3(ul, r0), ul[2]);
+        const double F = fma(-curv, dot3(dl, r0), dl[2]);
         const double G = fma(curv, dot3(r0, r0), -2.0 * r0[2]);
-        const double square = fma(F, F, -curv * uu * G);
+        const double square = fma(F, F, -curv * G);
         hit_ok = square >= 0.0;
         t = fast_div(G, F + fast_sqrt(square));
-        h[0] = fma(ul[0], t, r0[0]); h[1] = fma(ul[1], t, r0[1]); h[2] = fma(ul[2], t, r0[2]);
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
         // unit normal (-c x, -c y, sqrt(1 - c^2 r^2)); on the vertex branch of the sphere
         // sqrt(1 - c^2 r^2) == 1 - c z exactly (surface equation), which saves the sqrt.
         // The far branch (1 - c z <= 0) keeps the reference's sag-based value.
@@ -305,13 +295,13 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
         nrm[0] = -curv * h[0]; nrm[1] = -curv * h[1]; nrm[2] = gz;
     } else {
         const double cc1 = 1.0 + cc;
-        const double F = ul[2] - curv * fma(ul[0], r0[0], fma(ul[1], r0[1], ul[2] * r0[2] * cc1));
+        const double F = dl[2] - curv * fma(dl[0], r0[0], fma(dl[1], r0[1], dl[2] * r0[2] * cc1));
         const double G = curv * fma(r0[0], r0[0], fma(r0[1], r0[1], r0[2] * r0[2] * cc1)) - 2.0 * r0[2];
-        const double H = fma(-cc * curv * ul[2], ul[2], -curv * uu);
+        const double H = fma(-cc * curv * dl[2], dl[2], -curv);
         const double square = fma(F, F, H * G);
         hit_ok = square >= 0.0;
         t = fast_div(G, F + fast_sqrt(square));
-        h[0] = fma(ul[0], t, r0[0]); h[1] = fma(ul[1], t, r0[1]); h[2] = fma(ul[2], t, r0[2]);
+        h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
         // grad = (-c x, -c y, sqrt(1 - (1+cc) c^2 r^2)); the z component equals
         // 1 - c (1+cc) z on the vertex branch (see the sphere case)
         double gx = -curv * h[0], gy = -curv * h[1];
@@ -334,21 +324,17 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
     }
     const bool hit = ok && hit_ok && ap_ok;
 
-    // Snell via in-plane k (material_isotropic.py:175-185 / :224) with |n| = 1:
-    //   k_in.k_in = k.k - (k.n)^2,  k2 = k_in + xi n = k + (xi - k.n) n,
-    //   mirror: k2 = -k_in + xi n = -k + (xi + k.n) n
+    // Snell via in-plane k (material_isotropic.py:175-185 / :224)
     const double kn = dot3(kl, nrm);
-    const double kk = u_is_k ? uu : dot3(kl, kl);
-    const double square2 = fma(kn, kn, st.n2sq - kk);
+    const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
+    const double square2 = st.n2sq - dot3(kin, kin);
     const double xi = fast_sqrt(square2);
     const bool alive = hit && (square2 > 0.0);
     double k2[3];
     if (st.interaction == PYR_REFLECT) {
-        const double f = xi + kn;
-        k2[0] = fma(f, nrm[0], -kl[0]); k2[1] = fma(f, nrm[1], -kl[1]); k2[2] = fma(f, nrm[2], -kl[2]);
+        k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
     } else {
-        const double f = xi - kn;
-        k2[0] = fma(f, nrm[0], kl[0]); k2[1] = fma(f, nrm[1], kl[1]); k2[2] = fma(f, nrm[2], kl[2]);
+        k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
     }
     if (ident) { r.k[0] = k2[0]; r.k[1] = k2[1]; r.k[2] = k2[2]; }
     else rot(st.frame.r, k2, r.k);
@@ -499,27 +485,20 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 // direction of energy transport (ray.py:136-152): Poynting vector of the
-                // user's (k, E) on the first segment, k wherever E.k = 0 is guaranteed.
-                // Left unnormalised for the lean step, normalised for the general one.
-                const bool general_step = GENERAL && st.aux >= 0;
-                double u[3], uu;
-                bool u_is_k = false;
+                // user's (k, E) on the first segment, k/|k| wherever E.k = 0 is guaranteed
+                double d[3];
                 if (st.dir_mode == PYR_DIR_POYNTING && (WITH_E || s == 0)) {
-                    const double *e = WITH_E ? ray[j].e : in[j].e;
-                    poynting_vec3(ray[j].k, e, u);
-                    uu = dot3(u, u);
+                    if (WITH_E) poynting_dir(ray[j].k, ray[j].e, d);
+                    else poynting_dir(ray[j].k, in[j].e, d);
                 } else {
-                    u[0] = ray[j].k[0]; u[1] = ray[j].k[1]; u[2] = ray[j].k[2];
-                    uu = (st.knorm2 > 0.0) ? st.knorm2 : dot3(u, u);
-                    u_is_k = true;
+                    const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm
+                                                            : fast_rsqrt(dot3(ray[j].k, ray[j].k));
+                    d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
                 }
-                if (general_step) {
-                    const double inv = fast_rsqrt(uu);
-                    double d[3] = {u[0] * inv, u[1] * inv, u[2] * inv};
-                    fl[j] = step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j]);
-                } else {
-                    fl[j] = step_lean<WITH_E>(st, ray[j], u, uu, u_is_k, hit[j]);
-                }
+                // steps without an auxiliary record (conic shape, homogeneous isotropic
+                // media, aperture in the shape frame) always take the tuned path
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j])
+                                                 : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
             // ---- record the step ----
@@ -756,7 +735,6 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         d.n2sq = u.after.n * u.after.n;
         d.inv_knorm = (u.dir_mode == PYR_DIR_K && u.k_norm_hint > 0.0 &&
                        u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / u.k_norm_hint : 0.0;
-        d.knorm2 = d.inv_knorm > 0.0 ? u.k_norm_hint * u.k_norm_hint : 0.0;
         d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
         d.ld_out = u.ld_out > 0 ? u.ld_out : n_rays;
         d.ld_out2 = u.ld_out2 > 0 ? u.ld_out2 : 2 * d.ld_out;
