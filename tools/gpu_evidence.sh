@@ -8,7 +8,9 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
 timeout 600 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 1800 gpurun_out/bench.json
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err; tail -c 900 gpurun_out/bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/bench_under_ncu.log 2>&1
-for cfg in "c2_doublegauss 0 trace_real 2 c2" "c3_asphere 0 trace_real 1 c3" "c4_anisotropic 1000000 trace_complex 3 c4" "c5_grin 1000000 trace_real 1 c5"; do
+CAPTURES=${CAPTURES:-"c2_doublegauss:0:trace_real:2:c2 c3_asphere:0:trace_real:1:c3 c4_anisotropic:1000000:trace_complex:3:c4 c5_grin:1000000:trace_real:1:c5"}
+for cfg in $CAPTURES; do
+  cfg=${cfg//:/ }
   set -- $cfg
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$3 -s $4 -c 1 -f -o gpurun_out/prof_final_$5 python tools/profile_target.py $1 $2 4 > gpurun_out/ncu_$5.log 2>&1; tail -1 gpurun_out/ncu_$5.log
 done
