@@ -401,35 +401,56 @@ def _lazy_efield(k):
     return t.to(k.dtype)
 
 
+class _Lazy(object):
+    """A value computed on first use (device work is deferred until a bundle field
+    is actually read: building the RayPath of a trace launches nothing)."""
+    __slots__ = ("fn", "val", "done")
+
+    def __init__(self, fn):
+        (self.fn, self.val, self.done) = (fn, None, False)
+
+    def __call__(self):
+        if not self.done:
+            (self.val, self.done) = (self.fn(), True)
+            self.fn = None
+        return self.val
+
+
+def _const(v):
+    lz = _Lazy(None)
+    (lz.val, lz.done) = (v, True)
+    return lz
+
+
 class _BundleBuilder(object):
     """Materialises one RayBundle of a traced path on first field access.
 
-    start_*: state right after the deflection that opens the bundle (full
-    width, before compaction); `mask` marks the rays the reference keeps
-    (material_isotropic.py:194-199); hit / hitmask: record of the next
-    intersect (None for the last bundle, which has a single row).
+    start_x / mask / ids: lazies of the state right after the deflection that opens
+    the bundle (full width), of the rays the reference keeps
+    (material_isotropic.py:194-199) and of their ids; hit / hit_flags: record of the
+    next intersect (None for the last bundle, which has a single row).
     """
 
-    def __init__(self, start_x, start_k, start_e, mask, ids, hit, hitmask):
+    def __init__(self, start_x, start_k, start_e, mask, ids, hit, hit_flags):
         (self.start_x, self.start_k, self.start_e) = (start_x, start_k, start_e)
-        (self.mask, self.ids, self.hit, self.hitmask) = (mask, ids, hit, hitmask)
+        (self.mask, self.ids, self.hit, self.hit_flags) = (mask, ids, hit, hit_flags)
         self.cache = None
 
     def build(self):
         if self.cache is not None:
             return self.cache
-        mask = self.mask
+        mask = self.mask()
         if mask is None or bool(mask.all()):
             def take(t):
                 return t
         else:
             def take(t):
                 return t[..., mask]
-        x0 = take(self.start_x)
+        x0 = take(self.start_x())
         k0 = take(self.start_k)
         e_full = self.start_e if self.start_e is not None else _lazy_efield(self.start_k)
         e0 = take(e_full)
-        ids = take(self.ids)
+        ids = take(self.ids())
         ones = torch.ones(x0.shape[-1], dtype=torch.bool, device=x0.device)
         if self.hit is None:
             out = {"x": x0.unsqueeze(0), "k": k0.unsqueeze(0),
@@ -439,7 +460,7 @@ class _BundleBuilder(object):
             x = torch.stack((x0, take(self.hit)))
             out = {"x": x, "k": k0.unsqueeze(0).expand(2, -1, -1),
                    "Efield": e0.unsqueeze(0).expand(2, -1, -1),
-                   "valid": torch.stack((ones, take(self.hitmask))),
+                   "valid": torch.stack((ones, take(_hit_mask(self.hit_flags)))),
                    "rayID": ids}
         self.cache = out
         return out
@@ -458,10 +479,12 @@ def paths_from_record(rec, splitup=False):
     dev = rec.x0.device
     nsplit = sum(1 for s in rec.split if s)
     npaths = (2 ** nsplit) if splitup else 1
-    e0 = rec.e0
-    if e0 is None:
-        e0 = torch.zeros_like(rec.x0)
-        e0[1] = 1.0
+
+    def default_e0():
+        e = torch.zeros_like(rec.x0)
+        e[1] = 1.0
+        return e
+    e0 = rec.e0 if rec.e0 is not None else None
     paths = []
     for p in range(npaths):
         def block(width):
@@ -472,15 +495,16 @@ def paths_from_record(rec, splitup=False):
             b = p % (width // n0)
             return slice(b * n0, (b + 1) * n0)
 
-        (sx, sk, se) = (rec.x0, rec.k0, e0)
-        mask = None
-        ids = torch.arange(n0, device=dev)
+        sx = _const(rec.x0)
+        (sk, se) = (rec.k0, e0 if e0 is not None else default_e0())
+        mask = _const(None)
+        ids = _Lazy(lambda: torch.arange(n0, device=dev))
         bundles = []
         for s in range(nsteps):
             blk_in = block(rec.n_in[s])
             hit = rec.hit[s][:, blk_in]
             fl = rec.flags[s][blk_in]
-            bb = _BundleBuilder(sx, sk, se, mask, ids, hit, _hit_mask(fl))
+            bb = _BundleBuilder(sx, sk, se, mask, ids, hit, fl)
             splitted = bool(s >= 1 and rec.split[s - 1] and not splitup)
             bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
                                      wave=rec.wave, splitted=splitted))
@@ -490,13 +514,13 @@ def paths_from_record(rec, splitup=False):
             # survivors: the device ALIVE bit is cumulative; an anisotropic
             # deflection keeps every ray it was handed (material_anisotropic.py
             # :87-100 has no validity filter), which the kernel mirrors
-            mask = _alive_mask(fl)
             if rec.split[s] and not splitup:
-                sx = torch.cat((hit, hit), dim=1)
-                mask = torch.cat((mask, mask))
-                ids = torch.cat((ids, ids))
+                sx = _Lazy(lambda hit=hit: torch.cat((hit, hit), dim=1))
+                mask = _Lazy(lambda fl=fl: torch.cat((_alive_mask(fl), _alive_mask(fl))))
+                ids = _Lazy(lambda ids=ids: torch.cat((ids(), ids())))
             else:
-                sx = hit
+                sx = _const(hit)
+                mask = _Lazy(lambda fl=fl: _alive_mask(fl))
         bb = _BundleBuilder(sx, sk, se, mask, ids, None, None)
         splitted = bool(nsteps >= 1 and rec.split[nsteps - 1] and not splitup)
         bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},

@@ -29,14 +29,26 @@ def _mro_names(obj):
     return {c.__name__ for c in type(obj).__mro__}
 
 
+_FRAME_CACHE = None      # id(lc) -> PyrFrame, alive only inside one lower() call
+
+
 def _frame(lc):
+    if _FRAME_CACHE is not None:
+        hit = _FRAME_CACHE.get(id(lc))
+        if hit is not None:
+            return hit
+    f = _frame_uncached(lc)
+    if _FRAME_CACHE is not None:
+        _FRAME_CACHE[id(lc)] = f
+    return f
+
+
+def _frame_uncached(lc):
     f = nat.PyrFrame()
-    b = np.asarray(lc.localbasis, dtype=float)
-    o = np.asarray(lc.globalcoordinates, dtype=float)
-    for i in range(3):
-        for j in range(3):
-            f.r[i * 3 + j] = b[i, j]
-        f.o[i] = o[i]
+    b = np.ascontiguousarray(lc.localbasis, dtype=np.float64)
+    o = np.ascontiguousarray(lc.globalcoordinates, dtype=np.float64)
+    C.memmove(f.r, b.ctypes.data, 72)
+    C.memmove(f.o, o.ctypes.data, 24)
     return f
 
 
@@ -213,6 +225,15 @@ class LoweredStep(object):
 def lower(system, elementsequence, wave, splitup=False):
     """Returns list[LoweredStep] for `elementsequence`
     = [(elemkey, [(surfkey, {"is_mirror": .., "is_stop": ..}), ...]), ...]."""
+    global _FRAME_CACHE
+    _FRAME_CACHE = {}
+    try:
+        return _lower(system, elementsequence, wave)
+    finally:
+        _FRAME_CACHE = None
+
+
+def _lower(system, elementsequence, wave):
     background = system.material_background
     out = []
     last_deflector = None          # medium object that set |k| last
