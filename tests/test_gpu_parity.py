@@ -349,3 +349,57 @@ def test_raytrace_convenience_function():
     assert np.isclose(rms, onp.rms_spot(ref[-1]["x"][-1], onp.centroid(ref[-1]["x"][-1])),
                       rtol=1e-9)
     assert xy.shape[0] == 2
+
+
+def _random_spec(seed):
+    """A random but traceable chain: decentered / tilted conics (both tilt orders),
+    random glasses, apertures of all three kinds, an occasional mirror."""
+    rng = np.random.default_rng(seed)
+    surfaces = [configs._conic("stop", 0.0, opt={"is_stop": True})]
+    mats = {}
+    inside = False
+    nsurf = int(rng.integers(3, 7))
+    for i in range(nsurf):
+        lc = {"decx": float(rng.uniform(-0.3, 0.3)), "decy": float(rng.uniform(-0.3, 0.3)),
+              "tiltx": float(rng.uniform(-0.05, 0.05)), "tilty": float(rng.uniform(-0.05, 0.05)),
+              "tiltz": float(rng.uniform(-1.0, 1.0)), "tiltThenDecenter": int(rng.integers(0, 2))}
+        mat = None
+        if not inside or rng.random() < 0.4:
+            mat = "g%d" % i
+            mats[mat] = ("ConstantIndexGlass", {"n": float(rng.uniform(1.3, 1.9))})
+        inside = mat is not None
+        kind = int(rng.integers(0, 3))
+        ap = None if kind == 0 else (configs._circ(float(rng.uniform(6.0, 9.0))) if kind == 1 else
+                                     ("RectangularAperture", {"width": float(rng.uniform(9, 14)),
+                                                              "height": float(rng.uniform(9, 14))}))
+        surfaces.append(configs._conic("s%d" % i, float(rng.uniform(2.0, 6.0)),
+                                       curv=float(rng.uniform(-0.03, 0.03)),
+                                       cc=float(rng.choice([0.0, -1.0, float(rng.uniform(-2, 2))])),
+                                       mat=mat, aperture=ap, **lc))
+    if inside:
+        surfaces.append(configs._conic("exit", 3.0, curv=float(rng.uniform(-0.01, 0.01)), mat=None))
+    if rng.random() < 0.5:
+        surfaces.append(configs._conic("mirror", 10.0, curv=float(rng.uniform(-0.005, 0.005)),
+                                       opt={"is_mirror": True}, tiltx=float(rng.uniform(-0.1, 0.1))))
+    surfaces.append(configs._conic("image", 15.0))
+    return {"name": "random%d" % seed, "surfaces": surfaces, "materials": mats,
+            "bundle": {"rings": 9, "radius": float(rng.uniform(4.0, 7.0)), "z0": -3.0}}
+
+
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_systems_match_oracle(seed):
+    import pyrate_np as onp
+    spec = _random_spec(seed)
+    rng = np.random.default_rng(1000 + seed)
+    kdir = rng.normal(size=3) * 0.03
+    kdir[2] = 1.0
+    kdir /= np.linalg.norm(kdir)
+    efield = rng.normal(size=3)                      # generic E0: Poynting first segment
+    (x0, k0, e0) = configs.config_bundle(spec, None, tuple(kdir), tuple(efield))
+    (s, seq) = configs.build_system(spec, pb.api())
+    paths = s.seqtrace(pb.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    assert len(paths[0].raybundles) == len(ref[0])
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                        "rayID": rb["rayID"]}, 1e-10, "%s b%d" % (spec["name"], ib))
