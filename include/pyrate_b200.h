@@ -37,7 +37,9 @@ extern "C" {
 
 #define PYR_ABI_VERSION 1
 
-#define PYR_MAX_COEFF 32        /* asphere coefficients / XY-polynomial terms */
+#define PYR_MAX_COEFF 80        /* asphere coefficients / XY-polynomial terms (a
+                                   Zernike series up to Fringe term 36 expands into
+                                   66 monomials)                                   */
 #define PYR_MAX_GRIN_PARAMS 8
 
 /* error codes */

@@ -54,6 +54,7 @@ TRACES = [
     ("x6_biconic", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
     ("x7_two_elements", 5, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
     ("x8_crystal_mirror", 2, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
+    ("x9_zernike", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
 ]
 
 
@@ -148,6 +149,12 @@ def dump_shapes(api):
     out["xy_sag"] = xy.getSag(x, y)
     out["xy_grad"] = xy.getGrad(x, y)
     out["xy_normal"] = xy.getNormal(x, y)
+    rngz = np.random.default_rng(21)
+    for (nm, cls, ncoef) in (("zf", api.ZernikeFringe, 25), ("za", api.ZernikeANSI, 21)):
+        co = rngz.normal(size=ncoef) * 0.02
+        zs = cls.p(lc, normradius=5.0, coefficients=list(co))
+        out[nm + "_coeffs"] = co
+        out[nm + "_sag"] = zs.getSag(x, y)
     bic = api.Biconic.p(lc, curvx=0.03, ccx=-0.6, curvy=-0.02, ccy=0.4,
                         coefficients=[(1e-3, 0.3), (-2e-5, -0.2)])
     out["bic_params"] = np.array([0.03, -0.6, -0.02, 0.4, 1e-3, 0.3, -2e-5, -0.2])

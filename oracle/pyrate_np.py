@@ -176,8 +176,67 @@ def biconic_grad(cx, cy, ccx, ccy, coeffs, x, y):
     return np.vstack((gx, gy, np.ones_like(x)))
 
 
+def _zernike_nm(kind, j):
+    """Single index -> (n, m): ZernikeFringe.jtonm :1118-1124, ZernikeANSI.jtonm :1139-1143."""
+    if kind == "ZernikeFringe":
+        nsq = math.ceil(math.sqrt(j)) ** 2
+        m = int(math.ceil((nsq - j) / 2))
+        n = int(2 * math.sqrt(nsq) - 2) - m
+        return (n, int((-1) ** ((nsq - j) % 2)) * m)
+    j -= 1
+    n = math.floor((-1. + math.sqrt(1. + 8. * j)) * 0.5)
+    return (n, -(n - 2 * j + n * (n + 1)))
+
+
+def _zernike_term(n, m, x, y):
+    """Z_n^m = R_n^|m|(rho) cos / sin(|m| phi) (zernike_norm :1058-1083) and its x, y
+    derivatives, through w = x + i y:  rho^|m| cos(|m| phi) = Re w^|m|, sin -> Im.
+
+    NOTE: the reference's own gradient (gradzernike_norm :1085-1095) divides the angular
+    term by rho once instead of twice and is therefore inconsistent with its sag for
+    every term with m != 0 (and NaN on the axis); the restatement keeps the correct
+    derivative, and parity with the reference is pinned on the sag and, for traces, on
+    rotationally symmetric series (m = 0), where the reference gradient is right."""
+    om = abs(m)
+    w = x + 1j * y
+    r2 = x * x + y * y
+    wm = w ** om if om > 0 else np.ones_like(w)
+    dwm = om * w ** (om - 1) if om > 0 else np.zeros_like(w)
+    pick = (lambda z: z.imag) if m < 0 else (lambda z: z.real)
+    ang = pick(wm)
+    (ang_x, ang_y) = (pick(dwm), pick(1j * dwm))
+    rad = np.zeros_like(x)
+    drad = np.zeros_like(x)                  # d rad / d (r2)
+    for k in range((n - om) // 2 + 1):
+        c = ((-1) ** k * math.factorial(n - k) /
+             (math.factorial(k) * math.factorial((n + om) // 2 - k) *
+              math.factorial((n - om) // 2 - k)))
+        q = (n - om) // 2 - k
+        rad = rad + c * r2 ** q
+        if q >= 1:
+            drad = drad + c * q * r2 ** (q - 1)
+    return (rad * ang, 2 * x * drad * ang + rad * ang_x, 2 * y * drad * ang + rad * ang_y)
+
+
+def zernike_sag_grad(shape, x, y):
+    nr = shape["normradius"]
+    (xp, yp) = (x / nr, y / nr)
+    f = np.zeros_like(x)
+    fx = np.zeros_like(x)
+    fy = np.zeros_like(x)
+    for (j, val) in enumerate(shape["coefficients"], 1):
+        (n, m) = _zernike_nm(shape["kind"], j)
+        (z, zx, zy) = _zernike_term(n, m, xp, yp)
+        f = f + val * z
+        fx = fx + val * zx / nr
+        fy = fy + val * zy / nr
+    return (f, fx, fy)
+
+
 def shape_sag(shape, x, y):
     kind = shape["kind"]
+    if kind.startswith("Zernike"):
+        return zernike_sag_grad(shape, x, y)[0]
     if kind == "Biconic":
         return biconic_sag(shape["curvx"], shape["curvy"], shape["ccx"], shape["ccy"],
                            shape["coefficients"], x, y)
@@ -192,6 +251,9 @@ def shape_sag(shape, x, y):
 
 def shape_grad(shape, x, y):
     kind = shape["kind"]
+    if kind.startswith("Zernike"):
+        (_, fx, fy) = zernike_sag_grad(shape, x, y)
+        return np.vstack((-fx, -fy, np.ones_like(x)))
     if kind == "Biconic":
         return biconic_grad(shape["curvx"], shape["curvy"], shape["ccx"], shape["ccy"],
                             shape["coefficients"], x, y)
@@ -600,7 +662,7 @@ def system_from_spec(spec):
         shape = dict(skw)
         shape["kind"] = skind
         shape["frame"] = frame
-        if skind in ("Asphere", "Biconic"):
+        if skind in ("Asphere", "Biconic", "ZernikeFringe", "ZernikeANSI"):
             shape.setdefault("coefficients", [])
         if surf["aperture"] is None:
             ap = {"kind": "Base"}

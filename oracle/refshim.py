@@ -50,7 +50,8 @@ def api():
     from pyrateoptics.raytracer.localcoordinates import LocalCoordinates
     from pyrateoptics.raytracer.surface import Surface
     from pyrateoptics.raytracer.surface_shape import (Conic, Asphere, Biconic,
-                                                      XYPolynomials)
+                                                      XYPolynomials, ZernikeFringe,
+                                                      ZernikeANSI)
     from pyrateoptics.raytracer.aperture import (BaseAperture,
                                                  CircularAperture,
                                                  RectangularAperture)

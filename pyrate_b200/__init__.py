@@ -22,6 +22,7 @@ from .raytracer.optical_system import OpticalSystem  # noqa: F401
 from .raytracer.ray import RayBundle, RayPath  # noqa: F401
 from .raytracer.surface import Surface  # noqa: F401
 from .raytracer.surface_shape import (Asphere, Biconic, Conic, XYPolynomials,  # noqa: F401
+                                      ZernikeANSI, ZernikeFringe,
                                       accessible_shapes)
 
 __version__ = "0.1.0"
@@ -33,6 +34,7 @@ def api():
         OpticalSystem=OpticalSystem, OpticalElement=OpticalElement,
         LocalCoordinates=LocalCoordinates, Surface=Surface, Conic=Conic,
         Asphere=Asphere, Biconic=Biconic, XYPolynomials=XYPolynomials,
+        ZernikeFringe=ZernikeFringe, ZernikeANSI=ZernikeANSI,
         BaseAperture=BaseAperture,
         CircularAperture=CircularAperture, RectangularAperture=RectangularAperture,
         ConstantIndexGlass=ConstantIndexGlass, ModelGlass=ModelGlass,

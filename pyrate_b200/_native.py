@@ -7,7 +7,7 @@ the library is missing or was built for another ABI, loading raises.
 import ctypes as C
 import os
 
-MAX_COEFF = 32
+MAX_COEFF = 80
 MAX_GRIN_PARAMS = 8
 
 (SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY, SHAPE_BICONIC) = (0, 1, 2, 3)

@@ -453,6 +453,32 @@ X8_CRYSTAL_MIRROR = {   # reflection inside a birefringent medium
     "s_counted": 3,
 }
 
+_ZF_SYM = [0.0] * 16       # rotationally symmetric Fringe series: Z4, Z9, Z16 (m = 0)
+(_ZF_SYM[3], _ZF_SYM[8], _ZF_SYM[15]) = (-0.35, 0.02, -0.004)
+X9_ZERNIKE = {
+    "name": "x9_zernike",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 4.0, curv=1. / 70.0, mat="glass"),
+        {"name": "back", "lc": {"decz": 6.0, "decx": 0.4, "tilty": 1.5 * math.pi / 180.0},
+         "shape": ("ZernikeFringe", {"normradius": 10.0, "coefficients": _ZF_SYM}),
+         "aperture": None, "mat": None, "opt": {}},
+        _conic("image", 55.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.62})},
+    "bundle": {"rings": 6, "radius": 7.0, "z0": -3.0},
+    "s_counted": 2,
+}
+_ZF_GEN = [0.0, 0.01, -0.02, -0.3, 0.03, -0.02, 0.015, -0.01, 0.02, 0.004, -0.006, 0.003,
+           -0.002, 0.004, -0.003, -0.004]
+X10_ZERNIKE_GENERAL = dict(X9_ZERNIKE, name="x10_zernike_general", surfaces=[
+    X9_ZERNIKE["surfaces"][0], X9_ZERNIKE["surfaces"][1],
+    dict(X9_ZERNIKE["surfaces"][2],
+         shape=("ZernikeFringe", {"normradius": 10.0, "coefficients": _ZF_GEN})),
+    X9_ZERNIKE["surfaces"][3]])
+# x10 is traced against the oracle only (the reference's Zernike gradient is inconsistent
+# with its sag for m != 0 terms, see oracle/pyrate_np.py:_zernike_term)
+
 CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
-                                       X8_CRYSTAL_MIRROR)})
+                                       X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL)})

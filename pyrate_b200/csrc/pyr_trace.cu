@@ -719,7 +719,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         const PyrStep &u = steps[s];
         DStep &d = P.steps[s];
         if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_BICONIC) return PYR_E_UNSUPPORTED;
-        if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > PYR_MAX_COEFF / 2) return PYR_E_BADARG;
+        if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > 16) return PYR_E_BADARG;
         if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
         if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
         if (u.split && s != n_steps - 1) return PYR_E_BADARG;

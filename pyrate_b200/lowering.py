@@ -143,6 +143,21 @@ def _xy_terms(shape):
     return terms
 
 
+def _zernike_terms(shape):
+    """Zernike series (reference or mirror object) -> monomial terms; the index
+    convention comes from the object's own jtonm (Fringe / ANSI)."""
+    from .raytracer.surface_shape import zernike_monomials
+    total = {}
+    for i in range(int(shape.annotations["numcoefficients"])):
+        val = _value(shape.params["Z" + str(i + 1)])
+        if val == 0.0:
+            continue
+        (n, m) = type(shape).jtonm(i + 1)
+        for (key, v) in zernike_monomials(int(n), int(m)).items():
+            total[key] = total.get(key, 0.0) + val * v
+    return [(px, py, c) for ((px, py), c) in sorted(total.items()) if c != 0.0]
+
+
 def lower_surface(surface, st):
     """Fill shape / aperture fields of PyrStep `st`."""
     shape = surface.shape
@@ -170,15 +185,18 @@ def lower_surface(surface, st):
         (st.curv, st.cc) = (_value(shape.params["curvx"]), _value(shape.params["ccx"]))
         (st.curv2, st.cc2) = (_value(shape.params["curvy"]), _value(shape.params["ccy"]))
         ncoef = int(shape.annotations["numcoefficients"])
-        if ncoef > nat.MAX_COEFF // 2:
+        if ncoef > 16:
             raise LoweringError("too many biconic coefficient pairs")
         st.n_coeff = ncoef
         for i in range(ncoef):
             st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
             st.coeff[16 + i] = _value(shape.params["B" + str(2 * i + 2)])
-    elif "XYPolynomials" in names:
+    elif "XYPolynomials" in names or "Zernike" in names:
         st.shape_kind = nat.SHAPE_XYPOLY
-        terms = _xy_terms(shape)
+        if "Zernike" in names:
+            terms = _zernike_terms(shape)
+        else:
+            terms = _xy_terms(shape)
         if len(terms) > nat.MAX_COEFF:
             raise LoweringError("too many XY polynomial terms")
         st.normradius = _value(shape.params["normradius"])

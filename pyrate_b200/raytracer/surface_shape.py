@@ -298,5 +298,154 @@ class XYPolynomials(ExplicitShape):
         return h
 
 
+def _poly_mul(a, b):
+    out = {}
+    for ((ax, ay), av) in a.items():
+        for ((bx, by), bv) in b.items():
+            key = (ax + bx, ay + by)
+            out[key] = out.get(key, 0.0) + av * bv
+    return out
+
+
+def zernike_monomials(n, m):
+    """Unnormalised Zernike polynomial Z_n^m = R_n^|m|(rho) cos / sin(|m| phi) (the
+    reference's convention, surface_shape.py:1058-1083: m < 0 -> sin) as a dict
+    {(px, py): coefficient} of monomials x^px y^py in the normalised coordinates."""
+    import math
+    om = abs(m)
+    # angular part: Re / Im of (x + i y)^om
+    ang = {}
+    for j in range(om + 1):
+        c = math.comb(om, j)
+        # i^j: j even -> real (-1)^(j/2), j odd -> imaginary (-1)^((j-1)/2)
+        if m >= 0 and j % 2 == 0:
+            ang[(om - j, j)] = ang.get((om - j, j), 0.0) + c * (-1) ** (j // 2)
+        if m < 0 and j % 2 == 1:
+            ang[(om - j, j)] = ang.get((om - j, j), 0.0) + c * (-1) ** ((j - 1) // 2)
+    if om == 0 and m >= 0:
+        ang = {(0, 0): 1.0}
+    r2 = {(2, 0): 1.0, (0, 2): 1.0}
+    total = {}
+    for k in range((n - om) // 2 + 1):
+        coef = ((-1) ** k * math.factorial(n - k) /
+                (math.factorial(k) * math.factorial((n + om) // 2 - k) *
+                 math.factorial((n - om) // 2 - k)))
+        term = {(0, 0): coef}
+        for _ in range((n - om) // 2 - k):          # rho^(n - 2k) = rho^om (rho^2)^((n-om)/2-k)
+            term = _poly_mul(term, r2)
+        for (key, v) in _poly_mul(term, ang).items():
+            total[key] = total.get(key, 0.0) + v
+    return {k: v for (k, v) in total.items() if v != 0.0}
+
+
+class Zernike(ExplicitShape):
+    """Zernike series z = sum_j Z_j zern_j(x / R, y / R) (reference surface_shape.py
+    :927-1113).  The series is expanded into monomials once (`getXYTerms`), which is also
+    what the device evaluates (PYR_SHAPE_XYPOLY) -- unlike the reference's polar
+    gradient (:1085-1095) the result is finite on the axis."""
+
+    @classmethod
+    def p(cls, lc, normradius=1., coefficients=None, name=""):
+        coefficients = [] if coefficients is None else list(coefficients)
+        plist = [("normradius", normradius)] + \
+                [("Z" + str(i + 1), v) for (i, v) in enumerate(coefficients)]
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc, plist)
+        ann["numcoefficients"] = len(coefficients)
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_Zernike"
+
+    def getZernikeParameters(self):
+        return (self.params["normradius"](),
+                [self.params["Z" + str(i + 1)]()
+                 for i in range(self.annotations["numcoefficients"])])
+
+    @staticmethod
+    def jtonm(j):
+        raise NotImplementedError()
+
+    @staticmethod
+    def nmtoj(n_m_pair):
+        raise NotImplementedError()
+
+    def getXYTerms(self):
+        """(normradius, [(xpow, ypow, coefficient), ...]) of the whole series."""
+        (nr, zc) = self.getZernikeParameters()
+        total = {}
+        for (j, val) in enumerate(zc, 1):
+            if val == 0.0:
+                continue
+            (n, m) = self.jtonm(j)
+            for (key, v) in zernike_monomials(n, m).items():
+                total[key] = total.get(key, 0.0) + val * v
+        return (nr, [(px, py, c) for ((px, py), c) in sorted(total.items()) if c != 0.0])
+
+    def getCentralCurvature(self):
+        (nr, terms) = self.getXYTerms()
+        return sum(c / nr ** 2 for (px, py, c) in terms if (px, py) in ((2, 0), (0, 2)))
+
+    def F(self, x, y):
+        (nr, terms) = self.getXYTerms()
+        res = _lib(x).zeros_like(x)
+        for (px, py, c) in terms:
+            res = res + x ** px * y ** py * (c / nr ** (px + py))
+        return res
+
+    def gradF(self, x, y, z):
+        xp = _lib(x)
+        (nr, terms) = self.getXYTerms()
+        gx = xp.zeros_like(x)
+        gy = xp.zeros_like(x)
+        for (px, py, c) in terms:
+            c = c / nr ** (px + py)
+            if px >= 1:
+                gx = gx - px * x ** (px - 1) * y ** py * c
+            if py >= 1:
+                gy = gy - py * x ** px * y ** (py - 1) * c
+        return xp.stack((gx, gy, xp.ones_like(x)))
+
+
+class ZernikeFringe(Zernike):
+
+    def setKind(self):
+        self.kind = "shape_ZernikeFringe"
+
+    @staticmethod
+    def jtonm(j):
+        import math
+        nsq = math.ceil(math.sqrt(j)) ** 2
+        m_plus_n = int(2 * math.sqrt(nsq) - 2)
+        m = int(math.ceil((nsq - j) / 2))
+        n = m_plus_n - m
+        return (n, int((-1) ** ((nsq - j) % 2)) * m)
+
+    @staticmethod
+    def nmtoj(n_m_pair):
+        (n, m) = n_m_pair
+        sign = (m > 0) - (m < 0)
+        return int(((n + abs(m)) / 2 + 1) ** 2 - 2 * abs(m) + (1 - sign) / 2)
+
+
+class ZernikeANSI(Zernike):
+
+    def setKind(self):
+        self.kind = "shape_ZernikeANSI"
+
+    @staticmethod
+    def jtonm(j):
+        import math
+        j -= 1
+        n = math.floor((-1. + math.sqrt(1. + 8. * j)) * 0.5)
+        m = n - 2 * j + n * (n + 1)
+        return (n, -m)
+
+    @staticmethod
+    def nmtoj(n_m_pair):
+        (n, m) = n_m_pair
+        return int(((n + 2) * n + m) / 2) + 1
+
+
 accessible_shapes = {"shape_Conic": Conic, "shape_Asphere": Asphere,
-                     "shape_Biconic": Biconic, "shape_XYPolynomials": XYPolynomials}
+                     "shape_Biconic": Biconic, "shape_XYPolynomials": XYPolynomials,
+                     "shape_ZernikeFringe": ZernikeFringe, "shape_ZernikeANSI": ZernikeANSI}

@@ -74,6 +74,14 @@ def test_shapes_match_reference_fixture():
     assert np.allclose(sh.getSag(x, y), g["asph_sag"], rtol=1e-14)
     assert np.allclose(sh.getGrad(x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
     assert np.allclose(sh.getNormal(x, y), g["asph_normal"], rtol=1e-13, atol=1e-16)
+    for (nm, cls) in (("zf", pb.ZernikeFringe), ("za", pb.ZernikeANSI)):
+        zs = cls.p(lc, normradius=5.0, coefficients=list(g[nm + "_coeffs"]))
+        assert np.allclose(zs.getSag(x, y), g[nm + "_sag"], rtol=1e-12, atol=1e-15)
+        # gradient: consistent with the sag (central differences), which the
+        # reference's polar formula is not for m != 0 (surface_shape.py:1085-1095)
+        h = 1e-6
+        gnum = -(zs.getSag(x + h, y) - zs.getSag(x - h, y)) / (2 * h)
+        assert np.allclose(zs.getGrad(x, y)[0], gnum, rtol=1e-6, atol=1e-8)
     bp = g["bic_params"]
     sh = pb.Biconic.p(lc, curvx=bp[0], ccx=bp[1], curvy=bp[2], ccy=bp[3],
                       coefficients=[(bp[4], bp[5]), (bp[6], bp[7])])
@@ -137,6 +145,13 @@ def _step_bytes(ls):
     ctypes.memmove(ctypes.addressof(st), ctypes.addressof(ls.st), ctypes.sizeof(nat.PyrStep))
     (st.out_x, st.out_k, st.out_e, st.out_flags) = (None, None, None, None)
     return bytes(st)
+
+
+def test_zernike_index_conventions():
+    for j in range(1, 38):
+        assert pb.ZernikeFringe.nmtoj(pb.ZernikeFringe.jtonm(j)) == j
+        assert pb.ZernikeANSI.nmtoj(pb.ZernikeANSI.jtonm(j)) == j
+    assert pb.ZernikeFringe.jtonm(4) == (2, 0) and pb.ZernikeFringe.jtonm(9) == (4, 0)
 
 
 @pytest.mark.parametrize("name", sorted(configs.CONFIGS))

@@ -66,6 +66,9 @@ def test_shapes_match_reference():
     sh = {"kind": "Asphere", "curv": ap[0], "cc": ap[1], "coefficients": list(ap[2:])}
     assert np.allclose(onp.shape_sag(sh, x, y), g["asph_sag"], rtol=1e-14)
     assert np.allclose(onp.shape_grad(sh, x, y), g["asph_grad"], rtol=1e-13, atol=1e-16)
+    for (nm, kind) in (("zf", "ZernikeFringe"), ("za", "ZernikeANSI")):
+        sh = {"kind": kind, "normradius": 5.0, "coefficients": list(g[nm + "_coeffs"])}
+        assert np.allclose(onp.shape_sag(sh, x, y), g[nm + "_sag"], rtol=1e-12, atol=1e-15)
     bp = g["bic_params"]
     sh = {"kind": "Biconic", "curvx": bp[0], "ccx": bp[1], "curvy": bp[2], "ccy": bp[3],
           "coefficients": [(bp[4], bp[5]), (bp[6], bp[7])]}
