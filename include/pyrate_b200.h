@@ -172,6 +172,17 @@ typedef struct PyrStep {
     double *out_e;              /* (3, n_out)  E field after deflection, global    */
     uint8_t *out_flags;         /* (n)         PYR_RAY_* bits                      */
     int64_t ld_out;             /* leading dimension of out_x / out_k / out_e      */
+    /* optional GRIN integrator history of the segment ending at this surface (the rows
+     * the reference appends per integrator step, material_grin.py:198-205); all NULL =
+     * off.  Row r of ray i: hist_x[(r*3 + c)*ld_out + i] (frozen position, global),
+     * hist_k likewise (k = p/n there), hist_valid[r*ld_out + i]; hist_count[i] = rows
+     * the ray produced (<= hist_rows; later rows of the lock-step reference repeat the
+     * last one).                                                                     */
+    double *grin_hist_x;
+    double *grin_hist_k;
+    uint8_t *grin_hist_valid;
+    int32_t *grin_hist_count;
+    int64_t grin_hist_rows;
     int64_t ld_out2;            /* split step only: leading dimension of out_k /
                                    out_e (width 2n: mode a of ray i in column i,
                                    mode b in column n + i, the reference's hstack

@@ -52,7 +52,11 @@ class PyrStep(C.Structure):
                 ("before", PyrMedium), ("after", PyrMedium),
                 ("out_x", C.c_void_p), ("out_k", C.c_void_p),
                 ("out_e", C.c_void_p), ("out_flags", C.c_void_p),
-                ("ld_out", C.c_int64), ("ld_out2", C.c_int64)]
+                ("ld_out", C.c_int64),
+                ("grin_hist_x", C.c_void_p), ("grin_hist_k", C.c_void_p),
+                ("grin_hist_valid", C.c_void_p), ("grin_hist_count", C.c_void_p),
+                ("grin_hist_rows", C.c_int64),
+                ("ld_out2", C.c_int64)]
 
 
 class PyrRaysIn(C.Structure):

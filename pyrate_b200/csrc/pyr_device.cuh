@@ -51,6 +51,10 @@ struct DAux {
     int32_t n_coeff, newton_maxit;
     DFrame aperture_frame;
     DMedium before, after;
+    double *hist_x, *hist_k;       // optional GRIN integrator history
+    uint8_t *hist_valid;
+    int32_t *hist_count;
+    int64_t hist_rows;
 };
 
 struct DStep {

@@ -51,9 +51,12 @@ __device__ __forceinline__ bool grin_inside(const DMedium &m, const double q[3])
 // until the next surface (shape of the current step) is crossed.  On return x is
 // the last position BEFORE the crossing and k = p/n there (both global);
 // returns validity (energy, boundary, step cap).
+// History (aux->hist_*, optional): one row per integrator step with the frozen state
+// the reference appends (material_grin.py:195-205).
 __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind, const DAux *aux,
                                                double curv, double cc, double x[3],
-                                               const double d[3], double k[3]) {
+                                               const double d[3], double k[3],
+                                               int64_t ray_index, int64_t ld_hist) {
     const double c0 = 1.0 / (2.0 * (2.0 - 1.2599210498948732));
     const double c1 = (1.0 - 1.2599210498948732) / (2.0 * (2.0 - 1.2599210498948732));
     const double d0 = 1.0 / (2.0 - 1.2599210498948732);
@@ -90,10 +93,26 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
         l2g_point(m.to_shape, q, xs);
         const bool crossed = xs[2] - shape_sag(shape_kind, aux, curv, cc, xs[0], xs[1]) > 0.0;
         if (!grin_inside(m, q)) valid = false;
-        if (crossed || !valid) break;
-        uq[0] = q[0]; uq[1] = q[1]; uq[2] = q[2];
-        up[0] = p[0]; up[1] = p[1]; up[2] = p[2];
-        if (it == cap - 1) valid = false;
+        const bool stop = crossed || !valid;
+        if (!stop) {
+            uq[0] = q[0]; uq[1] = q[1]; uq[2] = q[2];
+            up[0] = p[0]; up[1] = p[1]; up[2] = p[2];
+            if (it == cap - 1) valid = false;
+        }
+        if (aux->hist_count && ray_index >= 0) aux->hist_count[ray_index] = it + 1;
+        if (aux->hist_x && ray_index >= 0 && it < aux->hist_rows) {
+            double gq[3], kq[3], kg[3], dummy[3];
+            const double invn = 1.0 / grin_index(m, uq, dummy, false);
+            kq[0] = up[0] * invn; kq[1] = up[1] * invn; kq[2] = up[2] * invn;
+            l2g_point(m.frame, uq, gq);
+            rot(m.frame.r, kq, kg);
+            for (int c = 0; c < 3; ++c) {
+                aux->hist_x[((int64_t)it * 3 + c) * ld_hist + ray_index] = gq[c];
+                if (aux->hist_k) aux->hist_k[((int64_t)it * 3 + c) * ld_hist + ray_index] = kg[c];
+            }
+            if (aux->hist_valid) aux->hist_valid[(int64_t)it * ld_hist + ray_index] = valid ? 1 : 0;
+        }
+        if (stop) break;
     }
     const double inv = 1.0 / grin_index(m, uq, g, false);
     const double kl[3] = {up[0] * inv, up[1] * inv, up[2] * inv};

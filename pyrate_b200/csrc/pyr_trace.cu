@@ -133,14 +133,16 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 // One sequence entry for one ray (real k, E).  Returns the flag byte.
 template <bool WITH_E, bool HAS_GRIN>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
-                                              Ray<WITH_E> &r, double d[3], double hit_g[3]) {
+                                              Ray<WITH_E> &r, double d[3], double hit_g[3],
+                                              int64_t ray_index) {
     constexpr bool GENERAL = true;
     const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
 
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
     if (HAS_GRIN && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
-        const bool v = grin_propagate(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k);
+        const bool v = grin_propagate(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k,
+                                      ok ? ray_index : -1, st.ld_out);
         ok = ok && v;
         const double inv = fast_rsqrt(dot3(r.k, r.k));
         d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
@@ -497,7 +499,8 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j])
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j],
+                                                                                   in_range[j] ? base + j : -1)
                                                  : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
 
@@ -774,6 +777,8 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                 a.xpow[i] = u.xpow[i]; a.ypow[i] = u.ypow[i];
             }
             a.curv2 = u.curv2; a.cc2 = u.cc2;
+            a.hist_x = u.grin_hist_x; a.hist_k = u.grin_hist_k; a.hist_valid = u.grin_hist_valid;
+            a.hist_count = u.grin_hist_count; a.hist_rows = u.grin_hist_rows;
             a.normradius = u.normradius != 0.0 ? u.normradius : 1.0;
             a.newton_tol = u.newton_tol > 0.0 ? u.newton_tol : 1e-14;
             a.n_coeff = u.n_coeff;

@@ -68,6 +68,7 @@ class TraceRecord(object):
         self.split = []
         self.lowered = None
         self.wave = None
+        self.grin_hist = {}     # step index -> {"x": (M,3,n), "k": (M,3,n), "valid": (M,n), "count": (n)}
 
 
 def _empty(shape, dtype, device, pool):
@@ -202,11 +203,14 @@ class RecordPool(object):
 
 
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
-          pool=None, events=None):
+          pool=None, events=None, grin_history=False, _hist_rows=None):
     """Run the lowered sequence on the device.  Returns a TraceRecord.
 
     events: optional list; a (start, end) pair of CUDA timing events is appended
-    per native launch (kernel-only timing for benchmarks)."""
+    per native launch (kernel-only timing for benchmarks).
+    grin_history: also record every integrator step of GRIN segments (the rows the
+    reference appends, material_grin.py:198-205).  Memory grows with steps x rays:
+    meant for small bundles.  Runs the trace twice (step counts first)."""
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
@@ -313,6 +317,24 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
             for i in range(lo, hi):
                 st = steps[i]
                 r = i - lo
+                (st.grin_hist_x, st.grin_hist_k, st.grin_hist_valid, st.grin_hist_count) = \
+                    (None, None, None, None)
+                st.grin_hist_rows = 0
+                if grin_history and st.before.kind == nat.MEDIUM_ISO_GRIN and not seg_complex:
+                    cnt = torch.zeros((ld,), dtype=torch.int32, device=device)
+                    st.grin_hist_count = cnt.data_ptr()
+                    h = {"count": cnt[:n]}
+                    if _hist_rows is not None and _hist_rows.get(i, 0) > 0:
+                        m = int(_hist_rows[i])
+                        h["x"] = torch.zeros((m, 3, ld), dtype=torch.float64, device=device)
+                        h["k"] = torch.zeros((m, 3, ld), dtype=torch.float64, device=device)
+                        h["valid"] = torch.zeros((m, ld), dtype=torch.uint8, device=device)
+                        (st.grin_hist_x, st.grin_hist_k, st.grin_hist_valid) = \
+                            (h["x"].data_ptr(), h["k"].data_ptr(), h["valid"].data_ptr())
+                        st.grin_hist_rows = m
+                        h["rows"] = m
+                        h["n"] = n
+                    rec.grin_hist[i] = h
                 st.out_x = xbuf[r].data_ptr()
                 st.out_flags = fbuf[r].data_ptr()
                 st.ld_out = ld
@@ -375,6 +397,13 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                     cur_e = ebuf[r] if ebuf is not None else None
                     ld_k = ld
                     n_x = n
+    if grin_history and _hist_rows is None and rec.grin_hist:
+        # first pass gave the step counts; second pass records the rows
+        rows = {i: int(h["count"].max().item()) if h["count"].numel() else 0
+                for (i, h) in rec.grin_hist.items()}
+        return trace(lowered, x0, k0, e0, wave, record_e=record_e, device=device,
+                     stream=stream, pool=pool, events=events, grin_history=True,
+                     _hist_rows=rows)
     return rec
 
 
@@ -431,9 +460,10 @@ class _BundleBuilder(object):
     next intersect (None for the last bundle, which has a single row).
     """
 
-    def __init__(self, start_x, start_k, start_e, mask, ids, hit, hit_flags):
+    def __init__(self, start_x, start_k, start_e, mask, ids, hit, hit_flags, hist=None):
         (self.start_x, self.start_k, self.start_e) = (start_x, start_k, start_e)
         (self.mask, self.ids, self.hit, self.hit_flags) = (mask, ids, hit, hit_flags)
+        self.hist = hist
         self.cache = None
 
     def build(self):
@@ -456,6 +486,23 @@ class _BundleBuilder(object):
             out = {"x": x0.unsqueeze(0), "k": k0.unsqueeze(0),
                    "Efield": e0.unsqueeze(0), "valid": ones.unsqueeze(0),
                    "rayID": ids}
+        elif self.hist is not None and "x" in self.hist:
+            # GRIN segment with integrator history: rows = start, one per integrator
+            # step (lock-step: a finished ray repeats its last row), the intersection
+            h = self.hist
+            (m, n) = (h["rows"], h["n"])
+            last = (h["count"].to(torch.int64) - 1).clamp(min=0)
+            row = torch.minimum(torch.arange(m, device=x0.device)[:, None], last[None, :])
+            hx = take(torch.gather(h["x"][:, :, :n], 0, row[:, None, :].expand(m, 3, n)))
+            hk = take(torch.gather(h["k"][:, :, :n], 0, row[:, None, :].expand(m, 3, n)))
+            hv = take(torch.gather(h["valid"][:, :n], 0, row) != 0)
+            hv = torch.cummin(hv.to(torch.uint8), dim=0).values != 0
+            x = torch.cat((x0.unsqueeze(0), hx, take(self.hit).unsqueeze(0)))
+            k = torch.cat((k0.unsqueeze(0), hk, hk[-1:]))
+            e = _lazy_efield(k) if self.start_e is None else \
+                torch.cat((e0.unsqueeze(0), _lazy_efield(k[1:])))
+            valid = torch.cat((ones.unsqueeze(0), hv, take(_hit_mask(self.hit_flags)).unsqueeze(0)))
+            out = {"x": x, "k": k, "Efield": e, "valid": valid, "rayID": ids}
         else:
             x = torch.stack((x0, take(self.hit)))
             out = {"x": x, "k": k0.unsqueeze(0).expand(2, -1, -1),
@@ -504,7 +551,8 @@ def paths_from_record(rec, splitup=False):
             blk_in = block(rec.n_in[s])
             hit = rec.hit[s][:, blk_in]
             fl = rec.flags[s][blk_in]
-            bb = _BundleBuilder(sx, sk, se, mask, ids, hit, fl)
+            bb = _BundleBuilder(sx, sk, se, mask, ids, hit, fl,
+                                hist=rec.grin_hist.get(s) if not splitup else None)
             splitted = bool(s >= 1 and rec.split[s - 1] and not splitup)
             bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
                                      wave=rec.wave, splitted=splitted))
@@ -541,7 +589,7 @@ def paths_from_record(rec, splitup=False):
 # entry used by OpticalSystem.seqtrace
 # ---------------------------------------------------------------------------
 def seqtrace(system, initialbundle, elementsequence, splitup=False,
-             record_e=False):
+             record_e=False, grin_history=False):
     lowered = lowering.lower(system, elementsequence, initialbundle.wave,
                              splitup=splitup)
     if initialbundle.x.shape[0] != 1:
@@ -551,7 +599,8 @@ def seqtrace(system, initialbundle, elementsequence, splitup=False,
     else:
         (x0, k0, e0) = (initialbundle.x[0], initialbundle.k[0],
                         initialbundle.Efield[0])
-    rec = trace(lowered, x0, k0, e0, initialbundle.wave, record_e=record_e)
+    rec = trace(lowered, x0, k0, e0, initialbundle.wave, record_e=record_e,
+                grin_history=grin_history)
     paths = paths_from_record(rec, splitup=splitup)
     for p in paths:
         p.record = rec

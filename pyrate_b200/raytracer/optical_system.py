@@ -39,7 +39,7 @@ class OpticalSystem(LocalCoordinatesTreeBase):
             self.elements.pop(key)
 
     def seqtrace(self, initialbundle, elementsequence, splitup=False,
-                 record_efield=False):
+                 record_efield=False, grin_history=False):
         """Sequential trace on the GPU.
 
         :param initialbundle: RayBundle (never written)
@@ -51,8 +51,12 @@ class OpticalSystem(LocalCoordinatesTreeBase):
                         media (otherwise `Efield` of isotropic bundles is
                         produced on demand as some unit vector perpendicular to
                         k -- the reference's own choice is SVD-arbitrary)
+        :param grin_history: record every integrator step of GRIN segments in the
+                        bundle rows like the reference does (small bundles only:
+                        steps x rays x 49 B)
         :return: list[RayPath]
         """
         from .. import engine
         return engine.seqtrace(self, initialbundle, elementsequence,
-                               splitup=splitup, record_e=record_efield)
+                               splitup=splitup, record_e=record_efield,
+                               grin_history=grin_history)

@@ -61,6 +61,37 @@ def test_matches_oracle_on_larger_bundles(name, rings):
                                         "rayID": rb["rayID"]}, tol, "%s b%d" % (name, ib))
 
 
+def test_grin_history_rows_match_reference_and_oracle():
+    """Opt-in integrator history: the GRIN bundle carries one row per integrator
+    step like the reference's (material_grin.py:198-205); fixture rows [0, P-2, P-1]
+    and the row count are the unmodified reference's, every row is checked
+    against the oracle."""
+    import pyrate_np as onp
+    g = util.load_golden("c5_grin")
+    spec = configs.CONFIGS["c5_grin"]
+    (s, seq) = configs.build_system(spec, pb.api())
+    bundle = pb.RayBundle(g["x0"], g["k0"], g["E0"], wave=configs.DLINE)
+    path = s.seqtrace(bundle, seq, grin_history=True)[0].raybundles
+    rpath = util.golden_paths(g)[0]
+    ref = onp.seqtrace(onp.system_from_spec(spec), g["x0"], g["k0"], g["E0"],
+                       wave=configs.DLINE, per_ray_energy=True)[0]
+    assert len(path) == len(rpath)
+    seen = 0
+    for (ib, (b, rb, ob)) in enumerate(zip(path, rpath, ref)):
+        d = b.numpy()
+        assert d["x"].shape[0] == rb["rows"], (ib, d["x"].shape, rb["rows"])
+        if rb["rows"] <= 3:
+            continue
+        seen += 1
+        rows = [0, rb["rows"] - 2, rb["rows"] - 1]
+        sub = {"x": d["x"][rows], "k": d["k"][rows], "valid": d["valid"][rows],
+               "rayID": d["rayID"]}
+        util.compare_bundle(sub, rb, 1e-9, "history vs fixture b%d" % ib)
+        util.compare_bundle(d, {"x": ob["x"], "k": ob["k"], "valid": ob["valid"],
+                                "rayID": ob["rayID"]}, 1e-9, "history vs oracle b%d" % ib)
+    assert seen == 1
+
+
 def test_efield_invariants_and_input_untouched():
     spec = configs.CONFIGS["c2_doublegauss"]
     (x0, k0, e0) = configs.config_bundle(spec, 12)
