@@ -325,10 +325,25 @@ def run_gpu(args):
                "h2d_bytes_per_step": ht.h2d_bytes, "d2h_bytes_per_step": ht.d2h_bytes,
                "ms_per_step": 1e3 * float(dt.item()),
                "what": "pyr_trace_host: pinned host x0,k0,E0 -> H2D -> trace -> D2H of the "
-                       "image-plane record (x, k, flags) + 8 spot sums, 3-slot pipeline"}
+                       "image-plane record (x, k, flags) + 8 spot sums, 4-slot pipeline, "
+                       "ramped chunks"}
         (c2, rms2) = engine.spot_from_sums(ht.spot8, origin)
         e2e["spot_rms"] = rms2
         e2e["spot_count"] = float(ht.spot8[3])
+        if world == 1:
+            # informational: the same call with E0=None, the reference's default field
+            # (0,1,0) (ray.py:71-73; perpendicular to this on-axis bundle's k like the
+            # uploaded (1,0,0), so the trace is the same), which is not uploaded: 48 B/ray
+            ht(xp, kp, None)
+            sync()
+            t = time.perf_counter()
+            for _ in range(args.steps):
+                ht(xp, kp, None)
+            torch.cuda.synchronize(dev)
+            dt2 = (time.perf_counter() - t) / args.steps
+            e2e["default_e0"] = {"value": n * S_COUNTED / dt2, "ms_per_step": 1e3 * dt2,
+                                 "h2d_bytes_per_step": 48 * n,
+                                 "spot_rms": engine.spot_from_sums(ht.spot8, origin)[1]}
 
     if rank == 0:
         (peak, peak_kind) = measured_peaks()

@@ -1,7 +1,9 @@
 // End-to-end host entry of the C ABI: bundle in (pinned) host memory in, final
 // surface record + spot sums back in host memory.  The bundle is cut into chunks
-// that cycle through three device slots on three streams, so the H2D copy of
-// chunk c+1, the trace of chunk c and the D2H copy of chunk c-1 overlap.
+// that cycle through four device slots on four streams, so the H2D copy of
+// chunk c+1, the trace of chunk c and the D2H copy of chunk c-1 overlap.  The first
+// and last chunks are short (1/8, 1/4, 1/2 of the nominal size): the pipeline's
+// fill (first H2D with nothing to overlap) and drain (last D2H) shrink with them.
 #include <cuda_runtime.h>
 
 #include <vector>
@@ -14,9 +16,16 @@ int trace_entry(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
 }
 
 namespace {
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 
 int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+
+// three rows of a (3, n) array as ONE 2-D copy (measured: three 1-D copies per array
+// cost 16.95 ms instead of 15.44 ms per 1e7-ray pass, profiles/r01_e2e_pcie.txt)
+cudaError_t copy_rows(double *dst, size_t dst_ld, const double *src, size_t src_ld, size_t count,
+                      cudaMemcpyKind kind, cudaStream_t s) {
+    return cudaMemcpy2DAsync(dst, dst_ld * 8, src, src_ld * 8, count * 8, 3, kind, s);
+}
 
 struct SlotLayout {
     int64_t ld;          // padded chunk width (doubles)
@@ -68,11 +77,25 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0, cons
     if (ce != cudaSuccess) rc = (int)ce;
 
     std::vector<PyrStep> local(steps, steps + n_steps);
-    const size_t hp = (size_t)n_rays * 8;           // host pitch
-    const size_t dp = (size_t)L.ld * 8;             // device pitch
-    int64_t chunk_idx = 0;
-    for (int64_t off = 0; off < n_rays && rc == PYR_OK; off += chunk_rays, ++chunk_idx) {
-        const int64_t cn = (n_rays - off < chunk_rays) ? n_rays - off : chunk_rays;
+    // chunk schedule: ramp up, nominal chunks, ramp down (multiples of 32 rays)
+    std::vector<int64_t> sizes;
+    {
+        int64_t ramp[3] = {round_up(chunk_rays / 8, 32), round_up(chunk_rays / 4, 32),
+                           round_up(chunk_rays / 2, 32)};
+        int64_t ramp_total = 2 * (ramp[0] + ramp[1] + ramp[2]);
+        if (chunk_rays >= 4096 && n_rays >= ramp_total + chunk_rays) {
+            int64_t body = n_rays - ramp_total;
+            for (int i = 0; i < 3; ++i) sizes.push_back(ramp[i]);
+            while (body > 0) { sizes.push_back(body < chunk_rays ? body : chunk_rays); body -= chunk_rays; }
+            for (int i = 2; i >= 0; --i) sizes.push_back(ramp[i]);
+        } else {
+            for (int64_t off = 0; off < n_rays; off += chunk_rays)
+                sizes.push_back(n_rays - off < chunk_rays ? n_rays - off : chunk_rays);
+        }
+    }
+    int64_t off = 0;
+    for (size_t chunk_idx = 0; chunk_idx < sizes.size() && rc == PYR_OK; off += sizes[chunk_idx], ++chunk_idx) {
+        const int64_t cn = sizes[chunk_idx];
         const int slot = (int)(chunk_idx % kSlots);
         cudaStream_t s = st[slot];
         char *base = ws + slot * L.slot_bytes;
@@ -82,11 +105,11 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0, cons
         double *ox = de + 3 * L.ld;
         double *ok = ox + 3 * L.ld;
         uint8_t *of = reinterpret_cast<uint8_t *>(ok + 3 * L.ld);
-        ce = cudaMemcpy2DAsync(dx, dp, x0 + off, hp, (size_t)cn * 8, 3, cudaMemcpyHostToDevice, s);
+        ce = copy_rows(dx, L.ld, x0 + off, n_rays, cn, cudaMemcpyHostToDevice, s);
         if (ce == cudaSuccess)
-            ce = cudaMemcpy2DAsync(dk, dp, k0 + off, hp, (size_t)cn * 8, 3, cudaMemcpyHostToDevice, s);
+            ce = copy_rows(dk, L.ld, k0 + off, n_rays, cn, cudaMemcpyHostToDevice, s);
         if (ce == cudaSuccess && e0)
-            ce = cudaMemcpy2DAsync(de, dp, e0 + off, hp, (size_t)cn * 8, 3, cudaMemcpyHostToDevice, s);
+            ce = copy_rows(de, L.ld, e0 + off, n_rays, cn, cudaMemcpyHostToDevice, s);
         if (ce != cudaSuccess) { rc = (int)ce; break; }
         for (int i = 0; i < n_steps; ++i) {
             local[i].out_x = nullptr; local[i].out_k = nullptr; local[i].out_e = nullptr;
@@ -105,9 +128,9 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0, cons
             if (rc != PYR_OK) break;
         }
         if (x_last)
-            ce = cudaMemcpy2DAsync(x_last + off, hp, ox, dp, (size_t)cn * 8, 3, cudaMemcpyDeviceToHost, s);
+            ce = copy_rows(x_last + off, n_rays, ox, L.ld, cn, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && k_last)
-            ce = cudaMemcpy2DAsync(k_last + off, hp, ok, dp, (size_t)cn * 8, 3, cudaMemcpyDeviceToHost, s);
+            ce = copy_rows(k_last + off, n_rays, ok, L.ld, cn, cudaMemcpyDeviceToHost, s);
         if (ce == cudaSuccess && flags_last)
             ce = cudaMemcpyAsync(flags_last + off, of, (size_t)cn, cudaMemcpyDeviceToHost, s);
         if (ce != cudaSuccess) rc = (int)ce;

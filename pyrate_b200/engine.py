@@ -731,16 +731,18 @@ class HostTracer(object):
     def d2h_bytes(self):
         return 49 * self.n + 64
 
-    def __call__(self, x0, k0, e0):
+    def __call__(self, x0, k0, e0=None):
         """x0, k0, e0: contiguous (3, n) float64 CPU tensors (pinned for
-        overlap).  Returns (x_last, k_last, flags_last, spot8) host tensors."""
+        overlap); e0=None is the reference's default field (0, 1, 0)
+        (ray.py:71-73) and is not uploaded.  Returns (x_last, k_last,
+        flags_last, spot8) host tensors."""
         for t in (x0, k0, e0):
-            assert t.device.type == "cpu" and t.dtype == torch.float64 and \
-                t.is_contiguous() and t.shape == (3, self.n)
+            assert t is None or (t.device.type == "cpu" and t.dtype == torch.float64 and
+                                 t.is_contiguous() and t.shape == (3, self.n))
         with torch.cuda.device(self.device):
             nat.check(self.lib.pyr_trace_host(
                 self.steps, len(self.lowered), x0.data_ptr(), k0.data_ptr(),
-                e0.data_ptr(), self.n, self.x_last.data_ptr(),
+                None if e0 is None else e0.data_ptr(), self.n, self.x_last.data_ptr(),
                 self.k_last.data_ptr(), self.flags_last.data_ptr(),
                 self.spot8.data_ptr(), self.ws_ptr, self.ws_bytes, self.chunk))
         return (self.x_last, self.k_last, self.flags_last, self.spot8)

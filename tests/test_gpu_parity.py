@@ -149,20 +149,22 @@ def test_full_size_properties_double_gauss():
         assert util.relerr(got_k, ref[0][s + 2]["k"][0]) < 1e-10
 
 
-def test_host_entry_matches_device_path():
+@pytest.mark.parametrize("chunk,default_e", [(4000, False), (4096, False), (4096, True)])
+def test_host_entry_matches_device_path(chunk, default_e):
     """pyr_trace_host (chunked H2D -> trace -> D2H pipeline) against the device
-    resident path, with a chunk size that does not divide the bundle."""
+    resident path, with a chunk size that does not divide the bundle (4000: plain
+    schedule, 4096: ramped first/last chunks) and with the default field."""
     import torch
     from pyrate_b200 import engine, lowering
     spec = configs.CONFIGS["c2_doublegauss"]
-    (x0, k0, e0) = configs.config_bundle(spec, 60)        # 10 981 rays
+    (x0, k0, e0) = configs.config_bundle(spec, 70)        # 14 911 rays, E0 = (0,1,0)
     n = x0.shape[1]
     (s, seq) = configs.build_system(spec, pb.api())
     lowered = lowering.lower(s, seq, configs.DLINE)
     rec = engine.trace(lowered, x0, k0, e0, configs.DLINE)
-    ht = engine.HostTracer(lowered, n, chunk_rays=4000)
+    ht = engine.HostTracer(lowered, n, chunk_rays=chunk)
     (xp, kp, ep) = (torch.from_numpy(a).pin_memory() for a in (x0, k0, e0))
-    (xl, kl, fl, spot8) = ht(xp, kp, ep)
+    (xl, kl, fl, spot8) = ht(xp, kp, None if default_e else ep)
     assert np.array_equal(fl.numpy(), rec.flags[-1].cpu().numpy())
     assert np.array_equal(xl.numpy(), rec.hit[-1].cpu().numpy())
     assert np.array_equal(kl.numpy(), rec.k[-1].cpu().numpy())
