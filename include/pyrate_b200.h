@@ -35,12 +35,13 @@
 extern "C" {
 #endif
 
-#define PYR_ABI_VERSION 1
+#define PYR_ABI_VERSION 2
 
 #define PYR_MAX_COEFF 80        /* asphere coefficients / XY-polynomial terms (a
                                    Zernike series up to Fringe term 36 expands into
                                    66 monomials)                                   */
 #define PYR_MAX_GRIN_PARAMS 8
+#define PYR_MAX_TERMS 4         /* sub-shapes of a PYR_SHAPE_COMBINATION           */
 
 /* error codes */
 #define PYR_OK 0
@@ -54,11 +55,36 @@ enum PyrShapeKind {
     PYR_SHAPE_CONIC = 0,        /* Conic.intersect :289-325, closed form          */
     PYR_SHAPE_ASPHERE = 1,      /* ExplicitShape.intersect :448-465 + Asphere.F   */
     PYR_SHAPE_XYPOLY = 2,       /* ExplicitShape.intersect + XYPolynomials.F :785 */
-    PYR_SHAPE_BICONIC = 3       /* ExplicitShape.intersect + Biconic.F :618-629:
+    PYR_SHAPE_BICONIC = 3,      /* ExplicitShape.intersect + Biconic.F :618-629:
                                    curv/cc = x section, curv2/cc2 = y section,
                                    coeff[i] = A_(2i+2), coeff[16 + i] = B_(2i+2),
                                    n_coeff <= 16 pairs                             */
+    PYR_SHAPE_GRIDSAG = 4,      /* ExplicitShape.intersect + GridSag.F :866-880: the
+                                   bicubic tensor-product B-spline scipy's
+                                   RectBivariateSpline (FITPACK) fits through the
+                                   sag grid, evaluated like its ev(): arguments
+                                   clamped to the grid, de Boor basis             */
+    PYR_SHAPE_COMBINATION = 5   /* ExplicitShape.intersect + LinearCombination.F
+                                   :714-731: z = sum_i w_i (F_i(x - dx_i, y - dy_i)
+                                   + dz_i) over PyrStep.terms                      */
 };
+
+/* One sub-shape of a PYR_SHAPE_COMBINATION.  Its frame differs from the combination's
+ * by a translation (dx, dy, dz) only (the Zemax importer's decentred Zernike term,
+ * io/zmx.py:755-775).  Coefficients are the slice [coeff_off, coeff_off + coeff_len)
+ * of the step's coeff / xpow / ypow arrays in the layout of `kind`; a GRIDSAG term
+ * uses the step's grid_* arrays (at most one per step).  A Conic sub-shape is passed
+ * as ASPHERE with n_coeff = 0.                                                      */
+typedef struct PyrShapeTerm {
+    int32_t kind;               /* ASPHERE, XYPOLY, BICONIC or GRIDSAG             */
+    int32_t n_coeff;
+    int32_t coeff_off;
+    int32_t coeff_len;
+    double weight;
+    double dx, dy, dz;
+    double curv, cc, curv2, cc2;
+    double normradius;
+} PyrShapeTerm;
 
 /* raytracer/aperture.py:71-140 */
 enum PyrApertureKind {
@@ -183,6 +209,17 @@ typedef struct PyrStep {
     uint8_t *grin_hist_valid;
     int32_t *grin_hist_count;
     int64_t grin_hist_rows;
+    /* PYR_SHAPE_GRIDSAG: FITPACK representation (device pointers, caller-owned):
+     * knots grid_tx[grid_nx], grid_ty[grid_ny] (cubic: 4-fold end knots), coefficients
+     * grid_c[(grid_nx - 4) * (grid_ny - 4)], x index major                            */
+    const double *grid_tx;
+    const double *grid_ty;
+    const double *grid_c;
+    int32_t grid_nx, grid_ny;
+    /* PYR_SHAPE_COMBINATION */
+    int32_t n_terms;
+    int32_t reserved0;
+    PyrShapeTerm terms[PYR_MAX_TERMS];
     int64_t ld_out2;            /* split step only: leading dimension of out_k /
                                    out_e (width 2n: mode a of ray i in column i,
                                    mode b in column n + i, the reference's hstack

@@ -55,6 +55,8 @@ TRACES = [
     ("x7_two_elements", 5, (0, np.sin(2 * DEG), np.cos(2 * DEG)), (1, 0, 0), False, ""),
     ("x8_crystal_mirror", 2, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
     ("x9_zernike", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
+    ("x11_gridsag", 5, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
+    ("x12_combination", 5, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
 ]
 
 
@@ -165,6 +167,34 @@ def dump_shapes(api):
     print("shapes.npz")
 
 
+def dump_shapes2(api):
+    """GridSag and LinearCombination sag / gradient (separate file: shapes.npz predates
+    them)."""
+    rng = np.random.default_rng(33)
+    lc = api.LocalCoordinates.p(name="shapes2")
+    x = rng.uniform(-9.5, 9.5, 60)        # a few points outside the grid (clamped)
+    y = rng.uniform(-8.5, 8.5, 60)
+    out = {"x": x, "y": y}
+    grid = configs.X11_GRIDSAG["surfaces"][2]["shape"][1]["grid"]
+    gs = api.GridSag.p(lc, configs.grid_arrays(grid))
+    out["grid_sag"] = gs.getSag(x, y)
+    out["grid_grad"] = gs.getGrad(x, y)
+    xs = x * 0.7
+    ys = y * 0.7
+    (out["xs"], out["ys"]) = (xs, ys)
+    lcd = api.LocalCoordinates.p(name="shapes2_dec", decx=0.5, decy=-0.25)
+    lc.addChild(lcd)
+    asph = api.Asphere.p(lc, curv=1. / 45.0, cc=-0.8, coefficients=[2e-6, -1e-9])
+    xyp = api.XYPolynomials.p(lcd, normradius=10.0,
+                              coefficients=[(2, 0, 0.02), (1, 1, -0.01), (0, 3, 0.004)])
+    comb = api.LinearCombination.p(lc, list_of_coefficients_and_shapes=[(1.0, asph),
+                                                                       (0.5, xyp)])
+    out["comb_sag"] = comb.getSag(xs, ys)
+    out["comb_grad"] = comb.getGrad(xs, ys)
+    np.savez_compressed(os.path.join(OUT, "shapes2.npz"), **out)
+    print("shapes2.npz")
+
+
 def dump_aniso(api):
     rng = np.random.default_rng(11)
     lc = api.LocalCoordinates.p(name="aniso")
@@ -213,12 +243,21 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     api = refshim.api()
     np.random.seed(0)
+    only = [a.split("=", 1)[1].split(",") for a in sys.argv if a.startswith("--only=")]
+    if only:                 # regenerate selected fixtures: --only=x11_gridsag,shapes2
+        for t in TRACES:
+            if t[0] + t[5] in only[0]:
+                dump_trace(api, *t)
+        if "shapes2" in only[0]:
+            dump_shapes2(api)
+        return
     for t in TRACES:
         paths = dump_trace(api, *t)
         if t[0] == "c2_doublegauss" and t[5] == "":
             dump_spot(api, paths)
     dump_frames(api)
     dump_shapes(api)
+    dump_shapes2(api)
     dump_aniso(api)
 
 

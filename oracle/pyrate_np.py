@@ -233,8 +233,111 @@ def zernike_sag_grad(shape, x, y):
     return (f, fx, fy)
 
 
+# ---------------------------------------------------------------------------
+# GridSag (surface_shape.py:861-924): scipy.interpolate.RectBivariateSpline is a
+# third-party dependency of the reference (SciPy / FITPACK `regrid` for the fit,
+# `bispev` / `parder` for the evaluation; SciPy 1.18.1 here, the reference pins none).
+# The fit is taken from SciPy (knots tx, ty and B-spline coefficients c); the
+# evaluation is restated from FITPACK's published algorithm (fpbisp / fpbspl: clamp
+# the argument to the grid, locate the knot interval, de Boor-Cox recursion for the 4
+# non-zero cubic basis functions, tensor-product sum) and pinned against SciPy's own
+# ev() in tests/test_oracle_golden.py.
+# ---------------------------------------------------------------------------
+def gridsag_fit(xlin, ylin, zgrid):
+    from scipy.interpolate import RectBivariateSpline
+    sp = RectBivariateSpline(np.asarray(xlin, dtype=float), np.asarray(ylin, dtype=float),
+                             np.asarray(zgrid, dtype=float))
+    (tx, ty) = sp.get_knots()
+    return (np.array(tx), np.array(ty), np.array(sp.get_coeffs()))
+
+
+def _bspline_basis(t, x):
+    """Cubic basis values h (4, N) and derivatives dh (4, N) at x (N,) plus the interval
+    index l (N,), knots t with 4-fold end knots (fpbspl)."""
+    n = t.size
+    x = np.clip(x, t[3], t[n - 4])
+    l = np.clip(np.searchsorted(t, x, side="right") - 1, 3, n - 5)
+    h = np.zeros((4, x.size))
+    h[0] = 1.0
+    quad = None
+    for j in range(1, 4):
+        hh = h[:j].copy()
+        h[0] = 0.0
+        for i in range(1, j + 1):
+            (li, lj) = (l + i, l + i - j)
+            f = hh[i - 1] / (t[li] - t[lj])
+            h[i - 1] = h[i - 1] + f * (t[li] - x)
+            h[i] = f * (x - t[lj])
+        if j == 2:
+            quad = h[:3].copy()
+    dh = np.zeros_like(h)
+    for i in range(4):
+        a = quad[i - 1] / (t[l + i] - t[l + i - 3]) if i >= 1 else 0.0
+        b = quad[i] / (t[l + i + 1] - t[l + i - 2]) if i <= 2 else 0.0
+        dh[i] = 3.0 * (a - b)
+    return (h, dh, l)
+
+
+def gridsag_eval(spline, x, y):
+    """(F, dF/dx, dF/dy) of the bicubic spline (tx, ty, c) at points x, y (N,)."""
+    (tx, ty, c) = spline
+    shape = np.shape(x)
+    (x, y) = (np.ravel(np.asarray(x, dtype=float)), np.ravel(np.asarray(y, dtype=float)))
+    (hx, dhx, lx) = _bspline_basis(tx, x)
+    (hy, dhy, ly) = _bspline_basis(ty, y)
+    cm = c.reshape((tx.size - 4, ty.size - 4))
+    f = np.zeros_like(x)
+    fx = np.zeros_like(x)
+    fy = np.zeros_like(x)
+    for i in range(4):
+        for j in range(4):
+            cij = cm[lx - 3 + i, ly - 3 + j]
+            f = f + cij * hx[i] * hy[j]
+            fx = fx + cij * dhx[i] * hy[j]
+            fy = fy + cij * hx[i] * dhy[j]
+    return (f.reshape(shape), fx.reshape(shape), fy.reshape(shape))
+
+
+def _gridsag_spline(shape):
+    if "_spline" not in shape:
+        shape["_spline"] = gridsag_fit(shape["xlinspace"], shape["ylinspace"], shape["zgrid"])
+    return shape["_spline"]
+
+
+# ---------------------------------------------------------------------------
+# LinearCombination (surface_shape.py:709-777)
+# ---------------------------------------------------------------------------
+def lincomb_sag(shape, x, y):
+    """LinearCombination.F :714-731."""
+    xlocal = np.vstack((x, y, np.zeros_like(x)))
+    z = np.zeros_like(x)
+    for (coef, sub) in shape["terms"]:
+        xs = g2l_pts(sub["frame"], l2g_pts(shape["frame"], xlocal))
+        xs[2] = shape_sag(sub, xs[0], xs[1])
+        z = z + coef * g2l_pts(shape["frame"], l2g_pts(sub["frame"], xs))[2]
+    return z
+
+
+def lincomb_grad(shape, x, y):
+    """LinearCombination.gradF :733-754 (z component divided by the coefficient sum)."""
+    xlocal = np.vstack((x, y, np.zeros_like(x)))
+    g = np.zeros_like(xlocal)
+    total = 0.
+    for (coef, sub) in shape["terms"]:
+        xs = g2l_pts(sub["frame"], l2g_pts(shape["frame"], xlocal))
+        gs = shape_grad(sub, xs[0], xs[1])
+        g = g + coef * g2l_dir(shape["frame"], l2g_dir(sub["frame"], gs))
+        total += coef
+    g[2] = g[2] / total
+    return g
+
+
 def shape_sag(shape, x, y):
     kind = shape["kind"]
+    if kind == "GridSag":
+        return gridsag_eval(_gridsag_spline(shape), x, y)[0]
+    if kind == "LinearCombination":
+        return lincomb_sag(shape, x, y)
     if kind.startswith("Zernike"):
         return zernike_sag_grad(shape, x, y)[0]
     if kind == "Biconic":
@@ -251,6 +354,11 @@ def shape_sag(shape, x, y):
 
 def shape_grad(shape, x, y):
     kind = shape["kind"]
+    if kind == "GridSag":                                  # GridSag.gradF :871-880
+        (_, fx, fy) = gridsag_eval(_gridsag_spline(shape), x, y)
+        return np.vstack((-fx, -fy, np.ones_like(x)))
+    if kind == "LinearCombination":
+        return lincomb_grad(shape, x, y)
     if kind.startswith("Zernike"):
         (_, fx, fy) = zernike_sag_grad(shape, x, y)
         return np.vstack((-fx, -fy, np.ones_like(x)))
@@ -650,6 +758,25 @@ def _exec_grin_source(source, names):
     return [env[n] for n in names]
 
 
+def _shape_from_spec(skind, skw, frame):
+    if skind == "GridSag":
+        from pyrate_b200.configs import grid_arrays      # spec data -> arrays only
+        (xl, yl, zg) = grid_arrays(skw["grid"])
+        return {"kind": skind, "frame": frame, "xlinspace": xl, "ylinspace": yl, "zgrid": zg}
+    if skind == "LinearCombination":
+        terms = []
+        for (coef, tkind, tkw, dec) in skw["terms"]:
+            sub_frame = child_frame(frame, **dec) if dec else frame
+            terms.append((coef, _shape_from_spec(tkind, tkw, sub_frame)))
+        return {"kind": skind, "frame": frame, "terms": terms}
+    shape = dict(skw)
+    shape["kind"] = skind
+    shape["frame"] = frame
+    if skind in ("Asphere", "Biconic", "ZernikeFringe", "ZernikeANSI"):
+        shape.setdefault("coefficients", [])
+    return shape
+
+
 def system_from_spec(spec):
     frame = child_frame(ROOT_FRAME, decz=0.0)           # "object_lc0"
     background = {"kind": "ConstantIndexGlass", "n": 1.0, "frame": ROOT_FRAME}
@@ -659,11 +786,7 @@ def system_from_spec(spec):
     for surf in spec["surfaces"]:
         frame = child_frame(frame, **surf["lc"])
         (skind, skw) = surf["shape"]
-        shape = dict(skw)
-        shape["kind"] = skind
-        shape["frame"] = frame
-        if skind in ("Asphere", "Biconic", "ZernikeFringe", "ZernikeANSI"):
-            shape.setdefault("coefficients", [])
+        shape = _shape_from_spec(skind, skw, frame)
         if surf["aperture"] is None:
             ap = {"kind": "Base"}
         else:

@@ -51,7 +51,8 @@ def api():
     from pyrateoptics.raytracer.surface import Surface
     from pyrateoptics.raytracer.surface_shape import (Conic, Asphere, Biconic,
                                                       XYPolynomials, ZernikeFringe,
-                                                      ZernikeANSI)
+                                                      ZernikeANSI, GridSag,
+                                                      LinearCombination)
     from pyrateoptics.raytracer.aperture import (BaseAperture,
                                                  CircularAperture,
                                                  RectangularAperture)

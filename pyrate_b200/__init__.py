@@ -21,7 +21,8 @@ from .raytracer.optical_element import OpticalElement  # noqa: F401
 from .raytracer.optical_system import OpticalSystem  # noqa: F401
 from .raytracer.ray import RayBundle, RayPath  # noqa: F401
 from .raytracer.surface import Surface  # noqa: F401
-from .raytracer.surface_shape import (Asphere, Biconic, Conic, XYPolynomials,  # noqa: F401
+from .raytracer.surface_shape import (Asphere, Biconic, Conic, GridSag,  # noqa: F401
+                                      LinearCombination, XYPolynomials,
                                       ZernikeANSI, ZernikeFringe,
                                       accessible_shapes)
 
@@ -35,6 +36,7 @@ def api():
         LocalCoordinates=LocalCoordinates, Surface=Surface, Conic=Conic,
         Asphere=Asphere, Biconic=Biconic, XYPolynomials=XYPolynomials,
         ZernikeFringe=ZernikeFringe, ZernikeANSI=ZernikeANSI,
+        GridSag=GridSag, LinearCombination=LinearCombination,
         BaseAperture=BaseAperture,
         CircularAperture=CircularAperture, RectangularAperture=RectangularAperture,
         ConstantIndexGlass=ConstantIndexGlass, ModelGlass=ModelGlass,

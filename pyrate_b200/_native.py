@@ -7,10 +7,13 @@ the library is missing or was built for another ABI, loading raises.
 import ctypes as C
 import os
 
+ABI_VERSION = 2
 MAX_COEFF = 80
 MAX_GRIN_PARAMS = 8
 
-(SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY, SHAPE_BICONIC) = (0, 1, 2, 3)
+(SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY, SHAPE_BICONIC, SHAPE_GRIDSAG,
+ SHAPE_COMBINATION) = (0, 1, 2, 3, 4, 5)
+MAX_TERMS = 4
 (AP_BASE, AP_CIRCULAR, AP_RECTANGULAR) = (0, 1, 2)
 (REFRACT, REFLECT) = (0, 1)
 (MEDIUM_ISO_CONST, MEDIUM_ISO_GRIN, MEDIUM_ANISO) = (0, 1, 2)
@@ -36,6 +39,16 @@ class PyrMedium(C.Structure):
                 ("frame", PyrFrame)]
 
 
+class PyrShapeTerm(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_coeff", C.c_int32),
+                ("coeff_off", C.c_int32), ("coeff_len", C.c_int32),
+                ("weight", C.c_double),
+                ("dx", C.c_double), ("dy", C.c_double), ("dz", C.c_double),
+                ("curv", C.c_double), ("cc", C.c_double),
+                ("curv2", C.c_double), ("cc2", C.c_double),
+                ("normradius", C.c_double)]
+
+
 class PyrStep(C.Structure):
     _fields_ = [("shape_kind", C.c_int32), ("aperture_kind", C.c_int32),
                 ("interaction", C.c_int32), ("dir_mode", C.c_int32),
@@ -56,6 +69,11 @@ class PyrStep(C.Structure):
                 ("grin_hist_x", C.c_void_p), ("grin_hist_k", C.c_void_p),
                 ("grin_hist_valid", C.c_void_p), ("grin_hist_count", C.c_void_p),
                 ("grin_hist_rows", C.c_int64),
+                ("grid_tx", C.c_void_p), ("grid_ty", C.c_void_p),
+                ("grid_c", C.c_void_p),
+                ("grid_nx", C.c_int32), ("grid_ny", C.c_int32),
+                ("n_terms", C.c_int32), ("reserved0", C.c_int32),
+                ("terms", PyrShapeTerm * MAX_TERMS),
                 ("ld_out2", C.c_int64)]
 
 
@@ -109,6 +127,10 @@ def load():
                                    C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    if lib.pyr_version() != ABI_VERSION:
+        raise NativeError("pyrate_b200: libpyrate_b200.so has ABI version %d, "
+                          "_native.py expects %d (rebuild with `make`)" %
+                          (lib.pyr_version(), ABI_VERSION))
     if lib.pyr_sizeof_step() != C.sizeof(PyrStep) or \
             lib.pyr_sizeof_rays_in() != C.sizeof(PyrRaysIn):
         raise NativeError("pyrate_b200: struct layout mismatch between "

@@ -272,7 +272,7 @@ def build_system(spec, api):
             api.LocalCoordinates.p(name=surf["name"] + "_lc", **surf["lc"]),
             refname=refname)
         (shapekind, shapekw) = surf["shape"]
-        shape = getattr(api, shapekind).p(lc, **shapekw)
+        shape = make_shape(api, elem, lc, shapekind, shapekw, surf["name"])
         aperture = None
         if surf["aperture"] is not None:
             (apkind, apkw) = surf["aperture"]
@@ -291,6 +291,39 @@ def build_system(spec, api):
     for (key, el, _) in elems:
         s.addElement(key, el)
     return s, [(key, seq) for (key, _, seq) in elems]
+
+
+def grid_arrays(grid):
+    """Sag grid of a GridSag spec: {"x": (lo, hi, n), "y": (lo, hi, n), "poly":
+    [(c, px, py), ...]} -> (x, y, Z) with Z[i, j] = sum c x_i^px y_j^py."""
+    x = np.linspace(*grid["x"])
+    y = np.linspace(*grid["y"])
+    (xx, yy) = np.meshgrid(x, y, indexing="ij")
+    z = np.zeros_like(xx)
+    for (c, px, py) in grid["poly"]:
+        z = z + c * xx ** px * yy ** py
+    return (x, y, z)
+
+
+def make_shape(api, elem, lc, kind, kw, name):
+    """Shape object of a spec entry.  GridSag: kw = {"grid": ...} (grid_arrays);
+    LinearCombination: kw = {"terms": [(coefficient, kind, kw, decenter), ...]} with
+    decenter = None (the combination's frame) or {"decx": .., "decy": ..} (a child
+    frame, like the Zemax importer's decentred Zernike term, io/zmx.py:755-775)."""
+    if kind == "GridSag":
+        return api.GridSag.p(lc, grid_arrays(kw["grid"]))
+    if kind == "LinearCombination":
+        pairs = []
+        for (i, (coef, skind, skw, dec)) in enumerate(kw["terms"]):
+            sub_lc = lc
+            if dec:
+                sub_lc = elem.addLocalCoordinateSystem(
+                    api.LocalCoordinates.p(name="%s_term%d_lc" % (name, i), **dec),
+                    refname=lc.name)
+            pairs.append((coef, make_shape(api, elem, sub_lc, skind, skw,
+                                           "%s_term%d" % (name, i))))
+        return api.LinearCombination.p(lc, list_of_coefficients_and_shapes=pairs)
+    return getattr(api, kind).p(lc, **kw)
 
 
 def _make_material(api, lc, matspec, name):
@@ -479,6 +512,51 @@ X10_ZERNIKE_GENERAL = dict(X9_ZERNIKE, name="x10_zernike_general", surfaces=[
 # x10 is traced against the oracle only (the reference's Zernike gradient is inconsistent
 # with its sag for m != 0 terms, see oracle/pyrate_np.py:_zernike_term)
 
+X11_GRIDSAG = {     # measured-surface data: sag on a 41 x 33 grid (GridSag, :861-924)
+    "name": "x11_gridsag",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 4.0, curv=1. / 60.0, mat="glass"),
+        {"name": "back", "lc": {"decz": 6.0, "decy": -0.3, "tiltx": 1.0 * math.pi / 180.0},
+         "shape": ("GridSag", {"grid": {"x": (-9.0, 9.0, 41), "y": (-8.0, 8.0, 33),
+                                        "poly": [(-0.011, 2, 0), (-0.009, 0, 2), (4e-4, 1, 1),
+                                                 (2e-5, 3, 0), (-1.5e-5, 1, 2), (3e-6, 4, 0),
+                                                 (2e-6, 2, 2), (-1e-6, 0, 4)]}}),
+         "aperture": None, "mat": None, "opt": {}},
+        _conic("image", 50.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.55})},
+    "bundle": {"rings": 6, "radius": 7.0, "z0": -3.0},
+    "s_counted": 2,
+}
+
+_ZF_SYM2 = [0.0] * 9
+(_ZF_SYM2[3], _ZF_SYM2[8]) = (0.05, -0.008)
+X12_COMBINATION = {   # asphere + decentred XY polynomial + Zernike (m = 0): the shape the
+    # Zemax importer builds for "Zernike fringe sag" surfaces (io/zmx.py:755-775)
+    "name": "x12_combination",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        {"name": "front", "lc": {"decz": 4.0},
+         "shape": ("LinearCombination", {"terms": [
+             (1.0, "Asphere", {"curv": 1. / 45.0, "cc": -0.8, "coefficients": [2e-6, -1e-9]},
+              None),
+             (0.5, "XYPolynomials", {"normradius": 10.0,
+                                     "coefficients": [(2, 0, 0.02), (1, 1, -0.01),
+                                                      (0, 3, 0.004)]},
+              {"decx": 0.5, "decy": -0.25}),
+             (2.0, "ZernikeFringe", {"normradius": 10.0, "coefficients": _ZF_SYM2},
+              {"decx": -0.2, "decy": 0.1})]}),
+         "aperture": _circ(9.0), "mat": "glass", "opt": {}},
+        _conic("back", 5.0, curv=-1. / 80.0, mat=None),
+        _conic("image", 45.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.6})},
+    "bundle": {"rings": 6, "radius": 7.0, "z0": -2.0},
+    "s_counted": 2,
+}
+
 CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
-                                       X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL)})
+                                       X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL,
+                                       X11_GRIDSAG, X12_COMBINATION)})

@@ -321,7 +321,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             double t;
             bool hit_ok = true;
             if (st.shape_kind == PYR_SHAPE_CONIC) t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
-            else { double gfx, gfy; bool gok; t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
+            else { double gfx, gfy; bool gok; t = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
             const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
             double hit_g[3];
             l2g_point(st.frame, h, hit_g);
@@ -347,7 +347,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             if (st.shape_kind == PYR_SHAPE_CONIC)
                 conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
             else
-                explicit_normal(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+                explicit_normal<false>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
 
             cplx kl[3];
             crot_t(st.frame.r, r.k, kl);

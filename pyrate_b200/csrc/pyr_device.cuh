@@ -55,6 +55,13 @@ struct DAux {
     uint8_t *hist_valid;
     int32_t *hist_count;
     int64_t hist_rows;
+    // grid sag (FITPACK bicubic B-spline), device pointers
+    const double *grid_tx, *grid_ty, *grid_c;
+    int32_t grid_nx, grid_ny;
+    // linear combination: this record is term 0 and the following n_terms - 1 records
+    // are the other terms (each with its own coefficients / grid)
+    int32_t n_terms, term_kind;
+    double term_w, term_dx, term_dy, term_dz, term_curv, term_cc;
 };
 
 struct DStep {

@@ -53,6 +53,7 @@ __device__ __forceinline__ bool grin_inside(const DMedium &m, const double q[3])
 // returns validity (energy, boundary, step cap).
 // History (aux->hist_*, optional): one row per integrator step with the frozen state
 // the reference appends (material_grin.py:195-205).
+template <bool EXT>
 __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind, const DAux *aux,
                                                double curv, double cc, double x[3],
                                                const double d[3], double k[3],
@@ -91,7 +92,7 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
         if (fabs(dot3(p, p) - nq * nq) > m.energy_tol) valid = false;
         double xs[3];
         l2g_point(m.to_shape, q, xs);
-        const bool crossed = xs[2] - shape_sag(shape_kind, aux, curv, cc, xs[0], xs[1]) > 0.0;
+        const bool crossed = xs[2] - shape_sag<EXT>(shape_kind, aux, curv, cc, xs[0], xs[1]) > 0.0;
         if (!grin_inside(m, q)) valid = false;
         const bool stop = crossed || !valid;
         if (!stop) {

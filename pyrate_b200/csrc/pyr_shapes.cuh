@@ -3,6 +3,10 @@
 //   Conic.intersect :289-325, conic_function :206-219, getGrad :221-237
 //   ExplicitShape.intersect :448-465 (root of z0 + t dz - F(x0 + t dx, y0 + t dy))
 //   Asphere.F :529-537, gradF :539-555;  XYPolynomials.F :785-793, gradF :795-807
+//   Biconic.F :618-629;  GridSag.F / gradF :866-880 (scipy RectBivariateSpline.ev);
+//   LinearCombination.F / gradF :714-754
+// Template parameter EXT: the kernels that carry grid-sag / combination shapes are
+// separate instantiations, so the common shapes keep their register budget.
 #pragma once
 
 #include "pyr_device.cuh"
@@ -116,19 +120,115 @@ __device__ __forceinline__ void biconic_eval(const DAux &a, double cx, double kx
     F = f; Fx = fx; Fy = fy;
 }
 
-__device__ __forceinline__ void explicit_eval(int kind, const DAux &a, double curv, double cc,
-                                              double x, double y, double &F, double &Fx,
-                                              double &Fy) {
+// Cubic B-spline basis values h[0..3] and derivatives dh[0..3] of the knot interval
+// t[l] <= x < t[l+1] (de Boor / Cox recursion, FITPACK fpbspl); they weight the
+// coefficients l-3 .. l.
+__device__ __forceinline__ void bspline_basis(const double *__restrict__ t, int l, double x,
+                                              double h[4], double dh[4]) {
+    double tm[3], tp[3];                               // t[l-2..l], t[l+1..l+3]
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { tm[i] = __ldg(t + l - 2 + i); tp[i] = __ldg(t + l + 1 + i); }
+    // degree 1
+    const double f1 = 1.0 / (tp[0] - tm[2]);
+    double a0 = f1 * (tp[0] - x), a1 = f1 * (x - tm[2]);
+    // degree 2: basis l-2, l-1, l
+    const double g0 = a0 / (tp[0] - tm[1]), g1 = a1 / (tp[1] - tm[2]);
+    const double q0 = g0 * (tp[0] - x);
+    const double q1 = fma(g0, x - tm[1], g1 * (tp[1] - x));
+    const double q2 = g1 * (x - tm[2]);
+    // degree 3: basis l-3 .. l
+    const double r0 = 1.0 / (tp[0] - tm[0]), r1 = 1.0 / (tp[1] - tm[1]), r2 = 1.0 / (tp[2] - tm[2]);
+    const double e0 = q0 * r0, e1 = q1 * r1, e2 = q2 * r2;
+    h[0] = e0 * (tp[0] - x);
+    h[1] = fma(e0, x - tm[0], e1 * (tp[1] - x));
+    h[2] = fma(e1, x - tm[1], e2 * (tp[2] - x));
+    h[3] = e2 * (x - tm[2]);
+    // B'_{i,3} = 3 (B_{i,2} / (t_{i+3} - t_i) - B_{i+1,2} / (t_{i+4} - t_{i+1}))
+    dh[0] = -3.0 * e0;
+    dh[1] = 3.0 * (e0 - e1);
+    dh[2] = 3.0 * (e1 - e2);
+    dh[3] = 3.0 * e2;
+}
+
+// knot interval of x in t[3 .. n-4] (x already clamped): largest l in [3, n-5] with t[l] <= x
+__device__ __forceinline__ int bspline_interval(const double *__restrict__ t, int n, double x) {
+    int lo = 3, hi = n - 5;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(t + mid) <= x) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// Grid sag: value and gradient of the bicubic spline, arguments clamped to the grid
+// like FITPACK's bispev / parder (what RectBivariateSpline.ev does).
+__device__ __forceinline__ void gridsag_eval(const DAux &a, double x, double y, double &F,
+                                             double &Fx, double &Fy) {
+    const int nx = a.grid_nx, ny = a.grid_ny;
+    const double xc = fmin(fmax(x, __ldg(a.grid_tx + 3)), __ldg(a.grid_tx + nx - 4));
+    const double yc = fmin(fmax(y, __ldg(a.grid_ty + 3)), __ldg(a.grid_ty + ny - 4));
+    const int lx = bspline_interval(a.grid_tx, nx, xc);
+    const int ly = bspline_interval(a.grid_ty, ny, yc);
+    double hx[4], dhx[4], hy[4], dhy[4];
+    bspline_basis(a.grid_tx, lx, xc, hx, dhx);
+    bspline_basis(a.grid_ty, ly, yc, hy, dhy);
+    const int ncy = ny - 4;
+    const double *c = a.grid_c + (int64_t)(lx - 3) * ncy + (ly - 3);
+    double f = 0.0, fx = 0.0, fy = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        double row = 0.0, drow = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const double cij = __ldg(c + (int64_t)i * ncy + j);
+            row = fma(cij, hy[j], row);
+            drow = fma(cij, dhy[j], drow);
+        }
+        f = fma(hx[i], row, f);
+        fx = fma(dhx[i], row, fx);
+        fy = fma(hx[i], drow, fy);
+    }
+    F = f; Fx = fx; Fy = fy;
+}
+
+template <bool EXT>
+__device__ __forceinline__ void simple_eval(int kind, const DAux &a, double curv, double cc,
+                                            double x, double y, double &F, double &Fx,
+                                            double &Fy) {
     if (kind == PYR_SHAPE_ASPHERE) asphere_eval(a, curv, cc, x, y, F, Fx, Fy);
     else if (kind == PYR_SHAPE_BICONIC) biconic_eval(a, curv, cc, x, y, F, Fx, Fy);
+    else if (EXT && kind == PYR_SHAPE_GRIDSAG) gridsag_eval(a, x, y, F, Fx, Fy);
     else xypoly_eval(a, x, y, F, Fx, Fy);
 }
 
+template <bool EXT>
+__device__ __forceinline__ void explicit_eval(int kind, const DAux &a, double curv, double cc,
+                                              double x, double y, double &F, double &Fx,
+                                              double &Fy) {
+    if (EXT && kind == PYR_SHAPE_COMBINATION) {
+        // terms live in consecutive auxiliary records (pack() lays them out)
+        double f = 0.0, fx = 0.0, fy = 0.0;
+        for (int t = 0; t < a.n_terms; ++t) {
+            const DAux &at = (&a)[t];
+            double tf, tfx, tfy;
+            simple_eval<EXT>(at.term_kind, at, at.term_curv, at.term_cc, x - at.term_dx,
+                             y - at.term_dy, tf, tfx, tfy);
+            f = fma(at.term_w, tf + at.term_dz, f);
+            fx = fma(at.term_w, tfx, fx);
+            fy = fma(at.term_w, tfy, fy);
+        }
+        F = f; Fx = fx; Fy = fy;
+        return;
+    }
+    simple_eval<EXT>(kind, a, curv, cc, x, y, F, Fx, Fy);
+}
+
+template <bool EXT>
 __device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv, double cc,
                                             double x, double y) {
     if (kind == PYR_SHAPE_CONIC) return conic_sag(curv, cc, x, y);
     double F, Fx, Fy;
-    explicit_eval(kind, *a, curv, cc, x, y, F, Fx, Fy);
+    explicit_eval<EXT>(kind, *a, curv, cc, x, y, F, Fx, Fy);
     return F;
 }
 
@@ -138,6 +238,7 @@ __device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv
 // dF/dx, dF/dy of the last evaluation and `grad_ok` tells whether that evaluation
 // was within the convergence tolerance of the returned point -- then the surface
 // normal can reuse it instead of evaluating the shape once more.
+template <bool EXT>
 __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double curv, double cc,
                                              const double r0[3], const double d[3],
                                              bool active, double &gx, double &gy, bool &grad_ok) {
@@ -145,6 +246,9 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
     double t;
     if (kind == PYR_SHAPE_ASPHERE) t = conic_t(curv, cc, r0, d, ok);
     else if (kind == PYR_SHAPE_BICONIC) t = conic_t(0.5 * (curv + a.curv2), 0.5 * (cc + a.cc2), r0, d, ok);
+    else if (EXT && kind == PYR_SHAPE_COMBINATION && a.term_kind == PYR_SHAPE_ASPHERE &&
+             a.term_dx == 0.0 && a.term_dy == 0.0)
+        t = conic_t(a.term_w * a.term_curv, a.term_cc, r0, d, ok);   // leading base conic
     else t = -r0[2] * fast_rcp(d[2]);
     if (!isfinite(t)) t = 0.0;
     grad_ok = false;
@@ -153,7 +257,7 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
         const double x = fma(t, d[0], r0[0]);
         const double y = fma(t, d[1], r0[1]);
         double F;
-        explicit_eval(kind, a, curv, cc, x, y, F, gx, gy);
+        explicit_eval<EXT>(kind, a, curv, cc, x, y, F, gx, gy);
         const double res = fma(t, d[2], r0[2]) - F;
         const double dres = d[2] - fma(gx, d[0], gy * d[1]);
         double step = fast_div(res, dres);
@@ -169,10 +273,11 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
 }
 
 // unit normal of an explicit shape: grad = (-Fx, -Fy, 1)/|.|  (FreeShape.getGrad :420-423)
+template <bool EXT>
 __device__ __forceinline__ void explicit_normal(int kind, const DAux &a, double curv, double cc,
                                                 double x, double y, double n[3]) {
     double F, Fx, Fy;
-    explicit_eval(kind, a, curv, cc, x, y, F, Fx, Fy);
+    explicit_eval<EXT>(kind, a, curv, cc, x, y, F, Fx, Fy);
     const double inv = fast_rsqrt(fma(Fx, Fx, fma(Fy, Fy, 1.0)));
     n[0] = -Fx * inv; n[1] = -Fy * inv; n[2] = inv;
 }

@@ -131,7 +131,7 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 }
 
 // One sequence entry for one ray (real k, E).  Returns the flag byte.
-template <bool WITH_E, bool HAS_GRIN>
+template <bool WITH_E, bool HAS_GRIN, bool EXT>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
                                               Ray<WITH_E> &r, double d[3], double hit_g[3],
                                               int64_t ray_index) {
@@ -141,7 +141,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
 
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
     if (HAS_GRIN && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
-        const bool v = grin_propagate(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k,
+        const bool v = grin_propagate<EXT>(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k,
                                       ok ? ray_index : -1, st.ld_out);
         ok = ok && v;
         const double inv = fast_rsqrt(dot3(r.k, r.k));
@@ -168,7 +168,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
     } else {
-        t = explicit_t(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
+        t = explicit_t<EXT>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
     }
     const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
     if (st.bits & kRotIdentity) {
@@ -203,7 +203,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
         // gradient of the converged Newton iterate: within tol of the hit point
         normal_from_gradient(gfx, gfy, nrm);
     } else {
-        explicit_normal(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+        explicit_normal<EXT>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
     }
 
     // ---- deflection (material_isotropic.py:163-236), done in the shape frame ----
@@ -351,8 +351,8 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
 }
 
 // FEAT: 0 = lean steps only; 1 = + explicit shapes / own-frame apertures / partial
-// step modes; 3 = + GRIN media (separate instantiations keep the register budget of
-// the common cases small)
+// step modes; 3 = + GRIN media; 7 = + grid-sag / combination shapes (separate
+// instantiations keep the register budget of the common cases small)
 template <int RPT, bool WITH_E, int FEAT, int MINB = 1, int POLICY = 0, int BLOCK = 256>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
@@ -499,7 +499,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0>(P, st, ray[j], d, hit[j],
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0, (FEAT & 4) != 0>(P, st, ray[j], d, hit[j],
                                                                                    in_range[j] ? base + j : -1)
                                                  : step_lean<WITH_E>(st, ray[j], d, hit[j]);
             }
@@ -698,6 +698,7 @@ struct Packed {
     LaunchParams P;
     bool general;
     bool any_aniso;
+    bool extended;      // grid-sag / combination shapes present
 };
 
 static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
@@ -717,11 +718,37 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                 (!P.e || aligned16(P.e));
     out.general = false;
     out.any_aniso = false;
+    out.extended = false;
     int n_aux = 0;
     for (int s = 0; s < n_steps; ++s) {
         const PyrStep &u = steps[s];
         DStep &d = P.steps[s];
-        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_BICONIC) return PYR_E_UNSUPPORTED;
+        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_COMBINATION) return PYR_E_UNSUPPORTED;
+        const bool grid = u.shape_kind == PYR_SHAPE_GRIDSAG;
+        const bool comb = u.shape_kind == PYR_SHAPE_COMBINATION;
+        if (comb && (u.n_terms < 1 || u.n_terms > PYR_MAX_TERMS)) return PYR_E_BADARG;
+        bool uses_grid = grid;
+        if (comb) {
+            int grids = 0;
+            for (int t = 0; t < u.n_terms; ++t) {
+                const PyrShapeTerm &tm = u.terms[t];
+                if (tm.kind < PYR_SHAPE_ASPHERE || tm.kind > PYR_SHAPE_GRIDSAG) return PYR_E_UNSUPPORTED;
+                if (tm.coeff_off < 0 || tm.coeff_len < 0 || tm.coeff_off + tm.coeff_len > PYR_MAX_COEFF ||
+                    tm.n_coeff < 0)
+                    return PYR_E_BADARG;
+                if (tm.kind == PYR_SHAPE_BICONIC) {
+                    if (tm.n_coeff > 16 || (tm.n_coeff > 0 && tm.coeff_len < 16 + tm.n_coeff)) return PYR_E_BADARG;
+                } else if (tm.kind != PYR_SHAPE_GRIDSAG && tm.n_coeff > tm.coeff_len) {
+                    return PYR_E_BADARG;
+                }
+                if (tm.kind == PYR_SHAPE_GRIDSAG) ++grids;
+            }
+            if (grids > 1) return PYR_E_UNSUPPORTED;
+            uses_grid = grids == 1;
+        }
+        if (uses_grid && (!u.grid_tx || !u.grid_ty || !u.grid_c || u.grid_nx < 8 || u.grid_ny < 8))
+            return PYR_E_BADARG;
+        out.extended = out.extended || grid || comb;
         if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > 16) return PYR_E_BADARG;
         if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
         if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
@@ -768,7 +795,8 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                               u.after.kind != PYR_MEDIUM_ISO_CONST;
         d.aux = -1;
         if (need_aux) {
-            if (n_aux >= kMaxAux) return PYR_E_TOOLARGE;
+            const int n_rec = comb ? u.n_terms : 1;
+            if (n_aux + n_rec > kMaxAux) return PYR_E_TOOLARGE;
             DAux &a = P.aux[n_aux];
             const bool bic = u.shape_kind == PYR_SHAPE_BICONIC;
             for (int i = 0; i < PYR_MAX_COEFF; ++i) {
@@ -786,10 +814,39 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
             pack_frame(u.aperture_frame, a.aperture_frame);
             pack_medium(u.before, u.shape_frame, a.before);
             pack_medium(u.after, u.shape_frame, a.after);
-            d.aux = (int8_t)n_aux++;
+            a.grid_tx = u.grid_tx; a.grid_ty = u.grid_ty; a.grid_c = u.grid_c;
+            a.grid_nx = u.grid_nx; a.grid_ny = u.grid_ny;
+            a.n_terms = 0;
+            if (comb) {
+                // one auxiliary record per term, consecutive; record 0 also carries the
+                // step's frame / media payload filled in above
+                for (int t = 0; t < u.n_terms; ++t) {
+                    const PyrShapeTerm &tm = u.terms[t];
+                    DAux &r = P.aux[n_aux + t];
+                    for (int i = 0; i < PYR_MAX_COEFF; ++i) {
+                        const bool used = i < tm.coeff_len;
+                        r.coeff[i] = used ? u.coeff[tm.coeff_off + i] : 0.0;
+                        r.xpow[i] = used ? u.xpow[tm.coeff_off + i] : 0;
+                        r.ypow[i] = used ? u.ypow[tm.coeff_off + i] : 0;
+                    }
+                    r.n_coeff = tm.n_coeff;
+                    r.curv2 = tm.curv2; r.cc2 = tm.cc2;
+                    r.normradius = tm.normradius != 0.0 ? tm.normradius : 1.0;
+                    r.grid_tx = u.grid_tx; r.grid_ty = u.grid_ty; r.grid_c = u.grid_c;
+                    r.grid_nx = u.grid_nx; r.grid_ny = u.grid_ny;
+                    r.term_kind = tm.kind; r.term_w = tm.weight;
+                    r.term_dx = tm.dx; r.term_dy = tm.dy; r.term_dz = tm.dz;
+                    r.term_curv = tm.curv; r.term_cc = tm.cc;
+                }
+                a.n_terms = u.n_terms;
+            }
+            d.aux = (int8_t)n_aux;
+            n_aux += n_rec;
             out.general = true;
         }
     }
+    // the crystal kernel carries the common shapes only
+    if (out.extended && (flags & PYR_F_COMPLEX)) return PYR_E_UNSUPPORTED;
     return PYR_OK;
 }
 
@@ -871,6 +928,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     for (int s = 0; s < n_steps; ++s)
         has_grin = has_grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN ||
                    steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
+    if (pk.extended)   // grid-sag / combination shapes: the all-features instantiation
+        return with_e ? launch(trace_real_kernel<1, true, 7, 2>, pk.P, 1, stream)
+                      : launch(trace_real_kernel<1, false, 7, 2>, pk.P, 1, stream);
     if (has_grin)   // integrator loops do not interleave across rays: one ray per thread,
                     // more resident warps
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)

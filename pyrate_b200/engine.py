@@ -10,6 +10,8 @@ raises.
 """
 import ctypes as C
 
+import numpy as np
+
 import torch
 
 from . import _native as nat
@@ -22,12 +24,30 @@ MAX_AUX_PER_LAUNCH = 10         # kMaxAux
 
 
 def _needs_aux(st):
-    """Mirror of pack() in csrc/pyr_trace.cu: does this entry need a DAux record?"""
+    """Mirror of pack() in csrc/pyr_trace.cu: how many DAux records this entry needs."""
     same_frame = st.aperture_kind == nat.AP_BASE or \
         bytes(st.shape_frame) == bytes(st.aperture_frame)
-    return (st.shape_kind != nat.SHAPE_CONIC or not same_frame or
-            st.mode != nat.STEP_FULL or st.before.kind != nat.MEDIUM_ISO_CONST or
-            st.after.kind != nat.MEDIUM_ISO_CONST)
+    if st.shape_kind == nat.SHAPE_COMBINATION:
+        return int(st.n_terms)
+    return int(st.shape_kind != nat.SHAPE_CONIC or not same_frame or
+               st.mode != nat.STEP_FULL or st.before.kind != nat.MEDIUM_ISO_CONST or
+               st.after.kind != nat.MEDIUM_ISO_CONST)
+
+
+def bind_grid(st, device):
+    """Grid-sag spline arrays of a lowered step (lowering leaves them in st._grid):
+    upload once per device and point the step at them."""
+    g = getattr(st, "_grid", None)
+    if g is None:
+        return
+    cache = getattr(st, "_grid_dev", None)
+    if cache is None or cache[0] != device:
+        cache = (device, [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device)
+                          for a in g])
+        st._grid_dev = cache
+    (tx, ty, c) = cache[1]
+    (st.grid_tx, st.grid_ty, st.grid_c) = (tx.data_ptr(), ty.data_ptr(), c.data_ptr())
+    (st.grid_nx, st.grid_ny) = (tx.numel(), ty.numel())
 
 
 class DeviceRequired(RuntimeError):
@@ -89,6 +109,8 @@ def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
         return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
     for i in range(lo, hi):
+        if getattr(steps[i], "_grid", None) is not None:
+            bind_grid(steps[i], x.device)
         C.memmove(C.addressof(arr[i - lo]), C.addressof(steps[i]),
                   C.sizeof(nat.PyrStep))
     rin = nat.PyrRaysIn()
@@ -252,7 +274,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         lo = bounded[-1]
         (count, aux) = (0, 0)
         for i in range(lo, hi):
-            a = 1 if _needs_aux(lowered[i].st) else 0
+            a = _needs_aux(lowered[i].st)
             if count + 1 > MAX_STEPS_PER_LAUNCH or aux + a > MAX_AUX_PER_LAUNCH:
                 bounded.append(i)
                 (count, aux) = (0, 0)
@@ -709,6 +731,8 @@ class HostTracer(object):
         self.device = torch.device("cuda", torch.cuda.current_device()) \
             if device is None else torch.device(device)
         self.lowered = lowered
+        for ls in lowered:
+            bind_grid(ls.st, self.device)
         self.steps = lowering.step_array(lowered)
         self.n = int(n_rays)
         self.chunk = int(min(chunk_rays, max(self.n, 1)))

@@ -158,55 +158,149 @@ def _zernike_terms(shape):
     return [(px, py, c) for ((px, py), c) in sorted(total.items()) if c != 0.0]
 
 
-def lower_surface(surface, st):
-    """Fill shape / aperture fields of PyrStep `st`."""
-    shape = surface.shape
+def _grid_spline(shape):
+    """GridSag -> FITPACK representation (tx, ty, c) of the bicubic spline.
+
+    The reference keeps a scipy RectBivariateSpline in `interpolant`
+    (surface_shape.py:911-921); its knots and coefficients are read directly, so
+    the device evaluates the very same spline.  Objects without one (annotations
+    only) are fitted here the same way."""
+    interp = getattr(shape, "interpolant", None)
+    if interp is None:
+        from scipy.interpolate import RectBivariateSpline
+        ann = shape.annotations
+        interp = RectBivariateSpline(np.array(ann["xlinspace"]), np.array(ann["ylinspace"]),
+                                     np.array(ann["zgrid"]))
+    (tx, ty) = interp.get_knots()
+    c = interp.get_coeffs()
+    if tuple(interp.degrees) != (3, 3):
+        raise LoweringError("grid sag: bicubic splines only")
+    (tx, ty, c) = (np.ascontiguousarray(a, dtype=np.float64) for a in (tx, ty, c))
+    if c.size != (tx.size - 4) * (ty.size - 4) or tx.size < 8 or ty.size < 8:
+        raise LoweringError("grid sag: unexpected spline layout")
+    return (tx, ty, c)
+
+
+def _simple_shape(shape):
+    """One non-composite explicit shape -> dict(kind, curv, cc, curv2, cc2,
+    normradius, n_coeff, coeff, xpow, ypow, grid); coeff/xpow/ypow are lists in
+    the device layout of `kind`."""
     names = _mro_names(shape)
-    st.shape_frame = _frame(shape.lc)
+    d = {"curv": 0.0, "cc": 0.0, "curv2": 0.0, "cc2": 0.0, "normradius": 1.0,
+         "n_coeff": 0, "coeff": [], "xpow": [], "ypow": [], "grid": None}
     if "Cylinder" in names:
         raise LoweringError("Cylinder is dead code in the reference "
                             "(surface_shape.py:367-388) and not supported")
     if "Conic" in names:
-        st.shape_kind = nat.SHAPE_CONIC
-        st.curv = _value(shape.curvature)
-        st.cc = _value(shape.conic)
+        d["kind"] = nat.SHAPE_CONIC
+        d["curv"] = _value(shape.curvature)
+        d["cc"] = _value(shape.conic)
     elif "Asphere" in names:
-        st.shape_kind = nat.SHAPE_ASPHERE
-        st.curv = _value(shape.params["curv"])
-        st.cc = _value(shape.params["cc"])
+        d["kind"] = nat.SHAPE_ASPHERE
+        d["curv"] = _value(shape.params["curv"])
+        d["cc"] = _value(shape.params["cc"])
         ncoef = int(shape.annotations["numcoefficients"])
-        if ncoef > nat.MAX_COEFF:
-            raise LoweringError("too many asphere coefficients")
-        st.n_coeff = ncoef
-        for i in range(ncoef):
-            st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
+        d["n_coeff"] = ncoef
+        d["coeff"] = [_value(shape.params["A" + str(2 * i + 2)]) for i in range(ncoef)]
     elif "Biconic" in names:
-        st.shape_kind = nat.SHAPE_BICONIC
-        (st.curv, st.cc) = (_value(shape.params["curvx"]), _value(shape.params["ccx"]))
-        (st.curv2, st.cc2) = (_value(shape.params["curvy"]), _value(shape.params["ccy"]))
+        d["kind"] = nat.SHAPE_BICONIC
+        (d["curv"], d["cc"]) = (_value(shape.params["curvx"]), _value(shape.params["ccx"]))
+        (d["curv2"], d["cc2"]) = (_value(shape.params["curvy"]), _value(shape.params["ccy"]))
         ncoef = int(shape.annotations["numcoefficients"])
         if ncoef > 16:
             raise LoweringError("too many biconic coefficient pairs")
-        st.n_coeff = ncoef
-        for i in range(ncoef):
-            st.coeff[i] = _value(shape.params["A" + str(2 * i + 2)])
-            st.coeff[16 + i] = _value(shape.params["B" + str(2 * i + 2)])
+        d["n_coeff"] = ncoef
+        if ncoef:
+            co = [0.0] * (16 + ncoef)
+            for i in range(ncoef):
+                co[i] = _value(shape.params["A" + str(2 * i + 2)])
+                co[16 + i] = _value(shape.params["B" + str(2 * i + 2)])
+            d["coeff"] = co
     elif "XYPolynomials" in names or "Zernike" in names:
-        st.shape_kind = nat.SHAPE_XYPOLY
-        if "Zernike" in names:
-            terms = _zernike_terms(shape)
-        else:
-            terms = _xy_terms(shape)
-        if len(terms) > nat.MAX_COEFF:
-            raise LoweringError("too many XY polynomial terms")
-        st.normradius = _value(shape.params["normradius"])
-        st.n_coeff = len(terms)
-        for (i, (xp, yp, c)) in enumerate(terms):
+        d["kind"] = nat.SHAPE_XYPOLY
+        terms = _zernike_terms(shape) if "Zernike" in names else _xy_terms(shape)
+        d["normradius"] = _value(shape.params["normradius"])
+        d["n_coeff"] = len(terms)
+        for (xp, yp, c) in terms:
             if not (0 <= xp < 64 and 0 <= yp < 64):
                 raise LoweringError("XY exponent out of range")
-            (st.xpow[i], st.ypow[i], st.coeff[i]) = (xp, yp, c)
+            d["xpow"].append(xp)
+            d["ypow"].append(yp)
+            d["coeff"].append(c)
+    elif "GridSag" in names:
+        d["kind"] = nat.SHAPE_GRIDSAG
+        d["grid"] = _grid_spline(shape)
     else:
         raise LoweringError("unsupported shape class %s" % type(shape).__name__)
+    if len(d["coeff"]) > nat.MAX_COEFF:
+        raise LoweringError("too many shape coefficients (%d > %d)" %
+                            (len(d["coeff"]), nat.MAX_COEFF))
+    d["xpow"] += [0] * (len(d["coeff"]) - len(d["xpow"]))
+    d["ypow"] += [0] * (len(d["coeff"]) - len(d["ypow"]))
+    return d
+
+
+def _relative_offset(sub_lc, lc):
+    """Origin of `sub_lc` in the frame `lc`; the two frames may differ by a
+    translation only."""
+    (b, bs) = (np.asarray(lc.localbasis, dtype=float), np.asarray(sub_lc.localbasis, dtype=float))
+    if np.max(np.abs(b.T @ bs - np.eye(3))) > 1e-12:
+        raise LoweringError("LinearCombination: sub-shape frames rotated against the "
+                            "combination's frame are not supported")
+    return b.T @ (np.asarray(sub_lc.globalcoordinates, dtype=float) -
+                  np.asarray(lc.globalcoordinates, dtype=float))
+
+
+def lower_surface(surface, st):
+    """Fill shape / aperture fields of PyrStep `st`.  Grid-sag spline arrays (host
+    NumPy, uploaded by the engine) are left in `st._grid`."""
+    shape = surface.shape
+    names = _mro_names(shape)
+    st.shape_frame = _frame(shape.lc)
+    st._grid = None
+    if "LinearCombination" in names:
+        # surface_shape.py:709-777.  A Conic term is lowered as an asphere without
+        # coefficients: sag and TRUE sag gradient (the reference mixes the implicit
+        # conic gradient into the sum there, :738-752 "TODO: is this correct?")
+        coeffs = list(shape.annotations["list_shape_coefficients"])
+        subs = list(shape.list_shapes)
+        if not (1 <= len(subs) <= nat.MAX_TERMS) or len(coeffs) != len(subs):
+            raise LoweringError("LinearCombination: 1..%d terms supported" % nat.MAX_TERMS)
+        st.shape_kind = nat.SHAPE_COMBINATION
+        st.n_terms = len(subs)
+        off = 0
+        for (t, (w, sub)) in enumerate(zip(coeffs, subs)):
+            if "LinearCombination" in _mro_names(sub):
+                raise LoweringError("nested LinearCombination")
+            d = _simple_shape(sub)
+            tm = st.terms[t]
+            tm.kind = nat.SHAPE_ASPHERE if d["kind"] == nat.SHAPE_CONIC else d["kind"]
+            tm.weight = float(w)
+            (tm.dx, tm.dy, tm.dz) = [float(v) for v in _relative_offset(sub.lc, shape.lc)]
+            (tm.curv, tm.cc, tm.curv2, tm.cc2) = (d["curv"], d["cc"], d["curv2"], d["cc2"])
+            tm.normradius = d["normradius"]
+            tm.n_coeff = d["n_coeff"]
+            tm.coeff_off = off
+            tm.coeff_len = len(d["coeff"])
+            if off + tm.coeff_len > nat.MAX_COEFF:
+                raise LoweringError("LinearCombination: too many coefficients in total")
+            for (i, c) in enumerate(d["coeff"]):
+                (st.coeff[off + i], st.xpow[off + i], st.ypow[off + i]) = \
+                    (c, d["xpow"][i], d["ypow"][i])
+            off += tm.coeff_len
+            if d["grid"] is not None:
+                if st._grid is not None:
+                    raise LoweringError("LinearCombination: one GridSag term at most")
+                st._grid = d["grid"]
+    else:
+        d = _simple_shape(shape)
+        st.shape_kind = d["kind"]
+        (st.curv, st.cc, st.curv2, st.cc2) = (d["curv"], d["cc"], d["curv2"], d["cc2"])
+        st.normradius = d["normradius"]
+        st.n_coeff = d["n_coeff"]
+        for (i, c) in enumerate(d["coeff"]):
+            (st.coeff[i], st.xpow[i], st.ypow[i]) = (c, d["xpow"][i], d["ypow"][i])
+        st._grid = d["grid"]
     if st.shape_kind != nat.SHAPE_CONIC:
         ann = getattr(shape, "annotations", {})
         # The reference's fsolve stops at xtol = annotations["tol"] (1e-6) but

@@ -446,6 +446,107 @@ class ZernikeANSI(Zernike):
         return int(((n + 2) * n + m) / 2) + 1
 
 
+class GridSag(ExplicitShape):
+    """Sag given on a rectangular grid, interpolated by the bicubic spline scipy's
+    RectBivariateSpline fits through it (reference :861-924).  The device evaluates
+    the same spline from its FITPACK knots / coefficients (csrc/pyr_shapes.cuh);
+    the host-side getSag / getGrad below are for plotting and analysis (NumPy)."""
+
+    @classmethod
+    def p(cls, lc, xlin_ylin_zgrid, tol=1e-4, iterations=10, name=""):
+        (xlinspace, ylinspace, zgrid) = xlin_ylin_zgrid
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc, paramlist=())
+        ann["xlinspace"] = np.asarray(xlinspace).tolist()
+        ann["ylinspace"] = np.asarray(ylinspace).tolist()
+        ann["zgrid"] = np.asarray(zgrid).tolist()
+        ann["tol"] = tol
+        ann["iterations"] = iterations
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_GridSag"
+
+    def initialize_from_annotations(self):
+        from scipy.interpolate import RectBivariateSpline
+        self.interpolant = RectBivariateSpline(np.array(self.annotations["xlinspace"]),
+                                               np.array(self.annotations["ylinspace"]),
+                                               np.array(self.annotations["zgrid"]))
+
+    @staticmethod
+    def _host(a):
+        return a.detach().cpu().numpy() if (torch is not None and isinstance(a, torch.Tensor)) \
+            else np.asarray(a)
+
+    def F(self, x, y):
+        return self.interpolant.ev(self._host(x), self._host(y))
+
+    def gradF(self, x, y, z):
+        (x, y) = (self._host(x), self._host(y))
+        return np.stack((-self.interpolant.ev(x, y, dx=1), -self.interpolant.ev(x, y, dy=1),
+                         np.ones_like(x)))
+
+    def hessF(self, x, y, z):
+        (x, y) = (self._host(x), self._host(y))
+        h = np.zeros((3, 3) + x.shape)
+        h[0, 0] = -self.interpolant.ev(x, y, dx=2)
+        h[0, 1] = h[1, 0] = -self.interpolant.ev(x, y, dx=1, dy=1)
+        h[1, 1] = -self.interpolant.ev(x, y, dy=2)
+        return h
+
+    def getCentralCurvature(self):
+        h = self.hessF(np.zeros(1), np.zeros(1), None)
+        return float(-0.5 * (h[0, 0, 0] + h[1, 1, 0]))
+
+
+class LinearCombination(ExplicitShape):
+    """z = sum_i c_i F_i over sub-shapes (reference :709-777; the Zemax importer builds
+    asphere + decentred Zernike this way, io/zmx.py:755-775).  On the device the
+    sub-shape frames may differ from this shape's frame by a translation."""
+
+    @classmethod
+    def p(cls, lc, list_of_coefficients_and_shapes=None, name=""):
+        pairs = [] if list_of_coefficients_and_shapes is None else \
+            list(list_of_coefficients_and_shapes)
+        (ann, struct) = FreeShape.createAnnotationsAndStructure(lc)
+        ann["list_shape_coefficients"] = [c for (c, _) in pairs]
+        struct["list_shapes"] = [s for (_, s) in pairs]
+        return cls(ann, struct, name)
+
+    def setKind(self):
+        self.kind = "shape_LinearCombination"
+
+    def _offset(self, shape):
+        b = np.asarray(self.lc.localbasis, dtype=float)
+        return b.T @ (np.asarray(shape.lc.globalcoordinates, dtype=float) -
+                      np.asarray(self.lc.globalcoordinates, dtype=float))
+
+    def F(self, x, y):
+        z = 0.0
+        for (c, shape) in zip(self.annotations["list_shape_coefficients"], self.list_shapes):
+            o = self._offset(shape)
+            z = z + c * (shape.getSag(x - o[0], y - o[1]) + o[2])
+        return z
+
+    def gradF(self, x, y, z):
+        """Gradient of z - F.  Conic terms enter with the true sag gradient (the
+        reference adds their implicit-function gradient and renormalises the z
+        component by the sum of coefficients, :738-752)."""
+        xp = _lib(x)
+        (gx, gy) = (0.0, 0.0)
+        for (c, shape) in zip(self.annotations["list_shape_coefficients"], self.list_shapes):
+            o = self._offset(shape)
+            g = shape.getGrad(x - o[0], y - o[1])
+            gx = gx + c * g[0] / g[2]
+            gy = gy + c * g[1] / g[2]
+        return xp.stack((gx, gy, xp.ones_like(x)))
+
+    def getCentralCurvature(self):
+        return sum(c * s.getCentralCurvature() for (c, s) in
+                   zip(self.annotations["list_shape_coefficients"], self.list_shapes))
+
+
 accessible_shapes = {"shape_Conic": Conic, "shape_Asphere": Asphere,
                      "shape_Biconic": Biconic, "shape_XYPolynomials": XYPolynomials,
-                     "shape_ZernikeFringe": ZernikeFringe, "shape_ZernikeANSI": ZernikeANSI}
+                     "shape_ZernikeFringe": ZernikeFringe, "shape_ZernikeANSI": ZernikeANSI,
+                     "shape_GridSag": GridSag,
+                     "shape_LinearCombination": LinearCombination}

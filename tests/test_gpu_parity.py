@@ -45,7 +45,8 @@ def test_matches_reference_fixture(tag):
                                         ("x1_tilted", 25), ("x3_vignette", 30),
                                         ("c3_asphere", 12), ("x2_xypoly", 12),
                                         ("x6_biconic", 12), ("x9_zernike", 10),
-                                        ("x10_zernike_general", 10)])
+                                        ("x10_zernike_general", 10),
+                                        ("x11_gridsag", 10), ("x12_combination", 10)])
 def test_matches_oracle_on_larger_bundles(name, rings):
     import pyrate_np as onp
     spec = configs.CONFIGS[name]

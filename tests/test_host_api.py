@@ -98,6 +98,49 @@ def test_shapes_match_reference_fixture():
     assert np.allclose(sh.getNormal(xt, yt).numpy(), g["xy_normal"], rtol=1e-13, atol=1e-16)
 
 
+def test_gridsag_and_combination_mirrors_match_reference_fixture():
+    g = np.load(util.GOLDEN + "/shapes2.npz")
+    lc = pb.LocalCoordinates.p(name="s2")
+    grid = configs.X11_GRIDSAG["surfaces"][2]["shape"][1]["grid"]
+    gs = pb.GridSag.p(lc, configs.grid_arrays(grid))
+    assert gs.kind == "shape_GridSag"
+    assert np.allclose(gs.getSag(g["x"], g["y"]), g["grid_sag"], rtol=1e-14, atol=1e-16)
+    assert np.allclose(gs.getGrad(g["x"], g["y"]), g["grid_grad"], rtol=1e-13, atol=1e-16)
+    lcd = pb.LocalCoordinates.p(name="s2_dec", decx=0.5, decy=-0.25)
+    lc.addChild(lcd)
+    asph = pb.Asphere.p(lc, curv=1. / 45.0, cc=-0.8, coefficients=[2e-6, -1e-9])
+    xyp = pb.XYPolynomials.p(lcd, normradius=10.0,
+                             coefficients=[(2, 0, 0.02), (1, 1, -0.01), (0, 3, 0.004)])
+    comb = pb.LinearCombination.p(lc, list_of_coefficients_and_shapes=[(1.0, asph), (0.5, xyp)])
+    assert comb.kind == "shape_LinearCombination"
+    assert np.allclose(comb.getSag(g["xs"], g["ys"]), g["comb_sag"], rtol=1e-13, atol=1e-16)
+    assert np.allclose(comb.getGrad(g["xs"], g["ys"]), g["comb_grad"], rtol=1e-13, atol=1e-16)
+    # lowering: FITPACK arrays for the grid, one term record per sub-shape
+    from pyrate_b200 import _native as nat, lowering
+
+    class _S(object):
+        pass
+    (s1, s2) = (_S(), _S())
+    (s1.shape, s1.aperture) = (gs, pb.BaseAperture.p(lc))
+    (s2.shape, s2.aperture) = (comb, pb.BaseAperture.p(lc))
+    st = nat.PyrStep()
+    lowering.lower_surface(s1, st)
+    assert st.shape_kind == nat.SHAPE_GRIDSAG
+    (tx, ty, c) = st._grid
+    assert c.size == (tx.size - 4) * (ty.size - 4)
+    st = nat.PyrStep()
+    lowering.lower_surface(s2, st)
+    assert st.shape_kind == nat.SHAPE_COMBINATION and st.n_terms == 2
+    assert (st.terms[1].dx, st.terms[1].dy, st.terms[1].dz) == (0.5, -0.25, 0.0)
+    assert (st.terms[0].coeff_len, st.terms[1].coeff_off, st.terms[1].coeff_len) == (2, 2, 3)
+    rot = pb.LocalCoordinates.p(name="s2_rot", tiltx=0.1)
+    lc.addChild(rot)
+    bad = pb.LinearCombination.p(lc, [(1.0, pb.Asphere.p(rot, curv=0.01))])
+    s2.shape = bad
+    with pytest.raises(lowering.LoweringError):
+        lowering.lower_surface(s2, nat.PyrStep())
+
+
 def test_structural_errors_like_the_reference():
     s = pb.OpticalSystem.p()
     lc0 = s.addLocalCoordinateSystem(pb.LocalCoordinates.p(name="obj"),

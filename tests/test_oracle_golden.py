@@ -2,6 +2,8 @@
 from the unmodified reference (oracle/gen_golden.py) -- this is what pins the
 oracle.  Bit-level agreement is expected wherever the arithmetic is the same
 NumPy expression; the Newton-vs-fsolve and eig-ordering cases get tolerances."""
+import os
+
 import numpy as np
 import pytest
 
@@ -79,6 +81,38 @@ def test_shapes_match_reference():
     assert np.allclose(onp.shape_sag(sh, x, y), g["xy_sag"], rtol=1e-13, atol=1e-16)
     assert np.allclose(onp.shape_grad(sh, x, y), g["xy_grad"], rtol=1e-13, atol=1e-16)
     assert np.allclose(onp.shape_normal(sh, x, y), g["xy_normal"], rtol=1e-13, atol=1e-16)
+
+
+def test_gridsag_and_combination_match_reference():
+    """GridSag (FITPACK evaluation restated in NumPy) and LinearCombination sag /
+    gradient against the unmodified reference, and the restated spline evaluation
+    against SciPy's own ev() including points outside the grid (clamped)."""
+    from pyrate_b200 import configs
+    g = np.load(os.path.join(util.GOLDEN, "shapes2.npz"))
+    (x, y) = (g["x"], g["y"])
+    grid = configs.X11_GRIDSAG["surfaces"][2]["shape"][1]["grid"]
+    (xl, yl, zg) = configs.grid_arrays(grid)
+    sh = {"kind": "GridSag", "xlinspace": xl, "ylinspace": yl, "zgrid": zg,
+          "frame": onp.ROOT_FRAME}
+    assert util.relerr(onp.shape_sag(sh, x, y), g["grid_sag"]) < 1e-13
+    assert util.relerr(onp.shape_grad(sh, x, y), g["grid_grad"]) < 1e-12
+    from scipy.interpolate import RectBivariateSpline
+    sp = RectBivariateSpline(xl, yl, zg)
+    rng = np.random.default_rng(5)
+    (px, py) = (rng.uniform(-12, 12, 500), rng.uniform(-11, 11, 500))
+    (f, fx, fy) = onp.gridsag_eval(onp.gridsag_fit(xl, yl, zg), px, py)
+    assert np.max(np.abs(f - sp.ev(px, py))) < 1e-13
+    assert np.max(np.abs(fx - sp.ev(px, py, dx=1))) < 1e-12
+    assert np.max(np.abs(fy - sp.ev(px, py, dy=1))) < 1e-12
+    sub = onp.child_frame(onp.ROOT_FRAME, decx=0.5, decy=-0.25)
+    comb = {"kind": "LinearCombination", "frame": onp.ROOT_FRAME, "terms": [
+        (1.0, {"kind": "Asphere", "curv": 1. / 45.0, "cc": -0.8,
+               "coefficients": [2e-6, -1e-9], "frame": onp.ROOT_FRAME}),
+        (0.5, {"kind": "XYPolynomials", "normradius": 10.0,
+               "coefficients": [(2, 0, 0.02), (1, 1, -0.01), (0, 3, 0.004)],
+               "frame": sub})]}
+    assert util.relerr(onp.shape_sag(comb, g["xs"], g["ys"]), g["comb_sag"]) < 1e-13
+    assert util.relerr(onp.shape_grad(comb, g["xs"], g["ys"]), g["comb_grad"]) < 1e-13
 
 
 def test_aniso_modes_match_reference():
