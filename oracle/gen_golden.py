@@ -57,6 +57,7 @@ TRACES = [
     ("x9_zernike", 6, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
     ("x11_gridsag", 5, (np.sin(1 * DEG), 0, np.cos(1 * DEG)), (0, 1, 0), False, ""),
     ("x12_combination", 5, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
+    ("x13_tirglass", 6, (0, np.sin(1 * DEG), np.cos(1 * DEG)), (1, 0, 0), False, ""),
 ]
 
 

@@ -502,7 +502,7 @@ def local_surface_normal(step, mat, xglob):
 # ---------------------------------------------------------------------------
 def optical_index(mat, xlocal, wave):
     kind = mat["kind"]
-    if kind == "ConstantIndexGlass":          # :264
+    if kind in ("ConstantIndexGlass", "ConstantIndexGlassTIR"):   # :264, _tir.py:136
         return mat["n"]
     if kind == "ModelGlass":                  # :299-309 (Conrady)
         (n0, a, b) = mat["n0_A_B"]
@@ -547,6 +547,43 @@ def isotropic_deflect(mat, bundle, step, wave, mirror):
     e2 = efield_svd(k2v, eps)
     return (new_bundle(xg[:, valid], l2g_dir(fr, k2v), l2g_dir(fr, e2),
                        bundle["rayID"][valid]),)
+
+
+def isotropic_tir_deflect(mat, bundle, step, wave):
+    """IsotropicMaterialTIR.refract material_isotropic_tir.py:46-119 (angle form of
+    Snell's law), expression by expression.  Normalisations of reference
+    defects: k is rotated into the material frame (see below), validity is ANDed with the incoming bundle's and with finite normals
+    (the reference takes `1 - TIR` alone, :84, which revives vignetted rays), and the
+    E field is computed from the compacted k (the reference passes mismatched widths
+    to calc_e_field, :116, and raises as soon as one ray is totally reflected)."""
+    fr = mat["frame"]
+    xg = bundle["x"][-1]
+    # :52 takes k in GLOBAL coordinates while the normal (:66) is in the material frame;
+    # identical for material frames parallel to the global one (the pinned fixture),
+    # normalised to one frame here for the others
+    kin = g2l_dir(fr, bundle["k"][0])                       # :52 (row 0, same as -1 in
+    normk = np.sqrt(np.sum(kin ** 2, axis=0))               # a homogeneous medium)
+    index_before = normk
+    index_after = np.real(optical_index(mat, np.zeros((3, 1)), wave)) * np.ones(normk.shape)
+    dir_in = -(kin / normk)                                 # :63
+    normal = -local_surface_normal(step, mat, xg)           # :66
+    normal = normal / np.sqrt(np.sum(normal ** 2, axis=0))  # :69-71
+    costheta = np.sum(dir_in * normal, axis=0)              # :75
+    with np.errstate(invalid="ignore"):
+        sintheta = np.sqrt(1 - costheta ** 2)
+        sinthetadash = index_before / index_after * sintheta    # :79
+        tir = sinthetadash > 1.0                                # :82
+        costhetadash = np.sqrt(1 - sinthetadash ** 2)           # :87
+    valid = (~tir) & bundle["valid"][-1] & np.all(np.isfinite(normal), axis=0)
+    a = dir_in - costheta * normal                          # :91
+    aout = np.zeros(a.shape)
+    aout[:, valid] = -a[:, valid] * (index_before / index_after)[valid]   # :96-97
+    dir_out = -normal * costhetadash + aout                 # :99
+    dir_out = dir_out / np.sqrt(np.sum(dir_out ** 2, axis=0))             # :100-102
+    k2 = dir_out * index_after                              # :105
+    k2v = l2g_dir(fr, k2[:, valid])                         # :112
+    e2 = efield_svd(k2v, mat["n"] ** 2)
+    return (new_bundle(xg[:, valid], k2v, e2, bundle["rayID"][valid]),)
 
 
 # ---------------------------------------------------------------------------
@@ -685,6 +722,8 @@ def material_propagate(mat, bundle, step, **grin_kw):
 def material_deflect(mat, bundle, step, wave, mirror, splitup):
     if mat["kind"] == "AnisotropicMaterial":
         return anisotropic_deflect(mat, bundle, step, wave, mirror, splitup)
+    if mat["kind"] == "ConstantIndexGlassTIR" and not mirror:
+        return isotropic_tir_deflect(mat, bundle, step, wave)
     return isotropic_deflect(mat, bundle, step, wave, mirror)
 
 
@@ -800,7 +839,7 @@ def system_from_spec(spec):
         if key is not None and key not in mats:
             (mkind, mkw) = spec["materials"][key]
             m = {"kind": mkind, "frame": frame}
-            if mkind == "ConstantIndexGlass":
+            if mkind in ("ConstantIndexGlass", "ConstantIndexGlassTIR"):
                 m["n"] = mkw["n"]
             elif mkind == "ModelGlass":
                 m["n0_A_B"] = tuple(mkw["n0_A_B"])

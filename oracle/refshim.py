@@ -58,6 +58,8 @@ def api():
                                                  RectangularAperture)
     from pyrateoptics.raytracer.material.material_isotropic import (
         ConstantIndexGlass, ModelGlass)
+    from pyrateoptics.raytracer.material.material_isotropic_tir import (
+        ConstantIndexGlassTIR)
     from pyrateoptics.raytracer.material.material_anisotropic import (
         AnisotropicMaterial)
     from pyrateoptics.raytracer.material.material_grin import (

@@ -17,6 +17,8 @@ from .raytracer.material.material_glasscat import CatalogMaterial  # noqa: F401
 from .raytracer.material.material_grin import IsotropicGrinMaterial  # noqa: F401
 from .raytracer.material.material_isotropic import (ConstantIndexGlass,  # noqa: F401
                                                     ModelGlass)
+from .raytracer.material.material_isotropic_tir import (ConstantIndexGlassTIR,  # noqa: F401
+                                                        IsotropicMaterialTIR)
 from .raytracer.optical_element import OpticalElement  # noqa: F401
 from .raytracer.optical_system import OpticalSystem  # noqa: F401
 from .raytracer.ray import RayBundle, RayPath  # noqa: F401
@@ -40,6 +42,7 @@ def api():
         BaseAperture=BaseAperture,
         CircularAperture=CircularAperture, RectangularAperture=RectangularAperture,
         ConstantIndexGlass=ConstantIndexGlass, ModelGlass=ModelGlass,
+        ConstantIndexGlassTIR=ConstantIndexGlassTIR,
         AnisotropicMaterial=AnisotropicMaterial,
         IsotropicGrinMaterial=IsotropicGrinMaterial, RayBundle=RayBundle,
         RayPath=RayPath)

@@ -330,6 +330,8 @@ def _make_material(api, lc, matspec, name):
     (kind, kw) = matspec
     if kind == "ConstantIndexGlass":
         return api.ConstantIndexGlass.p(lc, n=kw["n"], name=name)
+    if kind == "ConstantIndexGlassTIR":
+        return api.ConstantIndexGlassTIR.p(lc, n=kw["n"], name=name)
     if kind == "ModelGlass":
         return api.ModelGlass.p(lc, n0_A_B=tuple(kw["n0_A_B"]), name=name)
     if kind == "AnisotropicMaterial":
@@ -556,7 +558,30 @@ X12_COMBINATION = {   # asphere + decentred XY polynomial + Zernike (m = 0): the
     "s_counted": 2,
 }
 
-CONFIGS.update({c["name"]: c for c in (X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
+X13_TIRGLASS = {   # IsotropicMaterialTIR (angle-form Snell, material_isotropic_tir.py:46-118)
+    # entered from a denser glass at a steep cemented surface: rim rays are totally
+    # internally reflected (-> invalid, dropped); no ray misses a surface or an aperture
+    "name": "x13_tirglass",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        _conic("front", 2.0, curv=1. / 12.0, mat="dense", decx=-0.1),
+        _conic("cement", 5.0, curv=-1. / 7.5, mat="light", decy=0.2),
+        _conic("back", 4.0, curv=1. / 90.0, cc=-1.5, mat=None, tiltx=1.0 * math.pi / 180.0),
+        _conic("image", 15.0),
+    ],
+    "materials": {"dense": ("ConstantIndexGlass", {"n": 1.9}),
+                  "light": ("ConstantIndexGlassTIR", {"n": 1.31})},
+    # The material frame (the cement surface's) is parallel to the global frame: the
+    # reference's TIR refract takes k in GLOBAL and the normal in MATERIAL coordinates
+    # (:52 vs :66) and is only right for such frames; the device uses one frame.
+    # radius 4: no TIR (the reference's TIR refract raises ValueError as soon as a ray
+    # is actually reflected, :116 mixes compacted and uncompacted widths); the TIR
+    # branch is traced against the oracle with a wider bundle (tests/test_gpu_parity.py)
+    "bundle": {"rings": 6, "radius": 4.0, "z0": -2.0},
+    "s_counted": 3,
+}
+
+CONFIGS.update({c["name"]: c for c in (X13_TIRGLASS, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
                                        X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL,
                                        X11_GRIDSAG, X12_COMBINATION)})

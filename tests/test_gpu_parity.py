@@ -62,6 +62,27 @@ def test_matches_oracle_on_larger_bundles(name, rings):
                                         "rayID": rb["rayID"]}, tol, "%s b%d" % (name, ib))
 
 
+def test_tir_glass_total_reflection_branch_matches_oracle():
+    """IsotropicMaterialTIR with rays that ARE totally reflected at the cemented
+    surface (the reference itself raises there, material_isotropic_tir.py:116): the
+    device drops them like the angle-form restatement does."""
+    import copy
+    import pyrate_np as onp
+    spec = copy.deepcopy(configs.CONFIGS["x13_tirglass"])
+    spec["bundle"]["radius"] = 7.0
+    deg = np.pi / 180.0
+    (x0, k0, e0) = configs.config_bundle(spec, 14, (0., np.sin(deg), np.cos(deg)), (1., 0., 0.))
+    (s, seq) = configs.build_system(spec, pb.api())
+    paths = s.seqtrace(pb.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    widths = [b.numpy()["x"].shape[2] for b in paths[0].raybundles]
+    assert widths[-1] < widths[0] and widths[-1] > 0          # some rays reflected, not all
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                        "rayID": rb["rayID"]}, util.TOL_CLOSED_FORM,
+                            "x13 tir b%d" % ib)
+
+
 def test_grin_history_rows_match_reference_and_oracle():
     """Opt-in integrator history: the GRIN bundle carries one row per integrator
     step like the reference's (material_grin.py:198-205); fixture rows [0, P-2, P-1]

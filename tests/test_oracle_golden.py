@@ -148,3 +148,19 @@ def test_known_answer_seed_vector():
                        [0.0, -0.04314208775168256, 0.9990689467020913], rtol=1e-13)
     assert np.allclose(path[3]["k"][0][:, 0],
                        [0.0, -0.06039952118111261, 1.522259388291602], rtol=1e-13)
+
+
+def test_tir_glass_angle_form_equals_vector_form():
+    """material_isotropic_tir.py:46-118 (angles) against material_isotropic.py:163-199
+    (k_par + xi n) on a bundle where rim rays are totally reflected."""
+    import copy
+    spec = copy.deepcopy(configs.CONFIGS["x13_tirglass"])
+    spec["bundle"]["radius"] = 7.0
+    deg = np.pi / 180.0
+    (x0, k0, e0) = configs.config_bundle(spec, 10, (0., np.sin(deg), np.cos(deg)), (1., 0., 0.))
+    a = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)[0]
+    spec["materials"]["light"] = ("ConstantIndexGlass", spec["materials"]["light"][1])
+    b = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)[0]
+    assert a[-1]["x"].shape[2] < x0.shape[1]
+    for (ba, bb) in zip(a, b):
+        util.compare_bundle(ba, bb, 1e-13, "tir forms")
