@@ -262,7 +262,7 @@ def main():
     dump_aniso(api)
 
 
-if __name__ == "__main__" and not ({"--rasters", "--glasscat"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--rasters", "--glasscat", "--paraxial"} & set(sys.argv)):
     main()
 
 
@@ -354,3 +354,83 @@ if __name__ == "__main__" and "--rasters" in sys.argv:
 if __name__ == "__main__" and "--glasscat" in sys.argv:
     refshim.install()
     dump_glasscat()
+
+
+PARAXIAL_CASES = [("c2_doublegauss", 3.0), ("x1_tilted", 2.0), ("x7_two_elements", 3.0),
+                  ("c1_doublet", 4.0)]
+
+
+def dump_paraxial():
+    """The paraxial callers of seqtrace in the unmodified reference: pilot bundles
+    (helpers.py:78-316), OpticalSystem.extractXYUV / para_seqtrace
+    (optical_system.py:105-214, optical_element.py:165-322, :381-469) and Aimy
+    (aim.py:46-320) on systems with the stop inside, tilted frames + a mirror, and two
+    elements."""
+    from pyrateoptics.raytracer.helpers import build_pilotbundle, build_pilotbundle_complex
+    from pyrateoptics.raytracer.aim import Aimy
+    api = refshim.api()
+    out = {}
+    for (name, stopsize) in PARAXIAL_CASES:
+        spec = configs.CONFIGS[name]
+        (s, seq) = configs.build_system(spec, api)
+        objsurf = s.elements[seq[0][0]].surfaces[seq[0][1][0][0]]
+        for (gen, fn) in (("real", build_pilotbundle), ("complex", build_pilotbundle_complex)):
+            pre = "%s_%s_" % (name, gen)
+            pbs = fn(objsurf, s.material_background, (0.1, 0.1), (1 * DEG, 1 * DEG),
+                     num_sampling_points=3)
+            pb = pbs[-1]
+            out[pre + "pilot_x"] = np.array(pb.x[0])
+            out[pre + "pilot_k"] = np.array(pb.k[0])
+            (m1, m2) = s.extractXYUV(pb, seq, pilotbundle_generation=gen)
+            out[pre + "m_obj_stop"] = m1
+            out[pre + "m_stop_img"] = m2
+            # per-pair matrices of the first element
+            pb = fn(objsurf, s.material_background, (0.1, 0.1), (1 * DEG, 1 * DEG),
+                    num_sampling_points=3)[-1]
+            (elemkey, subseq) = seq[0]
+            (ppath, mats) = s.elements[elemkey].calculateXYUV(
+                pb, subseq, s.material_background, pilotbundle_generation=gen)
+            (hitlist, _) = s.elements[elemkey].sequence_to_hitlist(subseq)
+            if name in ("c2_doublegauss", "x1_tilted"):       # (the others repeat these)
+                out[pre + "pair_matrices"] = np.array([mats[h] for h in hitlist])
+                out[pre + "pair_inverse"] = np.array([mats[(h[1], h[0], h[2])]
+                                                      for h in hitlist])
+                out[pre + "pilotpath_x"] = np.array(
+                    [b.x[-1] for b in ppath.raybundles[:len(hitlist) + 1]]).real
+                out[pre + "pilotpath_k"] = np.array(
+                    [b.k[-1] for b in ppath.raybundles[:len(hitlist) + 1]])
+            # linearised trace of a small fan
+            pb = fn(objsurf, s.material_background, (0.1, 0.1), (1 * DEG, 1 * DEG),
+                    num_sampling_points=3)[-1]
+            rng = np.random.default_rng(5)
+            x0 = np.vstack((rng.uniform(-1, 1, (2, 9)), np.zeros((1, 9)))) + \
+                np.array(pb.x[0][:, :1]).real
+            k0 = np.array(pb.k[0][:, :1]).real + \
+                np.vstack((rng.uniform(-0.02, 0.02, (2, 9)), np.zeros((1, 9))))
+            e0 = np.zeros((3, 9))
+            e0[1] = 1.0
+            (pp, rp) = s.para_seqtrace(pb, api.RayBundle(x0, k0, e0, wave=configs.DLINE), seq,
+                                       pilotbundle_generation=gen)
+            out[pre + "para_x0"] = x0
+            out[pre + "para_k0"] = k0
+            out[pre + "para_x"] = np.array([b.x[-1] for b in rp.raybundles])
+            out[pre + "para_k"] = np.array([b.k[-1] for b in rp.raybundles])
+            a = Aimy(s, seq, wave=configs.DLINE, num_pupil_points=24, stopsize=stopsize,
+                     pilotbundle_generation=gen)
+            out[pre + "aimy_m_obj_stop"] = a.m_obj_stop
+            b1 = a.aim(np.array([0.01, -0.02]), fieldtype="angle")
+            (out[pre + "aim_angle_x"], out[pre + "aim_angle_k"]) = (np.array(b1.x[0]), np.array(b1.k[0]))
+            try:        # the stop is the object surface in some cases: B block singular
+                b2 = a.aim(np.array([0.3, 0.1]), fieldtype="objectheight")
+                (out[pre + "aim_height_x"], out[pre + "aim_height_k"]) = \
+                    (np.array(b2.x[0]), np.array(b2.k[0]))
+            except np.linalg.LinAlgError:
+                pass
+            print(pre, pb.x.shape, np.linalg.cond(m2))
+    np.savez_compressed(os.path.join(OUT, "paraxial.npz"), **out)
+    print("paraxial.npz")
+
+
+if __name__ == "__main__" and "--paraxial" in sys.argv:
+    refshim.install()
+    dump_paraxial()

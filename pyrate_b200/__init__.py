@@ -117,3 +117,7 @@ def build_simple_optical_system(builduplist, material_db_path="", name=""):
 from .raytracer.analysis.optical_system_analysis import (OpticalSystemAnalysis,  # noqa: E402,F401
                                                          raytrace)
 from .raytracer.analysis.ray_analysis import RayBundleAnalysis  # noqa: E402,F401
+from .raytracer.analysis.optical_element_analysis import OpticalElementAnalysis  # noqa: E402,F401
+from .raytracer.aim import Aimy  # noqa: E402,F401
+from .raytracer.helpers import (build_pilotbundle, build_pilotbundle_complex,  # noqa: E402,F401
+                                choose_nearest)

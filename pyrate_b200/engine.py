@@ -63,6 +63,12 @@ def require_cuda():
     return lib
 
 
+def compute_device():
+    """The CUDA device ray data lives on (raises without one: no CPU fallback)."""
+    require_cuda()
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def _round_up(v, m):
     return (v + m - 1) // m * m
 

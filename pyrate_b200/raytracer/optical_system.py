@@ -9,7 +9,10 @@ is `list[RayPath]`, path = [b0, b0, b1, ..., bS] with (P, 3, N) bundle rows --
 but the rays live in CUDA tensors and the whole element sequence runs as one
 persistent sm_100a kernel.
 """
+import numpy as np
+
 from .localcoordinates import LocalCoordinates, LocalCoordinatesTreeBase
+from .ray import RayPath
 from .material.material_isotropic import ConstantIndexGlass
 
 
@@ -37,6 +40,74 @@ class OpticalSystem(LocalCoordinatesTreeBase):
     def removeElement(self, key):
         if key in self.elements:
             self.elements.pop(key)
+
+    def para_seqtrace(self, pilotbundle, initialbundle, elementsequence,
+                      pilotraypathsequence=None, use6x6=True,
+                      pilotbundle_generation="complex"):
+        """Linearised trace about a pilot ray, element by element (reference :105-128).
+        Returns (pilot RayPath, RayPath of the linearised bundles)."""
+        rpath = RayPath(initialbundle)
+        pilotpath = RayPath(pilotbundle)
+        if pilotraypathsequence is None:
+            pilotraypathsequence = tuple(0 for _ in elementsequence)
+        for ((elem, subseq), prp_nr) in zip(elementsequence, pilotraypathsequence):
+            (append_pilotpath, append_rpath) = self.elements[elem].para_seqtrace(
+                pilotpath.raybundles[-1], rpath.raybundles[-1], subseq,
+                self.material_background, pilotraypath_nr=prp_nr,
+                pilotbundle_generation=pilotbundle_generation)
+            rpath.appendRayPath(append_rpath)
+            pilotpath.appendRayPath(append_pilotpath)
+        return (pilotpath, rpath)
+
+    def sequence_to_hitlist(self, elementsequence):
+        return [(elem, self.elements[elem].sequence_to_hitlist(seq))
+                for (elem, seq) in elementsequence]
+
+    def extractXYUV(self, pilotbundle, elementsequence, pilotraypathsequence=None,
+                    pilotbundle_generation="complex"):
+        """(object -> stop, stop -> image) transfer matrices: products of the
+        per-surface-pair XYUV matrices on either side of the one surface flagged
+        `is_stop` (reference :134-214).  None (with a warning) unless exactly one stop
+        is flagged."""
+        pilotpath = RayPath(pilotbundle)
+        if pilotraypathsequence is None:
+            pilotraypathsequence = tuple(0 for _ in elementsequence)
+        stops_found = sum(1 for (_, subseq) in elementsequence
+                          for (_, options_dict) in subseq
+                          if options_dict.get("is_stop", False))
+        if stops_found != 1:
+            self.warning("%d stops found. need exactly 1!" % (stops_found,))
+            return None
+        size = 6 if pilotbundle_generation.lower() == "complex" else 4
+        lst_matrix_pairs = []
+        for ((elem, subseq), prp_nr) in zip(elementsequence, pilotraypathsequence):
+            (hitlist, optionshitlist_dict) = self.elements[elem].sequence_to_hitlist(subseq)
+            (append_pilotpath, elem_matrices) = self.elements[elem].calculateXYUV(
+                pilotpath.raybundles[-1], subseq, self.material_background,
+                pilotraypath_nr=prp_nr, pilotbundle_generation=pilotbundle_generation)
+            pilotpath.appendRayPath(append_pilotpath)
+            (m1, m2) = (np.eye(size), np.eye(size))
+            found_stop = False
+            for h in hitlist:
+                (d1, d2) = optionshitlist_dict[h]
+                if d1.get("is_stop", False) and not d2.get("is_stop", False):
+                    found_stop = True
+                if not found_stop:
+                    m1 = np.dot(elem_matrices[h], m1)
+                else:
+                    m2 = np.dot(elem_matrices[h], m2)
+            lst_matrix_pairs.append((m1, m2, found_stop))
+        (m_obj_stop, m_stop_img) = (np.eye(size), np.eye(size))
+        obj_stop_branch = True
+        for (m1, m2, found_stop) in lst_matrix_pairs:
+            if obj_stop_branch:
+                m_obj_stop = np.dot(m1, m_obj_stop)
+                if found_stop:
+                    m_stop_img = np.dot(m2, m_stop_img)
+                    obj_stop_branch = False
+            else:
+                m_stop_img = np.dot(m1, m_stop_img)
+        return (m_obj_stop, m_stop_img)
 
     def seqtrace(self, initialbundle, elementsequence, splitup=False,
                  record_efield=False, grin_history=False):
