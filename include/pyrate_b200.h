@@ -122,7 +122,9 @@ enum PyrGrinBoundary {
 
 /* which half of the step runs: the fused path always uses PYR_STEP_FULL; the two
  * partial modes back the reference's stand-alone plugin calls
- * Material.propagate / Surface.intersect and Material.refract / reflect          */
+ * Material.propagate / Surface.intersect and Material.refract / reflect, in the
+ * real-valued and in the complex-valued (PYR_F_COMPLEX: crystals, complex k) kernels;
+ * a splitting PYR_STEP_DEFLECT_ONLY step writes both modes (width 2n, ld_out2)       */
 enum PyrStepMode {
     PYR_STEP_FULL = 0,
     PYR_STEP_PROPAGATE_ONLY = 1, /* intersect + aperture; k, E unchanged            */

@@ -320,7 +320,8 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             rot_t(st.frame.r, d, dl);
             double t;
             bool hit_ok = true;
-            if (st.shape_kind == PYR_SHAPE_CONIC) t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
+            if (st.bits & kNoIntersect) t = 0.0;         // stand-alone refract / reflect: x is the hit point
+            else if (st.shape_kind == PYR_SHAPE_CONIC) t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
             else { double gfx, gfy; bool gok; t = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
             const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
             double hit_g[3];
@@ -354,8 +355,12 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             const bool mirror = st.interaction == PYR_REFLECT;
             cplx k2a[3], e2a[3], k2b[3], e2b[3];
             bool alive;
-            const bool aniso = st.after_kind == PYR_MEDIUM_ANISO;
-            if (aniso) {
+            const bool no_deflect = (st.bits & kNoDeflect) != 0;   // stand-alone propagate
+            const bool aniso = st.after_kind == PYR_MEDIUM_ANISO && !no_deflect;
+            if (no_deflect) {
+                for (int c = 0; c < 3; ++c) { k2a[c] = kl[c]; }
+                alive = hit;                 // k, E unchanged (material_anisotropic.py:58-68)
+            } else if (aniso) {
                 EpsInv ei;
                 eps_invariants(aux->after.eps, ei);      // eps already in the shape frame
                 aniso_modes(ei, kl, nrm, mirror, k2a, e2a, k2b, e2b);
@@ -395,6 +400,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
             cplx kga[3], ega[3], kgb[3], egb[3];
             crot(st.frame.r, k2a, kga);
             crot(st.frame.r, e2a, ega);
+            if (no_deflect) { for (int c = 0; c < 3; ++c) { kga[c] = r.k[c]; ega[c] = r.e[c]; } }
             const bool split = aniso && (st.bits & kSplit);
             if (aniso) { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
             const cplx qn = {qnan(), qnan()};
@@ -443,7 +449,6 @@ int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, 
     for (int s = 0; s < n_steps; ++s) {
         if (steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN)
             return PYR_E_UNSUPPORTED;
-        if (steps[s].mode != PYR_STEP_FULL) return PYR_E_UNSUPPORTED;
     }
     if (n_rays == 0) return PYR_OK;
     const int threads = 128;

@@ -25,6 +25,9 @@ constexpr uint32_t kApSameFrame = 2u;      // aperture.lc == shape.lc
 constexpr uint32_t kSplit = 4u;            // anisotropic ray doubling on this step
 constexpr uint32_t kSphere = 8u;           // cc == 0: |grad| == 1, no normalisation
 constexpr uint32_t kPlane = 16u;           // curv == 0 (and conic shape)
+constexpr uint32_t kOutVec2 = 32u;         // outputs allow 128-bit stores
+constexpr uint32_t kNoDeflect = 64u;       // PYR_STEP_PROPAGATE_ONLY
+constexpr uint32_t kNoIntersect = 128u;    // PYR_STEP_DEFLECT_ONLY
 
 struct DFrame {
     double r[9];

@@ -30,9 +30,6 @@
 
 namespace pyr {
 
-constexpr uint32_t kOutVec2 = 32u;   // DStep.bits: outputs allow 128-bit stores
-constexpr uint32_t kNoDeflect = 64u; // PYR_STEP_PROPAGATE_ONLY
-constexpr uint32_t kNoIntersect = 128u;  // PYR_STEP_DEFLECT_ONLY
 
 template <bool WITH_E>
 struct Ray {

@@ -638,36 +638,50 @@ def seqtrace(system, initialbundle, elementsequence, splitup=False,
 # ---------------------------------------------------------------------------
 # stand-alone plugin calls (Material.propagate / refract, Surface.intersect)
 # ---------------------------------------------------------------------------
-def _single_step(st, bundle, mode, record_e=True):
+def _single_step(st, bundle, mode, record_e=True, ignore_validity=False):
+    """One stand-alone plugin call: launch `st` in `mode` on the bundle's last row.
+    Returns (x, k, e, flags, n): k / e are 2n wide when the step splits (mode a in
+    column i, mode b in n + i) and complex whenever the fields or a medium are."""
     lib = require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
     x = as_tensor(bundle.x[-1], dev).contiguous()
     k = as_tensor(bundle.k[-1], dev).contiguous()
     e = as_tensor(bundle.Efield[-1], dev).contiguous()
-    if k.is_complex() or e.is_complex() or st.after.kind == nat.MEDIUM_ANISO or \
-            st.before.kind == nat.MEDIUM_ANISO:
-        raise NotImplementedError("stand-alone plugin calls with complex fields: "
-                                  "use OpticalSystem.seqtrace")
+    complex_ = bool(k.is_complex() or e.is_complex() or
+                    st.after.kind == nat.MEDIUM_ANISO or st.before.kind == nat.MEDIUM_ANISO)
+    if x.is_complex():
+        x = x.real.contiguous()
     n = x.shape[1]
     st.mode = mode
+    split = bool(complex_ and mode != nat.STEP_PROPAGATE_ONLY and
+                 st.after.kind == nat.MEDIUM_ANISO)
+    st.split = 1 if split else 0
     (xb, ld) = _padded(x)
-    (kb, _) = _padded(k)
-    (eb, _) = _padded(e)
+    (kb, _) = _padded(k, complex_)
+    (eb, _) = _padded(e, complex_)
+    ld2 = _round_up(2 * max(n, 1), LD_ALIGN) if split else ld
+    tail = (2,) if complex_ else ()
     ox = torch.empty((3, ld), dtype=torch.float64, device=dev)
-    ok = torch.empty((3, ld), dtype=torch.float64, device=dev)
-    oe = torch.empty((3, ld), dtype=torch.float64, device=dev)
+    ok = torch.empty((3, ld2) + tail, dtype=torch.float64, device=dev)
+    oe = torch.empty((3, ld2) + tail, dtype=torch.float64, device=dev)
     of = torch.empty((ld,), dtype=torch.uint8, device=dev)
     (st.out_x, st.out_k, st.out_e, st.out_flags) = (ox.data_ptr(), ok.data_ptr(),
                                                     oe.data_ptr(), of.data_ptr())
     st.ld_out = ld
-    alive = (bundle.valid[-1].to(dev).to(torch.uint8) * nat.RAY_ALIVE).contiguous()
+    st.ld_out2 = ld2
     alive_p = torch.zeros((ld,), dtype=torch.uint8, device=dev)
-    alive_p[:n] = alive
+    if ignore_validity:
+        alive_p[:n] = nat.RAY_ALIVE
+    else:
+        alive_p[:n] = bundle.valid[-1].to(dev).to(torch.uint8) * nat.RAY_ALIVE
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    flags = nat.F_RECORD_E | (nat.F_COMPLEX if complex_ else 0)
     with torch.cuda.device(dev):
-        _launch(lib, [st], 0, 1, xb, kb, eb, alive_p, n, n, ld,
-                nat.F_RECORD_E, stream)
-    return (ox[:, :n], ok[:, :n], oe[:, :n], of[:n])
+        _launch(lib, [st], 0, 1, xb, kb, eb, alive_p, n, n, ld, flags, stream)
+    width = 2 * n if split else n
+    if complex_:
+        (ok, oe) = (torch.view_as_complex(ok), torch.view_as_complex(oe))
+    return (ox[:, :n], ok[:, :width], oe[:, :width], of[:n], n)
 
 
 def _probe_medium():
@@ -689,7 +703,7 @@ def surface_intersect(surface, bundle, remove_rays_outside_aperture=True,
         lowering.lower_medium(medium, bundle.wave)
     st.after = _probe_medium()
     st.dir_mode = nat.DIR_POYNTING
-    (ox, ok, oe, of) = _single_step(st, bundle, nat.STEP_PROPAGATE_ONLY)
+    (ox, ok, oe, of, _) = _single_step(st, bundle, nat.STEP_PROPAGATE_ONLY)
     valid = _hit_mask(of) | ~bundle.valid[-1].to(of.device)
     # RayBundle.append ANDs with the previous row itself (ray.py:100)
     bundle.append(ox, ok if medium is not None else bundle.k[-1].to(ox.device),
@@ -711,18 +725,31 @@ def material_propagate(material, bundle, next_surface):
 
 
 def material_deflect(material, bundle, surface, mirror=False, splitup=False):
+    """Material.refract / reflect as a stand-alone call.  Isotropic media return one
+    bundle of the surviving rays (material_isotropic.py:194-199); anisotropic media
+    keep every ray they are handed and return both forward modes -- one bundle of 2N
+    rays in hstack order, or two bundles with `splitup` (material_anisotropic.py
+    :87-113, :133-155)."""
     st = nat.PyrStep()
     lowering.lower_surface(surface, st)
     st.aperture_kind = nat.AP_BASE
     st.before = _probe_medium()
     st.after = lowering.lower_medium(material, bundle.wave)
     st.interaction = nat.REFLECT if mirror else nat.REFRACT
-    st.dir_mode = nat.DIR_K
-    (ox, ok, oe, of) = _single_step(st, bundle, nat.STEP_DEFLECT_ONLY)
-    alive = _alive_mask(of)
+    aniso = st.after.kind == nat.MEDIUM_ANISO
+    st.dir_mode = nat.DIR_POYNTING if aniso else nat.DIR_K
+    (ox, ok, oe, of, n) = _single_step(st, bundle, nat.STEP_DEFLECT_ONLY,
+                                       ignore_validity=aniso)
     ids = bundle.rayID.to(ox.device)
-    return (RayBundle(ox[:, alive], ok[:, alive], oe[:, alive], ids[alive],
-                      wave=bundle.wave),)
+    if not aniso:
+        alive = _alive_mask(of)
+        return (RayBundle(ox[:, alive], ok[:, alive], oe[:, alive], ids[alive],
+                          wave=bundle.wave),)
+    if splitup:
+        return (RayBundle(ox, ok[:, :n], oe[:, :n], ids, wave=bundle.wave),
+                RayBundle(ox, ok[:, n:], oe[:, n:], ids, wave=bundle.wave))
+    return (RayBundle(torch.cat((ox, ox), dim=1), ok, oe, torch.cat((ids, ids)),
+                      wave=bundle.wave, splitted=True),)
 
 
 # ---------------------------------------------------------------------------

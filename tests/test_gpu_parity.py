@@ -270,7 +270,8 @@ def test_birefringent_larger_bundle_against_oracle():
             util.compare_bundle(d, rbd, 1e-10, "c4 b%d" % ib)
 
 
-@pytest.mark.parametrize("name", ["c1_doublet", "x1_tilted", "x3_vignette", "c5_grin"])
+@pytest.mark.parametrize("name", ["c1_doublet", "x1_tilted", "x3_vignette", "c5_grin",
+                                  "c4_anisotropic", "x4_biaxial", "x8_crystal_mirror"])
 def test_plugin_calls_reproduce_the_fused_trace(name):
     """The reference's plugin-level calls -- Material.propagate(bundle, surface)
     (mutates), Material.refract / reflect(bundle, surface) (fresh bundle) --
@@ -306,6 +307,55 @@ def test_plugin_calls_reproduce_the_fused_trace(name):
         assert util.relerr(da["x"][-1][:, v], db["x"][-1][:, v]) <= tol, ib
         assert util.relerr(da["x"][0], db["x"][0]) <= tol, ib
         assert util.relerr(da["k"][0], db["k"][0]) <= tol, ib
+        assert np.iscomplexobj(da["k"]) == np.iscomplexobj(db["k"]), ib
+        if np.iscomplexobj(db["k"]):
+            # same kernel, same mode order: the fields agree column by column
+            assert util.relerr(da["Efield"][0], db["Efield"][0]) <= 1e-9, ib
+            assert a.splitted == b.splitted, ib
+
+
+@pytest.mark.parametrize("name", ["c4_anisotropic", "x8_crystal_mirror"])
+def test_anisotropic_plugin_refract_against_oracle(name):
+    """AnisotropicMaterial.refract / reflect as stand-alone calls (material_anisotropic.py
+    :70-155), doubled and with `splitup`, against the oracle's restatement: children of a
+    ray are matched as an unordered pair (the mode order is LAPACK-arbitrary there)."""
+    import pyrate_np as onp
+    spec = configs.CONFIGS[name]
+    (s, seq) = configs.build_system(spec, pb.api())
+    deg = np.pi / 180.0
+    (x0, k0, e0) = configs.config_bundle(spec, 3, (0., np.sin(deg), np.cos(deg)), (1., 0., 0.))
+    elem = s.elements["stdelem"]
+    osys = onp.system_from_spec(spec)
+    # up to the first crystal surface with plugin calls
+    bundle = pb.RayBundle(x0, k0, e0, wave=configs.DLINE)
+    ob = onp.new_bundle(x0.copy(), k0.copy(), e0.copy())
+    (stop_key, front_key) = (seq[0][1][0][0], seq[0][1][1][0])
+    bg = s.material_background
+    bg.propagate(bundle, elem.surfaces[stop_key])
+    (bundle,) = bg.refract(bundle, elem.surfaces[stop_key])
+    bg.propagate(bundle, elem.surfaces[front_key])
+    onp.material_propagate(osys["background"], ob, osys["steps"][0])
+    (ob,) = onp.material_deflect(osys["background"], ob, osys["steps"][0], configs.DLINE,
+                                 False, False)
+    onp.material_propagate(osys["background"], ob, osys["steps"][1])
+    crystal = elem.materials[spec["surfaces"][1]["mat"]]
+    ocrystal = osys["steps"][1]["mat_plus"]
+    for mirror in (False, True):
+        call = crystal.reflect if mirror else crystal.refract
+        (doubled,) = call(bundle, elem.surfaces[front_key])
+        (odoubled,) = onp.material_deflect(ocrystal, ob, osys["steps"][1], configs.DLINE,
+                                           mirror, False)
+        d = doubled.numpy()
+        d["E"] = d["Efield"]
+        assert doubled.splitted and d["x"].shape[2] == 2 * x0.shape[1]
+        util.compare_birefringent_bundle(d, odoubled, 1e-9, "%s doubled mirror=%s" % (name, mirror))
+        pair = call(bundle, elem.surfaces[front_key], splitup=True)
+        assert len(pair) == 2
+        both = {f: np.concatenate([p.numpy()[f] for p in pair], axis=-1)
+                for f in ("x", "k", "Efield", "valid", "rayID")}
+        both["E"] = both["Efield"]
+        util.compare_birefringent_bundle(both, odoubled, 1e-9,
+                                         "%s split mirror=%s" % (name, mirror))
 
 
 def test_device_resident_unaligned_bundle_uses_plain_loads():
