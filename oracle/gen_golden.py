@@ -262,7 +262,7 @@ def main():
     dump_aniso(api)
 
 
-if __name__ == "__main__" and not ({"--rasters", "--glasscat", "--paraxial"} & set(sys.argv)):
+if __name__ == "__main__" and not ({"--rasters", "--glasscat", "--paraxial", "--pathanalysis"} & set(sys.argv)):
     main()
 
 
@@ -434,3 +434,26 @@ def dump_paraxial():
 if __name__ == "__main__" and "--paraxial" in sys.argv:
     refshim.install()
     dump_paraxial()
+
+
+def dump_pathanalysis():
+    """RayPathAnalysis (analysis/ray_analysis.py:170-213) of the unmodified reference on
+    the double-Gauss fixture bundle (5 degree field)."""
+    from pyrateoptics.raytracer.analysis.ray_analysis import RayPathAnalysis
+    api = refshim.api()
+    spec = configs.CONFIGS["c2_doublegauss"]
+    (s, seq) = configs.build_system(spec, api)
+    (x0, k0, e0) = configs.config_bundle(spec, 4, (0, np.sin(5 * DEG), np.cos(5 * DEG)), (1, 0, 0))
+    path = s.seqtrace(api.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)[0]
+    rpa = RayPathAnalysis(path)
+    np.savez_compressed(
+        os.path.join(OUT, "pathanalysis.npz"), x0=x0, k0=k0, E0=e0,
+        arc=rpa.get_arc_length(), phase=rpa.get_phase_difference(),
+        arc_2_9=rpa.get_arc_length(first=2, last=9),
+        rel=rpa.get_relative_phase_difference(referenceray=0, wavelength=configs.DLINE))
+    print("pathanalysis.npz")
+
+
+if __name__ == "__main__" and "--pathanalysis" in sys.argv:
+    refshim.install()
+    dump_pathanalysis()

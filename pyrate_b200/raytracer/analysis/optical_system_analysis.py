@@ -26,11 +26,25 @@ class OpticalSystemAnalysis(object):
 
     def __init__(self, os, seq, name=""):
         self.opticalsystem = os
-        self.sequence = seq
         self.name = name
+        self.sequence = seq
         self.field_raster = RectGrid()
         self.pupil_raster = RectGrid()
         self.initial_bundles = None
+
+    # ---- sequence + per-element analyses (reference :63-81) ----
+    def set_sequence(self, seq):
+        from .optical_element_analysis import OpticalElementAnalysis
+        self._sequence = seq
+        self.opticalelementanalysis_dict = {
+            elem: OpticalElementAnalysis(self.opticalsystem.elements[elem], elemseq,
+                                         name="oea_" + elem)
+            for (elem, elemseq) in seq}
+
+    def get_sequence(self):
+        return self._sequence
+
+    sequence = property(fget=get_sequence, fset=set_sequence)
 
     # ---- bundle generation (reference :83-165) ----
     def _background_index(self, wave):

@@ -89,3 +89,40 @@ class RayBundleAnalysis(object):
         stop = x.shape[0] - 1 + last_no if last_no <= 0 else -1 + last_no
         dph = x[first + 1:last] * k[first + 1:last] - x[first:stop] * k[first:stop]
         return dph.sum(1).sum(0)
+
+
+class RayPathAnalysis(object):
+    """Path integrals over all bundles of a RayPath (reference :170-213).  As in the
+    reference every bundle of the path must have the same width (no ray dropped on
+    the way), and the hand-over bundle that appears twice in a system-level path
+    (optical_system.py:74-91) is counted twice."""
+
+    def __init__(self, raypath, name=""):
+        self.raypath = raypath
+        self.name = name
+
+    def _sum(self, method, first, last):
+        total = None
+        for raybundle in self.raypath.raybundles[first:last]:
+            part = getattr(RayBundleAnalysis(raybundle), method)()
+            total = part.clone() if total is None else total + part
+        if total is None:
+            n = self.raypath.raybundles[0].x.shape[-1]
+            total = torch.zeros(n, dtype=torch.float64)
+        return total
+
+    def get_arc_length(self, first=0, last=None):
+        return self._sum("get_arc_length", first, last)
+
+    def get_phase_difference(self, first=0, last=None):
+        return self._sum("get_phase_difference", first, last)
+
+    def get_relative_phase_difference(self, first=0, last=None, referenceray=None,
+                                      wavelength=None):
+        """Phase differences relative to a chief ray, optionally in waves."""
+        res = self.get_phase_difference(first=first, last=last)
+        if referenceray is not None:
+            res = res - res[referenceray]
+        if wavelength is not None:
+            res = res / wavelength
+        return res

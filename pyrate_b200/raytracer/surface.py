@@ -50,3 +50,7 @@ class Surface(LocalCoordinatesTreeBase):
         """Shape intersect + aperture mask, appended to `raybundle` (device)."""
         from .. import engine
         engine.surface_intersect(self, raybundle, remove_rays_outside_aperture)
+
+    def getCentralCurvature(self, ray=None):
+        """Vertex curvature of the shape (reference :253-257)."""
+        return self.shape.getCentralCurvature()

@@ -509,3 +509,12 @@ def test_random_systems_match_oracle(seed):
     for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
         util.compare_bundle(b.numpy(), {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
                                         "rayID": rb["rayID"]}, 1e-10, "%s b%d" % (spec["name"], ib))
+
+
+def test_raypath_analysis_on_device_records():
+    """RayPathAnalysis over the lazily materialised device bundles of a traced path."""
+    import os
+    import test_ray_analysis_api as tra
+    g = np.load(os.path.join(util.GOLDEN, "pathanalysis.npz"))
+    paths = _device_paths("c2_doublegauss", g["x0"], g["k0"], g["E0"])
+    tra._check_path_analysis(paths[0], g)
