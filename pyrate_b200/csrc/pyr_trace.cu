@@ -763,6 +763,12 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         d.inv_knorm = (u.dir_mode == PYR_DIR_K && u.k_norm_hint > 0.0 &&
                        u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / u.k_norm_hint : 0.0;
         d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
+        {   // measurement knob (tools/ only): PYR_DEBUG_RECORD_LAST=1 records the last entry only,
+            // which times the arithmetic of a trace without its record stream
+            static const bool last_only = [] { const char *e = std::getenv("PYR_DEBUG_RECORD_LAST");
+                                               return e && std::atoi(e) != 0; }();
+            if (last_only && s != n_steps - 1) { d.out_x = d.out_k = d.out_e = nullptr; d.out_flags = nullptr; }
+        }
         d.ld_out = u.ld_out > 0 ? u.ld_out : n_rays;
         d.ld_out2 = u.ld_out2 > 0 ? u.ld_out2 : 2 * d.ld_out;
         d.shape_kind = (int8_t)u.shape_kind; d.aperture_kind = (int8_t)u.aperture_kind;
