@@ -164,3 +164,39 @@ def test_tir_glass_angle_form_equals_vector_form():
     assert a[-1]["x"].shape[2] < x0.shape[1]
     for (ba, bb) in zip(a, b):
         util.compare_bundle(ba, bb, 1e-13, "tir forms")
+
+
+def _live_reference_api():
+    import refshim
+    if not refshim.reference_available():
+        pytest.skip("reference tree not present (build container only)")
+    return refshim.api()
+
+
+@pytest.mark.parametrize("seed", list(range(16)))
+def test_oracle_matches_live_reference_on_random_systems(seed):
+    """Beyond the committed fixtures: the restatement against the UNMODIFIED reference,
+    imported live from /root/reference (build container only; skipped elsewhere), on
+    random decentred / tilted systems with all aperture kinds, mirrors and -- every
+    other seed -- mild aspheres / XY polynomials, for a random oblique field."""
+    api = _live_reference_api()
+    explicit = seed % 2 == 1
+    spec = util.random_spec(seed, explicit=explicit)
+    rng = np.random.default_rng(500 + seed)
+    (ax, ay) = rng.uniform(-0.03, 0.03, 2)
+    kdir = (np.sin(ax), np.sin(ay) * np.cos(ax), np.cos(ay) * np.cos(ax))
+    (x0, k0, e0) = configs.config_bundle(spec, 4, kdir, (0., 1., 0.))
+    (s, seq) = configs.build_system(spec, api)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref_paths = s.seqtrace(api.RayBundle(x0.copy(), k0.copy(), e0.copy(),
+                                             wave=configs.DLINE), seq)
+        paths = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    assert len(paths) == len(ref_paths) == 1
+    tol = 1e-9 if explicit else 1e-12
+    assert len(paths[0]) == len(ref_paths[0].raybundles)
+    for (ib, (b, rb)) in enumerate(zip(paths[0], ref_paths[0].raybundles)):
+        ref = {"x": np.asarray(rb.x), "k": np.asarray(rb.k), "valid": np.asarray(rb.valid),
+               "rayID": np.asarray(rb.rayID)}
+        util.compare_bundle(b, ref, tol, "seed %d b%d" % (seed, ib))

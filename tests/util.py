@@ -126,3 +126,53 @@ def compare_birefringent_bundle(got, ref, tol, what, check_e=True):
                     np.sum(np.abs(a) ** 2) * np.sum(np.abs(b) ** 2))
                 assert col > 1 - 1e-7, "%s ray %d: E not colinear (%.3e)" % (what, ray, 1 - col)
     return worst
+
+
+def random_spec(seed, explicit=False):
+    """A random but traceable chain: decentered / tilted conics (both tilt orders),
+    random glasses, apertures of all three kinds, an occasional mirror; with `explicit`
+    also a mild even asphere or XY polynomial in place of some conics."""
+    from pyrate_b200 import configs
+    rng = np.random.default_rng(seed)
+    surfaces = [configs._conic("stop", 0.0, opt={"is_stop": True})]
+    mats = {}
+    inside = False
+    nsurf = int(rng.integers(3, 7))
+    for i in range(nsurf):
+        lc = {"decx": float(rng.uniform(-0.3, 0.3)), "decy": float(rng.uniform(-0.3, 0.3)),
+              "tiltx": float(rng.uniform(-0.05, 0.05)), "tilty": float(rng.uniform(-0.05, 0.05)),
+              "tiltz": float(rng.uniform(-1.0, 1.0)), "tiltThenDecenter": int(rng.integers(0, 2))}
+        mat = None
+        if not inside or rng.random() < 0.4:
+            mat = "g%d" % i
+            mats[mat] = ("ConstantIndexGlass", {"n": float(rng.uniform(1.3, 1.9))})
+        inside = mat is not None
+        kind = int(rng.integers(0, 3))
+        ap = None if kind == 0 else (configs._circ(float(rng.uniform(6.0, 9.0))) if kind == 1 else
+                                     ("RectangularAperture", {"width": float(rng.uniform(9, 14)),
+                                                              "height": float(rng.uniform(9, 14))}))
+        surf = configs._conic("s%d" % i, float(rng.uniform(2.0, 6.0)),
+                              curv=float(rng.uniform(-0.03, 0.03)),
+                              cc=float(rng.choice([0.0, -1.0, float(rng.uniform(-2, 2))])),
+                              mat=mat, aperture=ap, **lc)
+        if explicit and rng.random() < 0.4:
+            if rng.random() < 0.5:
+                surf["shape"] = ("Asphere", {"curv": float(rng.uniform(-0.03, 0.03)),
+                                             "cc": float(rng.uniform(-1.5, 0.5)),
+                                             "coefficients": [float(rng.uniform(-1e-4, 1e-4)),
+                                                              float(rng.uniform(-1e-6, 1e-6)),
+                                                              float(rng.uniform(-1e-9, 1e-9))]})
+            else:
+                surf["shape"] = ("XYPolynomials", {"normradius": 10.0, "coefficients": [
+                    (2, 0, float(rng.uniform(-0.8, 0.8))), (0, 2, float(rng.uniform(-0.8, 0.8))),
+                    (1, 1, float(rng.uniform(-0.05, 0.05))), (3, 0, float(rng.uniform(-0.02, 0.02))),
+                    (2, 2, float(rng.uniform(-0.01, 0.01)))]})
+        surfaces.append(surf)
+    if inside:
+        surfaces.append(configs._conic("exit", 3.0, curv=float(rng.uniform(-0.01, 0.01)), mat=None))
+    if rng.random() < 0.5:
+        surfaces.append(configs._conic("mirror", 10.0, curv=float(rng.uniform(-0.005, 0.005)),
+                                       opt={"is_mirror": True}, tiltx=float(rng.uniform(-0.1, 0.1))))
+    surfaces.append(configs._conic("image", 15.0))
+    return {"name": "random%d" % seed, "surfaces": surfaces, "materials": mats,
+            "bundle": {"rings": 9, "radius": float(rng.uniform(4.0, 7.0)), "z0": -3.0}}
