@@ -600,16 +600,50 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 // ---------------------------------------------------------------------------
 // spot sums (analysis/ray_analysis.py:44-86): sum x, count, sum x^2
 // ---------------------------------------------------------------------------
+// VEC: rows 16-byte aligned (x aligned, ld even): two rays per thread and iteration with
+// 128-bit loads, two iterations in flight -- the kernel is a pure HBM read stream
+template <bool VEC>
 __global__ void __launch_bounds__(256)
-spot_sums_kernel(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
-                 double sx, double sy, double sz, double *out8) {
+spot_sums_kernel(const double *__restrict__ x, int64_t ld, const uint8_t *__restrict__ flags,
+                 uint32_t mask, int64_t n, double sx, double sy, double sz, double *out8) {
     double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        if (flags && !(flags[i] & mask)) continue;
-        const double a = x[i] - sx, b = x[ld + i] - sy, c = x[2 * ld + i] - sz;
+    auto add = [&](double px, double py, double pz, bool on) {
+        if (!on) return;
+        const double a = px - sx, b = py - sy, c = pz - sz;
         acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += 1.0;
         acc[4] = fma(a, a, acc[4]); acc[5] = fma(b, b, acc[5]); acc[6] = fma(c, c, acc[6]);
+    };
+    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
+    if (VEC) {
+        const int64_t pairs = n / 2;
+        const double2 *x0 = reinterpret_cast<const double2 *>(x);
+        const double2 *x1 = reinterpret_cast<const double2 *>(x + ld);
+        const double2 *x2 = reinterpret_cast<const double2 *>(x + 2 * ld);
+        const uchar2 *f2 = reinterpret_cast<const uchar2 *>(flags);
+        int64_t p = tid;
+        for (; p + nthreads < pairs; p += 2 * nthreads) {        // two independent pairs
+            const int64_t q = p + nthreads;
+            const double2 a0 = __ldcs(x0 + p), a1 = __ldcs(x1 + p), a2 = __ldcs(x2 + p);
+            const double2 b0 = __ldcs(x0 + q), b1 = __ldcs(x1 + q), b2 = __ldcs(x2 + q);
+            uchar2 fa = make_uchar2(255, 255), fb = fa;
+            if (flags) { fa = f2[p]; fb = f2[q]; }
+            add(a0.x, a1.x, a2.x, (fa.x & mask) != 0); add(a0.y, a1.y, a2.y, (fa.y & mask) != 0);
+            add(b0.x, b1.x, b2.x, (fb.x & mask) != 0); add(b0.y, b1.y, b2.y, (fb.y & mask) != 0);
+        }
+        for (; p < pairs; p += nthreads) {
+            const double2 a0 = __ldcs(x0 + p), a1 = __ldcs(x1 + p), a2 = __ldcs(x2 + p);
+            uchar2 fa = make_uchar2(255, 255);
+            if (flags) fa = f2[p];
+            add(a0.x, a1.x, a2.x, (fa.x & mask) != 0); add(a0.y, a1.y, a2.y, (fa.y & mask) != 0);
+        }
+        if (tid == 0 && (n & 1)) {
+            const int64_t i = n - 1;
+            add(x[i], x[ld + i], x[2 * ld + i], !flags || (flags[i] & mask) != 0);
+        }
+    } else {
+        for (int64_t i = tid; i < n; i += nthreads)
+            add(x[i], x[ld + i], x[2 * ld + i], !flags || (flags[i] & mask) != 0);
     }
     __shared__ double sm[8][7];
 #pragma unroll
@@ -995,8 +1029,14 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t ma
     const int64_t cap = (int64_t)pyr::sm_count() * 8;
     if (grid > cap) grid = cap;
     const double sx = shift ? shift[0] : 0.0, sy = shift ? shift[1] : 0.0, sz = shift ? shift[2] : 0.0;
-    pyr::spot_sums_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n, sx, sy,
-                                                                          sz, out8);
+    const bool vec = (reinterpret_cast<uintptr_t>(x) % 16 == 0) && (ld % 2 == 0) &&
+                     (!flags || reinterpret_cast<uintptr_t>(flags) % 2 == 0);
+    if (vec)
+        pyr::spot_sums_kernel<true><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n,
+                                                                                    sx, sy, sz, out8);
+    else
+        pyr::spot_sums_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n,
+                                                                                     sx, sy, sz, out8);
     cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? PYR_OK : (int)e;
 }

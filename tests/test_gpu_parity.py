@@ -492,3 +492,31 @@ def test_raypath_analysis_on_device_records():
     g = np.load(os.path.join(util.GOLDEN, "pathanalysis.npz"))
     paths = _device_paths("c2_doublegauss", g["x0"], g["k0"], g["E0"])
     tra._check_path_analysis(paths[0], g)
+
+
+@pytest.mark.parametrize("n", [1, 2, 7, 1000, 1001, 70001])
+def test_spot_sums_vector_and_scalar_paths(n):
+    """pyr_spot_sums: rows that allow 128-bit loads (padded records) and rows that do not
+    (odd leading dimension), with and without a flag mask, against NumPy."""
+    import torch
+    from pyrate_b200 import engine
+    rng = np.random.default_rng(n)
+    xh = rng.normal(size=(3, n)) * 3.0 + np.array([[1.0], [-2.0], [50.0]])
+    fh = rng.integers(0, 4, n).astype(np.uint8)
+    shift = [0.9, -2.1, 49.0]
+    dev = torch.device("cuda", 0)
+    ld = (n + 15) // 16 * 16
+    padded = torch.zeros((3, ld), dtype=torch.float64, device=dev)
+    padded[:, :n] = torch.from_numpy(xh).to(dev)
+    fpad = torch.zeros((ld,), dtype=torch.uint8, device=dev)
+    fpad[:n] = torch.from_numpy(fh).to(dev)
+    tight = torch.from_numpy(xh).to(dev)                         # ld = n
+    ftight = torch.from_numpy(fh).to(dev)
+    for (x, f) in ((padded[:, :n], fpad[:n]), (tight, ftight), (padded[:, :n], None),
+                   (tight, None)):
+        got = engine.spot_sums(x, f, shift=shift).cpu().numpy()
+        m = np.ones(n, dtype=bool) if f is None else (fh & 2) != 0
+        d = xh[:, m] - np.asarray(shift)[:, None]
+        assert got[3] == m.sum()
+        assert np.allclose(got[0:3], d.sum(1), rtol=1e-12, atol=1e-9)
+        assert np.allclose(got[4:7], (d * d).sum(1), rtol=1e-12, atol=1e-9)
