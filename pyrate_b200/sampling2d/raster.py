@@ -45,6 +45,51 @@ class RandomGrid(RectGrid):
         return (xp[keep], yp[keep])
 
 
+def poisson_disk_2d(width, height, radius, tries=30, rng=None):
+    """Poisson-disk ("blue noise") samples of [0, width) x [0, height) with pairwise
+    distance >= radius: Bridson's grid-accelerated dart throwing (the reference ships a
+    slower grid-based variant of the same hard-core process, sampling2d/pds.py).
+    Returns an (N, 2) array."""
+    rng = np.random.default_rng() if rng is None else rng
+    cell = radius / math.sqrt(2.0)
+    (gw, gh) = (int(math.ceil(width / cell)), int(math.ceil(height / cell)))
+    grid = -np.ones((gw, gh), dtype=np.int64)
+    pts = [np.array([rng.uniform(0, width), rng.uniform(0, height)])]
+    grid[int(pts[0][0] / cell), int(pts[0][1] / cell)] = 0
+    active = [0]
+    while active:
+        pick = int(rng.integers(len(active)))
+        base = pts[active[pick]]
+        for _ in range(tries):
+            (rad, ang) = (radius * math.sqrt(rng.uniform(1.0, 4.0)), rng.uniform(0, 2 * math.pi))
+            cand = base + rad * np.array([math.cos(ang), math.sin(ang)])
+            if not (0 <= cand[0] < width and 0 <= cand[1] < height):
+                continue
+            (ci, cj) = (int(cand[0] / cell), int(cand[1] / cell))
+            near = grid[max(ci - 2, 0):ci + 3, max(cj - 2, 0):cj + 3].ravel()
+            near = near[near >= 0]
+            if all(np.sum((pts[q] - cand) ** 2) >= radius * radius for q in near):
+                grid[ci, cj] = len(pts)
+                active.append(len(pts))
+                pts.append(cand)
+                break
+        else:
+            active.pop(pick)
+    return np.array(pts)
+
+
+class PoissonDiskSampling(RectGrid):
+    """Random pupil points with a minimum mutual distance (reference raster.py:106-125):
+    about `nray` points in the unit disk."""
+
+    def getGrid(self, nray, rng=None):
+        per_dim = max(1, int(round(math.sqrt(nray * 4.0 / math.pi))))
+        sample = poisson_disk_2d(2.0, 2.0, 1.0 / per_dim, rng=rng)
+        (xs, ys) = (sample[:, 0] - 1.0, sample[:, 1] - 1.0)
+        keep = xs ** 2 + ys ** 2 <= 1
+        return (xs[keep], ys[keep])
+
+
 class MeridionalFan(RectGrid):
     def getGrid(self, nray, phi=0.):
         lin = np.linspace(-1, 1, nray)

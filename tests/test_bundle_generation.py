@@ -38,3 +38,20 @@ def test_bundle_generators_match_reference():
     assert np.allclose(np.sum(e * k, axis=0), 0, atol=1e-15)
     osa.aim(40, props, bundletype="divergent", wave=configs.DLINE)
     assert osa.initial_bundles[0].x.shape == (1, 3, o.shape[1])
+
+
+def test_poisson_disk_sampling_properties():
+    """PoissonDiskSampling (reference raster.py:106-125 + pds.py) is random: checked by
+    its defining properties -- inside the unit disk, hard-core distance, sensible count."""
+    import math
+    import numpy as np
+    from pyrate_b200.sampling2d.raster import PoissonDiskSampling
+    nray = 200
+    (x, y) = PoissonDiskSampling().getGrid(nray, rng=np.random.default_rng(3))
+    assert np.all(x ** 2 + y ** 2 <= 1.0)
+    r = 1.0 / int(round(math.sqrt(nray * 4.0 / math.pi)))
+    d2 = (x[:, None] - x[None, :]) ** 2 + (y[:, None] - y[None, :]) ** 2
+    np.fill_diagonal(d2, np.inf)
+    assert d2.min() >= r * r * (1 - 1e-12)
+    # maximal Poisson-disk packings hold 0.6-0.9 points per r^2-cell of the disk area
+    assert 0.5 * math.pi / r ** 2 * 0.6 < x.size < math.pi / r ** 2
