@@ -35,12 +35,13 @@
 extern "C" {
 #endif
 
-#define PYR_ABI_VERSION 2
+#define PYR_ABI_VERSION 3
 
 #define PYR_MAX_COEFF 80        /* asphere coefficients / XY-polynomial terms (a
                                    Zernike series up to Fringe term 36 expands into
                                    66 monomials)                                   */
 #define PYR_MAX_GRIN_PARAMS 8
+#define PYR_MAX_WAVES 4         /* wavelength segments of one pyr_trace call        */
 #define PYR_MAX_TERMS 4         /* sub-shapes of a PYR_SHAPE_COMBINATION           */
 
 /* error codes */
@@ -226,6 +227,12 @@ typedef struct PyrStep {
                                    out_e (width 2n: mode a of ray i in column i,
                                    mode b in column n + i, the reference's hstack
                                    order, material_anisotropic.py:89-100)          */
+    /* wavelength batch (PyrRaysIn.n_waves > 1): index of the ISO_CONST media `before` /
+     * `after` for the rays of wavelength segment w (entry 0 repeats before.n / after.n;
+     * dispersion is the only thing that differs between the bundles of a batch: F, d, C
+     * bundles of one system, demos/demo_doublegauss.py:189-213, in ONE launch)         */
+    double before_n_w[PYR_MAX_WAVES];
+    double after_n_w[PYR_MAX_WAVES];
 } PyrStep;
 
 /* per-ray flag bits written to out_flags */
@@ -244,6 +251,13 @@ typedef struct PyrRaysIn {
     int64_t ld;                 /* leading dimension of x, k, e                    */
     int64_t n_x;                /* width of x/alive; ray i reads column i % n_x
                                    (n_x = n/2 right after a split step); 0 -> n    */
+    /* wavelength batch: the call carries n_waves (2..PYR_MAX_WAVES) bundles of different
+     * wavelength back to back; ray i belongs to segment w = number of entries
+     * wave_end[0..n_waves-2] that are <= i.  0 or 1 = one wavelength (before.n / after.n).
+     * Real-valued, non-splitting sequences of homogeneous isotropic media only.       */
+    int32_t n_waves;
+    int32_t reserved0;
+    int64_t wave_end[PYR_MAX_WAVES];
 } PyrRaysIn;
 
 /* flags of pyr_trace */

@@ -7,13 +7,14 @@ the library is missing or was built for another ABI, loading raises.
 import ctypes as C
 import os
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 MAX_COEFF = 80
 MAX_GRIN_PARAMS = 8
 
 (SHAPE_CONIC, SHAPE_ASPHERE, SHAPE_XYPOLY, SHAPE_BICONIC, SHAPE_GRIDSAG,
  SHAPE_COMBINATION) = (0, 1, 2, 3, 4, 5)
 MAX_TERMS = 4
+MAX_WAVES = 4
 (AP_BASE, AP_CIRCULAR, AP_RECTANGULAR) = (0, 1, 2)
 (REFRACT, REFLECT) = (0, 1)
 (MEDIUM_ISO_CONST, MEDIUM_ISO_GRIN, MEDIUM_ANISO) = (0, 1, 2)
@@ -74,12 +75,16 @@ class PyrStep(C.Structure):
                 ("grid_nx", C.c_int32), ("grid_ny", C.c_int32),
                 ("n_terms", C.c_int32), ("reserved0", C.c_int32),
                 ("terms", PyrShapeTerm * MAX_TERMS),
-                ("ld_out2", C.c_int64)]
+                ("ld_out2", C.c_int64),
+                ("before_n_w", C.c_double * MAX_WAVES),
+                ("after_n_w", C.c_double * MAX_WAVES)]
 
 
 class PyrRaysIn(C.Structure):
     _fields_ = [("x", C.c_void_p), ("k", C.c_void_p), ("e", C.c_void_p),
-                ("alive", C.c_void_p), ("ld", C.c_int64), ("n_x", C.c_int64)]
+                ("alive", C.c_void_p), ("ld", C.c_int64), ("n_x", C.c_int64),
+                ("n_waves", C.c_int32), ("reserved0", C.c_int32),
+                ("wave_end", C.c_int64 * MAX_WAVES)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",

@@ -581,7 +581,24 @@ X13_TIRGLASS = {   # IsotropicMaterialTIR (angle-form Snell, material_isotropic_
     "s_counted": 3,
 }
 
-CONFIGS.update({c["name"]: c for c in (X13_TIRGLASS, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
+def _conrady(nd, spread):
+    """Conrady coefficients (n0, A, B) with index nd at the d line and a dispersion
+    scale `spread` (ModelGlass: n = n0 + A / wave + B / wave^3.5, wave in mm)."""
+    (a, b) = (0.0100998734374e-3 * spread, 0.000328623343942 * (1e-3) ** 3.5 * spread)
+    return (nd - a / DLINE - b / DLINE ** 3.5, a, b)
+
+
+X14_DISPERSIVE = dict(C2_DOUBLEGAUSS, name="x14_dispersive", materials={
+    # the double-Gauss with dispersive (Conrady) glasses: wavelength batches F / d / C
+    "g1": ("ModelGlass", {"n0_A_B": _conrady(_N1, 1.0)}),
+    "g2": ("ModelGlass", {"n0_A_B": _conrady(_N2, 1.6)}),
+    "g3": ("ModelGlass", {"n0_A_B": _conrady(_N3, 2.2)})},
+    bundle={"rings": 8, "radius": 5.0, "z0": 0.0})
+X15_DISPERSIVE_ASPHERE = dict(C3_ASPHERE, name="x15_dispersive_asphere", materials={
+    "glass": ("ModelGlass", {"n0_A_B": _conrady(1.5168, 1.3)})},
+    bundle={"rings": 8, "radius": 11.43, "z0": -5.0})
+
+CONFIGS.update({c["name"]: c for c in (X13_TIRGLASS, X14_DISPERSIVE, X15_DISPERSIVE_ASPHERE, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
                                        X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL,
                                        X11_GRIDSAG, X12_COMBINATION)})

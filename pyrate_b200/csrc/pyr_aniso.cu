@@ -370,7 +370,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 const cplx kn = cdotr(kl, nrm);
                 cplx kin[3];
                 for (int c = 0; c < 3; ++c) kin[c] = kl[c] - nrm[c] * kn;
-                const cplx square = C(st.n2sq) - cdot(kin, kin);
+                const cplx square = C(st.n2sq[0]) - cdot(kin, kin);
                 // numpy orders complex numbers lexicographically: (re, im) > (0, 0)
                 const bool refr_ok = (square.re > 0.0 || (square.re == 0.0 && square.im > 0.0)) &&
                                      finite3(nrm);
@@ -446,6 +446,7 @@ int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, 
     int rc = pack_steps(steps, n_steps, rays, n_rays, flags, P, general, any_aniso);
     if (rc != PYR_OK) return rc;
     if (!rays->e) return PYR_E_BADARG;            // E defines the ray direction in crystals
+    if (rays->n_waves > 1) return PYR_E_UNSUPPORTED;
     for (int s = 0; s < n_steps; ++s) {
         if (steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN)
             return PYR_E_UNSUPPORTED;

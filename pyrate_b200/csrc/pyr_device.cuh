@@ -20,6 +20,7 @@ constexpr int kMaxSteps = 40;      // per launch (longer sequences are chunked)
 constexpr int kMaxAux = 10;
 
 // DStep.bits
+constexpr int kMaxWaves = PYR_MAX_WAVES;
 constexpr uint32_t kRotIdentity = 1u;      // shape frame rotation is the identity
 constexpr uint32_t kApSameFrame = 2u;      // aperture.lc == shape.lc
 constexpr uint32_t kSplit = 4u;            // anisotropic ray doubling on this step
@@ -71,8 +72,9 @@ struct DStep {
     DFrame frame;                  // shape frame (local -> global)
     double curv, cc;
     double ap0, ap1;               // circular: min^2, max^2; rectangular: w/2, h/2
-    double n2sq;                   // (index of the deflecting medium)^2, ISO_CONST
-    double inv_knorm;              // > 0: |k| known on entry (1/n of `before`)
+    double n2sq[kMaxWaves];        // (index of the deflecting medium)^2, ISO_CONST, per
+                                   // wavelength segment (entry 0 for a plain call)
+    double inv_knorm[kMaxWaves];   // > 0: |k| known on entry (1/n of `before`)
     double *out_x, *out_k, *out_e;
     uint8_t *out_flags;
     int64_t ld_out, ld_out2;
@@ -88,7 +90,8 @@ struct LaunchParams {
     int32_t n_steps;
     uint32_t flags;
     int32_t in_vec2;               // inputs allow 128-bit loads
-    int32_t pad;
+    int32_t n_waves;               // > 1: wavelength batch, ray i is in segment #{j: i >= wave_end[j]}
+    int64_t wave_end[kMaxWaves];
     DStep steps[kMaxSteps];
     DAux aux[kMaxAux];
 };

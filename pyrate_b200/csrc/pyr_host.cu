@@ -120,6 +120,8 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0, cons
         local[n_steps - 1].out_flags = of;
         PyrRaysIn in;
         in.x = dx; in.k = dk; in.e = e0 ? de : nullptr; in.alive = nullptr; in.ld = L.ld; in.n_x = cn;
+        in.n_waves = 0; in.reserved0 = 0;
+        for (int w = 0; w < PYR_MAX_WAVES; ++w) in.wave_end[w] = 0;
         rc = pyr::trace_entry(local.data(), n_steps, &in, cn, 0u, s);
         if (rc != PYR_OK) break;
         if (spot8) {

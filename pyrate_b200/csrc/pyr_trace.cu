@@ -131,7 +131,7 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 template <bool WITH_E, bool HAS_GRIN, bool EXT>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
                                               Ray<WITH_E> &r, double d[3], double hit_g[3],
-                                              int64_t ray_index) {
+                                              int64_t ray_index, int w = 0) {
     constexpr bool GENERAL = true;
     const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
@@ -207,7 +207,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     double kl[3];
     if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
     else rot_t(st.frame.r, r.k, kl);
-    double n2sq = st.n2sq;
+    double n2sq = st.n2sq[w];
     if (HAS_GRIN && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
         double q[3], g[3];
         g2l_point(aux->after.frame, hit_g, q);
@@ -255,7 +255,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
 //     already rejects NaN normals (no separate finite check).
 template <bool WITH_E>
 __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, const double d[3],
-                                              double hit_g[3]) {
+                                              double hit_g[3], int w = 0) {
     const bool ok = r.alive;
     const bool ident = (st.bits & kRotIdentity) != 0;
     double r0[3], dl[3], kl[3];
@@ -326,7 +326,7 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
     // Snell via in-plane k (material_isotropic.py:175-185 / :224)
     const double kn = dot3(kl, nrm);
     const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
-    const double square2 = st.n2sq - dot3(kin, kin);
+    const double square2 = st.n2sq[w] - dot3(kin, kin);
     const double xi = fast_sqrt(square2);
     const bool alive = hit && (square2 > 0.0);
     double k2[3];
@@ -377,7 +377,10 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr int TILE = BLOCK * RPT;
     // POLICY 3 (TMA record stores) stages the outputs in shared memory as well and
     // therefore keeps a single input stage (prefetch distance: one tile = 13 steps)
-    constexpr bool TMA_OUT = POLICY == 3 && RPT == 2;
+    constexpr bool TMA_OUT = (POLICY & 3) == 3 && RPT == 2;
+    // POLICY bit 8: wavelength batch -- per-ray segment index selects the media indices
+    // (own instantiations: the plain kernels keep their code)
+    constexpr bool MULTI = (POLICY & 8) != 0;
     constexpr int IN_STAGES = TMA_OUT ? 1 : 2;
     // record stages: x, k (and E) rows; E recording has room for one stage only
     constexpr int OUT_ROWS = WITH_E ? 9 : 6;
@@ -464,6 +467,17 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
         }
 
+        int wsel[RPT];
+#pragma unroll
+        for (int j = 0; j < RPT; ++j) {
+            wsel[j] = 0;
+            if (MULTI) {
+#pragma unroll
+                for (int q = 0; q < kMaxWaves - 1; ++q)
+                    wsel[j] += (q < P.n_waves - 1 && base + j >= P.wave_end[q]) ? 1 : 0;
+            }
+        }
+
         Ray<WITH_E> ray[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; ++j) {
@@ -490,15 +504,16 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                     if (WITH_E) poynting_dir(ray[j].k, ray[j].e, d);
                     else poynting_dir(ray[j].k, in[j].e, d);
                 } else {
-                    const double inv = (st.inv_knorm > 0.0) ? st.inv_knorm
-                                                            : fast_rsqrt(dot3(ray[j].k, ray[j].k));
+                    const double ik = st.inv_knorm[MULTI ? wsel[j] : 0];
+                    const double inv = (ik > 0.0) ? ik : fast_rsqrt(dot3(ray[j].k, ray[j].k));
                     d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
                 }
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
                 fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0, (FEAT & 4) != 0>(P, st, ray[j], d, hit[j],
-                                                                                   in_range[j] ? base + j : -1)
-                                                 : step_lean<WITH_E>(st, ray[j], d, hit[j]);
+                                                                                   in_range[j] ? base + j : -1,
+                                                                                   MULTI ? wsel[j] : 0)
+                                                 : step_lean<WITH_E>(st, ray[j], d, hit[j], MULTI ? wsel[j] : 0);
             }
 
             // ---- record the step ----
@@ -745,6 +760,14 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
     P.n_x = rays->n_x > 0 ? rays->n_x : n_rays;
     P.n_steps = n_steps;
     P.flags = flags;
+    if (rays->n_waves < 0 || rays->n_waves > kMaxWaves) return PYR_E_BADARG;
+    P.n_waves = rays->n_waves > 1 ? rays->n_waves : 1;
+    for (int w = 0; w < kMaxWaves; ++w) {
+        P.wave_end[w] = (w < P.n_waves - 1) ? rays->wave_end[w] : n_rays;
+        if (w < P.n_waves - 1 && (rays->wave_end[w] < (w ? rays->wave_end[w - 1] : 0) ||
+                                  rays->wave_end[w] > n_rays))
+            return PYR_E_BADARG;
+    }
     P.in_vec2 = (P.n_x == P.n) && (P.ld_in % 2 == 0) && aligned16(P.x) && aligned16(P.k) &&
                 (!P.e || aligned16(P.e));
     out.general = false;
@@ -793,9 +816,18 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
             d.ap0 = 0.5 * u.aperture_p[0];
             d.ap1 = 0.5 * u.aperture_p[1];
         }
-        d.n2sq = u.after.n * u.after.n;
-        d.inv_knorm = (u.dir_mode == PYR_DIR_K && u.k_norm_hint > 0.0 &&
-                       u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / u.k_norm_hint : 0.0;
+        const int n_waves = rays->n_waves > 1 ? rays->n_waves : 1;
+        for (int w = 0; w < kMaxWaves; ++w) {
+            const bool used = w < n_waves;
+            const double na = (n_waves > 1 && used) ? u.after_n_w[w] : u.after.n;
+            const double nb = (n_waves > 1 && used) ? u.before_n_w[w] : u.k_norm_hint;
+            d.n2sq[w] = na * na;
+            d.inv_knorm[w] = (u.dir_mode == PYR_DIR_K && u.k_norm_hint > 0.0 && nb > 0.0 &&
+                              u.before.kind == PYR_MEDIUM_ISO_CONST) ? 1.0 / nb : 0.0;
+        }
+        if (n_waves > 1 && (u.before.kind != PYR_MEDIUM_ISO_CONST || u.after.kind != PYR_MEDIUM_ISO_CONST ||
+                            u.split))
+            return PYR_E_UNSUPPORTED;        // a wavelength batch needs homogeneous isotropic media
         d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
         {   // measurement knob (tools/ only): PYR_DEBUG_RECORD_LAST=1 records the last entry only,
             // which times the arithmetic of a trace without its record stream
@@ -949,6 +981,16 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     bool with_e = (flags & PYR_F_RECORD_E) != 0;
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
+    if (pk.P.n_waves > 1) {
+        // wavelength batch: own instantiations of the two record-streaming kernels
+        bool grin_or_ext = pk.extended;
+        for (int s = 0; s < n_steps; ++s)
+            grin_or_ext = grin_or_ext || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN ||
+                          steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
+        if (with_e || grin_or_ext) return PYR_E_UNSUPPORTED;
+        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 11>, pk.P, 2, stream, true);
+        return launch(trace_real_kernel<2, false, 1, 2, 11>, pk.P, 2, stream, true);
+    }
     if (!pk.general) {
         if (with_e) return launch(trace_real_kernel<2, true, 0, 2, 3>, pk.P, 2, stream, true, true);
         // PYR_LEAN_VARIANT=50 selects per-thread STG records instead of the TMA record

@@ -110,7 +110,7 @@ def _alloc_rows(rows, n, device, complex_=False, pool=None):
 
 
 def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
-            events=None):
+            events=None, wave_end=None):
     if n == 0:
         return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
@@ -126,6 +126,10 @@ def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
     rin.alive = alive.data_ptr() if alive is not None else None
     rin.ld = ld_in
     rin.n_x = n_x
+    if wave_end is not None and len(wave_end) > 1:
+        rin.n_waves = len(wave_end)
+        for (w, end) in enumerate(wave_end):
+            rin.wave_end[w] = int(end)
     if events is not None:
         # CUDA events recorded back to back with the launch on the launch stream:
         # the pair brackets the kernel itself, not the host-side packing
@@ -231,11 +235,14 @@ class RecordPool(object):
 
 
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
-          pool=None, events=None, grin_history=False, _hist_rows=None):
+          pool=None, events=None, grin_history=False, _hist_rows=None, wave_end=None):
     """Run the lowered sequence on the device.  Returns a TraceRecord.
 
     events: optional list; a (start, end) pair of CUDA timing events is appended
     per native launch (kernel-only timing for benchmarks).
+    wave_end: wavelength batch (`lowering.lower_batch` table): cumulative ray counts of
+    the bundles that lie back to back in x0 / k0 / e0; segment w uses the w-th media
+    indices of every entry.  One launch for all wavelengths.
     grin_history: also record every integrator step of GRIN segments (the rows the
     reference appends, material_grin.py:198-205).  Memory grows with steps x rays:
     meant for small bundles.  Runs the trace twice (step counts first)."""
@@ -383,7 +390,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
             else:
                 cur_e_arg = cur_e
             _launch(lib, steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
-                    ld_k, flags, stream_ptr, events)
+                    ld_k, flags, stream_ptr, events, wave_end=wave_end)
             for i in range(lo, hi):
                 r = i - lo
                 rec.hit.append(xbuf[r, :, :n])
@@ -633,6 +640,66 @@ def seqtrace(system, initialbundle, elementsequence, splitup=False,
     for p in paths:
         p.record = rec
     return paths
+
+
+def _column_view(rec, lo, hi, lowered, wave):
+    """TraceRecord of the rays [lo, hi) of a batch record (zero-copy column slices)."""
+    sub = TraceRecord()
+    sub.lowered = lowered
+    sub.wave = wave
+    (sub.x0, sub.k0) = (rec.x0[:, lo:hi], rec.k0[:, lo:hi])
+    sub.e0 = rec.e0[:, lo:hi] if rec.e0 is not None else None
+    for s in range(len(rec.hit)):
+        sub.hit.append(rec.hit[s][:, lo:hi])
+        sub.k.append(rec.k[s][:, lo:hi])
+        sub.e.append(rec.e[s][:, lo:hi] if rec.e[s] is not None else None)
+        sub.flags.append(rec.flags[s][lo:hi])
+        sub.n_in.append(hi - lo)
+        sub.n_out.append(hi - lo)
+        sub.split.append(False)
+    return sub
+
+
+def seqtrace_batch(system, bundles, elementsequence, record_e=False):
+    """Trace several bundles of DIFFERENT wavelength through the same sequence in one
+    native launch per group of PYR_MAX_WAVES wavelengths (the F / d / C bundles of
+    demos/demo_doublegauss.py:189-213, which the reference traces one after the other).
+    Media indices are evaluated per wavelength at lowering time; the kernel picks them
+    per ray from the segment the ray lies in.  Returns one list[RayPath] per bundle,
+    exactly what `seqtrace` returns for it.  Sequences with crystals or GRIN media, and
+    record_e, fall back to one launch per bundle."""
+    bundles = list(bundles)
+    out = [None] * len(bundles)
+    if record_e or len(bundles) == 1:
+        return [seqtrace(system, b, elementsequence, record_e=record_e) for b in bundles]
+    for g0 in range(0, len(bundles), nat.MAX_WAVES):
+        group = bundles[g0:g0 + nat.MAX_WAVES]
+        waves = [b.wave for b in group]
+        try:
+            (per_wave, batch) = lowering.lower_batch(system, elementsequence, waves)
+        except lowering.LoweringError:
+            for (i, b) in enumerate(group):
+                out[g0 + i] = seqtrace(system, b, elementsequence)
+            continue
+        require_cuda()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        rows = []
+        for b in group:
+            rows.append([as_tensor(t[-1], dev) for t in (b.x, b.k, b.Efield)])
+            if any(t.is_complex() for t in rows[-1]):
+                raise ValueError("wavelength batches are real-valued")
+        (x0, k0, e0) = (torch.cat([r[c] for r in rows], dim=1) for c in range(3))
+        ends = np.cumsum([r[0].shape[1] for r in rows]).tolist()
+        rec = trace(batch, x0, k0, e0, waves[0], wave_end=ends)
+        lo = 0
+        for (i, (b, hi)) in enumerate(zip(group, ends)):
+            sub = _column_view(rec, lo, hi, per_wave[i], b.wave)
+            paths = paths_from_record(sub)
+            for p in paths:
+                p.record = sub
+            out[g0 + i] = paths
+            lo = hi
+    return out
 
 
 # ---------------------------------------------------------------------------

@@ -395,6 +395,32 @@ def _lower(system, elementsequence, wave):
     return out
 
 
+def lower_batch(system, elementsequence, waves):
+    """Lower one sequence for a batch of wavelengths (<= PYR_MAX_WAVES): returns
+    (per-wavelength lowered lists, the batch table).  The batch table is the first
+    wavelength's with `before_n_w` / `after_n_w` filled in; everything but the media
+    indices must agree between the wavelengths (it does: dispersion is the only
+    wavelength dependence of a sequence), and all media must be homogeneous isotropic."""
+    waves = [float(w) for w in waves]
+    if not (1 <= len(waves) <= nat.MAX_WAVES):
+        raise LoweringError("a wavelength batch holds 1..%d wavelengths" % nat.MAX_WAVES)
+    per_wave = [lower(system, elementsequence, w) for w in waves]
+    batch = lower(system, elementsequence, waves[0])
+    for (i, ls) in enumerate(batch):
+        st = ls.st
+        if st.before.kind != nat.MEDIUM_ISO_CONST or st.after.kind != nat.MEDIUM_ISO_CONST:
+            raise LoweringError("wavelength batches need homogeneous isotropic media "
+                                "(entry %r)" % (ls.surfkey,))
+        for (w, low) in enumerate(per_wave):
+            other = low[i].st
+            if (other.shape_kind, other.aperture_kind, other.interaction, other.dir_mode) != \
+                    (st.shape_kind, st.aperture_kind, st.interaction, st.dir_mode):
+                raise LoweringError("sequence differs between wavelengths")
+            st.before_n_w[w] = other.before.n
+            st.after_n_w[w] = other.after.n
+    return (per_wave, batch)
+
+
 def step_array(lowered):
     arr = (nat.PyrStep * len(lowered))()
     for (i, ls) in enumerate(lowered):

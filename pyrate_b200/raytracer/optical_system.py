@@ -41,6 +41,14 @@ class OpticalSystem(LocalCoordinatesTreeBase):
         if key in self.elements:
             self.elements.pop(key)
 
+    def seqtrace_batch(self, bundles, elementsequence, record_efield=False):
+        """`[self.seqtrace(b, elementsequence) for b in bundles]` for bundles of different
+        wavelength (e.g. the F, d, C bundles of demos/demo_doublegauss.py:189-213) in ONE
+        native launch: dispersion is resolved per wavelength at lowering time and the
+        kernel selects the media indices per ray.  Returns one list[RayPath] per bundle."""
+        from .. import engine
+        return engine.seqtrace_batch(self, bundles, elementsequence, record_e=record_efield)
+
     def para_seqtrace(self, pilotbundle, initialbundle, elementsequence,
                       pilotraypathsequence=None, use6x6=True,
                       pilotbundle_generation="complex"):

@@ -30,7 +30,7 @@ def test_struct_layouts_match():
     lib = nat.load()
     assert lib.pyr_sizeof_step() == ctypes.sizeof(nat.PyrStep)
     assert lib.pyr_sizeof_rays_in() == ctypes.sizeof(nat.PyrRaysIn)
-    assert lib.pyr_version() == 2
+    assert lib.pyr_version() == 3
 
 
 def test_strerror():

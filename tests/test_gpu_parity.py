@@ -520,3 +520,69 @@ def test_spot_sums_vector_and_scalar_paths(n):
         assert got[3] == m.sum()
         assert np.allclose(got[0:3], d.sum(1), rtol=1e-12, atol=1e-9)
         assert np.allclose(got[4:7], (d * d).sum(1), rtol=1e-12, atol=1e-9)
+
+
+FDC = (0.4861e-3, 0.5876e-3, 0.6563e-3)          # Fraunhofer F, d, C lines in mm
+
+
+@pytest.mark.parametrize("name", ["x14_dispersive", "x15_dispersive_asphere", "x1_tilted"])
+def test_wavelength_batch_one_launch(name):
+    """OpticalSystem.seqtrace_batch: F / d / C bundles of different sizes through a
+    dispersive system in ONE launch (per-ray selection of the media indices) against
+    one seqtrace per bundle (bit for bit for closed-form shapes: same kernel arithmetic)
+    and against the oracle at each wavelength."""
+    import pyrate_np as onp
+    import torch
+    spec = configs.CONFIGS[name]
+    (s, seq) = configs.build_system(spec, pb.api())
+    deg = np.pi / 180.0
+    bundles = []
+    raw = []
+    for (i, wave) in enumerate(FDC):
+        (x0, k0, e0) = configs.config_bundle(spec, 5 + 2 * i,       # 91, 169, 271 rays: segment
+                                             (0., np.sin((i - 1) * deg), np.cos((i - 1) * deg)),
+                                             (1., 0., 0.))          # borders inside a tile
+        raw.append((x0, k0, e0))
+        bundles.append(pb.RayBundle(x0, k0, e0, wave=wave))
+    batch = s.seqtrace_batch(bundles, seq)
+    assert len(batch) == 3
+    rec = batch[0][0].record
+    assert batch[1][0].record.hit[0].data_ptr() != rec.hit[0].data_ptr()      # column views
+    assert batch[1][0].record.hit[0].data_ptr() - rec.hit[0].data_ptr() == 8 * 91
+    tol = util.tolerance_of(name)
+    saw_dispersion = False
+    for (i, (wave, paths)) in enumerate(zip(FDC, batch)):
+        single = s.seqtrace(bundles[i], seq)
+        assert len(paths) == len(single) == 1
+        assert len(paths[0].raybundles) == len(single[0].raybundles)
+        (x0, k0, e0) = raw[i]
+        ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=wave)
+        for (ib, (a, b, rb)) in enumerate(zip(paths[0].raybundles, single[0].raybundles, ref[0])):
+            assert a.wave == wave
+            (da, db) = (a.numpy(), b.numpy())
+            for f in ("x", "k", "valid", "rayID"):
+                if tol == util.TOL_ITERATED and f in ("x", "k"):
+                    # Newton leaves the loop by a warp vote: the iteration count of a ray
+                    # depends on its warp neighbours, which differ between the two launches
+                    assert util.relerr(da[f], db[f]) < 1e-13, (i, ib, f)
+                else:
+                    assert np.array_equal(da[f], db[f], equal_nan=f in ("x", "k")), (i, ib, f)
+            util.compare_bundle(da, {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                     "rayID": rb["rayID"]}, tol, "%s wave %d b%d" % (name, i, ib))
+        if i:
+            last = paths[0].raybundles[-1].numpy()["k"]
+            saw_dispersion = saw_dispersion or not np.allclose(
+                last[..., :5], batch[0][0].raybundles[-1].numpy()["k"][..., :5], atol=1e-9)
+    assert saw_dispersion
+
+
+def test_wavelength_batch_falls_back_where_the_kernel_cannot_batch():
+    """Crystals / GRIN media: one launch per bundle, same results as seqtrace."""
+    spec = configs.CONFIGS["c5_grin"]
+    (s, seq) = configs.build_system(spec, pb.api())
+    bundles = [pb.RayBundle(*configs.config_bundle(spec, 2), wave=w) for w in FDC[:2]]
+    batch = s.seqtrace_batch(bundles, seq)
+    for (b, paths) in zip(bundles, batch):
+        single = s.seqtrace(b, seq)
+        (da, db) = (paths[0].raybundles[-1].numpy(), single[0].raybundles[-1].numpy())
+        assert np.array_equal(da["x"], db["x"], equal_nan=True)

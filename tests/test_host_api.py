@@ -239,3 +239,32 @@ def test_convenience_builders_match_spec_builder():
         assert _step_bytes(la) == _step_bytes(lb)
     with pytest.raises(NotImplementedError):
         pb.build_rotationally_symmetric_optical_system([(10.0, 0, 1.0, "N-BK7", "s", {})])
+
+
+FDC = (0.4861e-3, 0.5876e-3, 0.6563e-3)          # Fraunhofer F, d, C lines in mm
+
+
+def test_wavelength_batch_lowering():
+    """lower_batch: one step table for several wavelengths; only the media indices
+    differ and they equal the single-wavelength lowerings."""
+    from pyrate_b200 import _native as nat, lowering
+    (s, seq) = configs.build_system(configs.CONFIGS["x14_dispersive"], pb.api())
+    (per_wave, batch) = lowering.lower_batch(s, seq, FDC)
+    assert len(per_wave) == 3 and len(batch) == 13
+    seen_dispersion = False
+    for (i, ls) in enumerate(batch):
+        for w in range(3):
+            assert ls.st.after_n_w[w] == per_wave[w][i].st.after.n
+            assert ls.st.before_n_w[w] == per_wave[w][i].st.before.n
+        assert ls.st.after.n == per_wave[0][i].st.after.n
+        seen_dispersion = seen_dispersion or ls.st.after_n_w[0] != ls.st.after_n_w[2]
+        if ls.st.after.n != 1.0:
+            assert ls.st.after_n_w[0] > ls.st.after_n_w[1] > ls.st.after_n_w[2] > 1.0   # normal dispersion
+    assert seen_dispersion
+    with pytest.raises(lowering.LoweringError):
+        lowering.lower_batch(s, seq, FDC + (0.7e-3, 0.8e-3))
+    for name in ("c5_grin", "c4_anisotropic"):
+        (s2, seq2) = configs.build_system(configs.CONFIGS[name], pb.api())
+        with pytest.raises(lowering.LoweringError):
+            lowering.lower_batch(s2, seq2, FDC)
+    assert nat.MAX_WAVES == 4

@@ -32,7 +32,7 @@ def config_of(tag):
 def tolerance_of(name):
     return TOL_ITERATED if name in ("c3_asphere", "c5_grin", "x2_xypoly", "x6_biconic",
                                     "x9_zernike", "x10_zernike_general", "x11_gridsag",
-                                    "x12_combination") \
+                                    "x12_combination", "x15_dispersive_asphere") \
         else TOL_CLOSED_FORM
 
 
