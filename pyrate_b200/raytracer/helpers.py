@@ -104,12 +104,12 @@ def sorted_unit_modes_isotropic(n_index, kd, normal):
 
 def _finish(surfobj, mat, xlocobj, kconek, lck, wave):
     lcobj = surfobj.rootcoordinatesystem
-    xlocmat = mat.lc.returnOtherToActualPoints(xlocobj, lcobj)
+    # (the start medium is homogeneous: no dependence on the start points, which the
+    # reference hands to the eigen-solver as well, :176-183)
     kconemat = mat.lc.returnOtherToActualDirections(kconek, lck)
     xlocsurf = surfobj.shape.lc.returnOtherToActualPoints(xlocobj, lcobj)
     surfnormalmat = mat.lc.returnOtherToActualDirections(
         np.asarray(surfobj.shape.getNormal(xlocsurf[0], xlocsurf[1])), surfobj.shape.lc)
-    del xlocmat                                   # homogeneous medium: no x dependence
     (kvector_4, efield_4) = sorted_unit_modes_isotropic(
         _isotropic_index(mat, wave), kconemat, surfnormalmat)
     xglob = lcobj.returnLocalToGlobalPoints(xlocobj)

@@ -97,3 +97,29 @@ def test_views_are_lazy_and_numpy_export():
     k = path.raybundles[-1].k[0]
     assert torch.allclose((e * e).sum(0), torch.ones(5, dtype=torch.float64))
     assert float((e * k).sum(0).abs().max()) < 1e-14
+
+
+def test_batch_column_views():
+    """engine._column_view: the per-bundle records of a wavelength batch are zero-copy
+    column slices of the one batch record, and their RayPath views behave like those of
+    a stand-alone trace (compaction, rayID counted from the bundle's own first ray)."""
+    flags = [[3, 3, 1, 3, 3, 3, 0, 3, 3], [3, 3, 0, 3, 2, 3, 0, 3, 3]]
+    rec = _record(9, flags, [False, False])
+    lows = [[_Low(0), _Low(0)] for _ in range(3)]
+    ends = [2, 7, 9]
+    lo = 0
+    for (w, hi) in enumerate(ends):
+        sub = engine._column_view(rec, lo, hi, lows[w], 0.4e-3 + 0.1e-3 * w)
+        assert sub.hit[1].data_ptr() == rec.hit[1].data_ptr() + 8 * lo
+        assert sub.n_in == [hi - lo] * 2 and sub.wave == 0.4e-3 + 0.1e-3 * w
+        (path,) = engine.paths_from_record(sub)
+        b = path.raybundles
+        assert len(b) == 4 and b[0] is b[1] and b[0].wave == sub.wave
+        assert torch.equal(b[0].x[0], rec.x0[:, lo:hi]) and torch.equal(b[0].x[1], rec.hit[0][:, lo:hi])
+        alive0 = (torch.tensor(flags[0][lo:hi]) & 2) != 0
+        assert b[2].rayID.tolist() == torch.arange(hi - lo)[alive0].tolist()
+        assert torch.equal(b[2].k[0], rec.k[0][:, lo:hi][:, alive0])
+        alive1 = alive0 & ((torch.tensor(flags[1][lo:hi]) & 2) != 0)
+        assert b[3].rayID.tolist() == torch.arange(hi - lo)[alive1].tolist()
+        assert torch.equal(b[3].x[0], rec.hit[1][:, lo:hi][:, alive1])
+        lo = hi
