@@ -268,3 +268,41 @@ def test_wavelength_batch_lowering():
         with pytest.raises(lowering.LoweringError):
             lowering.lower_batch(s2, seq2, FDC)
     assert nat.MAX_WAVES == 4
+
+
+def test_shape_gradients_are_the_derivatives_of_their_sag():
+    """Every host shape mirror: getGrad(x, y) = (-dz/dx, -dz/dy, 1) of getSag by central
+    differences (the reference's own test idea, tests/test_surf_shape.py:287-353, applied
+    to all shape classes; the conic's implicit gradient is proportional to it)."""
+    lc = pb.LocalCoordinates.p(name="fd")
+    rng = np.random.default_rng(17)
+    x = rng.uniform(-3, 3, 25)
+    y = rng.uniform(-3, 3, 25)
+    zco = [0.0] * 16
+    (zco[3], zco[8], zco[15]) = (-0.05, 0.01, -0.002)       # m = 0 terms (see DESIGN section 7)
+    (xl, yl, zg) = configs.grid_arrays(configs.X11_GRIDSAG["surfaces"][2]["shape"][1]["grid"])
+    asph = pb.Asphere.p(lc, curv=-0.03, cc=-0.7, coefficients=[1e-3, -2e-5, 1e-7])
+    shapes = {
+        "conic": pb.Conic.p(lc, curv=0.07, cc=-0.4),
+        "asphere": asph,
+        "biconic": pb.Biconic.p(lc, curvx=0.03, ccx=-0.6, curvy=-0.02, ccy=0.4,
+                                coefficients=[(1e-3, 0.3), (-2e-5, -0.2)]),
+        "xypoly": pb.XYPolynomials.p(lc, normradius=10.0, coefficients=[
+            (2, 0, -0.9), (0, 2, -1.1), (1, 1, 0.05), (3, 0, 0.02), (1, 2, -0.03)]),
+        "zernike": pb.ZernikeFringe.p(lc, normradius=5.0, coefficients=zco),
+        "gridsag": pb.GridSag.p(lc, (xl, yl, zg)),
+        "combination": pb.LinearCombination.p(lc, list_of_coefficients_and_shapes=[
+            (1.0, asph), (0.5, pb.XYPolynomials.p(lc, normradius=10.0,
+                                                  coefficients=[(2, 0, 0.02), (0, 3, 0.004)]))]),
+    }
+    h = 1e-5
+    for (name, sh) in shapes.items():
+        sag = lambda a, b: np.asarray(sh.getSag(a.copy(), b.copy()), dtype=float)   # noqa: E731
+        dzdx = (sag(x + h, y) - sag(x - h, y)) / (2 * h)
+        dzdy = (sag(x, y + h) - sag(x, y - h)) / (2 * h)
+        g = np.asarray(sh.getGrad(x.copy(), y.copy()), dtype=float)
+        g = g / g[2]                                           # conic: implicit gradient
+        assert np.allclose(g[0], -dzdx, rtol=1e-6, atol=1e-8), name
+        assert np.allclose(g[1], -dzdy, rtol=1e-6, atol=1e-8), name
+        n = np.asarray(sh.getNormal(x.copy(), y.copy()), dtype=float)
+        assert np.allclose(np.sum(n * n, axis=0), 1.0, atol=1e-12), name
