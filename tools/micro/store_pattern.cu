@@ -105,6 +105,46 @@ __global__ void __launch_bounds__(256, 2) pattern_rw(const double *in, double *o
     }
 }
 
+// like pattern_rw (dynamic in-order), but a CTA takes GROUP consecutive tiles at a time and
+// reads all their inputs in one burst before it writes their records
+template <int TILE_T, int GROUP>
+__global__ void __launch_bounds__(256, 2) pattern_rw_group(const double *in, double *out, uint8_t *fl, int64_t n,
+                                                           int64_t ld, unsigned *counter) {
+    constexpr int TILE = TILE_T;
+    const int64_t ngroups = ((n + TILE - 1) / TILE + GROUP - 1) / GROUP;
+    __shared__ long long next_group;
+    int64_t grp = blockIdx.x;
+    while (grp < ngroups) {
+        if (threadIdx.x == 0) next_group = gridDim.x + atomicAdd(counter, 1u);
+        double2 acc[GROUP];
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+            acc[g] = make_double2(0.0, 0.0);
+            const int64_t i = (grp * GROUP + g) * TILE + threadIdx.x * 2;
+            if (i < n) {
+#pragma unroll
+                for (int row = 0; row < 9; ++row) {
+                    const double2 t = __ldcs(reinterpret_cast<const double2 *>(in + (int64_t)row * ld + i));
+                    acc[g].x += t.x; acc[g].y += t.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < GROUP; ++g) {
+            const int64_t i = (grp * GROUP + g) * TILE + threadIdx.x * 2;
+            for (int s = 0; s < S; ++s) {
+                if (i < n) {
+#pragma unroll
+                    for (int row = 0; row < ROWS; ++row)
+                        __stcs(reinterpret_cast<double2 *>(out + ((int64_t)s * ROWS + row) * ld + i), make_double2(acc[g].x, acc[g].y + row));
+                    __stcs(reinterpret_cast<uchar2 *>(fl + (int64_t)s * ld + i), make_uchar2(3, 3));
+                }
+            }
+        }
+        __syncthreads(); grp = next_group; __syncthreads();
+    }
+}
+
 template <int POL>
 __device__ __forceinline__ void st2(double2 *p, double2 v) {
     if (POL == 0) *p = v;
@@ -183,6 +223,12 @@ int main(int argc, char **argv) {
             snprintf(nm, sizeof nm, "R+W NON-persistent, %d fma pairs/step", fm);
             timeit(nm, [&] { pattern_rw<512, false><<<nt512, 256, 95 * 1024>>>(in, out, fl, n, ld, counter, fm); });
         }
+        CK(cudaFuncSetAttribute(pattern_rw_group<512, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(pattern_rw_group<512, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        CK(cudaFuncSetAttribute(pattern_rw_group<512, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        timeit("R+W dynamic, input bursts of 2 tiles", [&] { cudaMemsetAsync(counter, 0, 4); pattern_rw_group<512, 2><<<296, 256, 95 * 1024>>>(in, out, fl, n, ld, counter); });
+        timeit("R+W dynamic, input bursts of 4 tiles", [&] { cudaMemsetAsync(counter, 0, 4); pattern_rw_group<512, 4><<<296, 256, 95 * 1024>>>(in, out, fl, n, ld, counter); });
+        timeit("R+W dynamic, input bursts of 8 tiles", [&] { cudaMemsetAsync(counter, 0, 4); pattern_rw_group<512, 8><<<296, 256, 95 * 1024>>>(in, out, fl, n, ld, counter); });
         timeit("persistent 1184 CTAs row layout cyclic (8/SM)", [&] { pattern<512><<<1184, 256>>>(out, fl, n, ld, 0, 0); });
         timeit("NON-persistent TILE 512  row layout + 400 FMAs/step", [&] { pattern<512><<<nt512, 256>>>(out, fl, n, ld, 4, 400); });
     }
