@@ -25,8 +25,15 @@ class LoweringError(Exception):
     pass
 
 
+_MRO_CACHE = {}
+
+
 def _mro_names(obj):
-    return {c.__name__ for c in type(obj).__mro__}
+    t = type(obj)
+    names = _MRO_CACHE.get(t)
+    if names is None:
+        names = _MRO_CACHE[t] = frozenset(c.__name__ for c in t.__mro__)
+    return names
 
 
 _FRAME_CACHE = None      # id(lc) -> PyrFrame, alive only inside one lower() call
@@ -45,10 +52,8 @@ def _frame(lc):
 
 def _frame_uncached(lc):
     f = nat.PyrFrame()
-    b = np.ascontiguousarray(lc.localbasis, dtype=np.float64)
-    o = np.ascontiguousarray(lc.globalcoordinates, dtype=np.float64)
-    C.memmove(f.r, b.ctypes.data, 72)
-    C.memmove(f.o, o.ctypes.data, 24)
+    f.r[:] = np.asarray(lc.localbasis, dtype=np.float64).reshape(-1).tolist()
+    f.o[:] = np.asarray(lc.globalcoordinates, dtype=np.float64).reshape(-1).tolist()
     return f
 
 
@@ -89,7 +94,21 @@ def _verify_grin_profile(mat, profile, samples=64):
                             "declared device boundary" % (getattr(mat, "name", "?"),))
 
 
+_MEDIUM_CACHE = None     # id(material) -> PyrMedium, alive only inside one lower() call
+
+
 def lower_medium(mat, wave):
+    if _MEDIUM_CACHE is not None:
+        hit = _MEDIUM_CACHE.get(id(mat))
+        if hit is not None:
+            return hit
+    m = _lower_medium_uncached(mat, wave)
+    if _MEDIUM_CACHE is not None:
+        _MEDIUM_CACHE[id(mat)] = m
+    return m
+
+
+def _lower_medium_uncached(mat, wave):
     m = nat.PyrMedium()
     names = _mro_names(mat)
     m.frame = _frame(mat.lc)
@@ -337,12 +356,12 @@ class LoweredStep(object):
 def lower(system, elementsequence, wave, splitup=False):
     """Returns list[LoweredStep] for `elementsequence`
     = [(elemkey, [(surfkey, {"is_mirror": .., "is_stop": ..}), ...]), ...]."""
-    global _FRAME_CACHE
-    _FRAME_CACHE = {}
+    global _FRAME_CACHE, _MEDIUM_CACHE
+    (_FRAME_CACHE, _MEDIUM_CACHE) = ({}, {})
     try:
         return _lower(system, elementsequence, wave)
     finally:
-        _FRAME_CACHE = None
+        (_FRAME_CACHE, _MEDIUM_CACHE) = (None, None)
 
 
 def _lower(system, elementsequence, wave):
