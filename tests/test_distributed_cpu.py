@@ -30,6 +30,15 @@ def _worker(rank, world, port, xfile, out):
     pd.allreduce_spot_sums(sums)
     (c, rms) = engine.spot_from_sums(sums)
     np.save(out % rank, np.array(list(c) + [rms, sums[3].item(), lo, hi]))
+    # the optional spot-diagram gather (BASELINE config 5: "NCCL spot gather"): surviving
+    # rays of every rank, ragged widths, on rank 0
+    flags = torch.full((xs.shape[1],), 3, dtype=torch.uint8)
+    flags[rank::3] = 1                                    # HIT but not ALIVE: dropped
+    pts = pd.gather_spot_points(xs, flags, dst=0)
+    if rank == 0:
+        np.save(out % 99, pts.numpy())
+    else:
+        assert pts is None
     dist.barrier()
     dist.destroy_process_group()
 
@@ -51,6 +60,12 @@ def test_sharded_spot_matches_reference_statistic(tmp_path):
     (lo0, hi0) = np.load(out % 0)[5:7]
     (lo1, hi1) = np.load(out % 1)[5:7]
     assert (lo0, hi0, hi1) == (0, n // 2, n) and lo1 == hi0
+    want = []
+    for (r, (lo, hi)) in enumerate(((int(lo0), int(hi0)), (int(lo1), int(hi1)))):
+        keep = np.ones(hi - lo, dtype=bool)
+        keep[r::3] = False
+        want.append(g["x"][:2, lo:hi][:, keep])
+    assert np.array_equal(np.load(out % 99), np.concatenate(want, axis=1))
 
 
 def test_shard_range_partitions():
