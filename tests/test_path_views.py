@@ -123,3 +123,37 @@ def test_batch_column_views():
         assert b[3].rayID.tolist() == torch.arange(hi - lo)[alive1].tolist()
         assert torch.equal(b[3].x[0], rec.hit[1][:, lo:hi][:, alive1])
         lo = hi
+
+
+def test_device_bundle_layout_rules():
+    """engine.device_bundle (device = "cpu" here: the rules are device independent):
+    rows that already live on the target device with ONE common row stride are used in
+    place; anything else lands in row-padded buffers (ld a multiple of 16 doubles, the
+    layout of the TMA-staged input path), complex promotion included."""
+    rng = np.random.default_rng(2)
+    (x, k, e) = (torch.from_numpy(rng.random((3, 37))) for _ in range(3))
+    (a, b, c) = engine.device_bundle(x, k, e, device="cpu")
+    assert (a.data_ptr(), b.data_ptr(), c.data_ptr()) == (x.data_ptr(), k.data_ptr(), e.data_ptr())
+    # one operand with a different row stride: everything is re-laid with a common ld
+    wide = torch.zeros((3, 64), dtype=torch.float64)
+    wide[:, :37] = k
+    (a, b, c) = engine.device_bundle(x, wide[:, :37], e, device="cpu")
+    assert {t.stride(0) for t in (a, b, c)} == {48} and all(t.shape == (3, 37) for t in (a, b, c))
+    assert torch.equal(a, x) and torch.equal(b, k) and torch.equal(c, e)
+    assert a.data_ptr() != x.data_ptr()
+    # padding columns are zero (the vector / TMA paths may read them)
+    full = torch.as_strided(a, (3, 48), (48, 1))
+    assert float(full[:, 37:].abs().max()) == 0.0
+    # complex promotion, E = None passes through, like_ld is honoured
+    (a, b, c) = engine.device_bundle(x, k, None, device="cpu", complex_=True)
+    assert c is None and b.dtype == torch.complex128 and a.dtype == torch.float64
+    assert a.stride(0) == b.stride(0) == 48 and torch.equal(b.real, k)
+    (a, b, c) = engine.device_bundle(x, k, e, device="cpu", like_ld=80)
+    assert {t.stride(0) for t in (a, b, c)} == {80}
+    # _padded: the per-launch view of one (3, n) array
+    (buf, ld) = engine._padded(x)
+    assert ld == 48 and buf.shape == (3, 48) and torch.equal(buf[:, :37], x)
+    (buf, ld) = engine._padded(x, pad=False)
+    assert ld == 37 and buf.data_ptr() == x.data_ptr()
+    (buf, ld) = engine._padded(k, True)
+    assert buf.shape == (3, 48, 2) and torch.equal(buf[:, :37, 0], k) and float(buf[..., 1].abs().max()) == 0.0
