@@ -95,3 +95,29 @@ def test_argument_validation_happens_before_any_device_work():
     assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 0, 0, None) == 0           # empty bundle
     assert lib.pyr_spot_sums(None, 0, None, 2, 1, None, None, None) == -1
     assert lib.pyr_trace_host(steps, 1, None, None, None, 1, None, None, None, None, None, 0, 1) == -1
+
+
+def test_wavelength_batch_argument_validation():
+    """PyrRaysIn.n_waves / wave_end (ABI v3): malformed segment tables and media a batch
+    cannot carry are rejected before any device work."""
+    lib = nat.load()
+    rays = nat.PyrRaysIn()
+    dummy = (ctypes.c_double * 8)()
+    rays.x = ctypes.addressof(dummy)
+    rays.k = ctypes.addressof(dummy)
+    steps = (nat.PyrStep * 1)(_one_step())
+    rays.n_waves = nat.MAX_WAVES + 1
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, 0, None) == -1        # too many segments
+    rays.n_waves = -1
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, 0, None) == -1
+    rays.n_waves = 3
+    (rays.wave_end[0], rays.wave_end[1]) = (60, 40)                               # not ascending
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, 0, None) == -1
+    (rays.wave_end[0], rays.wave_end[1]) = (40, 160)                              # beyond the bundle
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, 0, None) == -1
+    (rays.wave_end[0], rays.wave_end[1]) = (40, 60)
+    grin = (nat.PyrStep * 1)(_one_step())
+    grin[0].after.kind = nat.MEDIUM_ISO_GRIN
+    assert lib.pyr_trace(grin, 1, ctypes.byref(rays), 100, 0, None) == -2         # UNSUPPORTED
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, nat.F_COMPLEX, None) in (-1, -2)
+    assert ctypes.sizeof(nat.PyrRaysIn) == 6 * 8 + 8 + 8 * nat.MAX_WAVES
