@@ -629,6 +629,49 @@ def aniso_modes_sorted(eps, nrm, kpa):
     return (k4, e4)
 
 
+def uniaxial_decomposition(eps, tol=1e-12):
+    """(eps_o, eps_e, axis) of a real symmetric tensor with a twofold eigenvalue
+    (eps = eps_o 1 + (eps_e - eps_o) a a^T), or None for isotropic / biaxial tensors."""
+    eps = np.asarray(eps)
+    if np.iscomplexobj(eps):
+        if np.max(np.abs(eps.imag)) > tol:
+            return None
+        eps = eps.real
+    if np.max(np.abs(eps - eps.T)) > tol * np.max(np.abs(eps)):
+        return None
+    (w, v) = np.linalg.eigh(eps)
+    scale = np.max(np.abs(w))
+    if abs(w[0] - w[1]) <= tol * scale and abs(w[2] - w[1]) > tol * scale:
+        return (0.5 * (w[0] + w[1]), w[2], v[:, 2])
+    if abs(w[2] - w[1]) <= tol * scale and abs(w[0] - w[1]) > tol * scale:
+        return (0.5 * (w[1] + w[2]), w[0], v[:, 0])
+    return None
+
+
+def uniaxial_xi_roots(eps_o, eps_e, axis, nrm, kpa):
+    """Closed form of the four roots xi of the dispersion relation of a uniaxial crystal
+    for k = kpa + xi n (what calcXiEigenvectorsNorm, material.py:407-454, gets out of a
+    6x6 generalised eigen-solve and the device out of the Fresnel quartic): the quartic
+    factorises into the ordinary sphere  k.k = eps_o  and the extraordinary ellipsoid
+    eps_o k.k + (eps_e - eps_o) (k.a)^2 = eps_o eps_e.  Returns (4, N) complex:
+    ordinary +, ordinary -, extraordinary +, extraordinary -.  Groundwork for a
+    root-finder-free crystal step; pinned on the reference's
+    eigenvalues by tests/test_oracle_golden.py."""
+    nrm = np.asarray(nrm, dtype=float)
+    kpa = np.asarray(kpa, dtype=complex)
+    a = np.asarray(axis, dtype=float).reshape(3, 1)
+    delta = eps_e - eps_o
+    kk = np.sum(kpa * kpa, axis=0)
+    (ka, na) = (np.sum(kpa * a, axis=0), np.sum(nrm * a, axis=0))
+    kn = np.sum(kpa * nrm, axis=0)                       # 0 for an in-plane kpa; kept general
+    xo = np.sqrt(kn * kn - (kk - eps_o) + 0j)
+    qa = eps_o + delta * na * na
+    qb = eps_o * kn + delta * ka * na                    # half the linear coefficient
+    qc = eps_o * kk + delta * ka * ka - eps_o * eps_e
+    disc = np.sqrt(qb * qb - qa * qc + 0j)
+    return np.stack((-kn + xo, -kn - xo, (-qb + disc) / qa, (-qb - disc) / qa))
+
+
 def anisotropic_deflect(mat, bundle, step, wave, mirror, splitup):
     fr = mat["frame"]
     xg = bundle["x"][-1]

@@ -200,3 +200,40 @@ def test_oracle_matches_live_reference_on_random_systems(seed):
         ref = {"x": np.asarray(rb.x), "k": np.asarray(rb.k), "valid": np.asarray(rb.valid),
                "rayID": np.asarray(rb.rayID)}
         util.compare_bundle(b, ref, tol, "seed %d b%d" % (seed, ib))
+
+
+def test_uniaxial_closed_form_roots_match_reference_eigenvalues():
+    """The factorised dispersion relation of a uniaxial crystal against the xi eigenvalues
+    of the reference (MaxwellMaterial.calcXiEigenvectorsNorm, material.py:407-454, fixture
+    aniso_modes.npz), and against the LAPACK restatement for a rotated axis and oblique
+    complex in-plane vectors."""
+    g = np.load(util.GOLDEN + "/aniso_modes.npz")
+    dec = onp.uniaxial_decomposition(g["uniaxial_y_eps"])
+    assert dec is not None and np.allclose(np.abs(dec[2]), [0, 1, 0])
+    assert np.isclose(dec[0], 1.658 ** 2) and np.isclose(dec[1], 1.486 ** 2)
+    roots = onp.uniaxial_xi_roots(*dec, g["uniaxial_y_n"], g["uniaxial_y_kpa"])
+    ref = g["uniaxial_y_xi4"]
+    for j in range(ref.shape[1]):
+        assert np.allclose(np.sort_complex(roots[:, j]), np.sort_complex(ref[:, j]),
+                           rtol=1e-10, atol=1e-12), j
+    assert onp.uniaxial_decomposition(g["biaxial_rot_eps"]) is None
+    assert onp.uniaxial_decomposition(2.25 * np.eye(3)) is None
+    # rotated axis, complex kpa: every root must satisfy the full dispersion relation
+    rng = np.random.default_rng(9)
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    (eo, ee) = (2.4, 2.9)
+    eps = eo * np.eye(3) + (ee - eo) * np.outer(axis, axis)
+    dec = onp.uniaxial_decomposition(eps)
+    assert np.isclose(dec[0], eo) and np.isclose(dec[1], ee) and np.isclose(abs(dec[2] @ axis), 1.0)
+    n = rng.normal(size=(3, 20))
+    n /= np.linalg.norm(n, axis=0)
+    kin = rng.normal(size=(3, 20)) * 0.4 + 0.05j * rng.normal(size=(3, 20))
+    kpa = kin - np.sum(kin * n, axis=0) * n
+    roots = onp.uniaxial_xi_roots(*dec, n, kpa)
+    for r in range(4):
+        k = kpa + roots[r] * n
+        for j in range(20):
+            kj = k[:, j]
+            m = eps - np.dot(kj, kj) * np.eye(3) + np.outer(kj, kj)      # (eps - k.k 1 + k k^T) E = 0
+            assert abs(np.linalg.det(m)) < 1e-10, (r, j)
