@@ -569,13 +569,14 @@ def paths_from_record(rec, splitup=False):
     e0 = rec.e0 if rec.e0 is not None else None
     paths = []
     for p in range(npaths):
-        def block(width):
-            # after q splits the device bundle has 2^q blocks of n0 columns;
-            # path p lives in block p mod 2^q
+        def cols(t, width):
+            # after q splits the device bundle has 2^q blocks of n0 columns; path p
+            # lives in block p mod 2^q.  Without path forking the records already
+            # have exactly the bundle's width: no view op at all.
             if not splitup:
-                return slice(0, width)
+                return t
             b = p % (width // n0)
-            return slice(b * n0, (b + 1) * n0)
+            return t[..., b * n0:(b + 1) * n0]
 
         sx = _const(rec.x0)
         (sk, se) = (rec.k0, e0 if e0 is not None else default_e0())
@@ -583,17 +584,15 @@ def paths_from_record(rec, splitup=False):
         ids = _Lazy(lambda: torch.arange(n0, device=dev))
         bundles = []
         for s in range(nsteps):
-            blk_in = block(rec.n_in[s])
-            hit = rec.hit[s][:, blk_in]
-            fl = rec.flags[s][blk_in]
+            hit = cols(rec.hit[s], rec.n_in[s])
+            fl = cols(rec.flags[s], rec.n_in[s])
             bb = _BundleBuilder(sx, sk, se, mask, ids, hit, fl,
                                 hist=rec.grin_hist.get(s) if not splitup else None)
             splitted = bool(s >= 1 and rec.split[s - 1] and not splitup)
             bundles.append(RayBundle(_lazy={f: bb.field(f) for f in RayBundle._FIELDS},
                                      wave=rec.wave, splitted=splitted))
-            blk_out = block(rec.n_out[s])
-            sk = rec.k[s][:, blk_out]
-            se = rec.e[s][:, blk_out] if rec.e[s] is not None else None
+            sk = cols(rec.k[s], rec.n_out[s])
+            se = cols(rec.e[s], rec.n_out[s]) if rec.e[s] is not None else None
             # survivors: the device ALIVE bit is cumulative; an anisotropic
             # deflection keeps every ray it was handed (material_anisotropic.py
             # :87-100 has no validity filter), which the kernel mirrors
