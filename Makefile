@@ -13,7 +13,15 @@ $(OUT): $(SRC) $(HDR)
 	$(NVCC) $(NVFLAGS) -shared -o $@ $(SRC) 2> pyrate_b200/_lib/ptxas.log || (cat pyrate_b200/_lib/ptxas.log; exit 1)
 	@grep -E "registers|spill|error|warning" pyrate_b200/_lib/ptxas.log | grep -v "^$$" | head -60 || true
 
+# measurement build for tools/ (A/B knobs PYR_DEBUG_RECORD_LAST / PYR_LEAN_VARIANT compiled in);
+# never loaded by the package unless a tool calls _native.use_tools_library()
+TOOLS_OUT := pyrate_b200/_lib/libpyrate_b200_tools.so
+tools: $(TOOLS_OUT)
+$(TOOLS_OUT): $(SRC) $(HDR)
+	@mkdir -p pyrate_b200/_lib
+	$(NVCC) $(NVFLAGS) -DPYR_TOOLS -shared -o $@ $(SRC) 2> pyrate_b200/_lib/ptxas_tools.log || (cat pyrate_b200/_lib/ptxas_tools.log; exit 1)
+
 clean:
 	rm -rf pyrate_b200/_lib
 
-.PHONY: all clean
+.PHONY: all clean tools

@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define PYR_ABI_VERSION 3
+#define PYR_ABI_VERSION 4
 
 #define PYR_MAX_COEFF 80        /* asphere coefficients / XY-polynomial terms (a
                                    Zernike series up to Fringe term 36 expands into
@@ -241,6 +241,67 @@ typedef struct PyrStep {
 #define PYR_RAY_ALIVE 2u        /* survives the deflection: contained in the next
                                    RayBundle (material_isotropic.py:183-199)       */
 
+/* ---------------------------------------------------------------------------
+ * Bundle generation on the device (the callers right above seqtrace:
+ * OpticalSystemAnalysis.collimated_bundle / divergent_bundle,
+ * raytracer/analysis/optical_system_analysis.py:83-165, over the rasters of
+ * sampling2d/raster.py:36-166).  A bundle is fully described by (raster, radius, start
+ * point, direction, background index): ray i of the call is raster point `first + i`,
+ * computed in registers -- no start points, wave vectors or fields are read from
+ * memory.  The reference runs a generalised eigen-solve per ray here even in vacuum
+ * (material/material.py:476-497); in a homogeneous isotropic background the result is
+ * k = n d and any unit E perpendicular to it.
+ * ------------------------------------------------------------------------- */
+enum PyrRasterKind {
+    PYR_RASTER_HEXAPOLAR = 0,   /* ring j = 1..R carries 6 j points at radius j / R, angle
+                                   2 pi i / (6 j); point 0 is the centre; 1 + 3 R (R + 1)
+                                   points (BASELINE.json's "hexapolar-sampled bundles");
+                                   param = R                                          */
+    PYR_RASTER_RECT = 1,        /* RectGrid raster.py:36-60: square lattice x1d x x1d,
+                                   x1d = linspace(lin_start, lin_stop, param), clipped to
+                                   the unit disk; row-major (y index slow)             */
+    PYR_RASTER_HEX = 2,         /* HexGrid :62-91: lattice x1d x sqrt(3) x1d followed by
+                                   the same lattice shifted by (aux[0], aux[1]) = half a
+                                   cell, both clipped to the unit disk; param = nx     */
+    PYR_RASTER_CIRCULAR = 3     /* CircularGrid :150-166: param radii x param angles,
+                                   angle index slow; PYR_GEN_SQRT_R: r -> sqrt(r)      */
+};
+
+enum PyrBundleKind {
+    PYR_BUNDLE_COLLIMATED = 0,  /* x = radius * p + start, d = dir        (:83-125)    */
+    PYR_BUNDLE_DIVERGENT = 1    /* x = start, d from the angles angley + radius p_x,
+                                   anglex + radius p_y (:127-165); dir[0] = angley,
+                                   dir[1] = anglex                                     */
+};
+
+#define PYR_GEN_E_PERP 1u       /* E = unit vector perpendicular to d built from the
+                                   coordinate axis least aligned with d (else: e[])    */
+#define PYR_GEN_SQRT_R 2u       /* CircularGrid(requidistant=False)                    */
+
+typedef struct PyrBundleGen {
+    int32_t raster;             /* PyrRasterKind                                       */
+    int32_t bundle;             /* PyrBundleKind                                       */
+    uint32_t flags;             /* PYR_GEN_*                                           */
+    int32_t reserved0;
+    int64_t param;              /* see PyrRasterKind                                   */
+    int64_t first;              /* raster index of ray 0 of this call (shards, chunks) */
+    int64_t total;              /* points of the whole raster: first + n <= total      */
+    double lin_start, lin_step, lin_stop;   /* RECT / HEX: numpy.linspace as computed on
+                                   the host, x1d[i] = i * lin_step + lin_start, last
+                                   element = lin_stop (bit-identical coordinates)      */
+    double aux[2];              /* HEX: shift of the second lattice                    */
+    double radius;              /* collimated: pupil radius; divergent: angular radius */
+    double start[3];            /* startx, starty, startz                              */
+    double dir[3];              /* collimated: unit direction; divergent: angles       */
+    double e[3];                /* E field unless PYR_GEN_E_PERP                       */
+    double n_index;             /* background index: k = n_index * d                   */
+    const int64_t *rows;        /* RECT / HEX: DEVICE pointer to 2 * nrows + 1 entries:
+                                   rows[r] = number of kept points ahead of lattice row
+                                   r (r = 0..nrows, nrows = param, or 2 * param for
+                                   HEX: second lattice after the first), then
+                                   rows[nrows + 1 + r] = first kept x index of row r   */
+} PyrBundleGen;
+
 typedef struct PyrRaysIn {
     const double *x;            /* (3, n_x)  start points, global frame            */
     const double *k;            /* (3, n)    wave vectors (complex if flag)        */
@@ -258,6 +319,11 @@ typedef struct PyrRaysIn {
     int32_t n_waves;
     int32_t reserved0;
     int64_t wave_end[PYR_MAX_WAVES];
+    /* non-NULL (HOST pointer, copied into the launch): the rays are generated in the
+     * prologue of the trace kernel and x / k / e / alive are ignored (may be NULL).
+     * Real-valued, non-splitting sequences without E recording; anything else returns
+     * PYR_E_UNSUPPORTED (generate with pyr_generate_bundle and trace the arrays).       */
+    const PyrBundleGen *gen;
 } PyrRaysIn;
 
 /* flags of pyr_trace */
@@ -271,6 +337,7 @@ const char *pyr_strerror(int code);
  * can verify its struct layout before the first call. */
 int64_t pyr_sizeof_step(void);
 int64_t pyr_sizeof_rays_in(void);
+int64_t pyr_sizeof_bundle_gen(void);
 
 /* Number of CUDA devices visible (0 when the driver is missing). */
 int pyr_device_count(void);
@@ -283,7 +350,16 @@ int pyr_device_count(void);
  * Material.refract / reflect (material_isotropic.py:163-236,
  * material_anisotropic.py:70-155).  `steps` is HOST memory (copied into the
  * launch), the rays and all outputs are DEVICE memory on the current device.
- * One persistent kernel launch per call (long sequences are chunked).
+ * One persistent kernel launch per call.  Limits of one call: 40 steps and 10 steps
+ * that need an auxiliary record (explicit shape, own-frame aperture, GRIN / crystal
+ * medium, partial step mode; a PYR_SHAPE_COMBINATION counts one per term) --
+ * PYR_E_TOOLARGE beyond; a caller continues a longer sequence from the last record
+ * (x = out_x, k = out_k, alive = out_flags of the previous call's last step), which is
+ * what pyr_trace_host_io and the Python engine do.
+ * Output rows: when ld_out % 16 == 0 and all output pointers are 16-byte aligned the
+ * records leave as TMA bulk stores that may write the row pad up to the next multiple
+ * of 2 doubles of out_x / out_k / out_e and up to the next multiple of 16 BYTES of
+ * out_flags -- allocate out_flags with ld_out bytes, not n.
  */
 int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
               int64_t n_rays, uint32_t flags, void *stream);
@@ -302,6 +378,14 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
                   void *stream);
 
 /*
+ * Write rays [0, n) of the generated bundle (raster points gen->first ...) to DEVICE
+ * arrays x, k, e of leading dimension ld (any of them may be NULL): what
+ * collimated_bundle / divergent_bundle return, resident on the device.
+ */
+int pyr_generate_bundle(const PyrBundleGen *gen, int64_t n_rays, double *x, double *k,
+                        double *e, int64_t ld, void *stream);
+
+/*
  * End-to-end host entry: start points / wave vectors / E in (pinned) HOST
  * memory, final-surface record back in HOST memory.  Chunks the bundle,
  * overlaps H2D, trace and D2H on internal streams.  `workspace` is caller-owned
@@ -316,6 +400,32 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0,
                    double *x_last, double *k_last, uint8_t *flags_last,
                    double *spot8, void *workspace, int64_t workspace_bytes,
                    int64_t chunk_rays);
+
+/*
+ * General end-to-end host entry (pyr_trace_host is the special case "host arrays in,
+ * last record out").  Inputs: host arrays x0, k0, e0 of leading dimension n_rays, or a
+ * generator (no host->device traffic at all beyond the descriptor).  Outputs, all HOST
+ * memory and optional: the last record (x_last, k_last, flags_last: ld = n_rays), every
+ * record of the sequence like the S + 2 bundles OpticalSystem.seqtrace returns
+ * (raytracer/optical_system.py:73-94, ray.py:207-260): x_all / k_all as
+ * (n_steps, 3, n_rays), flags_all as (n_steps, n_rays), and the spot sums.  Sequences
+ * longer than one launch are continued internally.  Real-valued, non-splitting
+ * sequences (crystals go through pyr_trace with PYR_F_COMPLEX on device arrays).
+ */
+typedef struct PyrHostIO {
+    const double *x0, *k0, *e0;     /* e0 NULL = (0, 1, 0), ray.py:71-73                */
+    const PyrBundleGen *gen;        /* non-NULL: x0 / k0 / e0 are ignored               */
+    double *x_last, *k_last;
+    uint8_t *flags_last;
+    double *x_all, *k_all;
+    uint8_t *flags_all;
+    double *spot8;
+} PyrHostIO;
+
+int64_t pyr_trace_host_io_workspace(int32_t n_steps, int64_t chunk_rays, int32_t all_records);
+int pyr_trace_host_io(const PyrStep *steps, int32_t n_steps, const PyrHostIO *io,
+                      int64_t n_rays, void *workspace, int64_t workspace_bytes,
+                      int64_t chunk_rays);
 
 #ifdef __cplusplus
 }

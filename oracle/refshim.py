@@ -2,17 +2,24 @@
 
 Makes `/root/reference` importable under NumPy 2 / without matplotlib by
 installing three monkey-patches *before* `import pyrateoptics` (SURVEY.md
-Appendix C).  Nothing under /root/reference is modified.  This module is only
-usable in the build container (the GPU box has no /root/reference); it is used
-by `oracle/gen_golden.py` to produce the committed fixtures in `tests/golden/`
-and by the `not gpu` tests that cross-check the NumPy restatement against the
-live reference when it is present.
+Appendix C).  Nothing under /root/reference is modified.  In the build container
+it loads /root/reference; on the GPU box (no /root/reference) it loads the copy
+of the unmodified package that `oracle/make_ref.sh` staged under `oracle/_ref/`
+(git-ignored).  Used by `oracle/gen_golden.py` to produce the committed fixtures
+in `tests/golden/`, by the `not gpu` tests that cross-check the NumPy restatement
+against the live reference when it is present, and by `bench.py`'s CPU arm.
 """
 import os
 import sys
 import types
 
+_STAGED = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
 REFERENCE_ROOT = os.environ.get("PYRATE_REFERENCE_ROOT", "/root/reference")
+if not os.path.isdir(os.path.join(REFERENCE_ROOT, "pyrateoptics")) and \
+        os.path.isdir(os.path.join(_STAGED, "pyrateoptics")):
+    # the GPU box has no /root/reference: the unmodified package staged by
+    # oracle/make_ref.sh (bench.py's CPU arm, kind "reference")
+    REFERENCE_ROOT = _STAGED
 
 
 def reference_available():

@@ -7,7 +7,7 @@ the library is missing or was built for another ABI, loading raises.
 import ctypes as C
 import os
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 MAX_COEFF = 80
 MAX_GRIN_PARAMS = 8
 
@@ -24,6 +24,7 @@ MAX_WAVES = 4
 (STEP_FULL, STEP_PROPAGATE_ONLY, STEP_DEFLECT_ONLY) = (0, 1, 2)
 (RAY_HIT, RAY_ALIVE) = (1, 2)
 (F_COMPLEX, F_RECORD_E) = (1, 2)
+(E_BADARG, E_UNSUPPORTED, E_TOOLARGE, E_NODEVICE) = (-1, -2, -3, -4)
 
 
 class PyrFrame(C.Structure):
@@ -80,21 +81,54 @@ class PyrStep(C.Structure):
                 ("after_n_w", C.c_double * MAX_WAVES)]
 
 
+(RASTER_HEXAPOLAR, RASTER_RECT, RASTER_HEX, RASTER_CIRCULAR) = (0, 1, 2, 3)
+(BUNDLE_COLLIMATED, BUNDLE_DIVERGENT) = (0, 1)
+(GEN_E_PERP, GEN_SQRT_R) = (1, 2)
+
+
+class PyrBundleGen(C.Structure):
+    _fields_ = [("raster", C.c_int32), ("bundle", C.c_int32), ("flags", C.c_uint32),
+                ("reserved0", C.c_int32),
+                ("param", C.c_int64), ("first", C.c_int64), ("total", C.c_int64),
+                ("lin_start", C.c_double), ("lin_step", C.c_double), ("lin_stop", C.c_double),
+                ("aux", C.c_double * 2), ("radius", C.c_double),
+                ("start", C.c_double * 3), ("dir", C.c_double * 3), ("e", C.c_double * 3),
+                ("n_index", C.c_double), ("rows", C.c_void_p)]
+
+
 class PyrRaysIn(C.Structure):
     _fields_ = [("x", C.c_void_p), ("k", C.c_void_p), ("e", C.c_void_p),
                 ("alive", C.c_void_p), ("ld", C.c_int64), ("n_x", C.c_int64),
                 ("n_waves", C.c_int32), ("reserved0", C.c_int32),
-                ("wave_end", C.c_int64 * MAX_WAVES)]
+                ("wave_end", C.c_int64 * MAX_WAVES),
+                ("gen", C.POINTER(PyrBundleGen))]
+
+
+class PyrHostIO(C.Structure):
+    _fields_ = [("x0", C.c_void_p), ("k0", C.c_void_p), ("e0", C.c_void_p),
+                ("gen", C.POINTER(PyrBundleGen)),
+                ("x_last", C.c_void_p), ("k_last", C.c_void_p), ("flags_last", C.c_void_p),
+                ("x_all", C.c_void_p), ("k_all", C.c_void_p), ("flags_all", C.c_void_p),
+                ("spot8", C.c_void_p)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
                         "libpyrate_b200.so")
 
 EXPORTS = ("pyr_version", "pyr_strerror", "pyr_sizeof_step",
-           "pyr_sizeof_rays_in", "pyr_device_count", "pyr_trace",
-           "pyr_spot_sums", "pyr_trace_host_workspace", "pyr_trace_host")
+           "pyr_sizeof_rays_in", "pyr_sizeof_bundle_gen", "pyr_device_count", "pyr_trace",
+           "pyr_spot_sums", "pyr_generate_bundle", "pyr_trace_host_workspace",
+           "pyr_trace_host", "pyr_trace_host_io_workspace", "pyr_trace_host_io")
 
 _lib = None
+
+
+def use_tools_library():
+    """tools/ only: load the measurement build (`make tools`, -DPYR_TOOLS: A/B knobs
+    compiled in) instead of the product library.  Must be called before load()."""
+    global LIB_PATH
+    assert _lib is None, "library already loaded"
+    LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libpyrate_b200_tools.so")
 
 
 class NativeError(RuntimeError):
@@ -132,12 +166,22 @@ def load():
                                    C.c_void_p, C.c_void_p, C.c_int64,
                                    C.c_void_p, C.c_void_p, C.c_void_p,
                                    C.c_void_p, C.c_void_p, C.c_int64, C.c_int64]
+    lib.pyr_sizeof_bundle_gen.restype = C.c_int64
+    lib.pyr_generate_bundle.restype = C.c_int
+    lib.pyr_generate_bundle.argtypes = [C.POINTER(PyrBundleGen), C.c_int64, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+    lib.pyr_trace_host_io_workspace.restype = C.c_int64
+    lib.pyr_trace_host_io_workspace.argtypes = [C.c_int32, C.c_int64, C.c_int32]
+    lib.pyr_trace_host_io.restype = C.c_int
+    lib.pyr_trace_host_io.argtypes = [C.POINTER(PyrStep), C.c_int32, C.POINTER(PyrHostIO),
+                                      C.c_int64, C.c_void_p, C.c_int64, C.c_int64]
     if lib.pyr_version() != ABI_VERSION:
         raise NativeError("pyrate_b200: libpyrate_b200.so has ABI version %d, "
                           "_native.py expects %d (rebuild with `make`)" %
                           (lib.pyr_version(), ABI_VERSION))
     if lib.pyr_sizeof_step() != C.sizeof(PyrStep) or \
-            lib.pyr_sizeof_rays_in() != C.sizeof(PyrRaysIn):
+            lib.pyr_sizeof_rays_in() != C.sizeof(PyrRaysIn) or \
+            lib.pyr_sizeof_bundle_gen() != C.sizeof(PyrBundleGen):
         raise NativeError("pyrate_b200: struct layout mismatch between "
                           "_native.py and libpyrate_b200.so (%d vs %d)" %
                           (C.sizeof(PyrStep), lib.pyr_sizeof_step()))
@@ -147,5 +191,7 @@ def load():
 
 def check(code):
     if code != 0:
-        raise NativeError("pyrate_b200 native call failed (%d): %s" %
+        err = NativeError("pyrate_b200 native call failed (%d): %s" %
                           (code, load().pyr_strerror(code).decode()))
+        err.code = code
+        raise err

@@ -83,6 +83,20 @@ struct DStep {
     int8_t before_kind, after_kind, aux, pad0;
 };
 
+// bundle generator (PyrBundleGen packed for the launch, csrc/pyr_gen.cuh)
+struct DGen {
+    int32_t raster, bundle;
+    uint32_t flags;
+    int32_t on;                    // 0: no generator (rays are read from memory)
+    int64_t param, first;
+    double lin_start, lin_step, lin_stop;
+    double aux0, aux1;
+    double radius;
+    double start[3], dir[3], e[3];
+    double n_index;
+    const int64_t *rows;
+};
+
 struct LaunchParams {
     const double *x, *k, *e;
     const uint8_t *alive;
@@ -92,6 +106,7 @@ struct LaunchParams {
     int32_t in_vec2;               // inputs allow 128-bit loads
     int32_t n_waves;               // > 1: wavelength batch, ray i is in segment #{j: i >= wave_end[j]}
     int64_t wave_end[kMaxWaves];
+    DGen gen;
     DStep steps[kMaxSteps];
     DAux aux[kMaxAux];
 };

@@ -65,6 +65,9 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
     const double cs[4] = {c0, c1, c1, c0};
     const double ds[4] = {d0, d1, d0, 0.0};
 
+    // dead / out-of-range rays carry NaN: every comparison below would be false for them
+    // and the loop would only end at the step cap -- they do not enter the integrator
+    if (ray_index < 0) return false;
     double q[3], p[3], g[3];
     g2l_point(m.frame, x, q);
     rot_t(m.frame.r, d, p);
@@ -89,11 +92,12 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
                 p[2] = fma(f, g[2], p[2]);
             }
         }
-        if (fabs(dot3(p, p) - nq * nq) > m.energy_tol) valid = false;
+        if (!(fabs(dot3(p, p) - nq * nq) <= m.energy_tol)) valid = false;     // NaN-safe
         double xs[3];
         l2g_point(m.to_shape, q, xs);
-        const bool crossed = xs[2] - shape_sag<EXT>(shape_kind, aux, curv, cc, xs[0], xs[1]) > 0.0;
-        if (!grin_inside(m, q)) valid = false;
+        const double gap = xs[2] - shape_sag<EXT>(shape_kind, aux, curv, cc, xs[0], xs[1]);
+        const bool crossed = gap > 0.0;
+        if (!grin_inside(m, q) || gap != gap) valid = false;               // NaN sag: off the shape
         const bool stop = crossed || !valid;
         if (!stop) {
             uq[0] = q[0]; uq[1] = q[1]; uq[2] = q[2];

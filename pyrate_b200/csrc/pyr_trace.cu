@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "pyr_device.cuh"
+#include "pyr_gen.cuh"
 #include "pyr_grin.cuh"
 #include "pyr_shapes.cuh"
 
@@ -90,13 +91,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
 // and never re-read by the kernel; 1: default write-back; 2: cache-global (st.global.cg).
 template <int POLICY>
 __device__ __forceinline__ void store_stream(double *p, double v) {
-    if (POLICY == 0 || POLICY == 3) __stcs(p, v); else if (POLICY == 2) __stcg(p, v); else *p = v;
+    if ((POLICY & 3) == 0 || (POLICY & 3) == 3) __stcs(p, v); else if ((POLICY & 3) == 2) __stcg(p, v); else *p = v;
 }
 template <int POLICY>
 __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
     double2 *q = reinterpret_cast<double2 *>(p);
     const double2 v = make_double2(a, b);
-    if (POLICY == 0 || POLICY == 3) __stcs(q, v); else if (POLICY == 2) __stcg(q, v); else *q = v;
+    if ((POLICY & 3) == 0 || (POLICY & 3) == 3) __stcs(q, v); else if ((POLICY & 3) == 2) __stcg(q, v); else *q = v;
 }
 
 // d from (k, E): ray.py:140-152 for real k, E
@@ -354,6 +355,9 @@ template <int RPT, bool WITH_E, int FEAT, int MINB = 1, int POLICY = 0, int BLOC
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
     constexpr bool GENERAL = FEAT != 0;
+    // POLICY bit 16: the rays are generated in registers from P.gen (csrc/pyr_gen.cuh): no
+    // input rows are read and no input stage exists
+    constexpr bool GEN = (POLICY & 16) != 0;
     const int64_t n = P.n;
     // Step table: one cooperative copy from the parameter block into shared memory;
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
@@ -367,7 +371,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     }
     __syncthreads();
     const bool need_e0 = sst[0].dir_mode == PYR_DIR_POYNTING;
-    const bool load_e = (WITH_E || need_e0) && P.e != nullptr;
+    const bool load_e = !GEN && (WITH_E || need_e0) && P.e != nullptr;
 
     // Input staging (aligned bundles): a CTA owns tiles of TILE consecutive rays; the
     // rows of the tile two iterations ahead are pulled into shared memory by the TMA
@@ -381,7 +385,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // POLICY bit 8: wavelength batch -- per-ray segment index selects the media indices
     // (own instantiations: the plain kernels keep their code)
     constexpr bool MULTI = (POLICY & 8) != 0;
-    constexpr int IN_STAGES = TMA_OUT ? 1 : 2;
+    constexpr int IN_STAGES = GEN ? 0 : (TMA_OUT ? 1 : 2);
     // record stages: x, k (and E) rows; E recording has room for one stage only
     constexpr int OUT_ROWS = WITH_E ? 9 : 6;
     constexpr int OUT_STAGES = WITH_E ? 1 : 2;
@@ -390,7 +394,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     double *out_buf = stage_buf + (size_t)IN_STAGES * 9 * TILE;   // [OUT_STAGES][OUT_ROWS][TILE]
     unsigned char *out_fl = reinterpret_cast<unsigned char *>(out_buf + OUT_STAGES * OUT_ROWS * TILE);
     unsigned store_count = 0;
-    const bool staged = P.in_vec2 != 0;
+    const bool staged = !GEN && P.in_vec2 != 0;
     const int rows = load_e ? 9 : 6;
     auto issue_tile = [&](int64_t tile, int stage) {
         const int64_t t0 = tile * TILE;
@@ -417,14 +421,18 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     int it = 0;
     for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
         const int64_t base = tile * TILE + (int64_t)threadIdx.x * RPT;
-        const int stage = it % IN_STAGES;
+        const int stage = GEN ? 0 : it % (IN_STAGES > 0 ? IN_STAGES : 1);
         // WITH_E == false still needs E for the first segment's Poynting direction
         Ray<true> in[RPT];
         bool in_range[RPT];
 #pragma unroll
         for (int j = 0; j < RPT; ++j) in_range[j] = base + j < n;
-        if (staged) {
-            mbar_wait(&full_bar[stage], (it / IN_STAGES) & 1);
+        if (GEN) {
+#pragma unroll
+            for (int j = 0; j < RPT; ++j)
+                gen_ray(P.gen, in_range[j] ? base + j : 0, in[j].x, in[j].k, in[j].e);
+        } else if (staged) {
+            mbar_wait(&full_bar[stage], (it / (IN_STAGES > 0 ? IN_STAGES : 1)) & 1);
             const double *src = stage_buf + (size_t)stage * 9 * TILE + threadIdx.x * RPT;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
@@ -464,7 +472,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
         for (int j = 0; j < RPT; ++j) {
             const int64_t i = in_range[j] ? base + j : 0;
             const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
-            in[j].alive = in_range[j] && (P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
+            in[j].alive = in_range[j] && ((!GEN && P.alive) ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true);
         }
 
         int wsel[RPT];
@@ -677,6 +685,25 @@ spot_sums_kernel(const double *__restrict__ x, int64_t ld, const uint8_t *__rest
 }
 
 // ---------------------------------------------------------------------------
+// stand-alone bundle generation (collimated_bundle / divergent_bundle resident on the device)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+generate_bundle_kernel(const __grid_constant__ DGen g, int64_t n, double *__restrict__ x,
+                       double *__restrict__ k, double *__restrict__ e, int64_t ld) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double rx[3], rk[3], re[3];
+        gen_ray(g, i, rx, rk, re);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            if (x) x[c * ld + i] = rx[c];
+            if (k) k[c * ld + i] = rk[c];
+            if (e) e[c * ld + i] = re[c];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side: pack the public step table into launch parameters
 // ---------------------------------------------------------------------------
 static void pack_frame(const PyrFrame &f, DFrame &d) {
@@ -740,6 +767,39 @@ static void pack_medium(const PyrMedium &m, const PyrFrame &shape, DMedium &d) {
 
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// auxiliary records (DAux) a step needs in the launch: 0 for the lean case (conic shape,
+// aperture in the shape frame, homogeneous isotropic media, full step), one per term of a
+// combination, else 1
+int step_aux_records(const PyrStep &u) {
+    const bool ap_same = u.aperture_kind == PYR_AP_BASE || frame_equal(u.shape_frame, u.aperture_frame);
+    if (u.shape_kind == PYR_SHAPE_COMBINATION) return u.n_terms > 0 ? u.n_terms : 1;
+    const bool need = u.shape_kind != PYR_SHAPE_CONIC || !ap_same || u.mode != PYR_STEP_FULL ||
+                      u.before.kind != PYR_MEDIUM_ISO_CONST || u.after.kind != PYR_MEDIUM_ISO_CONST;
+    return need ? 1 : 0;
+}
+
+// PyrBundleGen -> DGen (validated)
+int pack_gen(const PyrBundleGen *g, int64_t n_rays, DGen &d) {
+    std::memset(&d, 0, sizeof(d));
+    if (!g) return PYR_OK;
+    if (g->raster < PYR_RASTER_HEXAPOLAR || g->raster > PYR_RASTER_CIRCULAR) return PYR_E_UNSUPPORTED;
+    if (g->bundle != PYR_BUNDLE_COLLIMATED && g->bundle != PYR_BUNDLE_DIVERGENT) return PYR_E_UNSUPPORTED;
+    if (g->param < 0 || g->first < 0 || n_rays < 0 || g->first + n_rays > g->total) return PYR_E_BADARG;
+    if ((g->raster == PYR_RASTER_RECT || g->raster == PYR_RASTER_HEX) && (!g->rows || g->param < 1))
+        return PYR_E_BADARG;
+    if (g->raster == PYR_RASTER_CIRCULAR && g->param < 1) return PYR_E_BADARG;
+    if (g->raster == PYR_RASTER_HEXAPOLAR && g->total != 1 + 3 * g->param * (g->param + 1)) return PYR_E_BADARG;
+    if (g->raster == PYR_RASTER_CIRCULAR && g->total != g->param * g->param) return PYR_E_BADARG;
+    d.raster = g->raster; d.bundle = g->bundle; d.flags = g->flags; d.on = 1;
+    d.param = g->param; d.first = g->first;
+    d.lin_start = g->lin_start; d.lin_step = g->lin_step; d.lin_stop = g->lin_stop;
+    d.aux0 = g->aux[0]; d.aux1 = g->aux[1];
+    d.radius = g->radius; d.n_index = g->n_index;
+    for (int i = 0; i < 3; ++i) { d.start[i] = g->start[i]; d.dir[i] = g->dir[i]; d.e[i] = g->e[i]; }
+    d.rows = g->rows;
+    return PYR_OK;
+}
+
 struct Packed {
     LaunchParams P;
     bool general;
@@ -751,9 +811,13 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                 uint32_t flags, Packed &out) {
     if (!steps || !rays || n_steps <= 0 || n_rays < 0) return PYR_E_BADARG;
     if (n_steps > kMaxSteps) return PYR_E_TOOLARGE;
-    if (!rays->x || !rays->k) return PYR_E_BADARG;
+    if (!rays->gen && (!rays->x || !rays->k)) return PYR_E_BADARG;
     LaunchParams &P = out.P;
     std::memset(&P, 0, sizeof(P));
+    if (rays->gen) {
+        const int rc = pack_gen(rays->gen, n_rays, P.gen);
+        if (rc != PYR_OK) return rc;
+    }
     P.x = rays->x; P.k = rays->k; P.e = rays->e; P.alive = rays->alive;
     P.ld_in = rays->ld > 0 ? rays->ld : n_rays;
     P.n = n_rays;
@@ -768,7 +832,8 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                                   rays->wave_end[w] > n_rays))
             return PYR_E_BADARG;
     }
-    P.in_vec2 = (P.n_x == P.n) && (P.ld_in % 2 == 0) && aligned16(P.x) && aligned16(P.k) &&
+    if (rays->gen) { P.x = P.k = P.e = nullptr; P.alive = nullptr; P.n_x = n_rays; P.ld_in = n_rays; }
+    P.in_vec2 = !rays->gen && (P.n_x == P.n) && (P.ld_in % 2 == 0) && aligned16(P.x) && aligned16(P.k) &&
                 (!P.e || aligned16(P.e));
     out.general = false;
     out.any_aniso = false;
@@ -829,12 +894,14 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
                             u.split))
             return PYR_E_UNSUPPORTED;        // a wavelength batch needs homogeneous isotropic media
         d.out_x = u.out_x; d.out_k = u.out_k; d.out_e = u.out_e; d.out_flags = u.out_flags;
-        {   // measurement knob (tools/ only): PYR_DEBUG_RECORD_LAST=1 records the last entry only,
-            // which times the arithmetic of a trace without its record stream
+#ifdef PYR_TOOLS
+        {   // measurement knob (tools/ builds only, `make tools`): PYR_DEBUG_RECORD_LAST=1 records
+            // the last entry only, which times the arithmetic of a trace without its record stream
             static const bool last_only = [] { const char *e = std::getenv("PYR_DEBUG_RECORD_LAST");
                                                return e && std::atoi(e) != 0; }();
             if (last_only && s != n_steps - 1) { d.out_x = d.out_k = d.out_e = nullptr; d.out_flags = nullptr; }
         }
+#endif
         d.ld_out = u.ld_out > 0 ? u.ld_out : n_rays;
         d.ld_out2 = u.ld_out2 > 0 ? u.ld_out2 : 2 * d.ld_out;
         d.shape_kind = (int8_t)u.shape_kind; d.aperture_kind = (int8_t)u.aperture_kind;
@@ -859,12 +926,9 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         d.bits = bits;
         const bool aniso = u.before.kind == PYR_MEDIUM_ANISO || u.after.kind == PYR_MEDIUM_ANISO;
         out.any_aniso = out.any_aniso || aniso;
-        const bool need_aux = u.shape_kind != PYR_SHAPE_CONIC || !ap_same || u.mode != PYR_STEP_FULL ||
-                              u.before.kind != PYR_MEDIUM_ISO_CONST ||
-                              u.after.kind != PYR_MEDIUM_ISO_CONST;
+        const int n_rec = step_aux_records(u);
         d.aux = -1;
-        if (need_aux) {
-            const int n_rec = comb ? u.n_terms : 1;
+        if (n_rec > 0) {
             if (n_aux + n_rec > kMaxAux) return PYR_E_TOOLARGE;
             DAux &a = P.aux[n_aux];
             const bool bic = u.shape_kind == PYR_SHAPE_BICONIC;
@@ -944,13 +1008,14 @@ int sm_count() {
 
 template <typename K>
 static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, bool tma_out = false,
-                  bool with_e = false, int threads = 256) {   // threads == kernel's BLOCK argument
+                  bool with_e = false, int threads = 256, bool gen = false) {   // threads == kernel's BLOCK
     // dynamic shared memory: input stages of rpt x 9 doubles per thread (two, or one plus
     // two output stages of rpt x 6 doubles + flag bytes when records leave through the TMA)
     const size_t tile = (size_t)threads * rpt;
     const size_t out_stages = with_e ? 1 : 2, out_rows = with_e ? 9 : 6;
-    const size_t smem = tma_out ? tile * 9 * 8 + out_stages * out_rows * tile * 8 + out_stages * tile
-                                : 2 * tile * 9 * 8;
+    const size_t in_stages = gen ? 0 : (tma_out ? 1 : 2);      // a generated bundle has no input stage
+    const size_t smem = in_stages * tile * 9 * 8 +
+                        (tma_out ? out_stages * out_rows * tile * 8 + out_stages * tile : 0) + 16;
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     int per_sm = 0;
@@ -981,6 +1046,17 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     bool with_e = (flags & PYR_F_RECORD_E) != 0;
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
+    if (pk.P.gen.on) {
+        // generated bundle: own instantiations (no input stage) of the lean, the general and
+        // the GRIN kernel; everything else is traced from arrays (pyr_generate_bundle)
+        bool grin = false;
+        for (int s = 0; s < n_steps; ++s)
+            grin = grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
+        if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
+        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+        if (grin) return launch(trace_real_kernel<1, false, 3, 2, 16>, pk.P, 1, stream, false, false, 256, true);
+        return launch(trace_real_kernel<2, false, 1, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+    }
     if (pk.P.n_waves > 1) {
         // wavelength batch: own instantiations of the two record-streaming kernels
         bool grin_or_ext = pk.extended;
@@ -993,14 +1069,16 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     }
     if (!pk.general) {
         if (with_e) return launch(trace_real_kernel<2, true, 0, 2, 3>, pk.P, 2, stream, true, true);
+#ifdef PYR_TOOLS
         // PYR_LEAN_VARIANT=50 selects per-thread STG records instead of the TMA record
-        // path (A/B knob for tools/; not part of the ABI).  Other configurations that
-        // were measured and rejected are listed in profiles/r01_final_kernels.md.
+        // path (A/B knob of tools/ builds only).  Other configurations that were measured
+        // and rejected are listed in profiles/r01_final_kernels.md.
         static const int variant = [] {
             const char *e = std::getenv("PYR_LEAN_VARIANT");
             return e ? std::atoi(e) : 0;
         }();
         if (variant == 50) return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
+#endif
         return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
     }
     bool has_grin = false;
@@ -1033,6 +1111,24 @@ extern "C" {
 int pyr_version(void) { return PYR_ABI_VERSION; }
 int64_t pyr_sizeof_step(void) { return (int64_t)sizeof(PyrStep); }
 int64_t pyr_sizeof_rays_in(void) { return (int64_t)sizeof(PyrRaysIn); }
+int64_t pyr_sizeof_bundle_gen(void) { return (int64_t)sizeof(PyrBundleGen); }
+
+int pyr_generate_bundle(const PyrBundleGen *gen, int64_t n_rays, double *x, double *k, double *e,
+                        int64_t ld, void *stream) {
+    if (!gen || n_rays < 0) return PYR_E_BADARG;
+    pyr::DGen d;
+    const int rc = pyr::pack_gen(gen, n_rays, d);
+    if (rc != PYR_OK) return rc;
+    if (n_rays == 0) return PYR_OK;
+    if (ld <= 0) ld = n_rays;
+    if (ld < n_rays) return PYR_E_BADARG;
+    int64_t grid = (n_rays + 255) / 256;
+    const int64_t cap = (int64_t)pyr::sm_count() * 8;
+    if (grid > cap) grid = cap;
+    pyr::generate_bundle_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(d, n_rays, x, k, e, ld);
+    cudaError_t err = cudaGetLastError();
+    return err == cudaSuccess ? PYR_OK : (int)err;
+}
 
 const char *pyr_strerror(int code) {
     switch (code) {

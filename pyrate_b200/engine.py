@@ -84,7 +84,10 @@ class TraceRecord(object):
     """
 
     def __init__(self):
-        self.x0 = self.k0 = self.e0 = None
+        self._x0 = self._k0 = self._e0 = None
+        self.gen = None         # bundlegen.BundleGen of a generated trace (x0 / k0 / e0 lazy)
+        self.n0 = 0
+        self.device = None
         self.hit = []
         self.k = []
         self.e = []
@@ -95,6 +98,18 @@ class TraceRecord(object):
         self.lowered = None
         self.wave = None
         self.grin_hist = {}     # step index -> {"x": (M,3,n), "k": (M,3,n), "valid": (M,n), "count": (n)}
+
+    def _initial(self, i):
+        v = (self._x0, self._k0, self._e0)[i]
+        if v is None and self.gen is not None:
+            # the kernel generated the rays in registers; the caller wants to look at the
+            # initial bundle: one pyr_generate_bundle launch, on first access only
+            v = self.gen.materialise(self.device)[i]
+        return v
+
+    x0 = property(lambda self: self._initial(0), lambda self, v: setattr(self, "_x0", v))
+    k0 = property(lambda self: self._initial(1), lambda self, v: setattr(self, "_k0", v))
+    e0 = property(lambda self: self._initial(2), lambda self, v: setattr(self, "_e0", v))
 
 
 def _empty(shape, dtype, device, pool):
@@ -110,20 +125,23 @@ def _alloc_rows(rows, n, device, complex_=False, pool=None):
 
 
 def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
-            events=None, wave_end=None):
+            events=None, wave_end=None, gen=None, device=None):
     if n == 0:
         return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
     for i in range(lo, hi):
         if getattr(steps[i], "_grid", None) is not None:
-            bind_grid(steps[i], x.device)
+            bind_grid(steps[i], x.device if x is not None else device)
         C.memmove(C.addressof(arr[i - lo]), C.addressof(steps[i]),
                   C.sizeof(nat.PyrStep))
     rin = nat.PyrRaysIn()
-    rin.x = x.data_ptr()
-    rin.k = k.data_ptr()
-    rin.e = e.data_ptr() if e is not None else None
-    rin.alive = alive.data_ptr() if alive is not None else None
+    if gen is not None:
+        rin.gen = C.pointer(gen)    # PyrBundleGen: the kernel generates the rays itself
+    else:
+        rin.x = x.data_ptr()
+        rin.k = k.data_ptr()
+        rin.e = e.data_ptr() if e is not None else None
+        rin.alive = alive.data_ptr() if alive is not None else None
     rin.ld = ld_in
     rin.n_x = n_x
     if wave_end is not None and len(wave_end) > 1:
@@ -234,8 +252,27 @@ class RecordPool(object):
         return t
 
 
+def _gen_fusable(lowered, record_e, grin_history, wave_end):
+    """Can the trace kernel generate the rays itself (PyrRaysIn.gen)?  Real-valued,
+    non-splitting sequences without E recording, grid-sag / combination shapes,
+    wavelength batches or integrator history; otherwise the bundle is written out once
+    (pyr_generate_bundle) and traced from the arrays."""
+    if record_e or grin_history or wave_end is not None:
+        return False
+    for (i, ls) in enumerate(lowered):
+        st = ls.st
+        if nat.MEDIUM_ANISO in (st.before.kind, st.after.kind) or st.split:
+            return False
+        if st.shape_kind in (nat.SHAPE_GRIDSAG, nat.SHAPE_COMBINATION):
+            return False
+        if i > 0 and st.dir_mode == nat.DIR_POYNTING:
+            return False
+    return True
+
+
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
-          pool=None, events=None, grin_history=False, _hist_rows=None, wave_end=None):
+          pool=None, events=None, grin_history=False, _hist_rows=None, wave_end=None,
+          gen=None):
     """Run the lowered sequence on the device.  Returns a TraceRecord.
 
     events: optional list; a (start, end) pair of CUDA timing events is appended
@@ -249,17 +286,32 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
-    complex_in = bool(as_tensor(k0).is_complex() or
-                      (e0 is not None and as_tensor(e0).is_complex()))
-    (x0, k0, e0) = device_bundle(x0, k0, e0, device, complex_in)
-    if x0.is_complex():
-        raise ValueError("ray positions must be real")
-    n0 = x0.shape[1]
+    if gen is not None and (gen.materialised or
+                            not _gen_fusable(lowered, record_e, grin_history, wave_end)):
+        (x0, k0, e0) = gen.materialise(device)
+        gen = None
     nsteps = len(lowered)
     rec = TraceRecord()
     rec.lowered = lowered
     rec.wave = wave
-    (rec.x0, rec.k0, rec.e0) = (x0, k0, e0)
+    rec.device = device
+    if gen is not None:
+        # `gen`: a bundlegen.BundleGen -- the rays are generated in the prologue of the
+        # first launch; x0 / k0 / e0 of the record materialise on first access
+        complex_in = False
+        n0 = gen.n
+        rec.gen = gen
+        gen_desc = gen.descriptor(device)
+    else:
+        complex_in = bool(as_tensor(k0).is_complex() or
+                          (e0 is not None and as_tensor(e0).is_complex()))
+        (x0, k0, e0) = device_bundle(x0, k0, e0, device, complex_in)
+        if x0.is_complex():
+            raise ValueError("ray positions must be real")
+        n0 = x0.shape[1]
+        (rec.x0, rec.k0, rec.e0) = (x0, k0, e0)
+        gen_desc = None
+    rec.n0 = n0
     steps = [ls.st for ls in lowered]
     stream_ptr = C.c_void_p(torch.cuda.current_stream(device).cuda_stream
                             if stream is None else stream)
@@ -300,13 +352,18 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         pool.begin()
     with torch.cuda.device(device):
         # device_bundle() guarantees unit column stride and ONE leading dimension
-        (cur_x, ld_x) = (x0, max(x0.stride(0), 1))
+        if gen is not None:
+            (cur_x, ld_x, x0, k0) = (None, max(n0, 1), None, None)
+        else:
+            (cur_x, ld_x) = (x0, max(x0.stride(0), 1))
         if complex_in:
             (cur_k, ld_k) = (torch.view_as_real(k0), ld_x)
         else:
             (cur_k, ld_k) = (k0, ld_x)
         cur_e = None
-        if e0 is not None:
+        if gen is not None:
+            pass
+        elif e0 is not None:
             cur_e = torch.view_as_real(e0) if complex_in else e0
         elif complex_in or first_aniso is not None:
             tmp = torch.zeros((3, n0), dtype=torch.float64, device=device)
@@ -390,7 +447,8 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
             else:
                 cur_e_arg = cur_e
             _launch(lib, steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
-                    ld_k, flags, stream_ptr, events, wave_end=wave_end)
+                    ld_k, flags, stream_ptr, events, wave_end=wave_end,
+                    gen=gen_desc if ci == 0 else None, device=device)
             for i in range(lo, hi):
                 r = i - lo
                 rec.hit.append(xbuf[r, :, :n])
@@ -436,7 +494,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         # first pass gave the step counts; second pass records the rows
         rows = {i: int(h["count"].max().item()) if h["count"].numel() else 0
                 for (i, h) in rec.grin_hist.items()}
-        return trace(lowered, x0, k0, e0, wave, record_e=record_e, device=device,
+        return trace(lowered, rec.x0, rec.k0, rec.e0, wave, record_e=record_e, device=device,
                      stream=stream, pool=pool, events=events, grin_history=True,
                      _hist_rows=rows)
     return rec
@@ -512,8 +570,10 @@ class _BundleBuilder(object):
             def take(t):
                 return t[..., mask]
         x0 = take(self.start_x())
-        k0 = take(self.start_k)
-        e_full = self.start_e if self.start_e is not None else _lazy_efield(self.start_k)
+        start_k = self.start_k() if isinstance(self.start_k, _Lazy) else self.start_k
+        start_e = self.start_e() if isinstance(self.start_e, _Lazy) else self.start_e
+        k0 = take(start_k)
+        e_full = start_e if start_e is not None else _lazy_efield(start_k)
         e0 = take(e_full)
         ids = take(self.ids())
         ones = torch.ones(x0.shape[-1], dtype=torch.bool, device=x0.device)
@@ -534,7 +594,7 @@ class _BundleBuilder(object):
             hv = torch.cummin(hv.to(torch.uint8), dim=0).values != 0
             x = torch.cat((x0.unsqueeze(0), hx, take(self.hit).unsqueeze(0)))
             k = torch.cat((k0.unsqueeze(0), hk, hk[-1:]))
-            e = _lazy_efield(k) if self.start_e is None else \
+            e = _lazy_efield(k) if start_e is None else \
                 torch.cat((e0.unsqueeze(0), _lazy_efield(k[1:])))
             valid = torch.cat((ones.unsqueeze(0), hv, take(_hit_mask(self.hit_flags)).unsqueeze(0)))
             out = {"x": x, "k": k, "Efield": e, "valid": valid, "rayID": ids}
@@ -557,8 +617,9 @@ def paths_from_record(rec, splitup=False):
     forks the path (2^m paths of n0 rays), otherwise it doubles the rays
     (one path, hstack order, material_anisotropic.py:87-113)."""
     nsteps = len(rec.hit)
-    n0 = rec.x0.shape[1]
-    dev = rec.x0.device
+    generated = rec.gen is not None and rec._x0 is None
+    n0 = rec.n0 if generated else rec.x0.shape[1]
+    dev = rec.device if generated else rec.x0.device
     nsplit = sum(1 for s in rec.split if s)
     npaths = (2 ** nsplit) if splitup else 1
 
@@ -566,7 +627,7 @@ def paths_from_record(rec, splitup=False):
         e = torch.zeros_like(rec.x0)
         e[1] = 1.0
         return e
-    e0 = rec.e0 if rec.e0 is not None else None
+    e0 = None if generated else rec.e0
     paths = []
     for p in range(npaths):
         def cols(t, width):
@@ -578,8 +639,13 @@ def paths_from_record(rec, splitup=False):
             b = p % (width // n0)
             return t[..., b * n0:(b + 1) * n0]
 
-        sx = _const(rec.x0)
-        (sk, se) = (rec.k0, e0 if e0 is not None else default_e0())
+        if generated:
+            # lazies: the first bundle's fields call pyr_generate_bundle when first read
+            sx = _Lazy(lambda: rec.x0)
+            (sk, se) = (_Lazy(lambda: rec.k0), _Lazy(lambda: rec.e0))
+        else:
+            sx = _const(rec.x0)
+            (sk, se) = (rec.k0, e0 if e0 is not None else default_e0())
         mask = _const(None)
         ids = _Lazy(lambda: torch.arange(n0, device=dev))
         bundles = []
@@ -626,6 +692,15 @@ def seqtrace(system, initialbundle, elementsequence, splitup=False,
              record_e=False, grin_history=False):
     lowered = lowering.lower(system, elementsequence, initialbundle.wave,
                              splitup=splitup)
+    gen = getattr(initialbundle, "generator", None)
+    if gen is not None:
+        # a generated bundle (OpticalSystemAnalysis.aim): the kernel expands it in registers
+        rec = trace(lowered, None, None, None, initialbundle.wave, record_e=record_e,
+                    grin_history=grin_history, gen=gen)
+        paths = paths_from_record(rec, splitup=splitup)
+        for p in paths:
+            p.record = rec
+        return paths
     if initialbundle.x.shape[0] != 1:
         x0 = initialbundle.x[-1]
         k0 = initialbundle.k[-1]
@@ -689,7 +764,15 @@ def seqtrace_batch(system, bundles, elementsequence, record_e=False):
                 raise ValueError("wavelength batches are real-valued")
         (x0, k0, e0) = (torch.cat([r[c] for r in rows], dim=1) for c in range(3))
         ends = np.cumsum([r[0].shape[1] for r in rows]).tolist()
-        rec = trace(batch, x0, k0, e0, waves[0], wave_end=ends)
+        try:
+            rec = trace(batch, x0, k0, e0, waves[0], wave_end=ends)
+        except nat.NativeError as err:
+            if getattr(err, "code", None) != nat.E_UNSUPPORTED:
+                raise
+            # a feature the batch instantiations do not carry: one launch per bundle
+            for (i, b) in enumerate(group):
+                out[g0 + i] = seqtrace(system, b, elementsequence)
+            continue
         lo = 0
         for (i, (b, hi)) in enumerate(zip(group, ends)):
             sub = _column_view(rec, lo, hi, per_wave[i], b.wave)
@@ -822,10 +905,14 @@ def material_deflect(material, bundle, surface, mirror=False, splitup=False):
 # end-to-end host entry (pyr_trace_host): host bundle in, final record out
 # ---------------------------------------------------------------------------
 class HostTracer(object):
-    """Reusable binding of pyr_trace_host for one lowered (real, non-splitting)
-    sequence: owns the device workspace and pinned result buffers."""
+    """Reusable binding of pyr_trace_host_io for one lowered (real, non-splitting)
+    sequence: owns the device workspace and pinned result buffers.
 
-    def __init__(self, lowered, n_rays, chunk_rays=1 << 20, device=None):
+    all_records=True also returns the hit points / wave vectors / flags of EVERY
+    sequence entry -- what the S + 2 bundles of OpticalSystem.seqtrace carry
+    (optical_system.py:73-94) -- in pinned (n_steps, 3, n) / (n_steps, n) arrays."""
+
+    def __init__(self, lowered, n_rays, chunk_rays=1 << 20, device=None, all_records=False):
         self.lib = require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) \
             if device is None else torch.device(device)
@@ -835,7 +922,9 @@ class HostTracer(object):
         self.steps = lowering.step_array(lowered)
         self.n = int(n_rays)
         self.chunk = int(min(chunk_rays, max(self.n, 1)))
-        nbytes = self.lib.pyr_trace_host_workspace(len(lowered), self.chunk)
+        self.all_records = bool(all_records)
+        ns = len(lowered)
+        nbytes = self.lib.pyr_trace_host_io_workspace(ns, self.chunk, int(self.all_records))
         self.workspace = torch.empty((nbytes + 256,), dtype=torch.uint8,
                                      device=self.device)
         off = (-self.workspace.data_ptr()) % 256
@@ -845,29 +934,49 @@ class HostTracer(object):
         self.k_last = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
         self.flags_last = torch.empty((self.n,), dtype=torch.uint8).pin_memory()
         self.spot8 = torch.zeros((8,), dtype=torch.float64).pin_memory()
+        self.x_all = self.k_all = self.flags_all = None
+        if self.all_records:
+            self.x_all = torch.empty((ns, 3, self.n), dtype=torch.float64).pin_memory()
+            self.k_all = torch.empty((ns, 3, self.n), dtype=torch.float64).pin_memory()
+            self.flags_all = torch.empty((ns, self.n), dtype=torch.uint8).pin_memory()
+        self.h2d_bytes = 0
+        self.d2h_bytes = 0
 
-    @property
-    def h2d_bytes(self):
-        return 72 * self.n
-
-    @property
-    def d2h_bytes(self):
-        return 49 * self.n + 64
-
-    def __call__(self, x0, k0, e0=None):
-        """x0, k0, e0: contiguous (3, n) float64 CPU tensors (pinned for
-        overlap); e0=None is the reference's default field (0, 1, 0)
-        (ray.py:71-73) and is not uploaded.  Returns (x_last, k_last,
-        flags_last, spot8) host tensors."""
-        for t in (x0, k0, e0):
-            assert t is None or (t.device.type == "cpu" and t.dtype == torch.float64 and
-                                 t.is_contiguous() and t.shape == (3, self.n))
+    def __call__(self, x0=None, k0=None, e0=None, gen=None):
+        """x0, k0, e0: contiguous (3, n) float64 CPU tensors (pinned for overlap);
+        e0=None is the reference's default field (0, 1, 0) (ray.py:71-73) and is not
+        uploaded.  gen: a bundlegen.BundleGen instead of the arrays -- nothing but the
+        descriptor crosses the bus on the way in.  Returns (x_last, k_last, flags_last,
+        spot8) host tensors (and fills x_all / k_all / flags_all with all_records)."""
+        io = nat.PyrHostIO()
+        ns = len(self.lowered)
+        if gen is not None:
+            assert gen.n == self.n
+            desc = gen.descriptor(self.device)
+            io.gen = C.pointer(desc)
+            self.h2d_bytes = C.sizeof(nat.PyrBundleGen) + ns * C.sizeof(nat.PyrStep) + \
+                (0 if gen.raster.rows is None else 0)        # row table: uploaded once, cached
+        else:
+            for t in (x0, k0, e0):
+                assert t is None or (t.device.type == "cpu" and t.dtype == torch.float64 and
+                                     t.is_contiguous() and t.shape == (3, self.n))
+            io.x0 = x0.data_ptr()
+            io.k0 = k0.data_ptr()
+            io.e0 = None if e0 is None else e0.data_ptr()
+            self.h2d_bytes = (72 if e0 is not None else 48) * self.n + ns * C.sizeof(nat.PyrStep)
+        io.x_last = self.x_last.data_ptr()
+        io.k_last = self.k_last.data_ptr()
+        io.flags_last = self.flags_last.data_ptr()
+        io.spot8 = self.spot8.data_ptr()
+        self.d2h_bytes = 49 * self.n + 64
+        if self.all_records:
+            io.x_all = self.x_all.data_ptr()
+            io.k_all = self.k_all.data_ptr()
+            io.flags_all = self.flags_all.data_ptr()
+            self.d2h_bytes += 49 * self.n * ns
         with torch.cuda.device(self.device):
-            nat.check(self.lib.pyr_trace_host(
-                self.steps, len(self.lowered), x0.data_ptr(), k0.data_ptr(),
-                None if e0 is None else e0.data_ptr(), self.n, self.x_last.data_ptr(),
-                self.k_last.data_ptr(), self.flags_last.data_ptr(),
-                self.spot8.data_ptr(), self.ws_ptr, self.ws_bytes, self.chunk))
+            nat.check(self.lib.pyr_trace_host_io(self.steps, ns, C.byref(io), self.n,
+                                                 self.ws_ptr, self.ws_bytes, self.chunk))
         return (self.x_last, self.k_last, self.flags_last, self.spot8)
 
 

@@ -13,6 +13,7 @@ names of the reference), so the *reference's own* object graph lowers too --
 that is how identical systems are fed to both engines in the parity tests.
 """
 import ctypes as C
+import threading
 
 import numpy as np
 
@@ -36,17 +37,25 @@ def _mro_names(obj):
     return names
 
 
-_FRAME_CACHE = None      # id(lc) -> PyrFrame, alive only inside one lower() call
+class _Caches(threading.local):
+    """Per-thread caches that live for ONE lower() call (two threads may lower at the
+    same time, e.g. one per GPU): frames by id(lc), media by (id(material), wave)."""
+    frames = None
+    media = None
+
+
+_CACHES = _Caches()
 
 
 def _frame(lc):
-    if _FRAME_CACHE is not None:
-        hit = _FRAME_CACHE.get(id(lc))
+    cache = _CACHES.frames
+    if cache is not None:
+        hit = cache.get(id(lc))
         if hit is not None:
             return hit
     f = _frame_uncached(lc)
-    if _FRAME_CACHE is not None:
-        _FRAME_CACHE[id(lc)] = f
+    if cache is not None:
+        cache[id(lc)] = f
     return f
 
 
@@ -94,17 +103,16 @@ def _verify_grin_profile(mat, profile, samples=64):
                             "declared device boundary" % (getattr(mat, "name", "?"),))
 
 
-_MEDIUM_CACHE = None     # id(material) -> PyrMedium, alive only inside one lower() call
-
-
 def lower_medium(mat, wave):
-    if _MEDIUM_CACHE is not None:
-        hit = _MEDIUM_CACHE.get(id(mat))
+    cache = _CACHES.media
+    key = (id(mat), wave)
+    if cache is not None:
+        hit = cache.get(key)
         if hit is not None:
             return hit
     m = _lower_medium_uncached(mat, wave)
-    if _MEDIUM_CACHE is not None:
-        _MEDIUM_CACHE[id(mat)] = m
+    if cache is not None:
+        cache[key] = m
     return m
 
 
@@ -356,12 +364,11 @@ class LoweredStep(object):
 def lower(system, elementsequence, wave, splitup=False):
     """Returns list[LoweredStep] for `elementsequence`
     = [(elemkey, [(surfkey, {"is_mirror": .., "is_stop": ..}), ...]), ...]."""
-    global _FRAME_CACHE, _MEDIUM_CACHE
-    (_FRAME_CACHE, _MEDIUM_CACHE) = ({}, {})
+    (_CACHES.frames, _CACHES.media) = ({}, {})
     try:
         return _lower(system, elementsequence, wave)
     finally:
-        (_FRAME_CACHE, _MEDIUM_CACHE) = (None, None)
+        (_CACHES.frames, _CACHES.media) = (None, None)
 
 
 def _lower(system, elementsequence, wave):
@@ -430,6 +437,11 @@ def lower_batch(system, elementsequence, waves):
         if st.before.kind != nat.MEDIUM_ISO_CONST or st.after.kind != nat.MEDIUM_ISO_CONST:
             raise LoweringError("wavelength batches need homogeneous isotropic media "
                                 "(entry %r)" % (ls.surfkey,))
+        if st.shape_kind in (nat.SHAPE_GRIDSAG, nat.SHAPE_COMBINATION):
+            raise LoweringError("wavelength batches do not carry grid-sag / combination "
+                                "shapes (entry %r): one launch per bundle" % (ls.surfkey,))
+        if i > 0 and st.dir_mode == nat.DIR_POYNTING:
+            raise LoweringError("wavelength batches need k-directed segments")
         for (w, low) in enumerate(per_wave):
             other = low[i].st
             if (other.shape_kind, other.aperture_kind, other.interaction, other.dir_mode) != \

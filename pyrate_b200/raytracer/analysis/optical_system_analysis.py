@@ -1,8 +1,12 @@
 """Bundle generation and trace wrappers (host API mirror of reference
 raytracer/analysis/optical_system_analysis.py:43-320): the callers right above
-`seqtrace`.  Bundles are built on the host in O(N) NumPy -- the reference runs a
-3x3 generalised eigen-solve PER RAY for this even in vacuum
-(material/material.py:476-497) -- and every trace goes through the native engine.
+`seqtrace`.  `aim()` describes the bundle by a generator (pyrate_b200.bundlegen:
+raster, radius, start, direction, index -- 176 bytes) that the trace kernel expands in
+registers, so a bundle of 1e7 rays never crosses the PCIe bus and is never read from
+HBM; `collimated_bundle` / `divergent_bundle` return the reference's explicit
+(origin, k, E) arrays, built in O(N) NumPy -- the reference runs a 3x3 generalised
+eigen-solve PER RAY for this even in vacuum (material/material.py:476-497).  Every
+trace goes through the native engine.
 """
 import numpy as np
 
@@ -89,7 +93,35 @@ class OpticalSystemAnalysis(object):
         unit[2] = np.cos(ay + radius * gx) * np.cos(ax + radius * gy)
         return self._bundle(origin, unit, wave)
 
+    def bundle_generator(self, nrays, properties_dict=None, bundletype="collimated",
+                         wave=standard_wavelength):
+        """The bundle of collimated_bundle / divergent_bundle as a device generator
+        (pyrate_b200.bundlegen.BundleGen), or None for rasters without one."""
+        from ... import bundlegen
+        from ..._native import BUNDLE_COLLIMATED, BUNDLE_DIVERGENT
+        p = properties_dict or {}
+        spec = bundlegen.spec_for_raster(p.get("raster", RectGrid()), nrays)
+        if spec is None:
+            return None
+        (ay, ax) = (p.get("angley", 0.0), p.get("anglex", 0.0))
+        start = (p.get("startx", 0.), p.get("starty", 0.), p.get("startz", 0.))
+        n = self._background_index(wave)
+        if bundletype == "collimated":
+            unit = (float(np.sin(ay) * np.cos(ax)), float(np.sin(ax)),
+                    float(np.cos(ay) * np.cos(ax)))
+            return bundlegen.BundleGen(spec, BUNDLE_COLLIMATED, p.get("radius", 1.0), start,
+                                       unit, None, n)
+        return bundlegen.BundleGen(spec, BUNDLE_DIVERGENT, p.get("radius", 45.0 * degree),
+                                   start, (ay, ax, 0.0), None, n)
+
     def aim(self, numrays, rays_dict, bundletype="collimated", wave=standard_wavelength):
+        import torch
+        gen = self.bundle_generator(numrays, rays_dict, bundletype, wave) \
+            if torch.cuda.is_available() else None
+        if gen is not None:
+            # described, not built: the trace kernel generates the rays in registers
+            self.initial_bundles = [RayBundle(generator=gen, wave=wave)]
+            return
         make = {"collimated": self.collimated_bundle,
                 "divergent": self.divergent_bundle}[bundletype]
         (org, kvec, evec) = make(numrays, rays_dict, wave=wave)

@@ -31,12 +31,27 @@ class RayBundle(object):
     _FIELDS = ("x", "k", "Efield", "valid", "rayID")
 
     def __init__(self, x0=None, k0=None, Efield0=None, rayID=None,
-                 wave=standard_wavelength, splitted=False, _lazy=None):
+                 wave=standard_wavelength, splitted=False, _lazy=None, generator=None):
         self.wave = wave
         self.splitted = splitted
         self._store = {}
+        self.generator = generator
         if _lazy is not None:
             self._store.update(_lazy)
+            return
+        if generator is not None:
+            # a bundle described by a generator (pyrate_b200.bundlegen.BundleGen): traced
+            # without ever existing in memory; the fields materialise on the device (one
+            # pyr_generate_bundle launch) when somebody reads them
+            def field(i):
+                return lambda: generator.materialise()[i].unsqueeze(0)
+
+            def dev():
+                return generator.materialise()[0].device
+            self._store = {"x": field(0), "k": field(1), "Efield": field(2),
+                           "valid": lambda: torch.ones((1, generator.n), dtype=torch.bool,
+                                                       device=dev()),
+                           "rayID": lambda: torch.arange(generator.n, device=dev())}
             return
         x0 = as_tensor(x0)
         k0 = as_tensor(k0, x0.device)

@@ -30,7 +30,8 @@ def test_struct_layouts_match():
     lib = nat.load()
     assert lib.pyr_sizeof_step() == ctypes.sizeof(nat.PyrStep)
     assert lib.pyr_sizeof_rays_in() == ctypes.sizeof(nat.PyrRaysIn)
-    assert lib.pyr_version() == 3
+    assert lib.pyr_sizeof_bundle_gen() == ctypes.sizeof(nat.PyrBundleGen)
+    assert lib.pyr_version() == 4
 
 
 def test_strerror():
@@ -120,4 +121,41 @@ def test_wavelength_batch_argument_validation():
     grin[0].after.kind = nat.MEDIUM_ISO_GRIN
     assert lib.pyr_trace(grin, 1, ctypes.byref(rays), 100, 0, None) == -2         # UNSUPPORTED
     assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 100, nat.F_COMPLEX, None) in (-1, -2)
-    assert ctypes.sizeof(nat.PyrRaysIn) == 6 * 8 + 8 + 8 * nat.MAX_WAVES
+    assert ctypes.sizeof(nat.PyrRaysIn) == 6 * 8 + 8 + 8 * nat.MAX_WAVES + 8
+
+
+def test_bundle_generator_argument_validation():
+    """PyrBundleGen (ABI v4): malformed descriptors and sequences the generating kernels do
+    not carry are rejected before any device work."""
+    from pyrate_b200 import bundlegen
+    lib = nat.load()
+    gen = bundlegen.hexapolar_collimated(10, 5.0, 0.0).descriptor("cpu")
+    n = gen.total
+    assert lib.pyr_generate_bundle(None, n, None, None, None, n, None) == -1
+    bad = nat.PyrBundleGen.from_buffer_copy(gen)
+    bad.raster = 17
+    assert lib.pyr_generate_bundle(ctypes.byref(bad), n, None, None, None, n, None) == -2
+    bad = nat.PyrBundleGen.from_buffer_copy(gen)
+    bad.first = 5                                         # first + n > total
+    assert lib.pyr_generate_bundle(ctypes.byref(bad), n, None, None, None, n, None) == -1
+    bad = nat.PyrBundleGen.from_buffer_copy(gen)
+    bad.total = n + 1                                     # not 1 + 3 R (R + 1)
+    assert lib.pyr_generate_bundle(ctypes.byref(bad), n, None, None, None, n, None) == -1
+    bad = nat.PyrBundleGen.from_buffer_copy(gen)
+    bad.raster = nat.RASTER_RECT                          # clipped lattice without its row table
+    assert lib.pyr_generate_bundle(ctypes.byref(bad), n, None, None, None, n, None) == -1
+    assert lib.pyr_generate_bundle(ctypes.byref(gen), 0, None, None, None, 0, None) == 0
+    # a trace call with a generator needs no ray arrays ...
+    rays = nat.PyrRaysIn()
+    rays.gen = ctypes.pointer(gen)
+    steps = (nat.PyrStep * 1)(_one_step())
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), 0, 0, None) == 0
+    # ... but only real-valued, non-batched sequences without E recording
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), n, nat.F_RECORD_E, None) == -2
+    rays.n_waves = 2
+    rays.wave_end[0] = 10
+    assert lib.pyr_trace(steps, 1, ctypes.byref(rays), n, 0, None) == -2
+    # host entry: generator or arrays, crystals refused
+    io = nat.PyrHostIO()
+    assert lib.pyr_trace_host_io(steps, 1, ctypes.byref(io), 10, None, 0, 4) == -1
+    assert lib.pyr_trace_host_io_workspace(13, 1 << 20, 1) > lib.pyr_trace_host_io_workspace(13, 1 << 20, 0) > 0

@@ -576,9 +576,11 @@ def test_wavelength_batch_one_launch(name):
     assert saw_dispersion
 
 
-def test_wavelength_batch_falls_back_where_the_kernel_cannot_batch():
-    """Crystals / GRIN media: one launch per bundle, same results as seqtrace."""
-    spec = configs.CONFIGS["c5_grin"]
+@pytest.mark.parametrize("name", ["c5_grin", "x11_gridsag", "x12_combination"])
+def test_wavelength_batch_falls_back_where_the_kernel_cannot_batch(name):
+    """Crystals / GRIN media / grid-sag and combination shapes: one launch per bundle,
+    same results as seqtrace."""
+    spec = configs.CONFIGS[name]
     (s, seq) = configs.build_system(spec, pb.api())
     bundles = [pb.RayBundle(*configs.config_bundle(spec, 2), wave=w) for w in FDC[:2]]
     batch = s.seqtrace_batch(bundles, seq)
@@ -586,3 +588,167 @@ def test_wavelength_batch_falls_back_where_the_kernel_cannot_batch():
         single = s.seqtrace(b, seq)
         (da, db) = (paths[0].raybundles[-1].numpy(), single[0].raybundles[-1].numpy())
         assert np.array_equal(da["x"], db["x"], equal_nan=True)
+
+
+# ---------------------------------------------------------------------------
+# BASELINE configs 3-5 at (or near) their stated sizes
+# ---------------------------------------------------------------------------
+def test_full_size_asphere_strided_subsample():
+    """C3 at BASELINE size (9 997 351 rays through the even asphere, Newton intersect):
+    a strided subsample against the oracle at every surface, every ray alive, |k| = n."""
+    import torch
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c3_asphere"]
+    (x0, k0, e0) = configs.config_bundle(spec)
+    assert x0.shape[1] == 9997351
+    paths = _device_paths("c3_asphere", x0, k0, e0)
+    rec = paths[0].record
+    nidx = [ls.st.after.n for ls in rec.lowered]
+    for (s, k) in enumerate(rec.k):
+        alive = (rec.flags[s] & 2) != 0
+        assert bool(alive.all())
+        assert float((torch.sqrt((k * k).sum(0)) - nidx[s]).abs().max()) < 1e-12
+    sub = np.arange(0, x0.shape[1], 1009)                       # 9 909 rays
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0[:, sub], k0[:, sub], e0[:, sub])
+    worst = 0.0
+    for s in range(len(rec.hit)):
+        ex = util.relerr(rec.hit[s][:, sub].cpu().numpy(), ref[0][s + 1]["x"][-1])
+        ek = util.relerr(rec.k[s][:, sub].cpu().numpy(), ref[0][s + 2]["k"][0])
+        worst = max(worst, ex, ek)
+        assert ex < util.TOL_ITERATED and ek < util.TOL_ITERATED, (s, ex, ek)
+    print("c3 full size: worst rel err %.3e" % worst)
+    assert worst < 1e-11          # measured ~1e-15; the contract is 1e-6
+
+
+def test_grin_1e5_rays_against_oracle_including_last_grin_row():
+    """C5 with 99 919 rays (hexapolar R = 182) against the oracle with the per-ray energy
+    test: every bundle, hit points and k after every surface -- including k at the end of
+    the GRIN segment (the frozen p/n of the last integrator row)."""
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c5_grin"]
+    (x0, k0, e0) = configs.config_bundle(spec, 182)
+    assert x0.shape[1] == 99919
+    paths = _device_paths("c5_grin", x0, k0, e0)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE,
+                       per_ray_energy=True, history=False)
+    assert len(paths[0].raybundles) == len(ref[0])
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        d = b.numpy()
+        rbd = {"x": rb["x"], "k": rb["k"], "valid": rb["valid"], "rayID": rb["rayID"]}
+        if rb["x"].shape[0] == 3:
+            # oracle rows of the GRIN bundle: start, last integrator row, intersection;
+            # device bundle (history off): start, intersection -- and the NEXT bundle's
+            # k is the refraction of the last integrator row's k (checked there)
+            rbd = {"x": rb["x"][[0, 2]], "k": rb["k"][[0, 0]], "valid": rb["valid"][[0, 2]],
+                   "rayID": rb["rayID"]}
+        util.compare_bundle(d, rbd, 1e-9, "c5 1e5 b%d" % ib)
+
+
+def test_grin_last_row_k_matches_reference_fixture():
+    """k at the LAST GRIN row of the reference fixture (material_grin.py:198-199, p/n of
+    the frozen state) against the device history rows."""
+    g = util.load_golden("c5_grin")
+    spec = configs.CONFIGS["c5_grin"]
+    (s, seq) = configs.build_system(spec, pb.api())
+    path = s.seqtrace(pb.RayBundle(g["x0"], g["k0"], g["E0"], wave=configs.DLINE), seq,
+                      grin_history=True)[0].raybundles
+    rpath = util.golden_paths(g)[0]
+    seen = 0
+    for (b, rb) in zip(path, rpath):
+        if rb["rows"] <= 3:
+            continue
+        seen += 1
+        d = b.numpy()
+        v = rb["valid"][-1].astype(bool)
+        assert util.relerr(d["k"][-1][:, v], rb["k"][-1][:, v]) < 1e-9
+        assert util.relerr(d["k"][-2][:, v], rb["k"][-2][:, v]) < 1e-9
+    assert seen == 1
+
+
+def test_grin_full_shard_strided_subsample():
+    """One GPU's shard of BASELINE config 5 (1e8 rays over 8 GPUs = 12.5e6 rays; here the
+    central 12.5e6 rays of the R = 5773 raster would need the host to build 1e8 points, so
+    the test uses R = 2041: 12 501 127 rays): strided subsample against the oracle."""
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c5_grin"]
+    (x0, k0, e0) = configs.config_bundle(spec, 2041)
+    paths = _device_paths("c5_grin", x0, k0, e0)
+    rec = paths[0].record
+    sub = np.arange(0, x0.shape[1], 6007)                       # 2 082 rays
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0[:, sub], k0[:, sub], e0[:, sub],
+                       wave=configs.DLINE, per_ray_energy=True, history=False)[0]
+    # ref bundles: [b0, b0, b1, b2(GRIN: 3 rows), b3, b4]; valid rays are compacted, so
+    # compare through rayID
+    for s in range(len(rec.hit)):
+        rb = ref[s + 1]
+        ids = rb["rayID"]
+        hit = rec.hit[s][:, sub].cpu().numpy()[:, ids]
+        v = rb["valid"][-1]
+        assert util.relerr(hit[:, v], rb["x"][-1][:, v]) < 1e-9, s
+        fl = rec.flags[s][sub].cpu().numpy()
+        assert np.array_equal((fl[ids] & 1) != 0, v), s
+        nb = ref[s + 2]
+        k = rec.k[s][:, sub].cpu().numpy()[:, nb["rayID"]]
+        assert util.relerr(k, nb["k"][0]) < 1e-9, s
+
+
+def test_birefringent_1e4_rays_against_oracle():
+    """C4 with 10 267 rays (R = 58) -> 41 068 output rays against the oracle."""
+    import pyrate_np as onp
+    spec = configs.CONFIGS["c4_anisotropic"]
+    (x0, k0, e0) = configs.config_bundle(spec, 58, (0.0, np.sin(0.01), np.cos(0.01)),
+                                         (1.0, 0.0, 0.0))
+    assert x0.shape[1] == 10267
+    paths = _device_paths("c4_anisotropic", x0, k0, e0)
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)
+    # vectorised comparison: children of a ray are an unordered set -> sort the children
+    # of every parent by (Re kx, Re ky, Re kz) on both sides
+    for (ib, (b, rb)) in enumerate(zip(paths[0].raybundles, ref[0])):
+        d = b.numpy()
+        assert d["x"].shape == rb["x"].shape, ib
+        if not np.iscomplexobj(rb["k"]):
+            util.compare_bundle(d, {"x": rb["x"], "k": rb["k"], "valid": rb["valid"],
+                                    "rayID": rb["rayID"]}, 1e-10, "c4 1e4 b%d" % ib)
+            continue
+
+        def order(ids, k, x):
+            key = np.round(k[0].real / 1e-7) * 1e-7      # modes differ by >> 1e-7 in k
+            return np.lexsort((x[-1][0], key[2], key[1], key[0], ids))
+        (og, orf) = (order(d["rayID"], d["k"], d["x"]), order(rb["rayID"], rb["k"], rb["x"]))
+        assert np.array_equal(d["rayID"][og], rb["rayID"][orf]), ib
+        assert np.array_equal(d["valid"][:, og], rb["valid"][:, orf]), ib
+        assert util.relerr(d["x"][:, :, og], rb["x"][:, :, orf]) < 1e-9, ib
+        assert util.relerr(d["k"][:, :, og], rb["k"][:, :, orf]) < 1e-9, ib
+
+
+def test_grin_without_boundary_dead_rays_do_not_spin():
+    """A GRIN medium with boundary kind 'none', rays that are vignetted before they enter
+    it and a ray count that is not a multiple of the tile: dead / out-of-range rays must
+    not enter the integrator (NaN never satisfies its exit tests; they would run to the
+    1e6-step cap).  The whole trace has to finish in well under a second."""
+    import copy
+    import time
+    import torch
+    import pyrate_np as onp
+    spec = copy.deepcopy(configs.CONFIGS["c5_grin"])
+    mat = spec["materials"]["grin"][1]
+    mat["device_profile"] = dict(mat["device_profile"], boundary={"kind": "none", "params": []})
+    mat["source"] = mat["source"].replace("return x[0]**2 + x[1]**2 < 10.**2",
+                                          "return np.ones_like(x[0], dtype=bool)")
+    spec["bundle"] = dict(spec["bundle"], radius=6.0)          # aperture radius is 5: vignetting
+    (x0, k0, e0) = configs.config_bundle(spec, 11)             # 397 rays, not a multiple of 256
+    (s, seq) = configs.build_system(spec, pb.api())
+    bundle = pb.RayBundle(x0, k0, e0, wave=configs.DLINE)
+    s.seqtrace(bundle, seq)                                     # warm-up (library load)
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    paths = s.seqtrace(bundle, seq)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t
+    assert dt < 0.5, "trace took %.3f s: dead rays spin in the GRIN integrator" % dt
+    ref = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE,
+                       per_ray_energy=True, history=False)
+    last = paths[0].raybundles[-1].numpy()
+    assert 0 < last["x"].shape[2] < x0.shape[1]
+    assert np.array_equal(last["rayID"], ref[0][-1]["rayID"])
+    assert util.relerr(last["x"], ref[0][-1]["x"]) < 1e-9
