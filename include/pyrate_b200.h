@@ -65,9 +65,15 @@ enum PyrShapeKind {
                                    RectBivariateSpline (FITPACK) fits through the
                                    sag grid, evaluated like its ev(): arguments
                                    clamped to the grid, de Boor basis             */
-    PYR_SHAPE_COMBINATION = 5   /* ExplicitShape.intersect + LinearCombination.F
+    PYR_SHAPE_COMBINATION = 5,  /* ExplicitShape.intersect + LinearCombination.F
                                    :714-731: z = sum_i w_i (F_i(x - dx_i, y - dy_i)
                                    + dz_i) over PyrStep.terms                      */
+    PYR_SHAPE_CYLINDER = 6      /* Cylinder :328-388: conic section in y, extruded
+                                   along x: c (y^2 + (1 + cc) z^2) - 2 z = 0, closed
+                                   form.  The reference's intersect is dead code
+                                   (it reads a non-existent attribute, :380) and its
+                                   H omits d_x; this is the corrected quadratic:
+                                   H = -c (d_y^2 + (1 + cc) d_z^2)                 */
 };
 
 /* One sub-shape of a PYR_SHAPE_COMBINATION.  Its frame differs from the combination's
@@ -376,6 +382,20 @@ int pyr_trace(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
 int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
                   uint32_t mask, int64_t n, const double *shift, double *out8,
                   void *stream);
+
+/*
+ * Spot-diagram points of OpticalSystemAnalysis.get_spot (analysis/
+ * optical_system_analysis.py:283-303): x, y of the rays whose `flags & mask` is non-zero
+ * (flags NULL = all), in the frame `frame` (HOST pointer, NULL = global coordinates; the
+ * reference uses the last surface's frame), compacted into DEVICE array xy (2, ld_out):
+ * xy[c * ld_out + j], j < *count.  *count (DEVICE int64) receives the number of selected
+ * rays -- nothing is read back to the host, so the call can be followed directly by a
+ * collective on fixed-width buffers.  Points beyond ld_out are counted but not stored.
+ * The order of the points is unspecified (a spot diagram is a point set).
+ */
+int pyr_spot_points(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask,
+                    int64_t n, const PyrFrame *frame, double *xy, int64_t ld_out,
+                    int64_t *count, void *stream);
 
 /*
  * Write rays [0, n) of the generated bundle (raster points gen->first ...) to DEVICE

@@ -345,6 +345,8 @@ def shape_sag(shape, x, y):
                            shape["coefficients"], x, y)
     if kind == "Conic":
         return conic_sag(shape["curv"], shape["cc"], x, y)
+    if kind == "Cylinder":                                 # Cylinder.getSag :360-367
+        return conic_sag(shape["curv"], shape["cc"], np.zeros_like(x), y)
     if kind == "Asphere":
         return asphere_sag(shape["curv"], shape["cc"], shape["coefficients"], x, y)
     if kind == "XYPolynomials":
@@ -367,6 +369,12 @@ def shape_grad(shape, x, y):
                             shape["coefficients"], x, y)
     if kind == "Conic":
         return conic_grad(shape["curv"], shape["cc"], x, y)
+    if kind == "Cylinder":
+        # gradient of the cylinder's own implicit function c (y^2 + (1+cc) z^2) - 2 z (the
+        # reference inherits Conic.getGrad, whose x component contradicts Cylinder.getSag)
+        g = conic_grad(shape["curv"], shape["cc"], np.zeros_like(x), y)
+        g[0] = 0.0
+        return g
     if kind == "Asphere":
         return asphere_grad(shape["curv"], shape["cc"], shape["coefficients"], x, y)
     if kind == "XYPolynomials":
@@ -454,6 +462,23 @@ def shape_intersect(shape, bundle):
         f = d[2] - curv * (d[0] * r0[0] + d[1] * r0[1] + d[2] * r0[2] * (1 + cc))
         g = curv * (r0[0] ** 2 + r0[1] ** 2 + r0[2] ** 2 * (1 + cc)) - 2 * r0[2]
         h = -curv - cc * curv * d[2] ** 2
+        square = f ** 2 + h * g
+        with np.errstate(invalid="ignore", divide="ignore"):
+            t = g / (f + np.sqrt(square))
+            hit = r0 + d * t
+            valid = square >= 0
+    elif shape["kind"] == "Cylinder":
+        # Cylinder.intersect :369-388 is dead code in the reference (it reads the
+        # non-existent raybundle.rayDir) and its H is the rotationally symmetric conic's.
+        # Corrected: the ray meets c (y^2 + (1+cc) z^2) - 2 z = 0 where
+        #   -H t^2 - 2 F t + G = 0  with  H = -c (d_y^2 + (1+cc) d_z^2);
+        # validity like Conic (square >= 0).  PARITY UNPINNED by construction: pinned on the
+        # limiting cases instead (tests: x-independence, equality with Conic for d_x = 0 rays
+        # in the plane x = 0, hit points satisfy the surface equation).
+        (curv, cc) = (shape["curv"], shape["cc"])
+        f = d[2] - curv * (d[1] * r0[1] + d[2] * r0[2] * (1 + cc))
+        g = curv * (r0[1] ** 2 + r0[2] ** 2 * (1 + cc)) - 2 * r0[2]
+        h = -curv * (d[1] ** 2 + (1 + cc) * d[2] ** 2)
         square = f ** 2 + h * g
         with np.errstate(invalid="ignore", divide="ignore"):
             t = g / (f + np.sqrt(square))

@@ -56,7 +56,7 @@ def api():
     from pyrateoptics.raytracer.optical_element import OpticalElement
     from pyrateoptics.raytracer.localcoordinates import LocalCoordinates
     from pyrateoptics.raytracer.surface import Surface
-    from pyrateoptics.raytracer.surface_shape import (Conic, Asphere, Biconic,
+    from pyrateoptics.raytracer.surface_shape import (Conic, Cylinder, Asphere, Biconic,
                                                       XYPolynomials, ZernikeFringe,
                                                       ZernikeANSI, GridSag,
                                                       LinearCombination)

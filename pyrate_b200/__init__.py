@@ -23,7 +23,7 @@ from .raytracer.optical_element import OpticalElement  # noqa: F401
 from .raytracer.optical_system import OpticalSystem  # noqa: F401
 from .raytracer.ray import RayBundle, RayPath  # noqa: F401
 from .raytracer.surface import Surface  # noqa: F401
-from .raytracer.surface_shape import (Asphere, Biconic, Conic, GridSag,  # noqa: F401
+from .raytracer.surface_shape import (Asphere, Biconic, Conic, Cylinder, GridSag,  # noqa: F401
                                       LinearCombination, XYPolynomials,
                                       ZernikeANSI, ZernikeFringe,
                                       accessible_shapes)
@@ -35,7 +35,7 @@ def api():
     """Class namespace for `pyrate_b200.configs.build_system(spec, api)`."""
     return types.SimpleNamespace(
         OpticalSystem=OpticalSystem, OpticalElement=OpticalElement,
-        LocalCoordinates=LocalCoordinates, Surface=Surface, Conic=Conic,
+        LocalCoordinates=LocalCoordinates, Surface=Surface, Conic=Conic, Cylinder=Cylinder,
         Asphere=Asphere, Biconic=Biconic, XYPolynomials=XYPolynomials,
         ZernikeFringe=ZernikeFringe, ZernikeANSI=ZernikeANSI,
         GridSag=GridSag, LinearCombination=LinearCombination,

@@ -215,11 +215,14 @@ class BundleGen(object):
         return self._cache is not None
 
     # ---- CPU restatement of the index arithmetic (tests only) ----
-    def points_host(self):
-        """Normalised raster coordinates of this shard, by the same index arithmetic
-        the device uses (csrc/pyr_gen.cuh: gen_point)."""
+    def points_host(self, index=None):
+        """Normalised raster coordinates of this shard (or of its rays `index`), by the
+        same index arithmetic the device uses (csrc/pyr_gen.cuh: gen_point)."""
         r = self.raster
-        idx = np.arange(self.first, self.first + self.n, dtype=np.int64)
+        if index is None:
+            idx = np.arange(self.first, self.first + self.n, dtype=np.int64)
+        else:
+            idx = self.first + np.asarray(index, dtype=np.int64)
         (ls, lstep, lstop) = r.lin
 
         def lin(i):
@@ -256,9 +259,9 @@ class BundleGen(object):
         phi = iphi.astype(np.float64) * r.aux[0]
         return rr * np.cos(phi), rr * np.sin(phi)
 
-    def arrays_host(self):
-        """(x0, k0, E0) NumPy arrays by the CPU restatement (tests only)."""
-        (px, py) = self.points_host()
+    def arrays_host(self, index=None):
+        """(x0, k0, E0) NumPy arrays by the CPU restatement (tests / parity samples only)."""
+        (px, py) = self.points_host(index)
         n = px.size
         x = np.empty((3, n))
         d = np.empty((3, n))

@@ -598,7 +598,27 @@ X15_DISPERSIVE_ASPHERE = dict(C3_ASPHERE, name="x15_dispersive_asphere", materia
     "glass": ("ModelGlass", {"n0_A_B": _conrady(1.5168, 1.3)})},
     bundle={"rings": 8, "radius": 11.43, "z0": -5.0})
 
-CONFIGS.update({c["name"]: c for c in (X13_TIRGLASS, X14_DISPERSIVE, X15_DISPERSIVE_ASPHERE, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
+X16_CYLINDER = {   # cylinder lenses (conic sections in y extruded along x), tilted about z so that
+    # the extrusion axis is not a coordinate axis of the bundle, one parabolic and one
+    # elliptic section; the rear cylinder sits in a crossed orientation
+    "name": "x16_cylinder",
+    "surfaces": [
+        _conic("stop", 0.0, opt={"is_stop": True}),
+        {"name": "front", "lc": {"decz": 3.0, "tiltz": 20.0 * math.pi / 180.0},
+         "shape": ("Cylinder", {"curv": 1. / 30.0, "cc": -1.0}),
+         "aperture": _circ(9.0), "mat": "glass", "opt": {}},
+        {"name": "back", "lc": {"decz": 5.0, "tiltz": 70.0 * math.pi / 180.0,
+                                "tiltx": 1.0 * math.pi / 180.0},
+         "shape": ("Cylinder", {"curv": -1. / 45.0, "cc": 0.4}),
+         "aperture": None, "mat": None, "opt": {}},
+        _conic("image", 40.0),
+    ],
+    "materials": {"glass": ("ConstantIndexGlass", {"n": 1.5168})},
+    "bundle": {"rings": 8, "radius": 7.0, "z0": -3.0},
+    "s_counted": 2,
+}
+
+CONFIGS.update({c["name"]: c for c in (X16_CYLINDER, X13_TIRGLASS, X14_DISPERSIVE, X15_DISPERSIVE_ASPHERE, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
                                        X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL,
                                        X11_GRIDSAG, X12_COMBINATION)})

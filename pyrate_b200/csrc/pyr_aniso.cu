@@ -14,8 +14,20 @@
 //   D(k) = det(eps) - (k.k) c2(eps) + k^T adj(eps) k + (k.k)(k^T eps k),  k = kpa + xi n
 // (det(-(k.k) I + k k^T + eps) expanded with the matrix determinant lemma; the
 // reference's own tests pin eigenvalues == polynomial roots, tests/test_material.py
-// :174-327), found with Aberth-Ehrlich iterations, and E is the null vector of the
+// :174-327).  For uniaxial (and isotropic) real tensors eps = eo 1 + (ee - eo) a a^T --
+// calcite, quartz, the BASELINE crystals -- the quartic factorises into the ordinary
+// sphere k.k = eo and the extraordinary ellipsoid eo k.k + (ee - eo)(k.a)^2 = eo ee: two
+// quadratics in xi, closed form (pinned on the reference's eigenvalues in the oracle,
+// oracle/pyrate_np.py uniaxial_xi_roots).  General (biaxial / complex) tensors keep the
+// Aberth-Ehrlich iteration, in an own kernel instantiation.  E is the null vector of the
 // 3x3 propagator at each root (cross product of its two most independent rows).
+//
+// ONE launch per complex stretch: a birefringent interface doubles the rays
+// (material_anisotropic.py:87-100); thread i walks the whole mode tree of its ray depth
+// first.  The record of a doubling step IS the stack: mode b's (x, k, E) is what the
+// step writes to column w + c of its record anyway, and the same thread reads it back
+// when it returns to that branch -- leaf t > 0 resumes at the split whose bit is the
+// lowest set bit of t.  All threads follow the same control flow.
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -90,29 +102,6 @@ __device__ __forceinline__ void poynting_vec(const cplx k[3], const cplx e[3], d
 // ---------------------------------------------------------------------------
 // Fresnel quartic in xi and its roots
 // ---------------------------------------------------------------------------
-struct EpsInv {           // invariants of eps used by the quartic
-    cplx eps[9];
-    cplx adj[9];
-    cplx c2, det;
-};
-
-__device__ __forceinline__ void eps_invariants(const double e18[18], EpsInv &v) {
-    for (int i = 0; i < 9; ++i) v.eps[i] = {e18[2 * i], e18[2 * i + 1]};
-    const cplx *m = v.eps;
-    // adjugate (transpose of the cofactor matrix)
-    v.adj[0] = m[4] * m[8] - m[5] * m[7];
-    v.adj[1] = m[2] * m[7] - m[1] * m[8];
-    v.adj[2] = m[1] * m[5] - m[2] * m[4];
-    v.adj[3] = m[5] * m[6] - m[3] * m[8];
-    v.adj[4] = m[0] * m[8] - m[2] * m[6];
-    v.adj[5] = m[2] * m[3] - m[0] * m[5];
-    v.adj[6] = m[3] * m[7] - m[4] * m[6];
-    v.adj[7] = m[1] * m[6] - m[0] * m[7];
-    v.adj[8] = m[0] * m[4] - m[1] * m[3];
-    v.det = m[0] * v.adj[0] + m[1] * v.adj[3] + m[2] * v.adj[6];
-    v.c2 = v.adj[0] + v.adj[4] + v.adj[8];          // sum of principal 2x2 minors
-}
-
 __device__ __forceinline__ cplx quad_form(const cplx m[9], const cplx a[3], const cplx b[3]) {
     cplx r = C(0.0);
     for (int i = 0; i < 3; ++i) r = r + a[i] * (m[3 * i] * b[0] + m[3 * i + 1] * b[1] + m[3 * i + 2] * b[2]);
@@ -201,82 +190,177 @@ __device__ __forceinline__ void null_vector(const cplx eps[9], const cplx k[3], 
     for (int i = 0; i < 3; ++i) e[i] = inv * out[i];
 }
 
-struct CRay {
-    double x[3];
-    cplx k[3], e[3];
-    bool alive;
-};
+// general null vector behind a call: the uniaxial kernel needs it only for degenerate
+// modes (propagation along the optic axis, isotropic tensors) and must not pay its
+// registers on the fast path
+__device__ __noinline__ void null_vector_call(const double *eps18, const cplx k[3], bool second, cplx e[3]) {
+    cplx eps[9];
+    for (int i = 0; i < 9; ++i) eps[i] = {eps18[2 * i], eps18[2 * i + 1]};
+    null_vector(eps, k, second, e);
+}
+
+// One mode k = p + xi n: unit null vector e of the propagator, weight of the reference's
+// eigenvector normalisation (unit 6-vector (xi E, E) -> |E|^2 = 1 / (1 + |xi|^2)) and the
+// Poynting sort key S.n in that normalisation (material.py:122-153, :214-223).
+//   UNI: uniaxial tensor eps = eo 1 + de a a^T.  Ordinary mode: E = k x a; extraordinary
+//   mode: E = eo a - (k.a) k  (A(k) E = 0 with A = -(k.k) 1 + k k^T + eps, given the
+//   respective dispersion relation).  Both vanish for k parallel to a: general null vector.
+template <bool UNI>
+__device__ __forceinline__ double mode_key(const DAux &ax, const cplx p[3], const double nrm[3],
+                                           cplx xi, bool extraordinary, bool second, cplx k[3],
+                                           cplx e[3], double &wgt) {
+    for (int i = 0; i < 3; ++i) k[i] = p[i] + nrm[i] * xi;
+    bool closed = false;
+    if (UNI) {
+        const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+        cplx ko[3];                                           // k x a
+        ko[0] = {k[1].re * a[2] - k[2].re * a[1], k[1].im * a[2] - k[2].im * a[1]};
+        ko[1] = {k[2].re * a[0] - k[0].re * a[2], k[2].im * a[0] - k[0].im * a[2]};
+        ko[2] = {k[0].re * a[1] - k[1].re * a[0], k[0].im * a[1] - k[1].im * a[0]};
+        const double cross2 = herm2(ko);
+        closed = ax.eps_e != ax.eps_o && cross2 > 1e-8 * herm2(k);
+        if (closed) {
+            if (extraordinary) {
+                const cplx ka = cdotr(k, a);
+                for (int i = 0; i < 3; ++i) e[i] = C(ax.eps_o * a[i]) - ka * k[i];
+                const double inv = rsqrt(herm2(e));
+                for (int i = 0; i < 3; ++i) e[i] = inv * e[i];
+            } else {
+                const double inv = rsqrt(cross2);
+                for (int i = 0; i < 3; ++i) e[i] = inv * ko[i];
+            }
+        }
+    }
+    if (!closed) {
+        if (UNI) {
+            null_vector_call(ax.after.eps, k, second, e);
+        } else {
+            cplx eps[9];
+            for (int i = 0; i < 9; ++i) eps[i] = {ax.after.eps[2 * i], ax.after.eps[2 * i + 1]};
+            null_vector(eps, k, second, e);
+        }
+    }
+    wgt = 1.0 / (1.0 + abs2(xi));
+    double s[3];
+    poynting_vec(k, e, s);
+    return wgt * dot3(s, nrm);
+}
 
 // Anisotropic deflection in the shape frame.  kl: incoming k (shape frame), nrm: unit
-// normal.  Produces the two selected modes (ka, ea), (kb, eb).
-__device__ __forceinline__ void aniso_modes(const EpsInv &ei, const cplx kl[3], const double nrm[3],
+// normal.  Produces the two selected modes (ka, ea), (kb, eb).  No dynamically indexed
+// local arrays (no stack frame): the four sort keys are computed first, the two selected
+// modes are then evaluated again.
+template <bool GENERAL_EPS>
+__device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], const double nrm[3],
                                             bool mirror, cplx ka[3], cplx ea[3], cplx kb[3],
                                             cplx eb[3]) {
     const cplx kn = cdotr(kl, nrm);
-    cplx p[3], nc[3];
-    for (int i = 0; i < 3; ++i) { p[i] = kl[i] - nrm[i] * kn; nc[i] = C(nrm[i]); }
+    cplx p[3];
+    for (int i = 0; i < 3; ++i) p[i] = kl[i] - nrm[i] * kn;
     bool ok = finite3(nrm) && cfinite(p[0]) && cfinite(p[1]) && cfinite(p[2]);
-    cplx xi[4];
-    if (ok) {
-        const cplx s0 = cdot(p, p), s1 = 2.0 * cdotr(p, nrm), s2 = C(dot3(nrm, nrm));
-        const cplx q0 = quad_form(ei.eps, p, p);
-        const cplx q1 = quad_form(ei.eps, p, nc) + quad_form(ei.eps, nc, p);
-        const cplx q2 = quad_form(ei.eps, nc, nc);
-        const cplx a0 = quad_form(ei.adj, p, p);
-        const cplx a1 = quad_form(ei.adj, p, nc) + quad_form(ei.adj, nc, p);
-        const cplx a2 = quad_form(ei.adj, nc, nc);
-        cplx c[5];
-        c[4] = s2 * q2;
-        c[3] = s1 * q2 + s2 * q1;
-        c[2] = s0 * q2 + s1 * q1 + s2 * q0 - ei.c2 * s2 + a2;
-        c[1] = s0 * q1 + s1 * q0 - ei.c2 * s1 + a1;
-        c[0] = s0 * q0 - ei.c2 * s0 + a0 + ei.det;
-        // starts: the roots of the isotropic medium with the mean permittivity,
-        // xi = +-sqrt(tr(eps)/3 - p.p), split by a few per cent off the real axis
-        const cplx third = {1.0 / 3.0, 0.0};
-        const cplx xi2 = third * (ei.eps[0] + ei.eps[4] + ei.eps[8]) - s0;
-        cplx r = csqrt_(xi2);
-        double scale = sqrt(abs2(r));
-        if (!(scale > 1e-3)) { scale = 1.0; r = C(1.0); }
-        const cplx z0[4] = {r * cplx{1.03, 0.02}, r * cplx{0.97, -0.02},
-                            r * cplx{-1.03, 0.02}, r * cplx{-0.97, -0.02}};
-        ok = quartic_roots(c, z0, scale, xi);
+    constexpr bool UNI = !GENERAL_EPS;
+    cplx xi0, xi1, xi2, xi3;
+    if (UNI) {
+        // closed form: ordinary +-, extraordinary +- (p.n = 0 by construction)
+        const double eo = ax.eps_o, de = ax.eps_e - ax.eps_o;
+        const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+        const cplx kk = cdot(p, p);
+        const cplx pa = cdotr(p, a);
+        const double na = dot3(nrm, a);
+        const cplx xo = csqrt_(C(eo) - kk);
+        const double qa = fma(de * na, na, eo);
+        const cplx qb = (de * na) * pa;                          // half the linear coefficient
+        const cplx qc = eo * kk + de * (pa * pa) - C(eo * ax.eps_e);
+        const cplx disc = csqrt_(qb * qb - qa * qc);
+        const double iqa = 1.0 / qa;
+        xi0 = xo; xi1 = -xo;
+        xi2 = iqa * (disc - qb); xi3 = iqa * (-disc - qb);
+        ok = ok && cfinite(xi0) && cfinite(xi2) && cfinite(xi3);
+    } else {
+        cplx nc[3];
+        for (int i = 0; i < 3; ++i) nc[i] = C(nrm[i]);
+        cplx xi[4];
+        if (ok) {
+            cplx eps[9];
+            for (int i = 0; i < 9; ++i) eps[i] = {ax.after.eps[2 * i], ax.after.eps[2 * i + 1]};
+            // invariants of eps: adjugate, sum of the principal 2x2 minors, determinant
+            cplx adj[9];
+            const cplx *mm = eps;
+            adj[0] = mm[4] * mm[8] - mm[5] * mm[7];
+            adj[1] = mm[2] * mm[7] - mm[1] * mm[8];
+            adj[2] = mm[1] * mm[5] - mm[2] * mm[4];
+            adj[3] = mm[5] * mm[6] - mm[3] * mm[8];
+            adj[4] = mm[0] * mm[8] - mm[2] * mm[6];
+            adj[5] = mm[2] * mm[3] - mm[0] * mm[5];
+            adj[6] = mm[3] * mm[7] - mm[4] * mm[6];
+            adj[7] = mm[1] * mm[6] - mm[0] * mm[7];
+            adj[8] = mm[0] * mm[4] - mm[1] * mm[3];
+            const cplx det = mm[0] * adj[0] + mm[1] * adj[3] + mm[2] * adj[6];
+            const cplx c2 = adj[0] + adj[4] + adj[8];
+            const cplx s0 = cdot(p, p), s1 = 2.0 * cdotr(p, nrm), s2 = C(dot3(nrm, nrm));
+            const cplx q0 = quad_form(eps, p, p);
+            const cplx q1 = quad_form(eps, p, nc) + quad_form(eps, nc, p);
+            const cplx q2 = quad_form(eps, nc, nc);
+            const cplx a0 = quad_form(adj, p, p);
+            const cplx a1 = quad_form(adj, p, nc) + quad_form(adj, nc, p);
+            const cplx a2 = quad_form(adj, nc, nc);
+            cplx c[5];
+            c[4] = s2 * q2;
+            c[3] = s1 * q2 + s2 * q1;
+            c[2] = s0 * q2 + s1 * q1 + s2 * q0 - c2 * s2 + a2;
+            c[1] = s0 * q1 + s1 * q0 - c2 * s1 + a1;
+            c[0] = s0 * q0 - c2 * s0 + a0 + det;
+            // starts: the roots of the isotropic medium with the mean permittivity,
+            // xi = +-sqrt(tr(eps)/3 - p.p), split by a few per cent off the real axis
+            const cplx third = {1.0 / 3.0, 0.0};
+            const cplx xi2s = third * (eps[0] + eps[4] + eps[8]) - s0;
+            cplx r = csqrt_(xi2s);
+            double scale = sqrt(abs2(r));
+            if (!(scale > 1e-3)) { scale = 1.0; r = C(1.0); }
+            const cplx z0[4] = {r * cplx{1.03, 0.02}, r * cplx{0.97, -0.02},
+                                r * cplx{-1.03, 0.02}, r * cplx{-0.97, -0.02}};
+            ok = quartic_roots(c, z0, scale, xi);
+        }
+        xi0 = xi[0]; xi1 = xi[1]; xi2 = xi[2]; xi3 = xi[3];
     }
     if (!ok) {
         const cplx q = {qnan(), qnan()};
         for (int i = 0; i < 3; ++i) { ka[i] = kb[i] = ea[i] = eb[i] = q; }
         return;
     }
-    // modes, Poynting sort key S.n with the reference's eigenvector normalisation
-    // (unit 6-vector (xi E, E) -> |E|^2 = 1/(1 + |xi|^2))
-    cplx km[4][3], em[4][3];
-    double key[4], wgt[4];
-    for (int m = 0; m < 4; ++m) {
-        for (int i = 0; i < 3; ++i) km[m][i] = p[i] + xi[m] * nc[i];
-        bool second = false;
-        for (int j = 0; j < m; ++j)
-            if (abs2(xi[m] - xi[j]) < 1e-14 * (1.0 + abs2(xi[m]))) second = !second;
-        null_vector(ei.eps, km[m], second, em[m]);
-        wgt[m] = 1.0 / (1.0 + abs2(xi[m]));
-        double s[3];
-        poynting_vec(km[m], em[m], s);
-        key[m] = wgt[m] * dot3(s, nrm);
-    }
-    int ord[4] = {0, 1, 2, 3};
-    for (int i = 1; i < 4; ++i) {                       // stable insertion sort, ascending
-        const int v = ord[i];
-        int j = i - 1;
-        while (j >= 0 && key[ord[j]] > key[v]) { ord[j + 1] = ord[j]; --j; }
-        ord[j + 1] = v;
-    }
-    const int ia = mirror ? ord[0] : ord[2];
-    const int ib = mirror ? ord[1] : ord[3];
-    const double sa = (mirror ? -1.0 : 1.0) * sqrt(wgt[ia]);
-    const double sb = (mirror ? -1.0 : 1.0) * sqrt(wgt[ib]);
+    // degenerate pairs (isotropic tensors, propagation along the optic axis): the second
+    // root of a pair takes the other vector of the two-dimensional null space
+    auto same = [](cplx a, cplx b) { return abs2(a - b) < 1e-14 * (1.0 + abs2(a)); };
+    const bool sec1 = same(xi1, xi0);
+    const bool sec2 = same(xi2, xi0) != same(xi2, xi1);
+    const bool sec3 = (same(xi3, xi0) != same(xi3, xi1)) != same(xi3, xi2);
+    // pass 1: sort keys S.n with the reference's eigenvector normalisation
+    double key0, key1, key2, key3, w;
+    key0 = mode_key<UNI>(ax, p, nrm, xi0, false, false, ka, ea, w);
+    key1 = mode_key<UNI>(ax, p, nrm, xi1, false, sec1, ka, ea, w);
+    key2 = mode_key<UNI>(ax, p, nrm, xi2, true, sec2, ka, ea, w);
+    key3 = mode_key<UNI>(ax, p, nrm, xi3, true, sec3, ka, ea, w);
+    // stable ascending rank of every key (what the reference's argsort gives)
+    const int r0 = (key1 < key0) + (key2 < key0) + (key3 < key0);
+    const int r1 = (key0 <= key1) + (key2 < key1) + (key3 < key1);
+    const int r2 = (key0 <= key2) + (key1 <= key2) + (key3 < key2);
+    const int r3 = (key0 <= key3) + (key1 <= key3) + (key2 <= key3);
+    const int ra = mirror ? 0 : 2, rb = mirror ? 1 : 3;      // material_anisotropic.py:89-91 / :133-134
+    cplx xa = xi2, xb = xi3;
+    bool seca = sec2, secb = sec3, exa = true, exb = true;
+    if (r0 == ra) { xa = xi0; seca = false; exa = false; } else if (r1 == ra) { xa = xi1; seca = sec1; exa = false; }
+    else if (r3 == ra) { xa = xi3; seca = sec3; }
+    if (r0 == rb) { xb = xi0; secb = false; exb = false; } else if (r1 == rb) { xb = xi1; secb = sec1; exb = false; }
+    else if (r2 == rb) { xb = xi2; secb = sec2; }
+    // pass 2: the two selected modes
+    double wa, wb;
+    mode_key<UNI>(ax, p, nrm, xa, exa, seca, ka, ea, wa);
+    mode_key<UNI>(ax, p, nrm, xb, exb, secb, kb, eb, wb);
     const double sgn = mirror ? -1.0 : 1.0;
+    const double sa = sgn * sqrt(wa), sb = sgn * sqrt(wb);
     for (int i = 0; i < 3; ++i) {
-        ka[i] = sgn * km[ia][i]; kb[i] = sgn * km[ib][i];
-        ea[i] = sa * em[ia][i]; eb[i] = sb * em[ib][i];
+        ka[i] = sgn * ka[i]; kb[i] = sgn * kb[i];
+        ea[i] = sa * ea[i]; eb[i] = sb * eb[i];
     }
 }
 
@@ -284,153 +368,201 @@ __device__ __forceinline__ void cstore(double *base, int64_t idx, cplx v) {
     __stcs(reinterpret_cast<double2 *>(base) + idx, make_double2(v.re, v.im));
 }
 __device__ __forceinline__ cplx cload(const double *base, int64_t idx) {
-    const double2 v = __ldcs(reinterpret_cast<const double2 *>(base) + idx);
+    const double2 v = __ldcg(reinterpret_cast<const double2 *>(base) + idx);
     return {v.x, v.y};
 }
 
-__global__ void __launch_bounds__(128)
+// split bookkeeping of a launch: step indices of the doubling steps (at most kMaxSplits)
+constexpr int kMaxSplits = 6;
+
+template <bool GENERAL_EPS>
+__global__ void __launch_bounds__(128, GENERAL_EPS ? 2 : 3)
 trace_complex_kernel(const __grid_constant__ LaunchParams P) {
     const int64_t n = P.n;
+    // doubling steps of this launch, in order (uniform over the grid)
+    int m = 0;
+    int split_step[kMaxSplits];
+#pragma unroll
+    for (int q = 0; q < kMaxSplits; ++q) split_step[q] = 0;
+    for (int s = 0; s < P.n_steps; ++s) {
+        if ((P.steps[s].bits & kSplit) && P.steps[s].after_kind == PYR_MEDIUM_ANISO &&
+            !(P.steps[s].bits & kNoDeflect)) {
+#pragma unroll
+            for (int q = 0; q < kMaxSplits; ++q)
+                if (q == m) split_step[q] = s;
+            ++m;
+        }
+    }
+    const unsigned leaves = 1u << m;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
-        CRay r;
-        const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
-        for (int c = 0; c < 3; ++c) {
-            r.x[c] = P.x[c * P.ld_in + ix];
-            r.k[c] = cload(P.k, c * P.ld_in + i);
-            r.e[c] = P.e ? cload(P.e, c * P.ld_in + i) : C(c == 1 ? 1.0 : 0.0);
-        }
-        r.alive = P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true;
-
-        for (int s = 0; s < P.n_steps; ++s) {
-            const DStep &st = P.steps[s];
-            const DAux *aux = st.aux >= 0 ? &P.aux[st.aux] : nullptr;
-            const bool ok = r.alive;
-
-            // direction of energy transport: always the Poynting vector here
-            double d[3];
-            {
-                double sv[3];
-                poynting_vec(r.k, r.e, sv);
-                const double inv = rsqrt(dot3(sv, sv));
-                d[0] = sv[0] * inv; d[1] = sv[1] * inv; d[2] = sv[2] * inv;
-            }
-            double r0[3], dl[3];
-            g2l_point(st.frame, r.x, r0);
-            rot_t(st.frame.r, d, dl);
-            double t;
-            bool hit_ok = true;
-            if (st.bits & kNoIntersect) t = 0.0;         // stand-alone refract / reflect: x is the hit point
-            else if (st.shape_kind == PYR_SHAPE_CONIC) t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
-            else { double gfx, gfy; bool gok; t = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
-            const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
-            double hit_g[3];
-            l2g_point(st.frame, h, hit_g);
-
-            bool ap_ok = true;
-            if (st.aperture_kind != PYR_AP_BASE) {
-                double ax = h[0], ay = h[1];
-                if (!(st.bits & kApSameFrame)) {
-                    double a[3];
-                    g2l_point(aux->aperture_frame, hit_g, a);
-                    ax = a[0]; ay = a[1];
-                }
-                if (st.aperture_kind == PYR_AP_CIRCULAR) {
-                    const double rr = fma(ax, ax, ay * ay);
-                    ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
-                } else {
-                    ap_ok = (ax >= -st.ap0) && (ax <= st.ap0) && (ay >= -st.ap1) && (ay <= st.ap1);
-                }
-            }
-            const bool hit = ok && hit_ok && ap_ok;
-
-            double nrm[3];
-            if (st.shape_kind == PYR_SHAPE_CONIC)
-                conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
-            else
-                explicit_normal<false>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
-
-            cplx kl[3];
-            crot_t(st.frame.r, r.k, kl);
-            const bool mirror = st.interaction == PYR_REFLECT;
-            cplx k2a[3], e2a[3], k2b[3], e2b[3];
+        for (unsigned t = 0; t < leaves; ++t) {
+            double x[3];
+            cplx k[3], e[3];
             bool alive;
-            const bool no_deflect = (st.bits & kNoDeflect) != 0;   // stand-alone propagate
-            const bool aniso = st.after_kind == PYR_MEDIUM_ANISO && !no_deflect;
-            if (no_deflect) {
-                for (int c = 0; c < 3; ++c) { k2a[c] = kl[c]; }
-                alive = hit;                 // k, E unchanged (material_anisotropic.py:58-68)
-            } else if (aniso) {
-                EpsInv ei;
-                eps_invariants(aux->after.eps, ei);      // eps already in the shape frame
-                aniso_modes(ei, kl, nrm, mirror, k2a, e2a, k2b, e2b);
-                alive = ok;          // no validity filter (material_anisotropic.py:87-100)
-            } else {
-                // isotropic deflection with complex k (material_isotropic.py:163-236)
-                const cplx kn = cdotr(kl, nrm);
-                cplx kin[3];
-                for (int c = 0; c < 3; ++c) kin[c] = kl[c] - nrm[c] * kn;
-                const cplx square = C(st.n2sq[0]) - cdot(kin, kin);
-                // numpy orders complex numbers lexicographically: (re, im) > (0, 0)
-                const bool refr_ok = (square.re > 0.0 || (square.re == 0.0 && square.im > 0.0)) &&
-                                     finite3(nrm);
-                const cplx xi = csqrt_(square);
-                for (int c = 0; c < 3; ++c) k2a[c] = (mirror ? -kin[c] : kin[c]) + nrm[c] * xi;
-                alive = hit && refr_ok;
-                // E: project the previous field (shape frame) onto the plane k2.E = 0
-                cplx el[3];
-                crot_t(st.frame.r, r.e, el);
-                const cplx kk = cdot(k2a, k2a);
-                cplx cc = cdot(el, k2a) / kk;
-                cplx tv[3] = {el[0] - cc * k2a[0], el[1] - cc * k2a[1], el[2] - cc * k2a[2]};
-                double tt = herm2(tv);
-                if (!(tt > 1e-24 * herm2(el))) {
-                    const double ax = abs2(k2a[0]), ay = abs2(k2a[1]), az = abs2(k2a[2]);
-                    cplx a[3] = {C(0.0), C(0.0), C(0.0)};
-                    if (ax <= ay && ax <= az) a[0] = C(1.0); else if (ay <= az) a[1] = C(1.0); else a[2] = C(1.0);
-                    cc = cdot(a, k2a) / kk;
-                    for (int c = 0; c < 3; ++c) tv[c] = a[c] - cc * k2a[c];
-                    tt = herm2(tv);
+            int s_begin;
+            int64_t col, w;                 // column of this branch and width of its level
+            if (t == 0) {
+                const int64_t ix = (P.n_x == n) ? i : i % P.n_x;
+                for (int c = 0; c < 3; ++c) {
+                    x[c] = P.x[c * P.ld_in + ix];
+                    k[c] = cload(P.k, c * P.ld_in + i);
+                    e[c] = P.e ? cload(P.e, c * P.ld_in + i) : C(c == 1 ? 1.0 : 0.0);
                 }
-                const double inv = rsqrt(tt);
-                for (int c = 0; c < 3; ++c) e2a[c] = inv * tv[c];
+                alive = P.alive ? (P.alive[ix] & PYR_RAY_ALIVE) != 0 : true;
+                s_begin = 0; col = i; w = n;
+            } else {
+                // mode b of split j = m - 1 - ctz(t); splits q < j follow the bits of t
+                const int j = m - 1 - (__ffs((int)t) - 1);
+                col = i; w = n;
+                int sj = 0;
+#pragma unroll
+                for (int q = 0; q < kMaxSplits; ++q) {
+                    if (q < j) { if ((t >> (m - 1 - q)) & 1u) col += w; w *= 2; }
+                    if (q == j) sj = split_step[q];
+                }
+                const DStep &st = P.steps[sj];
+                for (int c = 0; c < 3; ++c) {
+                    x[c] = __ldcg(st.out_x + c * st.ld_out + col);
+                    k[c] = cload(st.out_k, c * st.ld_out2 + w + col);
+                    e[c] = cload(st.out_e, c * st.ld_out2 + w + col);
+                }
+                alive = (__ldcg(st.out_flags + col) & PYR_RAY_ALIVE) != 0;
+                if (!alive) x[0] = x[1] = x[2] = qnan();
+                col += w; w *= 2;
+                s_begin = sj + 1;
             }
 
-            // ---- back to the global frame, record ----
-            cplx kga[3], ega[3], kgb[3], egb[3];
-            crot(st.frame.r, k2a, kga);
-            crot(st.frame.r, e2a, ega);
-            if (no_deflect) { for (int c = 0; c < 3; ++c) { kga[c] = r.k[c]; ega[c] = r.e[c]; } }
-            const bool split = aniso && (st.bits & kSplit);
-            if (aniso) { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
-            const cplx qn = {qnan(), qnan()};
-            if (!alive) {
-                for (int c = 0; c < 3; ++c) { kga[c] = ega[c] = kgb[c] = egb[c] = qn; }
-            }
-            const int64_t ld = st.ld_out;
-            if (st.out_x)
-                for (int c = 0; c < 3; ++c) __stcs(st.out_x + c * ld + i, ok ? hit_g[c] : qnan());
-            if (st.out_flags)
-                st.out_flags[i] = (uint8_t)((hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u));
-            if (split) {
-                const int64_t ld2 = st.ld_out2;
-                for (int c = 0; c < 3; ++c) {
-                    if (st.out_k) { cstore(st.out_k, c * ld2 + i, kga[c]); cstore(st.out_k, c * ld2 + n + i, kgb[c]); }
-                    if (st.out_e) { cstore(st.out_e, c * ld2 + i, ega[c]); cstore(st.out_e, c * ld2 + n + i, egb[c]); }
+            for (int s = s_begin; s < P.n_steps; ++s) {
+                const DStep &st = P.steps[s];
+                const DAux *aux = st.aux >= 0 ? &P.aux[st.aux] : nullptr;
+                const bool ok = alive;
+
+                // direction of energy transport: always the Poynting vector here
+                double d[3];
+                {
+                    double sv[3];
+                    poynting_vec(k, e, sv);
+                    const double inv = rsqrt(dot3(sv, sv));
+                    d[0] = sv[0] * inv; d[1] = sv[1] * inv; d[2] = sv[2] * inv;
                 }
-            } else {
+                double r0[3], dl[3];
+                g2l_point(st.frame, x, r0);
+                rot_t(st.frame.r, d, dl);
+                double tt;
+                bool hit_ok = true;
+                if (st.bits & kNoIntersect) tt = 0.0;        // stand-alone refract / reflect: x is the hit point
+                else if (st.shape_kind == PYR_SHAPE_CONIC) tt = conic_t(st.curv, st.cc, r0, dl, hit_ok);
+                else if (st.shape_kind == PYR_SHAPE_CYLINDER) tt = cylinder_t(st.curv, st.cc, r0, dl, hit_ok);
+                else { double gfx, gfy; bool gok; tt = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
+                const double h[3] = {fma(dl[0], tt, r0[0]), fma(dl[1], tt, r0[1]), fma(dl[2], tt, r0[2])};
+                double hit_g[3];
+                l2g_point(st.frame, h, hit_g);
+
+                bool ap_ok = true;
+                if (st.aperture_kind != PYR_AP_BASE) {
+                    double ax = h[0], ay = h[1];
+                    if (!(st.bits & kApSameFrame)) {
+                        double a[3];
+                        g2l_point(aux->aperture_frame, hit_g, a);
+                        ax = a[0]; ay = a[1];
+                    }
+                    if (st.aperture_kind == PYR_AP_CIRCULAR) {
+                        const double rr = fma(ax, ax, ay * ay);
+                        ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
+                    } else {
+                        ap_ok = (ax >= -st.ap0) && (ax <= st.ap0) && (ay >= -st.ap1) && (ay <= st.ap1);
+                    }
+                }
+                const bool hit = ok && hit_ok && ap_ok;
+
+                double nrm[3];
+                if (st.shape_kind == PYR_SHAPE_CONIC)
+                    conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
+                else if (st.shape_kind == PYR_SHAPE_CYLINDER)
+                    cylinder_normal(st.curv, st.cc, h[1], nrm);
+                else
+                    explicit_normal<false>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+
+                cplx kl[3];
+                crot_t(st.frame.r, k, kl);
+                const bool mirror = st.interaction == PYR_REFLECT;
+                cplx k2a[3], e2a[3], k2b[3], e2b[3];
+                const bool no_deflect = (st.bits & kNoDeflect) != 0;   // stand-alone propagate
+                const bool aniso = st.after_kind == PYR_MEDIUM_ANISO && !no_deflect;
+                if (no_deflect) {
+                    for (int c = 0; c < 3; ++c) { k2a[c] = kl[c]; }
+                    alive = hit;                 // k, E unchanged (material_anisotropic.py:58-68)
+                } else if (aniso) {
+                    aniso_modes<GENERAL_EPS>(*aux, kl, nrm, mirror, k2a, e2a, k2b, e2b);  // eps in the shape frame
+                    alive = ok;          // no validity filter (material_anisotropic.py:87-100)
+                } else {
+                    // isotropic deflection with complex k (material_isotropic.py:163-236)
+                    const cplx kn = cdotr(kl, nrm);
+                    cplx kin[3];
+                    for (int c = 0; c < 3; ++c) kin[c] = kl[c] - nrm[c] * kn;
+                    const cplx square = C(st.n2sq[0]) - cdot(kin, kin);
+                    // numpy orders complex numbers lexicographically: (re, im) > (0, 0)
+                    const bool refr_ok = (square.re > 0.0 || (square.re == 0.0 && square.im > 0.0)) &&
+                                         finite3(nrm);
+                    const cplx xi = csqrt_(square);
+                    for (int c = 0; c < 3; ++c) k2a[c] = (mirror ? -kin[c] : kin[c]) + nrm[c] * xi;
+                    alive = hit && refr_ok;
+                    // E: project the previous field (shape frame) onto the plane k2.E = 0
+                    cplx el[3];
+                    crot_t(st.frame.r, e, el);
+                    const cplx kk = cdot(k2a, k2a);
+                    cplx cc = cdot(el, k2a) / kk;
+                    cplx tv[3] = {el[0] - cc * k2a[0], el[1] - cc * k2a[1], el[2] - cc * k2a[2]};
+                    double t2 = herm2(tv);
+                    if (!(t2 > 1e-24 * herm2(el))) {
+                        const double ax = abs2(k2a[0]), ay = abs2(k2a[1]), az = abs2(k2a[2]);
+                        cplx a[3] = {C(0.0), C(0.0), C(0.0)};
+                        if (ax <= ay && ax <= az) a[0] = C(1.0); else if (ay <= az) a[1] = C(1.0); else a[2] = C(1.0);
+                        cc = cdot(a, k2a) / kk;
+                        for (int c = 0; c < 3; ++c) tv[c] = a[c] - cc * k2a[c];
+                        t2 = herm2(tv);
+                    }
+                    const double inv = rsqrt(t2);
+                    for (int c = 0; c < 3; ++c) e2a[c] = inv * tv[c];
+                }
+
+                // ---- back to the global frame, record ----
+                cplx kga[3], ega[3], kgb[3], egb[3];
+                crot(st.frame.r, k2a, kga);
+                crot(st.frame.r, e2a, ega);
+                if (no_deflect) { for (int c = 0; c < 3; ++c) { kga[c] = k[c]; ega[c] = e[c]; } }
+                const bool split = aniso && (st.bits & kSplit);
+                if (aniso) { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
+                const cplx qn = {qnan(), qnan()};
+                if (!alive) {
+                    for (int c = 0; c < 3; ++c) { kga[c] = ega[c] = kgb[c] = egb[c] = qn; }
+                }
+                const int64_t ld = st.ld_out;
+                if (st.out_x)
+                    for (int c = 0; c < 3; ++c) __stcs(st.out_x + c * ld + col, ok ? hit_g[c] : qnan());
+                if (st.out_flags)
+                    st.out_flags[col] = (uint8_t)((hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u));
+                if (split) {
+                    const int64_t ld2 = st.ld_out2;
+                    for (int c = 0; c < 3; ++c) {
+                        if (st.out_k) { cstore(st.out_k, c * ld2 + col, kga[c]); cstore(st.out_k, c * ld2 + w + col, kgb[c]); }
+                        if (st.out_e) { cstore(st.out_e, c * ld2 + col, ega[c]); cstore(st.out_e, c * ld2 + w + col, egb[c]); }
+                    }
+                    w *= 2;             // mode a keeps its column in the doubled level
+                } else {
+                    for (int c = 0; c < 3; ++c) {
+                        if (st.out_k) cstore(st.out_k, c * ld + col, kga[c]);
+                        if (st.out_e) cstore(st.out_e, c * ld + col, ega[c]);
+                    }
+                }
+                // continue with mode a
                 for (int c = 0; c < 3; ++c) {
-                    if (st.out_k) cstore(st.out_k, c * ld + i, kga[c]);
-                    if (st.out_e) cstore(st.out_e, c * ld + i, ega[c]);
+                    x[c] = alive ? hit_g[c] : qnan();
+                    k[c] = kga[c];
+                    e[c] = ega[c];
                 }
             }
-            // continue with mode a (a split step is always the last of the launch)
-            for (int c = 0; c < 3; ++c) {
-                r.x[c] = alive ? hit_g[c] : qnan();
-                r.k[c] = kga[c];
-                r.e[c] = ega[c];
-            }
-            r.alive = alive;
         }
     }
 }
@@ -439,30 +571,48 @@ int pack_steps(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int
                uint32_t flags, LaunchParams &P, bool &general, bool &any_aniso);   // pyr_trace.cu
 int sm_count();
 
+template <typename K>
+static int launch_complex(K kernel, const LaunchParams &P, int64_t n_rays, cudaStream_t stream) {
+    const int threads = 128;
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0);
+    if (e != cudaSuccess) return (int)e;
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (n_rays + threads - 1) / threads;
+    const int64_t cap = (int64_t)sm_count() * per_sm;
+    if (grid > cap) grid = cap;
+    kernel<<<(unsigned)grid, threads, 0, stream>>>(P);
+    e = cudaGetLastError();
+    return e == cudaSuccess ? PYR_OK : (int)e;
+}
+
 int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                   uint32_t flags, cudaStream_t stream) {
     static thread_local LaunchParams P;
     bool general = false, any_aniso = false;
     int rc = pack_steps(steps, n_steps, rays, n_rays, flags, P, general, any_aniso);
     if (rc != PYR_OK) return rc;
+    if (rays->gen) return PYR_E_UNSUPPORTED;
     if (!rays->e) return PYR_E_BADARG;            // E defines the ray direction in crystals
     if (rays->n_waves > 1) return PYR_E_UNSUPPORTED;
+    int splits = 0;
+    bool general_eps = false;
     for (int s = 0; s < n_steps; ++s) {
         if (steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN)
             return PYR_E_UNSUPPORTED;
+        const bool deflects = steps[s].after.kind == PYR_MEDIUM_ANISO && steps[s].mode != PYR_STEP_PROPAGATE_ONLY;
+        if (steps[s].split && deflects) {
+            ++splits;
+            // a doubling step that is not the last one is resumed from its own record
+            if (s != n_steps - 1 && (!steps[s].out_x || !steps[s].out_k || !steps[s].out_e || !steps[s].out_flags))
+                return PYR_E_BADARG;
+        }
+        if (deflects && P.steps[s].aux >= 0 && !P.aux[P.steps[s].aux].uniaxial) general_eps = true;
     }
+    if (splits > kMaxSplits) return PYR_E_TOOLARGE;
     if (n_rays == 0) return PYR_OK;
-    const int threads = 128;
-    int per_sm = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_complex_kernel, threads, 0);
-    if (e != cudaSuccess) return (int)e;
-    if (per_sm < 1) per_sm = 1;
-    int64_t grid = (n_rays + threads - 1) / threads;
-    const int64_t cap = (int64_t)sm_count() * per_sm;
-    if (grid > cap) grid = cap;
-    trace_complex_kernel<<<(unsigned)grid, threads, 0, stream>>>(P);
-    e = cudaGetLastError();
-    return e == cudaSuccess ? PYR_OK : (int)e;
+    return general_eps ? launch_complex(trace_complex_kernel<true>, P, n_rays, stream)
+                       : launch_complex(trace_complex_kernel<false>, P, n_rays, stream);
 }
 
 }  // namespace pyr

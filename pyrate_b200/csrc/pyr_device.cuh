@@ -66,6 +66,12 @@ struct DAux {
     // are the other terms (each with its own coefficients / grid)
     int32_t n_terms, term_kind;
     double term_w, term_dx, term_dy, term_dz, term_curv, term_cc;
+    // crystal payload of the DEFLECTING medium (`after`), everything in the shape frame:
+    // uniaxial / isotropic real tensors eps = eps_o 1 + (eps_e - eps_o) a a^T take the
+    // closed-form roots (the general case forms the invariants of the Fresnel quartic on
+    // the device: the kernel parameter block has no room for them)
+    int32_t uniaxial, pad1;
+    double eps_o, eps_e, axis[3];
 };
 
 struct DStep {

@@ -43,6 +43,26 @@ __device__ __forceinline__ void conic_normal(double curv, double cc, bool sphere
     n[0] = gx; n[1] = gy; n[2] = gz;
 }
 
+// Cylinder (conic section in y, extruded along x): the conic formulas with x dropped
+//   quadratic in t:  -H t^2 - 2 F t + G = 0,  H = -c (d_y^2 + (1 + cc) d_z^2)
+__device__ __forceinline__ double cylinder_t(double curv, double cc, const double r0[3],
+                                             const double d[3], bool &ok) {
+    const double cc1 = 1.0 + cc;
+    const double F = d[2] - curv * fma(d[1], r0[1], d[2] * r0[2] * cc1);
+    const double G = curv * fma(r0[1], r0[1], r0[2] * r0[2] * cc1) - 2.0 * r0[2];
+    const double H = -curv * fma(d[1], d[1], cc1 * d[2] * d[2]);
+    const double square = fma(F, F, H * G);
+    ok = square >= 0.0;
+    return fast_div(G, F + fast_sqrt(square));
+}
+
+__device__ __forceinline__ void cylinder_normal(double curv, double cc, double y, double n[3]) {
+    const double c2y2 = curv * curv * y * y;
+    const double gz = fast_sqrt(fma(-(1.0 + cc), c2y2, 1.0));        // s <= 0 -> NaN
+    const double inv = fast_rsqrt(fma(-cc, c2y2, 1.0));
+    n[0] = 0.0; n[1] = -curv * y * inv; n[2] = gz * inv;
+}
+
 __device__ __forceinline__ double conic_sag(double curv, double cc, double x, double y) {
     const double r2 = fma(x, x, y * y);
     const double s = fma(-(1.0 + cc) * curv * curv, r2, 1.0);
@@ -227,6 +247,7 @@ template <bool EXT>
 __device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv, double cc,
                                             double x, double y) {
     if (kind == PYR_SHAPE_CONIC) return conic_sag(curv, cc, x, y);
+    if (kind == PYR_SHAPE_CYLINDER) return conic_sag(curv, cc, 0.0, y);
     double F, Fx, Fy;
     explicit_eval<EXT>(kind, *a, curv, cc, x, y, F, Fx, Fy);
     return F;

@@ -165,6 +165,8 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
         t = 0.0;
     } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
+    } else if (st.shape_kind == PYR_SHAPE_CYLINDER) {
+        t = cylinder_t(st.curv, st.cc, r0, dl, hit_ok);
     } else {
         t = explicit_t<EXT>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
     }
@@ -197,6 +199,8 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     double nrm[3];
     if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
+    } else if (st.shape_kind == PYR_SHAPE_CYLINDER) {
+        cylinder_normal(st.curv, st.cc, h[1], nrm);
     } else if (grad_ok) {
         // gradient of the converged Newton iterate: within tol of the hit point
         normal_from_gradient(gfx, gfy, nrm);
@@ -685,6 +689,54 @@ spot_sums_kernel(const double *__restrict__ x, int64_t ld, const uint8_t *__rest
 }
 
 // ---------------------------------------------------------------------------
+// spot-diagram points (analysis/optical_system_analysis.py:283-303 get_spot): (x, y) of the
+// selected rays in the frame of the last surface, compacted.  One atomic per CTA and tile
+// on a device cursor (block-aggregated: ballot + popc per warp, warp totals scanned in
+// shared memory), order = tile arrival order, stable inside a tile.  No host round trip:
+// the count stays on the device.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+spot_points_kernel(const double *__restrict__ x, int64_t ld, const uint8_t *__restrict__ flags,
+                   uint32_t mask, int64_t n, const __grid_constant__ DFrame frame, int to_local,
+                   double *__restrict__ xy, int64_t ld_out, unsigned long long *cursor) {
+    __shared__ unsigned warp_count[8];
+    __shared__ unsigned long long tile_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t t0 = (int64_t)blockIdx.x * 256; t0 < n; t0 += (int64_t)gridDim.x * 256) {
+        const int64_t i = t0 + threadIdx.x;
+        bool on = i < n && (!flags || (flags[i] & mask) != 0);
+        double px = 0.0, py = 0.0;
+        if (on) {
+            const double p[3] = {__ldcs(x + i), __ldcs(x + ld + i), __ldcs(x + 2 * ld + i)};
+            if (to_local) {
+                double q[3];
+                g2l_point(frame, p, q);
+                px = q[0]; py = q[1];
+            } else {
+                px = p[0]; py = p[1];
+            }
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) warp_count[warp] = __popc(ballot);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned total = 0;
+            for (int w = 0; w < 8; ++w) { const unsigned c = warp_count[w]; warp_count[w] = total; total += c; }
+            tile_base = total ? atomicAdd(cursor, (unsigned long long)total) : 0ull;
+        }
+        __syncthreads();
+        if (on) {
+            const int64_t pos = (int64_t)tile_base + warp_count[warp] + __popc(ballot & ((1u << lane) - 1u));
+            if (pos < ld_out) {
+                __stcs(xy + pos, px);
+                __stcs(xy + ld_out + pos, py);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
 // stand-alone bundle generation (collimated_bundle / divergent_bundle resident on the device)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -765,6 +817,88 @@ static void pack_medium(const PyrMedium &m, const PyrFrame &shape, DMedium &d) {
     pack_frame(m.frame, d.frame);
 }
 
+// ---- crystal tensors (host side, at pack time) ----
+// eigen-decomposition of a real symmetric 3x3 matrix (cyclic Jacobi): w ascending, v columns
+static void jacobi3(const double a_in[9], double w[3], double v[9]) {
+    double a[9];
+    for (int i = 0; i < 9; ++i) { a[i] = a_in[i]; v[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+    for (int sweep = 0; sweep < 50; ++sweep) {
+        const double off = std::fabs(a[1]) + std::fabs(a[2]) + std::fabs(a[5]);
+        if (off < 1e-300) break;
+        for (int pq = 0; pq < 3; ++pq) {
+            const int p = pq == 2 ? 1 : 0, q = pq == 0 ? 1 : 2;
+            const double apq = a[p * 3 + q];
+            if (std::fabs(apq) < 1e-300) continue;
+            const double theta = (a[q * 3 + q] - a[p * 3 + p]) / (2.0 * apq);
+            const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+            const double c = 1.0 / std::sqrt(t * t + 1.0), sn = t * c;
+            for (int k = 0; k < 3; ++k) {          // A <- A J
+                const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+                a[k * 3 + p] = c * akp - sn * akq;
+                a[k * 3 + q] = sn * akp + c * akq;
+            }
+            for (int k = 0; k < 3; ++k) {          // A <- J^T A
+                const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+                a[p * 3 + k] = c * apk - sn * aqk;
+                a[q * 3 + k] = sn * apk + c * aqk;
+            }
+            for (int k = 0; k < 3; ++k) {
+                const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+                v[k * 3 + p] = c * vkp - sn * vkq;
+                v[k * 3 + q] = sn * vkp + c * vkq;
+            }
+        }
+    }
+    int idx[3] = {0, 1, 2};
+    const double d[3] = {a[0], a[4], a[8]};
+    for (int i = 0; i < 3; ++i)
+        for (int j = i + 1; j < 3; ++j)
+            if (d[idx[j]] < d[idx[i]]) { const int t = idx[i]; idx[i] = idx[j]; idx[j] = t; }
+    double vv[9];
+    for (int i = 0; i < 3; ++i) {
+        w[i] = d[idx[i]];
+        for (int k = 0; k < 3; ++k) vv[k * 3 + i] = v[k * 3 + idx[i]];
+    }
+    for (int i = 0; i < 9; ++i) v[i] = vv[i];
+}
+
+// Crystal payload of a deflecting medium: eps18 = complex 3x3 already rotated into the shape
+// frame.  Real symmetric tensors with a twofold (or threefold) eigenvalue are uniaxial
+// (isotropic): eps = eps_o 1 + (eps_e - eps_o) a a^T (oracle/pyrate_np.py
+// uniaxial_decomposition); everything else is solved through the Fresnel quartic.
+static void pack_crystal(const double eps18[18], DAux &a) {
+    a.uniaxial = 0;
+    a.eps_o = a.eps_e = 0.0;
+    a.axis[0] = a.axis[1] = 0.0; a.axis[2] = 1.0;
+    double re[9], scale = 0.0, imag = 0.0;
+    for (int i = 0; i < 9; ++i) {
+        re[i] = eps18[2 * i];
+        scale = std::fmax(scale, std::fabs(re[i]));
+        imag = std::fmax(imag, std::fabs(eps18[2 * i + 1]));
+    }
+    const double tol = 1e-12;
+    if (!(scale > 0.0) || imag > tol * scale) return;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j)
+            if (std::fabs(re[i * 3 + j] - re[j * 3 + i]) > tol * scale) return;
+    double w[3], v[9];
+    jacobi3(re, w, v);
+    const bool lo_pair = std::fabs(w[0] - w[1]) <= tol * scale;
+    const bool hi_pair = std::fabs(w[2] - w[1]) <= tol * scale;
+    if (lo_pair && hi_pair) {                      // isotropic tensor: both sheets coincide
+        a.uniaxial = 1;
+        a.eps_o = a.eps_e = (w[0] + w[1] + w[2]) / 3.0;
+    } else if (lo_pair) {
+        a.uniaxial = 1;
+        a.eps_o = 0.5 * (w[0] + w[1]); a.eps_e = w[2];
+        for (int k = 0; k < 3; ++k) a.axis[k] = v[k * 3 + 2];
+    } else if (hi_pair) {
+        a.uniaxial = 1;
+        a.eps_o = 0.5 * (w[1] + w[2]); a.eps_e = w[0];
+        for (int k = 0; k < 3; ++k) a.axis[k] = v[k * 3 + 0];
+    }
+}
+
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // auxiliary records (DAux) a step needs in the launch: 0 for the lean case (conic shape,
@@ -842,7 +976,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
     for (int s = 0; s < n_steps; ++s) {
         const PyrStep &u = steps[s];
         DStep &d = P.steps[s];
-        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_COMBINATION) return PYR_E_UNSUPPORTED;
+        if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_CYLINDER) return PYR_E_UNSUPPORTED;
         const bool grid = u.shape_kind == PYR_SHAPE_GRIDSAG;
         const bool comb = u.shape_kind == PYR_SHAPE_COMBINATION;
         if (comb && (u.n_terms < 1 || u.n_terms > PYR_MAX_TERMS)) return PYR_E_BADARG;
@@ -871,7 +1005,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > 16) return PYR_E_BADARG;
         if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
         if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
-        if (u.split && s != n_steps - 1) return PYR_E_BADARG;
+        if (u.split && s != n_steps - 1 && !(flags & PYR_F_COMPLEX)) return PYR_E_BADARG;
         pack_frame(u.shape_frame, d.frame);
         d.curv = u.curv; d.cc = u.cc;
         if (u.aperture_kind == PYR_AP_CIRCULAR) {
@@ -947,6 +1081,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
             pack_frame(u.aperture_frame, a.aperture_frame);
             pack_medium(u.before, u.shape_frame, a.before);
             pack_medium(u.after, u.shape_frame, a.after);
+            if (u.after.kind == PYR_MEDIUM_ANISO) pack_crystal(a.after.eps, a);
             a.grid_tx = u.grid_tx; a.grid_ty = u.grid_ty; a.grid_c = u.grid_c;
             a.grid_nx = u.grid_nx; a.grid_ny = u.grid_ny;
             a.n_terms = 0;
@@ -1176,6 +1311,28 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t ma
         pyr::spot_sums_kernel<false><<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(x, ld, flags, mask, n,
                                                                                      sx, sy, sz, out8);
     cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? PYR_OK : (int)e;
+}
+
+int pyr_spot_points(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
+                    const PyrFrame *frame, double *xy, int64_t ld_out, int64_t *count, void *stream) {
+    if (!x || !xy || !count || n < 0 || ld_out < 0) return PYR_E_BADARG;
+    if (ld <= 0) ld = n;
+    cudaError_t e = cudaMemsetAsync(count, 0, sizeof(int64_t), (cudaStream_t)stream);
+    if (e != cudaSuccess) return (int)e;
+    if (n == 0) return PYR_OK;
+    pyr::DFrame f;
+    std::memset(&f, 0, sizeof(f));
+    if (frame) {
+        for (int i = 0; i < 9; ++i) f.r[i] = frame->r[i];
+        for (int i = 0; i < 3; ++i) f.o[i] = frame->o[i];
+    }
+    int64_t grid = (n + 255) / 256;
+    const int64_t cap = (int64_t)pyr::sm_count() * 8;
+    if (grid > cap) grid = cap;
+    pyr::spot_points_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>(
+        x, ld, flags, mask, n, f, frame ? 1 : 0, xy, ld_out, reinterpret_cast<unsigned long long *>(count));
+    e = cudaGetLastError();
     return e == cudaSuccess ? PYR_OK : (int)e;
 }
 

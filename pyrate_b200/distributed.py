@@ -52,25 +52,53 @@ def global_spot(x_last, flags_last=None, shift=None):
     return c, rms, float(host[3])
 
 
-def gather_spot_points(x_last, flags_last=None, dst=0):
-    """Spot-diagram points (x, y of surviving rays) of all ranks on `dst`
-    (16 B/ray over NVLink); returns a (2, N) tensor on dst, None elsewhere."""
-    xy = x_last[:2]
-    if flags_last is not None:
-        xy = xy[:, (flags_last & 2) != 0]
-    xy = xy.contiguous()
+class SpotPoints(object):
+    """Spot-diagram points of all ranks on the destination rank: `xy` (world, 2, width)
+    and `counts` (world,) int64, both on the device; columns [0, counts[r]) of block r are
+    rank r's points.  Nothing here synchronises with the host; `points()` does (it has to
+    know the total to allocate)."""
+
+    def __init__(self, xy, counts):
+        (self.xy, self.counts) = (xy, counts)
+
+    def points(self):
+        c = [int(v) for v in self.counts.tolist()]
+        return torch.cat([self.xy[r, :, :c[r]] for r in range(len(c))], dim=1)
+
+
+def gather_fixed_width(xy, count, dst=0, out=None):
+    """Gather every rank's (2, width) point buffer and its point count on `dst` (one
+    gather of fixed-width buffers + one of the counts: no host round trip, no ragged
+    sizes on the wire).  `width` must be the same on all ranks.  Returns SpotPoints on
+    dst, None elsewhere; a single process returns its own buffer."""
+    count = count.reshape(1)
     if not (dist.is_initialized() and dist.get_world_size() > 1):
-        return xy
+        return SpotPoints(xy[None], count)
     world = dist.get_world_size()
-    count = torch.tensor([xy.shape[1]], dtype=torch.int64, device=xy.device)
-    counts = [torch.zeros_like(count) for _ in range(world)]
-    dist.all_gather(counts, count)
-    width = int(max(int(c.item()) for c in counts))
-    padded = torch.zeros((2, width), dtype=xy.dtype, device=xy.device)
-    padded[:, :xy.shape[1]] = xy
-    bufs = [torch.empty_like(padded) for _ in range(world)] \
-        if dist.get_rank() == dst else None
-    dist.gather(padded, bufs, dst=dst)
-    if dist.get_rank() != dst:
-        return None
-    return torch.cat([b[:, :int(c.item())] for (b, c) in zip(bufs, counts)], dim=1)
+    me = dist.get_rank()
+    if me == dst:
+        if out is None:
+            out = SpotPoints(torch.empty((world,) + tuple(xy.shape), dtype=xy.dtype, device=xy.device),
+                             torch.empty((world,), dtype=count.dtype, device=count.device))
+        dist.gather(xy, list(out.xy.unbind(0)), dst=dst)
+        dist.gather(count, list(out.counts.split(1)), dst=dst)
+        return out
+    dist.gather(xy, None, dst=dst)
+    dist.gather(count, None, dst=dst)
+    return None
+
+
+def gather_spot_points(x_last, flags_last=None, dst=0, width=None, frame=None, out=None,
+                       local=None):
+    """Spot diagram of all ranks on `dst`: each rank compacts (x, y) of its surviving
+    rays on the device (pyr_spot_points: block-aggregated atomic cursor, count stays on
+    the device) into a buffer of `width` columns (default: this rank's ray count -- pass
+    the largest shard size when shards differ), then ONE fixed-width gather over
+    NVLink (16 B/ray) plus the counts.  `frame`: PyrFrame of the last surface (the
+    reference's get_spot reports local coordinates), None = global.  `local` / `out`:
+    reusable buffers (engine.spot_points output / SpotPoints) for benchmark loops."""
+    from . import engine
+    n = x_last.shape[1]
+    width = n if width is None else int(width)
+    (xy, count) = engine.spot_points(x_last, flags_last, frame=frame, width=width, out=local)
+    return gather_fixed_width(xy, count, dst=dst, out=out)

@@ -21,6 +21,7 @@ from .raytracer.ray import RayBundle, RayPath, as_tensor
 LD_ALIGN = 16           # doubles: rows start on 128-byte boundaries
 MAX_STEPS_PER_LAUNCH = 40       # kMaxSteps
 MAX_AUX_PER_LAUNCH = 10         # kMaxAux
+MAX_SPLITS_PER_LAUNCH = 6       # kMaxSplits (csrc/pyr_aniso.cu)
 
 
 def _needs_aux(st):
@@ -324,27 +325,31 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         if ls.st.after.kind == nat.MEDIUM_ANISO or ls.st.before.kind == nat.MEDIUM_ANISO:
             first_aniso = i
             break
+    # ONE launch per stretch: the complex-valued kernel walks the mode tree of every ray
+    # itself (birefringent interfaces double the rays inside the launch), so the only cut
+    # is where the run turns complex
     cuts = [0]
     if first_aniso is not None and first_aniso > 0:
         cuts.append(first_aniso)
-    for (i, ls) in enumerate(lowered):
-        if ls.st.split and i + 1 < nsteps:
-            cuts.append(i + 1)
-    # one launch carries at most MAX_STEPS_PER_LAUNCH entries and MAX_AUX_PER_LAUNCH
-    # entries with an auxiliary record (kernel parameter block, csrc/pyr_device.cuh);
-    # longer sequences continue from the last recorded state in a further launch
+    # one launch carries at most MAX_STEPS_PER_LAUNCH entries, MAX_AUX_PER_LAUNCH entries
+    # with an auxiliary record (kernel parameter block, csrc/pyr_device.cuh) and
+    # MAX_SPLITS_PER_LAUNCH doubling steps; longer sequences continue from the last
+    # recorded state in a further launch
     cuts = sorted(set(cuts)) + [nsteps]
     bounded = [0]
     for hi in cuts[1:]:
         lo = bounded[-1]
-        (count, aux) = (0, 0)
+        (count, aux, splits) = (0, 0, 0)
         for i in range(lo, hi):
             a = _needs_aux(lowered[i].st)
-            if count + 1 > MAX_STEPS_PER_LAUNCH or aux + a > MAX_AUX_PER_LAUNCH:
+            sp = int(bool(lowered[i].st.split))
+            if count + 1 > MAX_STEPS_PER_LAUNCH or aux + a > MAX_AUX_PER_LAUNCH or \
+                    splits + sp > MAX_SPLITS_PER_LAUNCH:
                 bounded.append(i)
-                (count, aux) = (0, 0)
+                (count, aux, splits) = (0, 0, 0)
             count += 1
             aux += a
+            splits += sp
         bounded.append(hi)
     cuts = bounded
 
@@ -393,22 +398,37 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
             want_e = record_e or seg_complex or \
                 (first_aniso is not None and hi == first_aniso)
             rows = hi - lo
-            last_split = bool(steps[hi - 1].split)
-            (xbuf, ld) = _alloc_rows(rows, n, device, pool=pool)
-            fbuf = _empty((rows, ld), torch.uint8, device, pool)
-            if last_split:
-                (kbuf, _) = _alloc_rows(max(rows - 1, 1), n, device, seg_complex, pool=pool)
-                ld2 = _round_up(2 * n, LD_ALIGN)
-                klast = _empty((3, ld2, 2), torch.float64, device, pool)
-                elast = _empty((3, ld2, 2), torch.float64, device, pool)
-            else:
+            any_split = any(bool(steps[i].split) for i in range(lo, hi))
+            # per-step record buffers.  Real stretches (never doubling): one allocation per
+            # array, `rows` records of the bundle's width.  Complex stretches: the width
+            # doubles behind every birefringent interface (hstack order: mode a of column c
+            # stays in c, mode b goes to w + c, material_anisotropic.py:89-100), so every
+            # step gets buffers of its own width.
+            bufs = []            # per step: (x (3, ld), flags (ld), k, e, w_in, w_out, ld, ld2)
+            if not any_split:
+                (xbuf, ld) = _alloc_rows(rows, n, device, pool=pool)
+                fbuf = _empty((rows, ld), torch.uint8, device, pool)
                 (kbuf, _) = _alloc_rows(rows, n, device, seg_complex, pool=pool)
-            ebuf = None
-            if want_e:
-                (ebuf, _) = _alloc_rows(rows, n, device, seg_complex, pool=pool)
+                ebuf = None
+                if want_e:
+                    (ebuf, _) = _alloc_rows(rows, n, device, seg_complex, pool=pool)
+                for r in range(rows):
+                    bufs.append((xbuf[r], fbuf[r], kbuf[r], ebuf[r] if ebuf is not None else None,
+                                 n, n, ld, ld))
+            else:
+                w = n
+                for i in range(lo, hi):
+                    w_out = 2 * w if steps[i].split else w
+                    (ld, ld2) = (_round_up(max(w, 1), LD_ALIGN), _round_up(max(w_out, 1), LD_ALIGN))
+                    bufs.append((_empty((3, ld), torch.float64, device, pool),
+                                 _empty((ld,), torch.uint8, device, pool),
+                                 _empty((3, ld2, 2), torch.float64, device, pool),
+                                 _empty((3, ld2, 2), torch.float64, device, pool),
+                                 w, w_out, ld, ld2))
+                    w = w_out
             for i in range(lo, hi):
                 st = steps[i]
-                r = i - lo
+                (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[i - lo]
                 (st.grin_hist_x, st.grin_hist_k, st.grin_hist_valid, st.grin_hist_count) = \
                     (None, None, None, None)
                 st.grin_hist_rows = 0
@@ -427,16 +447,12 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                         h["rows"] = m
                         h["n"] = n
                     rec.grin_hist[i] = h
-                st.out_x = xbuf[r].data_ptr()
-                st.out_flags = fbuf[r].data_ptr()
+                st.out_x = bx.data_ptr()
+                st.out_flags = bf.data_ptr()
+                st.out_k = bk.data_ptr()
+                st.out_e = be.data_ptr() if be is not None else None
                 st.ld_out = ld
-                if last_split and i == hi - 1:
-                    st.out_k = klast.data_ptr()
-                    st.out_e = elast.data_ptr()
-                    st.ld_out2 = ld2      # k / e of a split step are 2n wide
-                else:
-                    st.out_k = kbuf[r].data_ptr()
-                    st.out_e = ebuf[r].data_ptr() if ebuf is not None else None
+                st.ld_out2 = ld2        # k / e of a doubling step are 2 w wide
             flags = 0
             if seg_complex:
                 flags |= nat.F_COMPLEX | nat.F_RECORD_E
@@ -450,46 +466,30 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                     ld_k, flags, stream_ptr, events, wave_end=wave_end,
                     gen=gen_desc if ci == 0 else None, device=device)
             for i in range(lo, hi):
-                r = i - lo
-                rec.hit.append(xbuf[r, :, :n])
-                rec.flags.append(fbuf[r, :n])
-                rec.n_in.append(n)
-                if last_split and i == hi - 1:
-                    rec.k.append(torch.view_as_complex(klast)[:, :2 * n])
-                    rec.e.append(torch.view_as_complex(elast)[:, :2 * n])
-                    rec.n_out.append(2 * n)
-                    rec.split.append(True)
+                (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[i - lo]
+                rec.hit.append(bx[:, :w_in])
+                rec.flags.append(bf[:w_in])
+                rec.n_in.append(w_in)
+                rec.n_out.append(w_out)
+                rec.split.append(w_out != w_in)
+                if seg_complex:
+                    rec.k.append(torch.view_as_complex(bk)[:, :w_out])
+                    rec.e.append(torch.view_as_complex(be)[:, :w_out])
                 else:
-                    if seg_complex:
-                        rec.k.append(torch.view_as_complex(kbuf[r])[:, :n])
-                        rec.e.append(torch.view_as_complex(ebuf[r])[:, :n])
-                    else:
-                        rec.k.append(kbuf[r, :, :n])
-                        rec.e.append(ebuf[r, :, :n] if ebuf is not None else None)
-                    rec.n_out.append(n)
-                    rec.split.append(False)
+                    rec.k.append(bk[:, :w_out])
+                    rec.e.append(be[:, :w_out] if be is not None else None)
             # state handed to the next stretch
             if hi < nsteps:
-                r = hi - 1 - lo
-                cur_x = xbuf[r]
-                ld_x = ld
-                cur_alive = fbuf[r]
-                if last_split:
-                    (cur_k, cur_e) = (klast, elast)
-                    ld_k = _round_up(2 * n, LD_ALIGN)
-                    n_x = n
-                    n = 2 * n
-                    if ld_k != ld_x:
-                        # x / alive are read with column i % n_x from rows of
-                        # leading dimension ld_k: re-pad to the common ld
-                        nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
-                        nx[:, :n_x] = cur_x[:, :n_x]
-                        (cur_x, ld_x) = (nx, ld_k)
-                else:
-                    cur_k = kbuf[r]
-                    cur_e = ebuf[r] if ebuf is not None else None
-                    ld_k = ld
-                    n_x = n
+                (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[-1]
+                (cur_x, ld_x, cur_alive) = (bx, ld, bf)
+                (cur_k, cur_e, ld_k) = (bk, be, ld2)
+                (n_x, n) = (w_in, w_out)
+                if ld_k != ld_x:
+                    # x / alive are read with column i % n_x from rows of leading
+                    # dimension ld_k: re-pad to the common ld
+                    nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
+                    nx[:, :n_x] = cur_x[:, :n_x]
+                    (cur_x, ld_x) = (nx, ld_k)
     if grin_history and _hist_rows is None and rec.grin_hist:
         # first pass gave the step counts; second pass records the rows
         rows = {i: int(h["count"].max().item()) if h["count"].numel() else 0
@@ -1000,6 +1000,31 @@ def spot_sums(x, flags=None, mask=nat.RAY_ALIVE, out=None, shift=None):
                                     flags.data_ptr() if flags is not None else None,
                                     mask, n, sh, out.data_ptr(), stream))
     return out
+
+
+def spot_points(x, flags=None, mask=nat.RAY_ALIVE, frame=None, width=None, out=None):
+    """(x, y) of the rays with `flags & mask` (flags None = all), compacted on the device:
+    returns (xy (2, width) float64, count () int64), both CUDA tensors -- the count is NOT
+    read back.  frame: nat.PyrFrame of the surface whose local coordinates are wanted
+    (OpticalSystemAnalysis.get_spot, reference :283-303), None = global.  Point order is
+    unspecified.  out: (xy, count) from a previous call to reuse."""
+    lib = require_cuda()
+    dev = x.device
+    assert x.dim() == 2 and x.shape[0] == 3 and x.stride(1) == 1
+    n = x.shape[1]
+    width = n if width is None else int(width)
+    if out is None:
+        out = (torch.empty((2, max(width, 1)), dtype=torch.float64, device=dev),
+               torch.zeros((), dtype=torch.int64, device=dev))
+    (xy, count) = out
+    assert xy.shape[1] >= min(width, max(n, 1)) and xy.is_contiguous()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    with torch.cuda.device(dev):
+        nat.check(lib.pyr_spot_points(x.data_ptr(), x.stride(0),
+                                      flags.data_ptr() if flags is not None else None,
+                                      mask, n, C.byref(frame) if frame is not None else None,
+                                      xy.data_ptr(), xy.shape[1], count.data_ptr(), stream))
+    return xy, count
 
 
 def spot_from_sums(s, shift=None):

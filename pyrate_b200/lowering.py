@@ -216,9 +216,12 @@ def _simple_shape(shape):
     d = {"curv": 0.0, "cc": 0.0, "curv2": 0.0, "cc2": 0.0, "normradius": 1.0,
          "n_coeff": 0, "coeff": [], "xpow": [], "ypow": [], "grid": None}
     if "Cylinder" in names:
-        raise LoweringError("Cylinder is dead code in the reference "
-                            "(surface_shape.py:367-388) and not supported")
-    if "Conic" in names:
+        # surface_shape.py:328-388: a Conic subclass whose own intersect is dead code in
+        # the reference (AttributeError at :380); traced with the corrected quadratic
+        d["kind"] = nat.SHAPE_CYLINDER
+        d["curv"] = _value(shape.curvature)
+        d["cc"] = _value(shape.conic)
+    elif "Conic" in names:
         d["kind"] = nat.SHAPE_CONIC
         d["curv"] = _value(shape.curvature)
         d["cc"] = _value(shape.conic)
@@ -328,7 +331,7 @@ def lower_surface(surface, st):
         for (i, c) in enumerate(d["coeff"]):
             (st.coeff[i], st.xpow[i], st.ypow[i]) = (c, d["xpow"][i], d["ypow"][i])
         st._grid = d["grid"]
-    if st.shape_kind != nat.SHAPE_CONIC:
+    if st.shape_kind not in (nat.SHAPE_CONIC, nat.SHAPE_CYLINDER):
         ann = getattr(shape, "annotations", {})
         # The reference's fsolve stops at xtol = annotations["tol"] (1e-6) but
         # lands at ~1e-15 residual; Newton is run to machine precision and

@@ -60,7 +60,23 @@ def _n_formula7(c, w):          # Herzberger
     return c[0] + c[1] / den + c[2] / den ** 2 + np.sum(a * w ** p)
 
 
-_FORMULAS = {"formula 1": _n_formula1, "formula 2": _n_formula2, "formula 3": _n_formula3,
+def _n_formula8(c, w):
+    """Retro: (n^2 - 1) / (n^2 + 2) = C1 + C2 w^2 / (w^2 - C3) + C4 w^2 (the database's
+    "Dispersion formulas" document; the reference declares the type but raises
+    NotImplementedError when it is evaluated, material_glasscat.py:403-407)."""
+    c = np.concatenate((c, np.zeros(max(0, 4 - len(c)))))
+    q = c[0] + c[1] * w ** 2 / (w ** 2 - c[2]) + c[3] * w ** 2
+    return np.sqrt((1 + 2 * q) / (1 - q))
+
+
+def _n_formula9(c, w):
+    """Exotic: n^2 = C1 + C2 / (w^2 - C3) + C4 (w - C5) / ((w - C5)^2 + C6) (same document;
+    NotImplementedError in the reference, :409-413)."""
+    c = np.concatenate((c, np.zeros(max(0, 6 - len(c)))))
+    return np.sqrt(c[0] + c[1] / (w ** 2 - c[2]) + c[3] * (w - c[4]) / ((w - c[4]) ** 2 + c[5]))
+
+
+_FORMULAS = {"formula 8": _n_formula8, "formula 9": _n_formula9, "formula 1": _n_formula1, "formula 2": _n_formula2, "formula 3": _n_formula3,
              "formula 4": _n_formula4, "formula 5": _n_formula5, "formula 6": _n_formula6,
              "formula 7": _n_formula7}
 
@@ -72,8 +88,6 @@ class IndexFormulaContainer(object):
         self.typ = typ
         self.coeff = np.asarray(coeff, dtype=float)
         self.waverange = np.asarray(waverange, dtype=float)
-        if typ in ("formula 8", "formula 9"):
-            raise NotImplementedError("dispersion %r (as in the reference)" % (typ,))
         if not (typ in _FORMULAS or typ.startswith("tabulated")):
             raise Exception("Bad dispersion function type: " + str(typ))
 

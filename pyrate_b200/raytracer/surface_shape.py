@@ -93,6 +93,29 @@ class Conic(Shape):
         return h
 
 
+class Cylinder(Conic):
+    """Conic section in y, extruded along x (reference surface_shape.py:328-388).  Sag and
+    `.p` as in the reference; gradient / Hessian of the actual surface (the reference
+    inherits Conic's rotationally symmetric ones, inconsistent with its own sag)."""
+
+    def setKind(self):
+        self.kind = "shape_Cylinder"
+
+    def getSag(self, x, y):
+        return self.conic_function(y * y + 0 * x)
+
+    def getGrad(self, x, y):
+        xp = _lib(x)
+        (curv, cc) = (self.curvature(), self.conic())
+        z = self.getSag(x, y)
+        return xp.stack((0 * x, -curv * y, 1. - curv * z * (1 + cc)))
+
+    def getHessian(self, x, y):
+        h = super(Cylinder, self).getHessian(x, y)
+        h[0, 0] = 0
+        return h
+
+
 class FreeShape(Shape):
 
     @staticmethod
@@ -545,7 +568,7 @@ class LinearCombination(ExplicitShape):
                    zip(self.annotations["list_shape_coefficients"], self.list_shapes))
 
 
-accessible_shapes = {"shape_Conic": Conic, "shape_Asphere": Asphere,
+accessible_shapes = {"shape_Conic": Conic, "shape_Cylinder": Cylinder, "shape_Asphere": Asphere,
                      "shape_Biconic": Biconic, "shape_XYPolynomials": XYPolynomials,
                      "shape_ZernikeFringe": ZernikeFringe, "shape_ZernikeANSI": ZernikeANSI,
                      "shape_GridSag": GridSag,

@@ -32,11 +32,20 @@ def _worker(rank, world, port, xfile, out):
     np.save(out % rank, np.array(list(c) + [rms, sums[3].item(), lo, hi]))
     # the optional spot-diagram gather (BASELINE config 5: "NCCL spot gather"): surviving
     # rays of every rank, ragged widths, on rank 0
+    # (the compaction itself is the native kernel pyr_spot_points on the GPU box; here the
+    # fixed-width buffer + count are made with torch and the COLLECTIVE logic is tested)
     flags = torch.full((xs.shape[1],), 3, dtype=torch.uint8)
     flags[rank::3] = 1                                    # HIT but not ALIVE: dropped
-    pts = pd.gather_spot_points(xs, flags, dst=0)
+    keep = (flags & 2) != 0
+    width = (x.shape[1] + world - 1) // world             # largest shard: same on all ranks
+    xy = torch.zeros((2, width), dtype=torch.float64)
+    xy[:, :int(keep.sum())] = xs[:2][:, keep]
+    pts = pd.gather_fixed_width(xy, keep.sum().to(torch.int64), dst=0)
     if rank == 0:
-        np.save(out % 99, pts.numpy())
+        assert pts.xy.shape == (world, 2, width) and pts.counts.tolist() == \
+            [int(((torch.arange(hi_ - lo_) % 3) != r).sum())
+             for (r, (lo_, hi_)) in enumerate(pd.shard_range(x.shape[1], q, world) for q in range(world))]
+        np.save(out % 99, pts.points().numpy())
     else:
         assert pts is None
     dist.barrier()

@@ -201,3 +201,45 @@ def test_host_entry_continues_long_sequences():
         if all_records:
             for s_ in (0, 17, 39, 40, 54):
                 assert util.relerr(ht.x_all[s_].numpy(), rec.hit[s_].cpu().numpy()) < 1e-13, s_
+
+
+def test_spot_points_compaction_on_device():
+    """pyr_spot_points: (x, y) of the surviving rays, compacted without a host round trip;
+    as a point SET equal to the NumPy selection, in global and in last-surface coordinates
+    (OpticalSystemAnalysis.get_spot, reference :283-303)."""
+    import torch
+    from pyrate_b200 import distributed as pd
+    from pyrate_b200 import engine, lowering
+    spec = configs.CONFIGS["x3_vignette"]                       # rays are dropped on the way
+    (x0, k0, e0) = configs.config_bundle(spec, 60)              # 10 981 rays
+    (s, seq) = configs.build_system(spec, pb.api())
+    lowered = lowering.lower(s, seq, configs.DLINE)
+    rec = engine.trace(lowered, x0, k0, e0, configs.DLINE)
+    (hit, fl) = (rec.hit[-1], rec.flags[-1])
+    keep = ((fl & 2) != 0).cpu().numpy()
+    assert 0 < keep.sum() < keep.size
+    want = hit.cpu().numpy()[:2][:, keep]
+
+    def as_set(a):
+        return a[:, np.lexsort((a[1], a[0]))]
+    (xy, count) = engine.spot_points(hit, fl)
+    assert int(count) == keep.sum()
+    assert np.array_equal(as_set(xy[:, :int(count)].cpu().numpy()), as_set(want))
+    frame = lowered[-1].st.shape_frame
+    (xyl, count2) = engine.spot_points(hit, fl, frame=frame)
+    o = np.array(list(frame.o))
+    r = np.array(list(frame.r)).reshape(3, 3)
+    local = (r.T @ (hit.cpu().numpy() - o[:, None]))[:2][:, keep]
+    got = as_set(xyl[:, :int(count2)].cpu().numpy())
+    assert np.max(np.abs(got - as_set(local))) < 1e-12
+    # too narrow a buffer: counted, not stored beyond the width
+    (xy3, count3) = engine.spot_points(hit, fl, width=100)
+    assert int(count3) == keep.sum() and xy3.shape == (2, 100)
+    # single-process "gather": same container the multi-rank path returns
+    pts = pd.gather_spot_points(hit, fl)
+    assert pts.xy.shape[0] == 1 and np.array_equal(as_set(pts.points().cpu().numpy()), as_set(want))
+    # odd sizes and no flags
+    for n in (1, 255, 256, 257, 1000):
+        (xy4, c4) = engine.spot_points(hit[:, :n])
+        assert int(c4) == n
+        assert np.array_equal(as_set(xy4[:, :n].cpu().numpy()), as_set(hit[:2, :n].cpu().numpy()))
