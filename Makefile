@@ -19,7 +19,7 @@ TOOLS_OUT := pyrate_b200/_lib/libpyrate_b200_tools.so
 tools: $(TOOLS_OUT)
 $(TOOLS_OUT): $(SRC) $(HDR)
 	@mkdir -p pyrate_b200/_lib
-	$(NVCC) $(NVFLAGS) -DPYR_TOOLS -shared -o $@ $(SRC) 2> pyrate_b200/_lib/ptxas_tools.log || (cat pyrate_b200/_lib/ptxas_tools.log; exit 1)
+	$(NVCC) $(NVFLAGS) -DPYR_TOOLS $(TOOLS_DEFS) -shared -o $@ $(SRC) 2> pyrate_b200/_lib/ptxas_tools.log || (cat pyrate_b200/_lib/ptxas_tools.log; exit 1)
 
 clean:
 	rm -rf pyrate_b200/_lib

@@ -334,12 +334,17 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
     const bool sec1 = same(xi1, xi0);
     const bool sec2 = same(xi2, xi0) != same(xi2, xi1);
     const bool sec3 = (same(xi3, xi0) != same(xi3, xi1)) != same(xi3, xi2);
-    // pass 1: sort keys S.n with the reference's eigenvector normalisation
-    double key0, key1, key2, key3, w;
-    key0 = mode_key<UNI>(ax, p, nrm, xi0, false, false, ka, ea, w);
-    key1 = mode_key<UNI>(ax, p, nrm, xi1, false, sec1, ka, ea, w);
-    key2 = mode_key<UNI>(ax, p, nrm, xi2, true, sec2, ka, ea, w);
-    key3 = mode_key<UNI>(ax, p, nrm, xi3, true, sec3, ka, ea, w);
+    // pass 1: sort keys S.n with the reference's eigenvector normalisation.  A rolled
+    // loop (one copy of the mode evaluation in the instruction stream, not four: the kernel
+    // was stalling on instruction fetch, profiles/r02_c4.md)
+    double key0 = 0.0, key1 = 0.0, key2 = 0.0, key3 = 0.0, w;
+#pragma unroll 1
+    for (int mi = 0; mi < 4; ++mi) {
+        const cplx xim = mi == 0 ? xi0 : (mi == 1 ? xi1 : (mi == 2 ? xi2 : xi3));
+        const bool secm = mi == 1 ? sec1 : (mi == 2 ? sec2 : (mi == 3 ? sec3 : false));
+        const double key = mode_key<UNI>(ax, p, nrm, xim, mi >= 2, secm, ka, ea, w);
+        if (mi == 0) key0 = key; else if (mi == 1) key1 = key; else if (mi == 2) key2 = key; else key3 = key;
+    }
     // stable ascending rank of every key (what the reference's argsort gives)
     const int r0 = (key1 < key0) + (key2 < key0) + (key3 < key0);
     const int r1 = (key0 <= key1) + (key2 < key1) + (key3 < key1);
@@ -352,10 +357,20 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
     else if (r3 == ra) { xa = xi3; seca = sec3; }
     if (r0 == rb) { xb = xi0; secb = false; exb = false; } else if (r1 == rb) { xb = xi1; secb = sec1; exb = false; }
     else if (r2 == rb) { xb = xi2; secb = sec2; }
-    // pass 2: the two selected modes
-    double wa, wb;
-    mode_key<UNI>(ax, p, nrm, xa, exa, seca, ka, ea, wa);
-    mode_key<UNI>(ax, p, nrm, xb, exb, secb, kb, eb, wb);
+    // pass 2: the two selected modes (same rolled evaluation; mode b first, it lands in kb / eb)
+    double wa = 0.0, wb = 0.0;
+#pragma unroll 1
+    for (int mi = 0; mi < 2; ++mi) {
+        const bool second_mode = mi == 0;
+        mode_key<UNI>(ax, p, nrm, second_mode ? xb : xa, second_mode ? exb : exa,
+                      second_mode ? secb : seca, ka, ea, w);
+        if (second_mode) {
+            for (int i = 0; i < 3; ++i) { kb[i] = ka[i]; eb[i] = ea[i]; }
+            wb = w;
+        } else {
+            wa = w;
+        }
+    }
     const double sgn = mirror ? -1.0 : 1.0;
     const double sa = sgn * sqrt(wa), sb = sgn * sqrt(wb);
     for (int i = 0; i < 3; ++i) {
@@ -375,8 +390,13 @@ __device__ __forceinline__ cplx cload(const double *base, int64_t idx) {
 // split bookkeeping of a launch: step indices of the doubling steps (at most kMaxSplits)
 constexpr int kMaxSplits = 6;
 
-template <bool GENERAL_EPS>
-__global__ void __launch_bounds__(128, GENERAL_EPS ? 2 : 3)
+// EXPLICIT: explicit shapes (asphere / XY polynomial / biconic Newton) present; crystals
+// between conics -- the common case -- run an instantiation without that code
+#ifndef PYR_C4_MINB
+#define PYR_C4_MINB 3          // resident CTAs per SM of the uniaxial kernel (tools builds vary it)
+#endif
+template <bool GENERAL_EPS, bool EXPLICIT>
+__global__ void __launch_bounds__(128, GENERAL_EPS ? 2 : PYR_C4_MINB)
 trace_complex_kernel(const __grid_constant__ LaunchParams P) {
     const int64_t n = P.n;
     // doubling steps of this launch, in order (uniform over the grid)
@@ -454,7 +474,8 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 if (st.bits & kNoIntersect) tt = 0.0;        // stand-alone refract / reflect: x is the hit point
                 else if (st.shape_kind == PYR_SHAPE_CONIC) tt = conic_t(st.curv, st.cc, r0, dl, hit_ok);
                 else if (st.shape_kind == PYR_SHAPE_CYLINDER) tt = cylinder_t(st.curv, st.cc, r0, dl, hit_ok);
-                else { double gfx, gfy; bool gok; tt = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
+                else if (EXPLICIT) { double gfx, gfy; bool gok; tt = explicit_t<false>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, gok); }
+                else tt = qnan();
                 const double h[3] = {fma(dl[0], tt, r0[0]), fma(dl[1], tt, r0[1]), fma(dl[2], tt, r0[2])};
                 double hit_g[3];
                 l2g_point(st.frame, h, hit_g);
@@ -481,8 +502,10 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                     conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
                 else if (st.shape_kind == PYR_SHAPE_CYLINDER)
                     cylinder_normal(st.curv, st.cc, h[1], nrm);
-                else
+                else if (EXPLICIT)
                     explicit_normal<false>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+                else
+                    nrm[0] = nrm[1] = nrm[2] = qnan();
 
                 cplx kl[3];
                 crot_t(st.frame.r, k, kl);
@@ -596,7 +619,7 @@ int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, 
     if (!rays->e) return PYR_E_BADARG;            // E defines the ray direction in crystals
     if (rays->n_waves > 1) return PYR_E_UNSUPPORTED;
     int splits = 0;
-    bool general_eps = false;
+    bool general_eps = false, explicit_shapes = false;
     for (int s = 0; s < n_steps; ++s) {
         if (steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN)
             return PYR_E_UNSUPPORTED;
@@ -608,11 +631,19 @@ int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, 
                 return PYR_E_BADARG;
         }
         if (deflects && P.steps[s].aux >= 0 && !P.aux[P.steps[s].aux].uniaxial) general_eps = true;
+        if (steps[s].shape_kind != PYR_SHAPE_CONIC && steps[s].shape_kind != PYR_SHAPE_CYLINDER &&
+            steps[s].mode != PYR_STEP_DEFLECT_ONLY)
+            explicit_shapes = true;
+        if (steps[s].shape_kind != PYR_SHAPE_CONIC && steps[s].shape_kind != PYR_SHAPE_CYLINDER)
+            explicit_shapes = true;             // (the normal of a deflect-only step needs it too)
     }
     if (splits > kMaxSplits) return PYR_E_TOOLARGE;
     if (n_rays == 0) return PYR_OK;
-    return general_eps ? launch_complex(trace_complex_kernel<true>, P, n_rays, stream)
-                       : launch_complex(trace_complex_kernel<false>, P, n_rays, stream);
+    if (explicit_shapes)
+        return general_eps ? launch_complex(trace_complex_kernel<true, true>, P, n_rays, stream)
+                           : launch_complex(trace_complex_kernel<false, true>, P, n_rays, stream);
+    return general_eps ? launch_complex(trace_complex_kernel<true, false>, P, n_rays, stream)
+                       : launch_complex(trace_complex_kernel<false, false>, P, n_rays, stream);
 }
 
 }  // namespace pyr

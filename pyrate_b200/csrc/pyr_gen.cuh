@@ -35,18 +35,20 @@ __device__ __forceinline__ void gen_point(const DGen &g, int64_t idx, double &px
     if (g.raster == PYR_RASTER_HEXAPOLAR) {
         if (idx <= 0) { px = 0.0; py = 0.0; return; }
         // ring j holds the indices [1 + 3 (j - 1) j, 1 + 3 j (j + 1))
-        int64_t j = (int64_t)floor((3.0 + sqrt(9.0 + 12.0 * (double)(idx - 1))) / 6.0);
+        // branch-free approximations + exact integer fix-up; the angle 2 pi i / (6 j) is
+        // evaluated as sincospi(i / (3 j)) (no Payne-Hanek reduction in the instruction
+        // stream: the generating kernels must stay small); <= 2 ulp from the host raster
+        int64_t j = (int64_t)((3.0 + fast_sqrt(9.0 + 12.0 * (double)(idx - 1))) * (1.0 / 6.0));
         if (j < 1) j = 1;
         if (idx < 1 + 3 * (j - 1) * j) --j;
         if (idx >= 1 + 3 * j * (j + 1)) ++j;
         const int64_t i = idx - (1 + 3 * (j - 1) * j);
-        const double ang = __ddiv_rn(__dmul_rn(6.283185307179586, (double)i),
-                                     __dmul_rn(6.0, (double)j));
-        const double rad = __ddiv_rn((double)j, (double)(g.param > 0 ? g.param : 1));
+        const double frac = fast_div((double)i, 3.0 * (double)j);
+        const double rad = (double)j * g.aux0;                      // aux0 = 1 / rings
         double s, c;
-        sincos(ang, &s, &c);
-        px = __dmul_rn(rad, c);
-        py = __dmul_rn(rad, s);
+        sincospi(frac, &s, &c);
+        px = rad * c;
+        py = rad * s;
     } else if (g.raster == PYR_RASTER_RECT) {
         const int64_t nrows = g.param;
         const int64_t r = gen_row_of(g.rows, nrows, idx);
@@ -74,9 +76,13 @@ __device__ __forceinline__ void gen_point(const DGen &g, int64_t idx, double &px
     }
 }
 
-// ray `i` of the call: x, k, e (global frame)
-__device__ __forceinline__ void gen_ray(const DGen &g, int64_t i, double x[3], double k[3],
-                                        double e[3]) {
+struct GenRay {
+    double x[3], k[3], e[3];
+};
+
+// ray `i` of the call: x, k, e (global frame) -- every raster / bundle kind
+__device__ __forceinline__ void gen_ray_any(const DGen &g, int64_t i, double x[3], double k[3],
+                                            double e[3]) {
     double px, py;
     gen_point(g, g.first + i, px, py);
     double d[3];
@@ -114,6 +120,45 @@ __device__ __forceinline__ void gen_ray(const DGen &g, int64_t i, double x[3], d
     } else {
         e[0] = g.e[0]; e[1] = g.e[1]; e[2] = g.e[2];
     }
+}
+
+// the general generator behind a call (results by value: registers), so that the trace
+// kernels inline only the hexapolar / collimated / fixed-field case of BASELINE's bundles
+// and stay small (instruction cache)
+__device__ __noinline__ GenRay gen_ray_call(const DGen &g, int64_t i) {
+    GenRay r;
+    gen_ray_any(g, i, r.x, r.k, r.e);
+    return r;
+}
+
+__device__ __forceinline__ void gen_ray(const DGen &g, int64_t i, double x[3], double k[3],
+                                        double e[3]) {
+    if (g.raster == PYR_RASTER_HEXAPOLAR && g.bundle == PYR_BUNDLE_COLLIMATED &&
+        !(g.flags & PYR_GEN_E_PERP)) {
+        const int64_t idx = g.first + i;
+        double px = 0.0, py = 0.0;
+        if (idx > 0) {
+            int64_t j = (int64_t)((3.0 + fast_sqrt(9.0 + 12.0 * (double)(idx - 1))) * (1.0 / 6.0));
+            if (j < 1) j = 1;
+            if (idx < 1 + 3 * (j - 1) * j) --j;
+            if (idx >= 1 + 3 * j * (j + 1)) ++j;
+            const int64_t m = idx - (1 + 3 * (j - 1) * j);
+            double s, c;
+            sincospi(fast_div((double)m, 3.0 * (double)j), &s, &c);
+            const double rad = (double)j * g.aux0;
+            px = rad * c;
+            py = rad * s;
+        }
+        x[0] = __dadd_rn(__dmul_rn(g.radius, px), g.start[0]);
+        x[1] = __dadd_rn(__dmul_rn(g.radius, py), g.start[1]);
+        x[2] = g.start[2];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { k[c] = __dmul_rn(g.n_index, g.dir[c]); e[c] = g.e[c]; }
+        return;
+    }
+    const GenRay r = gen_ray_call(g, i);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { x[c] = r.x[c]; k[c] = r.k[c]; e[c] = r.e[c]; }
 }
 
 }  // namespace pyr

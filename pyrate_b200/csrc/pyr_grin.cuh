@@ -8,15 +8,18 @@
 // lock-step with the slowest ray of the bundle.
 #pragma once
 
+#include "pyr_exp.cuh"
 #include "pyr_shapes.cuh"
 
 namespace pyr {
 
 // index n and gradient at material-frame position q
+// etab: the 2^(j/32) table of pyr_exp.cuh in shared memory
 __device__ __forceinline__ double grin_index(const DMedium &m, const double q[3], double g[3],
-                                             bool want_grad) {
+                                             bool want_grad, const double *etab) {
     if (m.profile == PYR_GRIN_GAUSSIAN_XY) {
-        const double ex = m.p[1] * exp(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]));
+        const double arg = -fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]);
+        const double ex = m.p[1] * (exp_tab_ok(arg) ? exp_tab(arg, etab) : exp(arg));
         if (want_grad) {
             g[0] = -2.0 * m.p[2] * q[0] * ex;
             g[1] = -2.0 * m.p[3] * q[1] * ex;
@@ -57,7 +60,8 @@ template <bool EXT>
 __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind, const DAux *aux,
                                                double curv, double cc, double x[3],
                                                const double d[3], double k[3],
-                                               int64_t ray_index, int64_t ld_hist) {
+                                               int64_t ray_index, int64_t ld_hist,
+                                               const double *etab) {
     const double c0 = 1.0 / (2.0 * (2.0 - 1.2599210498948732));
     const double c1 = (1.0 - 1.2599210498948732) / (2.0 * (2.0 - 1.2599210498948732));
     const double d0 = 1.0 / (2.0 - 1.2599210498948732);
@@ -71,7 +75,7 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
     double q[3], p[3], g[3];
     g2l_point(m.frame, x, q);
     rot_t(m.frame.r, d, p);
-    const double n0 = grin_index(m, q, g, false);
+    const double n0 = grin_index(m, q, g, false, etab);
     p[0] *= n0; p[1] *= n0; p[2] *= n0;
     double uq[3] = {q[0], q[1], q[2]}, up[3] = {p[0], p[1], p[2]};
     const double tau2 = 2.0 * m.ds;
@@ -84,7 +88,7 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
             q[0] = fma(tau2 * cs[s], p[0], q[0]);
             q[1] = fma(tau2 * cs[s], p[1], q[1]);
             q[2] = fma(tau2 * cs[s], p[2], q[2]);
-            nq = grin_index(m, q, g, s < 3);
+            nq = grin_index(m, q, g, s < 3, etab);
             if (s < 3) {
                 const double f = tau2 * ds[s] * nq;
                 p[0] = fma(f, g[0], p[0]);
@@ -107,7 +111,7 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
         if (aux->hist_count && ray_index >= 0) aux->hist_count[ray_index] = it + 1;
         if (aux->hist_x && ray_index >= 0 && it < aux->hist_rows) {
             double gq[3], kq[3], kg[3], dummy[3];
-            const double invn = 1.0 / grin_index(m, uq, dummy, false);
+            const double invn = 1.0 / grin_index(m, uq, dummy, false, etab);
             kq[0] = up[0] * invn; kq[1] = up[1] * invn; kq[2] = up[2] * invn;
             l2g_point(m.frame, uq, gq);
             rot(m.frame.r, kq, kg);
@@ -119,7 +123,7 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
         }
         if (stop) break;
     }
-    const double inv = 1.0 / grin_index(m, uq, g, false);
+    const double inv = 1.0 / grin_index(m, uq, g, false, etab);
     const double kl[3] = {up[0] * inv, up[1] * inv, up[2] * inv};
     l2g_point(m.frame, uq, x);
     rot(m.frame.r, kl, k);

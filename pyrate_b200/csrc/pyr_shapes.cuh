@@ -293,6 +293,72 @@ __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double cur
     return t;
 }
 
+// Even asphere (the common explicit shape): value, gradient factor dr (dF/dx = x dr,
+// dF/dy = y dr) and its derivative ddr = d(dr)/d(r^2) in one Horner pass.
+__device__ __forceinline__ void asphere_eval2(const DAux &a, double curv, double cc, double r2,
+                                              double &F, double &dr, double &ddr) {
+    const double K = curv * curv * (1.0 + cc);
+    double rsq;
+    const double sq = fast_sqrt_r(fma(-K, r2, 1.0), rsq);            // NaN outside
+    double p = 0.0, dp = 0.0, hp = 0.0;                              // p, p', p''/2
+    for (int i = a.n_coeff - 1; i >= 0; --i) {
+        hp = fma(hp, r2, dp);
+        dp = fma(dp, r2, p);
+        p = fma(p, r2, a.coeff[i]);
+    }
+    F = fma(curv * r2, fast_rcp(1.0 + sq), r2 * p);
+    dr = fma(curv, rsq, 2.0 * fma(r2, dp, p));
+    // d/dr2 [c / sq] = c K / (2 sq^3);  d/dr2 [2 (p + r2 p')] = 2 (2 p' + r2 p'')
+    ddr = fma(0.5 * curv * K, rsq * rsq * rsq, 4.0 * fma(r2, hp, dp));
+}
+
+// Newton for the even asphere, seeded with the base-conic hit.  Newton converges
+// quadratically: step_(k+1) ~ C step_k^2 with C estimated from the last two steps, so
+// once the PREDICTED next step is below the tolerance the iteration stops without the
+// confirming evaluation (two shape evaluations instead of three for a typical asphere)
+// and the gradient at the final point is obtained from the last evaluation to first order
+// in the (tiny) last step -- the omitted terms are O(step^2) ~ 1e-16.
+__device__ __forceinline__ double asphere_t(const DAux &a, double curv, double cc,
+                                            const double r0[3], const double d[3], bool active,
+                                            double &gx, double &gy, bool &grad_ok) {
+    bool ok;
+    double t = conic_t(curv, cc, r0, d, ok);
+    if (!isfinite(t)) t = 0.0;
+    grad_ok = false;
+    gx = gy = 0.0;
+    double prev = 0.0;                                   // |previous step|, 0 = none yet
+    for (int it = 0; it < a.newton_maxit; ++it) {
+        const double x = fma(t, d[0], r0[0]);
+        const double y = fma(t, d[1], r0[1]);
+        const double r2 = fma(x, x, y * y);
+        double F, dr, ddr;
+        asphere_eval2(a, curv, cc, r2, F, dr, ddr);
+        const double res = fma(t, d[2], r0[2]) - F;
+        const double xy = fma(x, d[0], y * d[1]);
+        const double dres = fma(-dr, xy, d[2]);
+        double step = fast_div(res, dres);
+        const bool bad = !isfinite(step);
+        if (bad) step = 0.0;
+        t -= step;
+        const double as = fabs(step), lim = a.newton_tol * (1.0 + fabs(t));
+        const bool conv = as <= lim;
+        // predicted next step |step|^2 C, C = |step| / prev^2; two orders of safety
+        const bool early = !conv && prev > 0.0 && as * as * as <= 0.01 * lim * prev * prev;
+        if (conv) {
+            gx = x * dr; gy = y * dr;                    // within tol of the returned point
+        } else if (early) {
+            const double xn = fma(-step, d[0], x), yn = fma(-step, d[1], y);
+            const double drn = fma(ddr, fma(xn, xn, yn * yn) - r2, dr);
+            gx = xn * drn; gy = yn * drn;
+        }
+        grad_ok = (conv || early) && !bad;
+        prev = as;
+        const bool done = bad || !active || conv || early;
+        if (__all_sync(__activemask(), done)) break;
+    }
+    return t;
+}
+
 // unit normal of an explicit shape: grad = (-Fx, -Fy, 1)/|.|  (FreeShape.getGrad :420-423)
 template <bool EXT>
 __device__ __forceinline__ void explicit_normal(int kind, const DAux &a, double curv, double cc,

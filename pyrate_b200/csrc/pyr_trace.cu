@@ -129,10 +129,14 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
 }
 
 // One sequence entry for one ray (real k, E).  Returns the flag byte.
-template <bool WITH_E, bool HAS_GRIN, bool EXT>
+// ASPH: the only explicit shape of the sequence is the even asphere -- the instantiation
+// carries neither the XY-polynomial / biconic evaluators nor the generic Newton loop (small
+// enough to stay resident in the instruction cache) and uses asphere_t
+template <bool WITH_E, bool HAS_GRIN, bool EXT, bool ASPH = false>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
                                               Ray<WITH_E> &r, double d[3], double hit_g[3],
-                                              int64_t ray_index, int w = 0) {
+                                              int64_t ray_index, int w = 0,
+                                              const double *etab = nullptr) {
     constexpr bool GENERAL = true;
     const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
@@ -140,7 +144,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
     if (HAS_GRIN && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
         const bool v = grin_propagate<EXT>(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k,
-                                      ok ? ray_index : -1, st.ld_out);
+                                      ok ? ray_index : -1, st.ld_out, etab);
         ok = ok && v;
         const double inv = fast_rsqrt(dot3(r.k, r.k));
         d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
@@ -165,8 +169,10 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
         t = 0.0;
     } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
-    } else if (st.shape_kind == PYR_SHAPE_CYLINDER) {
+    } else if (!ASPH && st.shape_kind == PYR_SHAPE_CYLINDER) {
         t = cylinder_t(st.curv, st.cc, r0, dl, hit_ok);
+    } else if (ASPH) {
+        t = asphere_t(*aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
     } else {
         t = explicit_t<EXT>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
     }
@@ -199,11 +205,15 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     double nrm[3];
     if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
         conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
-    } else if (st.shape_kind == PYR_SHAPE_CYLINDER) {
+    } else if (!ASPH && st.shape_kind == PYR_SHAPE_CYLINDER) {
         cylinder_normal(st.curv, st.cc, h[1], nrm);
     } else if (grad_ok) {
         // gradient of the converged Newton iterate: within tol of the hit point
         normal_from_gradient(gfx, gfy, nrm);
+    } else if (ASPH) {
+        double F, dr, ddr;
+        asphere_eval2(*aux, st.curv, st.cc, fma(h[0], h[0], h[1] * h[1]), F, dr, ddr);
+        normal_from_gradient(h[0] * dr, h[1] * dr, nrm);
     } else {
         explicit_normal<EXT>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
     }
@@ -216,7 +226,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     if (HAS_GRIN && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
         double q[3], g[3];
         g2l_point(aux->after.frame, hit_g, q);
-        const double nn = grin_index(aux->after, q, g, false);
+        const double nn = grin_index(aux->after, q, g, false, etab);
         n2sq = nn * nn;
     }
     const double kn = dot3(kl, nrm);
@@ -353,8 +363,9 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
 }
 
 // FEAT: 0 = lean steps only; 1 = + explicit shapes / own-frame apertures / partial
-// step modes; 3 = + GRIN media; 7 = + grid-sag / combination shapes (separate
-// instantiations keep the register budget of the common cases small)
+// step modes; 3 = + GRIN media; 7 = + grid-sag / combination shapes; 9 = like 1 with the
+// even asphere as the only explicit shape (separate instantiations keep the register
+// budget and the code size of the common cases small)
 template <int RPT, bool WITH_E, int FEAT, int MINB = 1, int POLICY = 0, int BLOCK = 256>
 __global__ void __launch_bounds__(BLOCK, MINB)
 trace_real_kernel(const __grid_constant__ LaunchParams P) {
@@ -367,6 +378,8 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
     // register-indexed constant loads.
     __shared__ DStep sst[kMaxSteps];
+    __shared__ double etab[(FEAT & 2) ? 32 : 1];          // 2^(j/32) of pyr_exp.cuh (GRIN profiles)
+    if ((FEAT & 2) && threadIdx.x < 32) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
     {
         const uint64_t *src = reinterpret_cast<const uint64_t *>(P.steps);
         uint64_t *dst = reinterpret_cast<uint64_t *>(sst);
@@ -522,9 +535,9 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0, (FEAT & 4) != 0>(P, st, ray[j], d, hit[j],
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0, (FEAT & 4) != 0, (FEAT & 8) != 0>(P, st, ray[j], d, hit[j],
                                                                                    in_range[j] ? base + j : -1,
-                                                                                   MULTI ? wsel[j] : 0)
+                                                                                   MULTI ? wsel[j] : 0, etab)
                                                  : step_lean<WITH_E>(st, ray[j], d, hit[j], MULTI ? wsel[j] : 0);
             }
 
@@ -745,7 +758,7 @@ generate_bundle_kernel(const __grid_constant__ DGen g, int64_t n, double *__rest
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
         double rx[3], rk[3], re[3];
-        gen_ray(g, i, rx, rk, re);
+        gen_ray_any(g, i, rx, rk, re);
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             if (x) x[c * ld + i] = rx[c];
@@ -928,6 +941,7 @@ int pack_gen(const PyrBundleGen *g, int64_t n_rays, DGen &d) {
     d.param = g->param; d.first = g->first;
     d.lin_start = g->lin_start; d.lin_step = g->lin_step; d.lin_stop = g->lin_stop;
     d.aux0 = g->aux[0]; d.aux1 = g->aux[1];
+    if (g->raster == PYR_RASTER_HEXAPOLAR) d.aux0 = 1.0 / (double)(g->param > 0 ? g->param : 1);
     d.radius = g->radius; d.n_index = g->n_index;
     for (int i = 0; i < 3; ++i) { d.start[i] = g->start[i]; d.dir[i] = g->dir[i]; d.e[i] = g->e[i]; }
     d.rows = g->rows;
@@ -936,6 +950,7 @@ int pack_gen(const PyrBundleGen *g, int64_t n_rays, DGen &d) {
 
 struct Packed {
     LaunchParams P;
+    uint32_t shape_mask;   // bit k: a step of shape kind k is present
     bool general;
     bool any_aniso;
     bool extended;      // grid-sag / combination shapes present
@@ -972,11 +987,13 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
     out.general = false;
     out.any_aniso = false;
     out.extended = false;
+    out.shape_mask = 0;
     int n_aux = 0;
     for (int s = 0; s < n_steps; ++s) {
         const PyrStep &u = steps[s];
         DStep &d = P.steps[s];
         if (u.shape_kind < PYR_SHAPE_CONIC || u.shape_kind > PYR_SHAPE_CYLINDER) return PYR_E_UNSUPPORTED;
+        out.shape_mask |= 1u << u.shape_kind;
         const bool grid = u.shape_kind == PYR_SHAPE_GRIDSAG;
         const bool comb = u.shape_kind == PYR_SHAPE_COMBINATION;
         if (comb && (u.n_terms < 1 || u.n_terms > PYR_MAX_TERMS)) return PYR_E_BADARG;
@@ -1181,6 +1198,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     bool with_e = (flags & PYR_F_RECORD_E) != 0;
     // a Poynting-direction step after the first needs E carried along
     for (int s = 1; s < n_steps; ++s) with_e = with_e || steps[s].dir_mode == PYR_DIR_POYNTING;
+    // conics + even aspheres only: the specialised general kernel
+    const bool asph_only = pk.general && !pk.extended &&
+                           (pk.shape_mask & ~((1u << PYR_SHAPE_CONIC) | (1u << PYR_SHAPE_ASPHERE))) == 0;
     if (pk.P.gen.on) {
         // generated bundle: own instantiations (no input stage) of the lean, the general and
         // the GRIN kernel; everything else is traced from arrays (pyr_generate_bundle)
@@ -1190,6 +1210,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
         if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true);
         if (grin) return launch(trace_real_kernel<1, false, 3, 2, 16>, pk.P, 1, stream, false, false, 256, true);
+        if (asph_only) return launch(trace_real_kernel<2, false, 9, 2, 19>, pk.P, 2, stream, true, false, 256, true);
         return launch(trace_real_kernel<2, false, 1, 2, 19>, pk.P, 2, stream, true, false, 256, true);
     }
     if (pk.P.n_waves > 1) {
@@ -1227,6 +1248,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
                     // more resident warps
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
+    if (asph_only && !with_e) return launch(trace_real_kernel<2, false, 9, 2, 3>, pk.P, 2, stream, true);
     return with_e ? launch(trace_real_kernel<2, true, 1, 2, 3>, pk.P, 2, stream, true, true)
                   : launch(trace_real_kernel<2, false, 1, 2, 3>, pk.P, 2, stream, true);
 }
