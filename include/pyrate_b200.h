@@ -384,6 +384,19 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
                   void *stream);
 
 /*
+ * One merit-function evaluation of an optimiser loop (the caller right above the path:
+ * optimize/optimize.py:73-91 calls seqtrace + RayBundleAnalysis.get_rms_spot_size once
+ * per function evaluation): pyr_trace, then pyr_spot_sums over the record of the LAST step
+ * (out_x / out_flags of steps[n_steps - 1], which must be set) about `shift`, then the 8
+ * sums are copied to HOST memory `spot8_host` (pinned for speed) and the stream is
+ * synchronised -- one call, three launches, one 64-byte read-back.  `spot8_dev`: DEVICE
+ * scratch of 8 doubles.
+ */
+int pyr_trace_spot(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
+                   int64_t n_rays, uint32_t flags, const double *shift, double *spot8_dev,
+                   double *spot8_host, void *stream);
+
+/*
  * Spot-diagram points of OpticalSystemAnalysis.get_spot (analysis/
  * optical_system_analysis.py:283-303): x, y of the rays whose `flags & mask` is non-zero
  * (flags NULL = all), in the frame `frame` (HOST pointer, NULL = global coordinates; the

@@ -1336,6 +1336,25 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t ma
     return e == cudaSuccess ? PYR_OK : (int)e;
 }
 
+int pyr_trace_spot(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
+                   uint32_t flags, const double *shift, double *spot8_dev, double *spot8_host,
+                   void *stream) {
+    if (!steps || n_steps <= 0 || !rays || !spot8_dev || !spot8_host || n_rays < 0) return PYR_E_BADARG;
+    const PyrStep &last = steps[n_steps - 1];
+    if (!last.out_x || last.split) return PYR_E_BADARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = pyr_trace(steps, n_steps, rays, n_rays, flags, stream);
+    if (rc != PYR_OK) return rc;
+    cudaError_t e = cudaMemsetAsync(spot8_dev, 0, 64, st);
+    if (e != cudaSuccess) return (int)e;
+    rc = pyr_spot_sums(last.out_x, last.ld_out > 0 ? last.ld_out : n_rays, last.out_flags, PYR_RAY_ALIVE,
+                       n_rays, shift, spot8_dev, stream);
+    if (rc != PYR_OK) return rc;
+    e = cudaMemcpyAsync(spot8_host, spot8_dev, 64, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e == cudaSuccess ? PYR_OK : (int)e;
+}
+
 int pyr_spot_points(const double *x, int64_t ld, const uint8_t *flags, uint32_t mask, int64_t n,
                     const PyrFrame *frame, double *xy, int64_t ld_out, int64_t *count, void *stream) {
     if (!x || !xy || !count || n < 0 || ld_out < 0) return PYR_E_BADARG;

@@ -26,7 +26,7 @@ def _specs(n):
 @pytest.mark.parametrize("kind", ["hexapolar", "rect", "hex", "circular", "circular_sqrt"])
 def test_generated_bundles_match_the_numpy_rasters(kind, n):
     """pyr_generate_bundle against the host construction (reference formulas): lattice
-    coordinates bit for bit, trigonometric rasters to 2 ulp, whole bundle and a shard."""
+    coordinates bit for bit, trigonometric rasters to a few ulp, whole bundle and a shard."""
     spec = _specs(n)[kind]
     lattice = kind in ("rect", "hex")
     for (bundle, radius, start, direction, efield) in (
@@ -41,8 +41,10 @@ def test_generated_bundles_match_the_numpy_rasters(kind, n):
         if lattice and bundle == nat.BUNDLE_COLLIMATED:
             assert np.array_equal(x, hx) and np.array_equal(k, hk)
         else:
-            assert np.max(np.abs(x - hx)) <= 4e-16 * max(1.0, radius, abs(start[2]))
-            assert np.max(np.abs(k - hk)) <= 1e-15
+            # sin / cos on the device (sincospi of the reduced argument for the hexapolar
+            # raster) against libm: a few ulp of the pupil radius
+            assert np.max(np.abs(x - hx)) <= 2e-15 * max(1.0, radius, abs(start[2]))
+            assert np.max(np.abs(k - hk)) <= 2e-15
         assert np.max(np.abs(e - he)) <= 1e-15
         assert np.max(np.abs(np.sum(e * k, axis=0))) < 1e-15
         (lo, hi) = (spec.total // 3, spec.total - 1)

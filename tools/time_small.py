@@ -50,3 +50,16 @@ def merit():
 
 
 print("seqtrace + RMS spot (merit function) %.3f ms" % timeit(merit))
+
+
+from pyrate_b200.merit import MeritTrace  # noqa: E402
+from pyrate_b200 import bundlegen  # noqa: E402
+
+mt = MeritTrace(s, seq, dev_bundle)
+print("MeritTrace (resident arrays): refresh + trace + spot sums + read-back  %.3f ms" % timeit(mt))
+print("MeritTrace (resident arrays): refresh only                          %.3f ms" % timeit(mt.refresh))
+print("MeritTrace (resident arrays): trace + spot sums + read-back          %.3f ms" %
+      timeit(lambda: mt(refresh=False)))
+mg = MeritTrace(s, seq, pb.RayBundle(generator=bundlegen.config_generator(spec, rings), wave=configs.DLINE))
+print("MeritTrace (generated bundle): refresh + trace + spot sums + read-back %.3f ms" % timeit(mg))
+print("rms %.12g vs general API %.12g" % (mt(), merit()))
