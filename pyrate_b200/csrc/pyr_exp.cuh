@@ -31,13 +31,19 @@ PYR_EXP_CONST double kExp2Tab[32] = {
     0x1.ae89f995ad3adp+0, 0x1.b7f76f2fb5e47p+0, 0x1.c199bdd85529cp+0, 0x1.cb720dcef9069p+0,
     0x1.d5818dcfba487p+0, 0x1.dfc97337b9b5fp+0, 0x1.ea4afa2a490dap+0, 0x1.f50765b6e4540p+0};
 
+// constants of exp_tab in a constant-bank array: the FP64 instructions take them as c[][]
+// operands (literals would be materialised with two uniform moves each, per use)
+PYR_EXP_CONST double kExpK[9] = {
+    0x1.71547652b82fep+5,        // 32 / ln 2
+    0x1.62e42fe000000p-6,        // ln 2 / 32, 24 trailing zero bits: n * hi exact
+    0x1.f473de6af278fp-35,       // ln 2 / 32 - hi
+    0x1.8p52,                    // 2^52 + 2^51: rounds to nearest integer
+    1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0};
+
 // `tab`: the table above (the kernels keep a copy in shared memory: a per-thread index into
 // constant memory would serialise)
 __host__ __device__ __forceinline__ double exp_tab(double x, const double *tab) {
-    const double kInvL = 0x1.71547652b82fep+5;        // 32 / ln 2
-    const double kLhi = 0x1.62e42fe000000p-6;         // ln 2 / 32, 24 trailing zero bits: n * kLhi exact
-    const double kLlo = 0x1.f473de6af278fp-35;
-    const double kMagic = 0x1.8p52;                   // 2^52 + 2^51: rounds to nearest integer
+    const double kInvL = kExpK[0], kLhi = kExpK[1], kLlo = kExpK[2], kMagic = kExpK[3];
     const double t = fma(x, kInvL, kMagic);
     const double nf = t - kMagic;
 #ifdef __CUDA_ARCH__
@@ -50,10 +56,10 @@ __host__ __device__ __forceinline__ double exp_tab(double x, const double *tab) 
     double r = fma(-nf, kLhi, x);
     r = fma(-nf, kLlo, r);
     // P(r) = r + r^2 (1/2 + r (1/6 + r (1/24 + r (1/120 + r (1/720 + r / 5040)))))
-    double p = fma(r, 1.0 / 5040.0, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
+    double p = fma(r, kExpK[4], kExpK[5]);
+    p = fma(p, r, kExpK[6]);
+    p = fma(p, r, kExpK[7]);
+    p = fma(p, r, kExpK[8]);
     p = fma(p, r, 0.5);
     p = fma(p * r, r, r);
     const double tj = tab[n & 31];

@@ -130,4 +130,91 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
     return valid;
 }
 
+// N rays of one thread integrated TOGETHER: every iteration advances all N rays by one
+// integrator step, straight-line (no branch between the rays), so the N independent
+// dependency chains interleave in the FP64 pipe -- the single-ray loop above is bound by the
+// latency of its own chain (drift -> exp -> kick, four times per step; profiles/r02_grin.md).
+// A ray that has stopped keeps stepping like in the reference's lock-step loop
+// (material_grin.py:139) but its frozen state (uq, up) and validity no longer change, so the
+// result of every ray is bit-identical to grin_propagate's.  No integrator history here
+// (the history mode runs the single-ray function).
+template <bool EXT, int N>
+__device__ __forceinline__ void grin_propagate_n(const DMedium &m, int shape_kind, const DAux *aux,
+                                                 double curv, double cc, double (*x)[3],
+                                                 const double (*d)[3], double (*k)[3],
+                                                 const bool *enter, bool *valid_out,
+                                                 const double *etab) {
+    const double c0 = 1.0 / (2.0 * (2.0 - 1.2599210498948732));
+    const double c1 = (1.0 - 1.2599210498948732) / (2.0 * (2.0 - 1.2599210498948732));
+    const double d0 = 1.0 / (2.0 - 1.2599210498948732);
+    const double d1 = -1.2599210498948732 / (2.0 - 1.2599210498948732);
+    const double cs[4] = {c0, c1, c1, c0};
+    const double ds[4] = {d0, d1, d0, 0.0};
+    double q[N][3], p[N][3], uq[N][3], up[N][3];
+    bool valid[N], done[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double g[3];
+        g2l_point(m.frame, x[j], q[j]);
+        rot_t(m.frame.r, d[j], p[j]);
+        const double n0 = grin_index(m, q[j], g, false, etab);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { p[j][c] *= n0; uq[j][c] = q[j][c]; up[j][c] = p[j][c]; }
+        valid[j] = enter[j];
+        done[j] = !enter[j];          // dead / out-of-range rays (NaN state) never enter
+    }
+    const double tau2 = 2.0 * m.ds;
+    const int cap = m.max_steps > 0 ? m.max_steps : 1000000;
+    for (int it = 0; it < cap; ++it) {
+        bool all_done = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double g[3], nq = 0.0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                q[j][0] = fma(tau2 * cs[s], p[j][0], q[j][0]);
+                q[j][1] = fma(tau2 * cs[s], p[j][1], q[j][1]);
+                q[j][2] = fma(tau2 * cs[s], p[j][2], q[j][2]);
+                nq = grin_index(m, q[j], g, s < 3, etab);
+                if (s < 3) {
+                    const double f = tau2 * ds[s] * nq;
+                    p[j][0] = fma(f, g[0], p[j][0]);
+                    p[j][1] = fma(f, g[1], p[j][1]);
+                    p[j][2] = fma(f, g[2], p[j][2]);
+                }
+            }
+            bool v = valid[j];
+            if (!(fabs(dot3(p[j], p[j]) - nq * nq) <= m.energy_tol)) v = false;     // NaN-safe
+            double xs[3];
+            l2g_point(m.to_shape, q[j], xs);
+            const double gap = xs[2] - shape_sag<EXT>(shape_kind, aux, curv, cc, xs[0], xs[1]);
+            const bool crossed = gap > 0.0;
+            if (!grin_inside(m, q[j]) || gap != gap) v = false;
+            const bool stop = crossed || !v;
+            const bool live = !done[j];
+            const bool advance = live && !stop;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                uq[j][c] = advance ? q[j][c] : uq[j][c];
+                up[j][c] = advance ? p[j][c] : up[j][c];
+            }
+            if (live) valid[j] = (advance && it == cap - 1) ? false : v;
+            done[j] = done[j] || stop;
+            all_done = all_done && done[j];
+        }
+        if (all_done) break;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        double g[3];
+        const double inv = 1.0 / grin_index(m, uq[j], g, false, etab);
+        const double kl[3] = {up[j][0] * inv, up[j][1] * inv, up[j][2] * inv};
+        if (enter[j]) {
+            l2g_point(m.frame, uq[j], x[j]);
+            rot(m.frame.r, kl, k[j]);
+        }
+        valid_out[j] = valid[j];
+    }
+}
+
 }  // namespace pyr

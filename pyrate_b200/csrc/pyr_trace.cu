@@ -136,7 +136,8 @@ template <bool WITH_E, bool HAS_GRIN, bool EXT, bool ASPH = false>
 __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
                                               Ray<WITH_E> &r, double d[3], double hit_g[3],
                                               int64_t ray_index, int w = 0,
-                                              const double *etab = nullptr) {
+                                              const double *etab = nullptr,
+                                              bool grin_media = HAS_GRIN) {
     constexpr bool GENERAL = true;
     const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
     bool ok = r.alive;
@@ -223,7 +224,7 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
     else rot_t(st.frame.r, r.k, kl);
     double n2sq = st.n2sq[w];
-    if (HAS_GRIN && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
+    if (grin_media && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
         double q[3], g[3];
         g2l_point(aux->after.frame, hit_g, q);
         const double nn = grin_index(aux->after, q, g, false, etab);
@@ -373,6 +374,8 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // POLICY bit 16: the rays are generated in registers from P.gen (csrc/pyr_gen.cuh): no
     // input rows are read and no input stage exists
     constexpr bool GEN = (POLICY & 16) != 0;
+    // FEAT bit 16: GRIN segments integrate the RPT rays of a thread together (no history)
+    constexpr bool GRIN_N = (FEAT & 16) != 0;
     const int64_t n = P.n;
     // Step table: one cooperative copy from the parameter block into shared memory;
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
@@ -518,13 +521,13 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 
         for (int s = 0; s < P.n_steps; ++s) {
             const DStep &st = sst[s];
-            double hit[RPT][3];
+            double hit[RPT][3], dd[RPT][3];
             uint32_t fl[RPT];
 #pragma unroll
             for (int j = 0; j < RPT; ++j) {
                 // direction of energy transport (ray.py:136-152): Poynting vector of the
                 // user's (k, E) on the first segment, k/|k| wherever E.k = 0 is guaranteed
-                double d[3];
+                double *d = dd[j];
                 if (st.dir_mode == PYR_DIR_POYNTING && (WITH_E || s == 0)) {
                     if (WITH_E) poynting_dir(ray[j].k, ray[j].e, d);
                     else poynting_dir(ray[j].k, in[j].e, d);
@@ -533,12 +536,39 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                     const double inv = (ik > 0.0) ? ik : fast_rsqrt(dot3(ray[j].k, ray[j].k));
                     d[0] = ray[j].k[0] * inv; d[1] = ray[j].k[1] * inv; d[2] = ray[j].k[2] * inv;
                 }
+            }
+            if (GRIN_N && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
+                // GRIN segment: the RPT rays of the thread are integrated together
+                // (interleaved dependency chains, csrc/pyr_grin.cuh grin_propagate_n)
+                const DAux *ga = &P.aux[st.aux];
+                double gx[RPT][3], gk[RPT][3];
+                bool enter[RPT], gvalid[RPT];
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    enter[j] = ray[j].alive && in_range[j];
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { gx[j][c] = ray[j].x[c]; gk[j][c] = ray[j].k[c]; }
+                }
+                grin_propagate_n<(FEAT & 4) != 0, RPT>(ga->before, st.shape_kind, ga, st.curv, st.cc, gx, dd, gk,
+                                                       enter, gvalid, etab);
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { ray[j].x[c] = gx[j][c]; ray[j].k[c] = gk[j][c]; }
+                    ray[j].alive = ray[j].alive && gvalid[j];
+                    const double inv = fast_rsqrt(dot3(ray[j].k, ray[j].k));
+                    dd[j][0] = ray[j].k[0] * inv; dd[j][1] = ray[j].k[1] * inv; dd[j][2] = ray[j].k[2] * inv;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < RPT; ++j) {
                 // steps without an auxiliary record (conic shape, homogeneous isotropic
                 // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0, (FEAT & 4) != 0, (FEAT & 8) != 0>(P, st, ray[j], d, hit[j],
+                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0 && !GRIN_N, (FEAT & 4) != 0, (FEAT & 8) != 0>(P, st, ray[j], dd[j], hit[j],
                                                                                    in_range[j] ? base + j : -1,
-                                                                                   MULTI ? wsel[j] : 0, etab)
-                                                 : step_lean<WITH_E>(st, ray[j], d, hit[j], MULTI ? wsel[j] : 0);
+                                                                                   MULTI ? wsel[j] : 0, etab,
+                                                                                   (FEAT & 2) != 0)
+                                                 : step_lean<WITH_E>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
             }
 
             // ---- record the step ----
@@ -1201,6 +1231,8 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     // conics + even aspheres only: the specialised general kernel
     const bool asph_only = pk.general && !pk.extended &&
                            (pk.shape_mask & ~((1u << PYR_SHAPE_CONIC) | (1u << PYR_SHAPE_ASPHERE))) == 0;
+    bool hist = false;                      // GRIN integrator history requested
+    for (int s = 0; s < n_steps; ++s) hist = hist || steps[s].grin_hist_x || steps[s].grin_hist_count;
     if (pk.P.gen.on) {
         // generated bundle: own instantiations (no input stage) of the lean, the general and
         // the GRIN kernel; everything else is traced from arrays (pyr_generate_bundle)
@@ -1209,6 +1241,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             grin = grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
         if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
         if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+        if (grin && !hist) return launch(trace_real_kernel<2, false, 19, 2, 19>, pk.P, 2, stream, true, false, 256, true);
         if (grin) return launch(trace_real_kernel<1, false, 3, 2, 16>, pk.P, 1, stream, false, false, 256, true);
         if (asph_only) return launch(trace_real_kernel<2, false, 9, 2, 19>, pk.P, 2, stream, true, false, 256, true);
         return launch(trace_real_kernel<2, false, 1, 2, 19>, pk.P, 2, stream, true, false, 256, true);
@@ -1244,8 +1277,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     if (pk.extended)   // grid-sag / combination shapes: the all-features instantiation
         return with_e ? launch(trace_real_kernel<1, true, 7, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 7, 2>, pk.P, 1, stream);
-    if (has_grin)   // integrator loops do not interleave across rays: one ray per thread,
-                    // more resident warps
+    if (has_grin && !with_e && !hist)   // two rays per thread, integrated together (interleaved chains)
+        return launch(trace_real_kernel<2, false, 19, 2, 3>, pk.P, 2, stream, true);
+    if (has_grin)   // history / E recording: one ray per thread
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
     if (asph_only && !with_e) return launch(trace_real_kernel<2, false, 9, 2, 3>, pk.P, 2, stream, true);

@@ -89,7 +89,8 @@ def test_fused_generation_equals_the_trace_of_the_same_rays_from_memory(name, ri
     rec_gen = engine.trace(lowered, None, None, None, configs.DLINE, gen=gen)
     assert rec_gen.gen is gen and rec_gen._x0 is None and not gen.materialised   # nothing was written out
     (x0, k0, e0) = gen.materialise()
-    assert np.max(np.abs(x0.cpu().numpy() - hx)) <= 4e-15 and np.array_equal(k0.cpu().numpy(), hk)
+    assert np.max(np.abs(x0.cpu().numpy() - hx)) <= 3e-15 * max(1.0, spec["bundle"]["radius"])
+    assert np.array_equal(k0.cpu().numpy(), hk)
     rec_mem = engine.trace(lowered, x0, k0, e0, configs.DLINE)
     newton = util.tolerance_of(name) == util.TOL_ITERATED and name != "c5_grin"
     for s_ in range(len(lowered)):
