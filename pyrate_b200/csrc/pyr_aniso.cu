@@ -246,6 +246,33 @@ __device__ __forceinline__ double mode_key(const DAux &ax, const cplx p[3], cons
     return wgt * dot3(s, nrm);
 }
 
+// Sort key of a closed-form uniaxial mode WITHOUT forming its field: with E_o = k x a
+// (E.k = 0) the Poynting vector is |E|^2 Re k, so the key is w Re(k).n; with
+// E_e = eo a - (k.a) k one has E.k = (k.a)(eo - k.k) and E.n = eo (a.n) - (k.a)(k.n), so
+// S.n / |E|^2 = Re(k.n) - Re((E.k) conj(E.n)) / |E|^2.  `closed` = false where the closed
+// forms degenerate (k parallel to a, isotropic tensor): the caller then uses mode_key.
+__device__ __forceinline__ double uni_key(const DAux &ax, const cplx p[3], const double nrm[3], cplx xi,
+                                          bool extraordinary, bool &closed) {
+    cplx k[3];
+    for (int i = 0; i < 3; ++i) k[i] = p[i] + nrm[i] * xi;
+    const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+    const double c0r = k[1].re * a[2] - k[2].re * a[1], c0i = k[1].im * a[2] - k[2].im * a[1];
+    const double c1r = k[2].re * a[0] - k[0].re * a[2], c1i = k[2].im * a[0] - k[0].im * a[2];
+    const double c2r = k[0].re * a[1] - k[1].re * a[0], c2i = k[0].im * a[1] - k[1].im * a[0];
+    const double cross2 = c0r * c0r + c0i * c0i + c1r * c1r + c1i * c1i + c2r * c2r + c2i * c2i;
+    closed = closed && ax.eps_e != ax.eps_o && cross2 > 1e-8 * herm2(k);
+    const double wgt = 1.0 / (1.0 + abs2(xi));
+    const cplx kn = cdotr(k, nrm);
+    if (!extraordinary) return wgt * kn.re;
+    const cplx ka = cdotr(k, a);
+    const cplx kk = cdot(k, k);
+    cplx e[3];
+    for (int i = 0; i < 3; ++i) e[i] = C(ax.eps_o * a[i]) - ka * k[i];
+    const cplx ek = ka * (C(ax.eps_o) - kk);
+    const cplx en = C(ax.eps_o * dot3(a, nrm)) - ka * kn;
+    return wgt * (kn.re - (ek * conj(en)).re / herm2(e));
+}
+
 // Anisotropic deflection in the shape frame.  kl: incoming k (shape frame), nrm: unit
 // normal.  Produces the two selected modes (ka, ea), (kb, eb).  No dynamically indexed
 // local arrays (no stack frame): the four sort keys are computed first, the two selected
@@ -338,6 +365,15 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
     // loop (one copy of the mode evaluation in the instruction stream, not four: the kernel
     // was stalling on instruction fetch, profiles/r02_c4.md)
     double key0 = 0.0, key1 = 0.0, key2 = 0.0, key3 = 0.0, w;
+    bool closed = UNI;
+    if (UNI) {
+        // uniaxial crystal: the four keys in closed form (no fields)
+        key0 = uni_key(ax, p, nrm, xi0, false, closed);
+        key1 = uni_key(ax, p, nrm, xi1, false, closed);
+        key2 = uni_key(ax, p, nrm, xi2, true, closed);
+        key3 = uni_key(ax, p, nrm, xi3, true, closed);
+    }
+    if (!closed)
 #pragma unroll 1
     for (int mi = 0; mi < 4; ++mi) {
         const cplx xim = mi == 0 ? xi0 : (mi == 1 ? xi1 : (mi == 2 ? xi2 : xi3));
@@ -466,9 +502,14 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                     const double inv = rsqrt(dot3(sv, sv));
                     d[0] = sv[0] * inv; d[1] = sv[1] * inv; d[2] = sv[2] * inv;
                 }
+                const bool ident = (st.bits & kRotIdentity) != 0;   // chain systems without tilts
                 double r0[3], dl[3];
-                g2l_point(st.frame, x, r0);
-                rot_t(st.frame.r, d, dl);
+                if (ident) {
+                    for (int c = 0; c < 3; ++c) { r0[c] = x[c] - st.frame.o[c]; dl[c] = d[c]; }
+                } else {
+                    g2l_point(st.frame, x, r0);
+                    rot_t(st.frame.r, d, dl);
+                }
                 double tt;
                 bool hit_ok = true;
                 if (st.bits & kNoIntersect) tt = 0.0;        // stand-alone refract / reflect: x is the hit point
@@ -478,7 +519,8 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 else tt = qnan();
                 const double h[3] = {fma(dl[0], tt, r0[0]), fma(dl[1], tt, r0[1]), fma(dl[2], tt, r0[2])};
                 double hit_g[3];
-                l2g_point(st.frame, h, hit_g);
+                if (ident) { for (int c = 0; c < 3; ++c) hit_g[c] = h[c] + st.frame.o[c]; }
+                else l2g_point(st.frame, h, hit_g);
 
                 bool ap_ok = true;
                 if (st.aperture_kind != PYR_AP_BASE) {
@@ -508,7 +550,8 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                     nrm[0] = nrm[1] = nrm[2] = qnan();
 
                 cplx kl[3];
-                crot_t(st.frame.r, k, kl);
+                if (ident) { for (int c = 0; c < 3; ++c) kl[c] = k[c]; }
+                else crot_t(st.frame.r, k, kl);
                 const bool mirror = st.interaction == PYR_REFLECT;
                 cplx k2a[3], e2a[3], k2b[3], e2b[3];
                 const bool no_deflect = (st.bits & kNoDeflect) != 0;   // stand-alone propagate
@@ -533,7 +576,8 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                     alive = hit && refr_ok;
                     // E: project the previous field (shape frame) onto the plane k2.E = 0
                     cplx el[3];
-                    crot_t(st.frame.r, e, el);
+                    if (ident) { for (int c = 0; c < 3; ++c) el[c] = e[c]; }
+                    else crot_t(st.frame.r, e, el);
                     const cplx kk = cdot(k2a, k2a);
                     cplx cc = cdot(el, k2a) / kk;
                     cplx tv[3] = {el[0] - cc * k2a[0], el[1] - cc * k2a[1], el[2] - cc * k2a[2]};
@@ -552,11 +596,14 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
 
                 // ---- back to the global frame, record ----
                 cplx kga[3], ega[3], kgb[3], egb[3];
-                crot(st.frame.r, k2a, kga);
-                crot(st.frame.r, e2a, ega);
+                if (ident) { for (int c = 0; c < 3; ++c) { kga[c] = k2a[c]; ega[c] = e2a[c]; } }
+                else { crot(st.frame.r, k2a, kga); crot(st.frame.r, e2a, ega); }
                 if (no_deflect) { for (int c = 0; c < 3; ++c) { kga[c] = k[c]; ega[c] = e[c]; } }
                 const bool split = aniso && (st.bits & kSplit);
-                if (aniso) { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
+                if (aniso) {
+                    if (ident) { for (int c = 0; c < 3; ++c) { kgb[c] = k2b[c]; egb[c] = e2b[c]; } }
+                    else { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
+                }
                 const cplx qn = {qnan(), qnan()};
                 if (!alive) {
                     for (int c = 0; c < 3; ++c) { kga[c] = ega[c] = kgb[c] = egb[c] = qn; }

@@ -18,8 +18,10 @@ namespace pyr {
 __device__ __forceinline__ double grin_index(const DMedium &m, const double q[3], double g[3],
                                              bool want_grad, const double *etab) {
     if (m.profile == PYR_GRIN_GAUSSIAN_XY) {
-        const double arg = -fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]);
-        const double ex = m.p[1] * (exp_tab_ok(arg) ? exp_tab(arg, etab) : exp(arg));
+        // (argument clamped to the range of exp_tab: e^-700 = 1e-304 stands for 0, e^700
+        // for overflow -- either way far outside any index profile)
+        const double arg = fmin(fmax(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]), -700.0), 700.0);
+        const double ex = m.p[1] * exp_tab(arg, etab);
         if (want_grad) {
             g[0] = -2.0 * m.p[2] * q[0] * ex;
             g[1] = -2.0 * m.p[3] * q[1] * ex;
@@ -130,18 +132,52 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
     return valid;
 }
 
+// ---- straight-line building blocks of the interleaved integrator ----
+template <int PROFILE>
+__device__ __forceinline__ double grin_index_t(const DMedium &m, const double q[3], double g[3],
+                                               const double *etab) {
+    if (PROFILE == PYR_GRIN_GAUSSIAN_XY) {
+        const double arg = fmin(fmax(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]), -700.0), 700.0);
+        const double ex = m.p[1] * exp_tab(arg, etab);
+        g[0] = -2.0 * m.p[2] * q[0] * ex;
+        g[1] = -2.0 * m.p[3] * q[1] * ex;
+        g[2] = 0.0;
+        return m.p[0] + ex;
+    }
+    const double r2 = fma(q[0], q[0], q[1] * q[1]);
+    const double z = q[2];
+    const double nr = fma(fma(fma(m.p[3], r2, m.p[2]), r2, m.p[1]), r2, m.p[0]);
+    const double nz = z * fma(fma(m.p[6], z, m.p[5]), z, m.p[4]);
+    const double dr = 2.0 * fma(fma(3.0 * m.p[3], r2, 2.0 * m.p[2]), r2, m.p[1]);
+    g[0] = q[0] * dr;
+    g[1] = q[1] * dr;
+    g[2] = fma(fma(3.0 * m.p[6], z, 2.0 * m.p[5]), z, m.p[4]);
+    return nr + nz;
+}
+
+// boundary test without a branch on the boundary kind
+__device__ __forceinline__ bool grin_inside_nb(const DMedium &m, const double q[3]) {
+    const double r2 = fma(q[0], q[0], q[1] * q[1]);
+    const bool cyl = r2 < m.b[0] * m.b[0];
+    const bool box = (fabs(q[0]) < m.b[0]) & (fabs(q[1]) < m.b[1]);
+    const bool sph = fma(q[2], q[2], r2) < m.b[0] * m.b[0];
+    const int k = m.boundary;
+    return (k == PYR_BND_NONE) | ((k == PYR_BND_CYLINDER) & cyl) | ((k == PYR_BND_BOX) & box) |
+           ((k == PYR_BND_SPHERE) & sph);
+}
+
 // N rays of one thread integrated TOGETHER: every iteration advances all N rays by one
-// integrator step, straight-line (no branch between the rays), so the N independent
-// dependency chains interleave in the FP64 pipe -- the single-ray loop above is bound by the
-// latency of its own chain (drift -> exp -> kick, four times per step; profiles/r02_grin.md).
-// A ray that has stopped keeps stepping like in the reference's lock-step loop
-// (material_grin.py:139) but its frozen state (uq, up) and validity no longer change, so the
-// result of every ray is bit-identical to grin_propagate's.  No integrator history here
+// integrator step in STRAIGHT-LINE code (profile fixed at compile time, conic next surface,
+// no branch between or inside the rays' steps), so that the compiler interleaves the N
+// independent dependency chains -- a warp issues in order, and the single-ray loop is bound
+// by the latency of its own chain (drift -> exp -> kick, four times per step;
+// profiles/r02_grin.md).  A ray that has stopped keeps stepping like in the reference's
+// lock-step loop (material_grin.py:139) but its frozen state (uq, up) and validity no longer
+// change, so every ray's result is bit-identical to grin_propagate's.  No integrator history
 // (the history mode runs the single-ray function).
-template <bool EXT, int N>
-__device__ __forceinline__ void grin_propagate_n(const DMedium &m, int shape_kind, const DAux *aux,
-                                                 double curv, double cc, double (*x)[3],
-                                                 const double (*d)[3], double (*k)[3],
+template <int PROFILE, int N>
+__device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, double cc,
+                                                 double (*x)[3], const double (*d)[3], double (*k)[3],
                                                  const bool *enter, bool *valid_out,
                                                  const double *etab) {
     const double c0 = 1.0 / (2.0 * (2.0 - 1.2599210498948732));
@@ -157,7 +193,7 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, int shape_kin
         double g[3];
         g2l_point(m.frame, x[j], q[j]);
         rot_t(m.frame.r, d[j], p[j]);
-        const double n0 = grin_index(m, q[j], g, false, etab);
+        const double n0 = grin_index_t<PROFILE>(m, q[j], g, etab);
 #pragma unroll
         for (int c = 0; c < 3; ++c) { p[j][c] *= n0; uq[j][c] = q[j][c]; up[j][c] = p[j][c]; }
         valid[j] = enter[j];
@@ -175,7 +211,7 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, int shape_kin
                 q[j][0] = fma(tau2 * cs[s], p[j][0], q[j][0]);
                 q[j][1] = fma(tau2 * cs[s], p[j][1], q[j][1]);
                 q[j][2] = fma(tau2 * cs[s], p[j][2], q[j][2]);
-                nq = grin_index(m, q[j], g, s < 3, etab);
+                nq = grin_index_t<PROFILE>(m, q[j], g, etab);
                 if (s < 3) {
                     const double f = tau2 * ds[s] * nq;
                     p[j][0] = fma(f, g[0], p[j][0]);
@@ -183,37 +219,56 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, int shape_kin
                     p[j][2] = fma(f, g[2], p[j][2]);
                 }
             }
-            bool v = valid[j];
-            if (!(fabs(dot3(p[j], p[j]) - nq * nq) <= m.energy_tol)) v = false;     // NaN-safe
+            const bool e_ok = fabs(dot3(p[j], p[j]) - nq * nq) <= m.energy_tol;      // NaN -> false
             double xs[3];
             l2g_point(m.to_shape, q[j], xs);
-            const double gap = xs[2] - shape_sag<EXT>(shape_kind, aux, curv, cc, xs[0], xs[1]);
+            const double gap = xs[2] - conic_sag(curv, cc, xs[0], xs[1]);
             const bool crossed = gap > 0.0;
-            if (!grin_inside(m, q[j]) || gap != gap) v = false;
-            const bool stop = crossed || !v;
+            const bool v = valid[j] & e_ok & grin_inside_nb(m, q[j]) & (gap == gap);
+            const bool stop = crossed | !v;
             const bool live = !done[j];
-            const bool advance = live && !stop;
+            const bool advance = live & !stop;
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
                 uq[j][c] = advance ? q[j][c] : uq[j][c];
                 up[j][c] = advance ? p[j][c] : up[j][c];
             }
-            if (live) valid[j] = (advance && it == cap - 1) ? false : v;
-            done[j] = done[j] || stop;
-            all_done = all_done && done[j];
+            valid[j] = live ? (v & !(advance & (it == cap - 1))) : valid[j];
+            done[j] = done[j] | stop;
+            all_done = all_done & done[j];
         }
         if (all_done) break;
     }
 #pragma unroll
     for (int j = 0; j < N; ++j) {
         double g[3];
-        const double inv = 1.0 / grin_index(m, uq[j], g, false, etab);
+        const double inv = 1.0 / grin_index_t<PROFILE>(m, uq[j], g, etab);
         const double kl[3] = {up[j][0] * inv, up[j][1] * inv, up[j][2] * inv};
         if (enter[j]) {
             l2g_point(m.frame, uq[j], x[j]);
             rot(m.frame.r, kl, k[j]);
         }
         valid_out[j] = valid[j];
+    }
+}
+
+// dispatcher of a thread's N rays: the interleaved loop for the catalogue profiles in front
+// of a conic surface, else one ray after the other through the general function
+template <bool EXT, int N>
+__device__ __forceinline__ void grin_propagate_rays(const DMedium &m, int shape_kind, const DAux *aux,
+                                                    double curv, double cc, double (*x)[3],
+                                                    const double (*d)[3], double (*k)[3],
+                                                    const bool *enter, bool *valid_out,
+                                                    const double *etab) {
+    if (shape_kind == PYR_SHAPE_CONIC && m.profile == PYR_GRIN_GAUSSIAN_XY) {
+        grin_propagate_n<PYR_GRIN_GAUSSIAN_XY, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
+    } else if (shape_kind == PYR_SHAPE_CONIC && m.profile == PYR_GRIN_POLY_RZ) {
+        grin_propagate_n<PYR_GRIN_POLY_RZ, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < N; ++j)
+            valid_out[j] = grin_propagate<EXT>(m, shape_kind, aux, curv, cc, x[j], d[j], k[j],
+                                               enter[j] ? 0 : -1, 0, etab);
     }
 }
 

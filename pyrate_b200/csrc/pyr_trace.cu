@@ -549,8 +549,8 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
 #pragma unroll
                     for (int c = 0; c < 3; ++c) { gx[j][c] = ray[j].x[c]; gk[j][c] = ray[j].k[c]; }
                 }
-                grin_propagate_n<(FEAT & 4) != 0, RPT>(ga->before, st.shape_kind, ga, st.curv, st.cc, gx, dd, gk,
-                                                       enter, gvalid, etab);
+                grin_propagate_rays<(FEAT & 4) != 0, RPT>(ga->before, st.shape_kind, ga, st.curv, st.cc, gx, dd, gk,
+                                                          enter, gvalid, etab);
 #pragma unroll
                 for (int j = 0; j < RPT; ++j) {
 #pragma unroll
