@@ -15,7 +15,7 @@ $(OUT): $(SRC) $(HDR)
 
 # measurement build for tools/ (A/B knobs PYR_DEBUG_RECORD_LAST / PYR_LEAN_VARIANT compiled in);
 # never loaded by the package unless a tool calls _native.use_tools_library()
-TOOLS_OUT := pyrate_b200/_lib/libpyrate_b200_tools.so
+TOOLS_OUT ?= pyrate_b200/_lib/libpyrate_b200_tools.so
 tools: $(TOOLS_OUT)
 $(TOOLS_OUT): $(SRC) $(HDR)
 	@mkdir -p pyrate_b200/_lib

@@ -123,12 +123,12 @@ EXPORTS = ("pyr_version", "pyr_strerror", "pyr_sizeof_step",
 _lib = None
 
 
-def use_tools_library():
-    """tools/ only: load the measurement build (`make tools`, -DPYR_TOOLS: A/B knobs
+def use_tools_library(name="libpyrate_b200_tools.so"):
+    """tools/ only: load a measurement build (`make tools`, -DPYR_TOOLS: A/B knobs
     compiled in) instead of the product library.  Must be called before load()."""
     global LIB_PATH
     assert _lib is None, "library already loaded"
-    LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), "libpyrate_b200_tools.so")
+    LIB_PATH = os.path.join(os.path.dirname(LIB_PATH), name)
 
 
 class NativeError(RuntimeError):

@@ -77,6 +77,42 @@ __host__ __device__ __forceinline__ double exp_tab(double x, const double *tab) 
 #endif
 }
 
+// N independent arguments, operation by operation (source-level interleave: a warp issues
+// in order, so the N Horner chains only overlap if their instructions alternate)
+template <int N>
+__device__ __forceinline__ void exp_tab_n(const double *x, double *out, const double *tab) {
+    const double kInvL = kExpK[0], kLhi = kExpK[1], kLlo = kExpK[2], kMagic = kExpK[3];
+    double t[N], r[N], p[N], tj[N];
+    int n[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) t[j] = fma(x[j], kInvL, kMagic);
+#pragma unroll
+    for (int j = 0; j < N; ++j) { n[j] = __double2loint(t[j]); t[j] = t[j] - kMagic; }
+#pragma unroll
+    for (int j = 0; j < N; ++j) tj[j] = tab[n[j] & 31];
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = fma(-t[j], kLhi, x[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) r[j] = fma(-t[j], kLlo, r[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(r[j], kExpK[4], kExpK[5]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], kExpK[6]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], kExpK[7]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], kExpK[8]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j], r[j], 0.5);
+#pragma unroll
+    for (int j = 0; j < N; ++j) p[j] = fma(p[j] * r[j], r[j], r[j]);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double res = fma(tj[j], p[j], tj[j]);
+        out[j] = __hiloint2double(__double2hiint(res) + ((n[j] >> 5) << 20), __double2loint(res));
+    }
+}
+
 // valid range of exp_tab (result and 2^k normal)
 __host__ __device__ __forceinline__ bool exp_tab_ok(double x) { return x > -700.0 && x < 700.0; }
 

@@ -133,26 +133,38 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
 }
 
 // ---- straight-line building blocks of the interleaved integrator ----
-template <int PROFILE>
-__device__ __forceinline__ double grin_index_t(const DMedium &m, const double q[3], double g[3],
-                                               const double *etab) {
+// index and gradient of N positions, operation by operation over the N rays
+template <int PROFILE, int N>
+__device__ __forceinline__ void grin_index_n(const DMedium &m, const double (*q)[3], double *nn,
+                                             double (*g)[3], const double *etab) {
     if (PROFILE == PYR_GRIN_GAUSSIAN_XY) {
-        const double arg = fmin(fmax(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]), -700.0), 700.0);
-        const double ex = m.p[1] * exp_tab(arg, etab);
-        g[0] = -2.0 * m.p[2] * q[0] * ex;
-        g[1] = -2.0 * m.p[3] * q[1] * ex;
-        g[2] = 0.0;
-        return m.p[0] + ex;
+        double arg[N], ex[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j)
+            arg[j] = fmin(fmax(-fma(m.p[2] * q[j][0], q[j][0], m.p[3] * q[j][1] * q[j][1]), -700.0), 700.0);
+        exp_tab_n<N>(arg, ex, etab);
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            ex[j] *= m.p[1];
+            g[j][0] = -2.0 * m.p[2] * q[j][0] * ex[j];
+            g[j][1] = -2.0 * m.p[3] * q[j][1] * ex[j];
+            g[j][2] = 0.0;
+            nn[j] = m.p[0] + ex[j];
+        }
+        return;
     }
-    const double r2 = fma(q[0], q[0], q[1] * q[1]);
-    const double z = q[2];
-    const double nr = fma(fma(fma(m.p[3], r2, m.p[2]), r2, m.p[1]), r2, m.p[0]);
-    const double nz = z * fma(fma(m.p[6], z, m.p[5]), z, m.p[4]);
-    const double dr = 2.0 * fma(fma(3.0 * m.p[3], r2, 2.0 * m.p[2]), r2, m.p[1]);
-    g[0] = q[0] * dr;
-    g[1] = q[1] * dr;
-    g[2] = fma(fma(3.0 * m.p[6], z, 2.0 * m.p[5]), z, m.p[4]);
-    return nr + nz;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double r2 = fma(q[j][0], q[j][0], q[j][1] * q[j][1]);
+        const double z = q[j][2];
+        const double nr = fma(fma(fma(m.p[3], r2, m.p[2]), r2, m.p[1]), r2, m.p[0]);
+        const double nz = z * fma(fma(m.p[6], z, m.p[5]), z, m.p[4]);
+        const double dr = 2.0 * fma(fma(3.0 * m.p[3], r2, 2.0 * m.p[2]), r2, m.p[1]);
+        g[j][0] = q[j][0] * dr;
+        g[j][1] = q[j][1] * dr;
+        g[j][2] = fma(fma(3.0 * m.p[6], z, 2.0 * m.p[5]), z, m.p[4]);
+        nn[j] = nr + nz;
+    }
 }
 
 // boundary test without a branch on the boundary kind
@@ -188,14 +200,17 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
     const double ds[4] = {d0, d1, d0, 0.0};
     double q[N][3], p[N][3], uq[N][3], up[N][3];
     bool valid[N], done[N];
+    double g[N][3], nq[N];
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        double g[3];
         g2l_point(m.frame, x[j], q[j]);
         rot_t(m.frame.r, d[j], p[j]);
-        const double n0 = grin_index_t<PROFILE>(m, q[j], g, etab);
+    }
+    grin_index_n<PROFILE, N>(m, q, nq, g, etab);
 #pragma unroll
-        for (int c = 0; c < 3; ++c) { p[j][c] *= n0; uq[j][c] = q[j][c]; up[j][c] = p[j][c]; }
+    for (int j = 0; j < N; ++j) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { p[j][c] *= nq[j]; uq[j][c] = q[j][c]; up[j][c] = p[j][c]; }
         valid[j] = enter[j];
         done[j] = !enter[j];          // dead / out-of-range rays (NaN state) never enter
     }
@@ -203,23 +218,29 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
     const int cap = m.max_steps > 0 ? m.max_steps : 1000000;
     for (int it = 0; it < cap; ++it) {
         bool all_done = true;
+        // stage-major: every operation on all N rays before the next one
 #pragma unroll
-        for (int j = 0; j < N; ++j) {
-            double g[3], nq = 0.0;
+        for (int s = 0; s < 4; ++s) {
 #pragma unroll
-            for (int s = 0; s < 4; ++s) {
+            for (int j = 0; j < N; ++j) {
                 q[j][0] = fma(tau2 * cs[s], p[j][0], q[j][0]);
                 q[j][1] = fma(tau2 * cs[s], p[j][1], q[j][1]);
                 q[j][2] = fma(tau2 * cs[s], p[j][2], q[j][2]);
-                nq = grin_index_t<PROFILE>(m, q[j], g, etab);
-                if (s < 3) {
-                    const double f = tau2 * ds[s] * nq;
-                    p[j][0] = fma(f, g[0], p[j][0]);
-                    p[j][1] = fma(f, g[1], p[j][1]);
-                    p[j][2] = fma(f, g[2], p[j][2]);
+            }
+            grin_index_n<PROFILE, N>(m, q, nq, g, etab);
+            if (s < 3) {
+#pragma unroll
+                for (int j = 0; j < N; ++j) {
+                    const double f = tau2 * ds[s] * nq[j];
+                    p[j][0] = fma(f, g[j][0], p[j][0]);
+                    p[j][1] = fma(f, g[j][1], p[j][1]);
+                    p[j][2] = fma(f, g[j][2], p[j][2]);
                 }
             }
-            const bool e_ok = fabs(dot3(p[j], p[j]) - nq * nq) <= m.energy_tol;      // NaN -> false
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const bool e_ok = fabs(dot3(p[j], p[j]) - nq[j] * nq[j]) <= m.energy_tol;      // NaN -> false
             double xs[3];
             l2g_point(m.to_shape, q[j], xs);
             const double gap = xs[2] - conic_sag(curv, cc, xs[0], xs[1]);
@@ -239,10 +260,10 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
         }
         if (all_done) break;
     }
+    grin_index_n<PROFILE, N>(m, uq, nq, g, etab);
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        double g[3];
-        const double inv = 1.0 / grin_index_t<PROFILE>(m, uq[j], g, etab);
+        const double inv = 1.0 / nq[j];
         const double kl[3] = {up[j][0] * inv, up[j][1] * inv, up[j][2] * inv};
         if (enter[j]) {
             l2g_point(m.frame, uq[j], x[j]);

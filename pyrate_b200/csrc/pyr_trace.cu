@@ -1217,6 +1217,19 @@ static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream,
 int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                   uint32_t flags, cudaStream_t stream);   // pyr_aniso.cu
 
+// GRIN kernels: rays per thread and resident CTAs per SM (tools builds vary them).  Measured
+// on C5 (12.5e6 rays, profiles/r02_grin.md): 1 ray x 2 CTAs 32.8 ms, 2 rays x 2 CTAs 35.0 ms
+// (ptxas re-serialises the two chains under the 128-register cap), 1 x 3 34.9, 1 x 4 36.0,
+// 2 x 1 40.9, 2 x 3 39.3 -- more warps or more rays per thread do not pay: the FP64 pipe is
+// the limit, so the default is the variant with the fewest instructions
+#ifndef PYR_GRIN_RPT
+#define PYR_GRIN_RPT 1
+#endif
+#ifndef PYR_GRIN_MINB
+#define PYR_GRIN_MINB 2
+#endif
+constexpr int kGrinPolicy = PYR_GRIN_RPT == 2 ? 3 : 0;       // TMA record stores need two rays per thread
+
 static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                       uint32_t flags, cudaStream_t stream) {
     if (flags & PYR_F_COMPLEX) return trace_complex(steps, n_steps, rays, n_rays, flags, stream);
@@ -1241,7 +1254,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             grin = grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
         if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
         if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true);
-        if (grin && !hist) return launch(trace_real_kernel<2, false, 19, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+        if (grin && !hist)
+            return launch(trace_real_kernel<PYR_GRIN_RPT, false, 19, PYR_GRIN_MINB, kGrinPolicy | 16>, pk.P,
+                          PYR_GRIN_RPT, stream, PYR_GRIN_RPT == 2, false, 256, true);
         if (grin) return launch(trace_real_kernel<1, false, 3, 2, 16>, pk.P, 1, stream, false, false, 256, true);
         if (asph_only) return launch(trace_real_kernel<2, false, 9, 2, 19>, pk.P, 2, stream, true, false, 256, true);
         return launch(trace_real_kernel<2, false, 1, 2, 19>, pk.P, 2, stream, true, false, 256, true);
@@ -1278,7 +1293,8 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         return with_e ? launch(trace_real_kernel<1, true, 7, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 7, 2>, pk.P, 1, stream);
     if (has_grin && !with_e && !hist)   // two rays per thread, integrated together (interleaved chains)
-        return launch(trace_real_kernel<2, false, 19, 2, 3>, pk.P, 2, stream, true);
+        return launch(trace_real_kernel<PYR_GRIN_RPT, false, 19, PYR_GRIN_MINB, kGrinPolicy>, pk.P, PYR_GRIN_RPT,
+                      stream, PYR_GRIN_RPT == 2);
     if (has_grin)   // history / E recording: one ray per thread
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);

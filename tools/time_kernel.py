@@ -11,7 +11,9 @@ import torch  # noqa: E402
 import pyrate_b200 as pb  # noqa: E402
 from pyrate_b200 import _native, configs, engine, lowering  # noqa: E402
 
-if os.environ.get("PYR_LEAN_VARIANT") or os.environ.get("PYR_DEBUG_RECORD_LAST"):
+if os.environ.get("PYR_TOOLS_LIB"):
+    _native.use_tools_library(os.environ["PYR_TOOLS_LIB"])     # a variant build (make tools TOOLS_OUT=...)
+elif os.environ.get("PYR_LEAN_VARIANT") or os.environ.get("PYR_DEBUG_RECORD_LAST"):
     _native.use_tools_library()      # the A/B knobs exist in the `make tools` build only
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_doublegauss"
