@@ -438,7 +438,8 @@ def run_leg(name, info, args, world, rank, dev, peak, torch, dist):
     for _ in range(3):
         rec = step()
     ev = []
-    ms = timed_region(lambda: step(ev), steps, sync, world, dist, dev, torch)
+    with ClockSampler(torch.cuda.current_device()) as leg_clocks:
+        ms = timed_region(lambda: step(ev), steps, sync, world, dist, dev, torch)
     launches = len(ev) // steps
     kms = torch.tensor([sum(a.elapsed_time(b) for (a, b) in ev) / steps], dtype=torch.float64, device=dev)
     entries = torch.tensor([float(sum(rec.n_out))], dtype=torch.float64, device=dev)
@@ -465,7 +466,8 @@ def run_leg(name, info, args, world, rank, dev, peak, torch, dist):
                             "algorithmic_bytes_all_ranks": algo,
                             "achieved": algo / (kms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
                             "frac": algo / (kms * 1e-3) / 1e9 / world / peak},
-               "spot_rms": rms, "spot_count": float(spot[3].item())}
+               "spot_rms": rms, "spot_count": float(spot[3].item()),
+               "clocks": leg_clocks.summary()}
         if info["gather"]:
             g = gather_buf["out"]
             out["gathered_points"] = int(g.counts.sum().item())

@@ -429,7 +429,9 @@ constexpr int kMaxSplits = 6;
 // EXPLICIT: explicit shapes (asphere / XY polynomial / biconic Newton) present; crystals
 // between conics -- the common case -- run an instantiation without that code
 #ifndef PYR_C4_MINB
-#define PYR_C4_MINB 3          // resident CTAs per SM of the uniaxial kernel (tools builds vary it)
+#define PYR_C4_MINB 2          // resident CTAs per SM of the uniaxial kernel (tools builds vary it):
+                               // 2 (254 registers, no spills) 0.98 ms on C4, 3 (168 registers, 670 B
+                               // of spills) 1.20 ms (profiles/r02_c4.md)
 #endif
 template <bool GENERAL_EPS, bool EXPLICIT>
 __global__ void __launch_bounds__(128, GENERAL_EPS ? 2 : PYR_C4_MINB)
