@@ -397,6 +397,29 @@ int pyr_trace_spot(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
                    double *spot8_host, void *stream);
 
 /*
+ * Reference-exact GRIN propagation of a SMALL bundle (opt-in; the fused kernels integrate
+ * every ray independently): IsotropicGrinMaterial.symplecticintegrator,
+ * material/material_grin.py:106-213, as written -- all rays step in lock-step until every
+ * ray is final (:139), rays that are already final keep moving and are invalidated if
+ * they leave the boundary afterwards (:189-190), and the energy test is summed over the
+ * bundle and invalidates ALL rays (:164-176).  `step`: before = the GRIN medium, shape /
+ * frames = the next surface (crossing test).  x, k (real), e (may be NULL: d = k/|k|),
+ * alive (may be NULL): DEVICE (3, n) / (n) arrays of leading dimension ld; out_x / out_k:
+ * the frozen state in front of the surface (k = v / n), out_alive: PYR_RAY_ALIVE where
+ * valid; `scratch`: DEVICE, pyr_grin_lockstep_scratch(ld) bytes; `iterations`: DEVICE
+ * int32, number of integrator steps taken = history rows.  Optional history (all NULL =
+ * off): row r of ray i at hist_x[(r * 3 + c) * ld + i], hist_k likewise,
+ * hist_valid[r * ld + i], r < hist_rows -- the rows the reference appends (:198-205).
+ * One CTA; cost grows with n / 1024: for bundle sizes the reference itself can handle.
+ */
+int64_t pyr_grin_lockstep_scratch(int64_t ld);
+int pyr_grin_lockstep(const PyrStep *step, const double *x, const double *k, const double *e,
+                      const uint8_t *alive, int64_t ld, int64_t n, double *out_x,
+                      double *out_k, uint8_t *out_alive, void *scratch, int32_t *iterations,
+                      double *hist_x, double *hist_k, uint8_t *hist_valid, int64_t hist_rows,
+                      void *stream);
+
+/*
  * Spot-diagram points of OpticalSystemAnalysis.get_spot (analysis/
  * optical_system_analysis.py:283-303): x, y of the rays whose `flags & mask` is non-zero
  * (flags NULL = all), in the frame `frame` (HOST pointer, NULL = global coordinates; the

@@ -117,7 +117,8 @@ LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
 
 EXPORTS = ("pyr_version", "pyr_strerror", "pyr_sizeof_step",
            "pyr_sizeof_rays_in", "pyr_sizeof_bundle_gen", "pyr_device_count", "pyr_trace",
-           "pyr_spot_sums", "pyr_spot_points", "pyr_trace_spot", "pyr_generate_bundle", "pyr_trace_host_workspace",
+           "pyr_spot_sums", "pyr_spot_points", "pyr_trace_spot", "pyr_generate_bundle",
+           "pyr_grin_lockstep", "pyr_grin_lockstep_scratch", "pyr_trace_host_workspace",
            "pyr_trace_host", "pyr_trace_host_io_workspace", "pyr_trace_host_io")
 
 _lib = None
@@ -170,6 +171,11 @@ def load():
     lib.pyr_trace_spot.argtypes = [C.POINTER(PyrStep), C.c_int32, C.POINTER(PyrRaysIn), C.c_int64,
                                    C.c_uint32, C.POINTER(C.c_double), C.c_void_p, C.c_void_p,
                                    C.c_void_p]
+    lib.pyr_grin_lockstep_scratch.restype = C.c_int64
+    lib.pyr_grin_lockstep_scratch.argtypes = [C.c_int64]
+    lib.pyr_grin_lockstep.restype = C.c_int
+    lib.pyr_grin_lockstep.argtypes = [C.POINTER(PyrStep)] + [C.c_void_p] * 4 + [C.c_int64, C.c_int64] + \
+        [C.c_void_p] * 8 + [C.c_int64, C.c_void_p]
     lib.pyr_spot_points.restype = C.c_int
     lib.pyr_spot_points.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_uint32, C.c_int64,
                                     C.POINTER(PyrFrame), C.c_void_p, C.c_int64, C.c_void_p,

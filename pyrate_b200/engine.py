@@ -253,6 +253,36 @@ class RecordPool(object):
         return t
 
 
+def _grin_lockstep(lib, st, x, k, e, alive, n, ld, device, stream, want_history):
+    """pyr_grin_lockstep on the state handed over to a GRIN segment: returns (x, k, alive,
+    hist) with fresh (3, ld) / (ld) buffers; hist = the reference's per-iteration rows."""
+    xo = torch.empty((3, ld), dtype=torch.float64, device=device)
+    ko = torch.empty((3, ld), dtype=torch.float64, device=device)
+    ao = torch.zeros((ld,), dtype=torch.uint8, device=device)
+    scratch = torch.empty((lib.pyr_grin_lockstep_scratch(ld),), dtype=torch.uint8, device=device)
+    iters = torch.zeros((1,), dtype=torch.int32, device=device)
+
+    def run(hx, hk, hv, rows):
+        nat.check(lib.pyr_grin_lockstep(
+            C.byref(st), x.data_ptr(), k.data_ptr(), e.data_ptr() if e is not None else None,
+            alive.data_ptr() if alive is not None else None, ld, n, xo.data_ptr(), ko.data_ptr(),
+            ao.data_ptr(), scratch.data_ptr(), iters.data_ptr(),
+            hx.data_ptr() if hx is not None else None, hk.data_ptr() if hk is not None else None,
+            hv.data_ptr() if hv is not None else None, rows, stream))
+    run(None, None, None, 0)
+    hist = None
+    if want_history:
+        m = int(iters.item())
+        hist = {"x": torch.zeros((m, 3, ld), dtype=torch.float64, device=device),
+                "k": torch.zeros((m, 3, ld), dtype=torch.float64, device=device),
+                "valid": torch.zeros((m, ld), dtype=torch.uint8, device=device),
+                "count": torch.full((n,), m, dtype=torch.int32, device=device),
+                "rows": m, "n": n}
+        if m > 0:
+            run(hist["x"], hist["k"], hist["valid"], m)
+    return xo, ko, ao, hist
+
+
 def _gen_fusable(lowered, record_e, grin_history, wave_end):
     """Can the trace kernel generate the rays itself (PyrRaysIn.gen)?  Real-valued,
     non-splitting sequences without E recording, grid-sag / combination shapes,
@@ -273,7 +303,7 @@ def _gen_fusable(lowered, record_e, grin_history, wave_end):
 
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
           pool=None, events=None, grin_history=False, _hist_rows=None, wave_end=None,
-          gen=None):
+          gen=None, grin_lockstep=False):
     """Run the lowered sequence on the device.  Returns a TraceRecord.
 
     events: optional list; a (start, end) pair of CUDA timing events is appended
@@ -283,12 +313,16 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     indices of every entry.  One launch for all wavelengths.
     grin_history: also record every integrator step of GRIN segments (the rows the
     reference appends, material_grin.py:198-205).  Memory grows with steps x rays:
-    meant for small bundles.  Runs the trace twice (step counts first)."""
+    meant for small bundles.  Runs the trace twice (step counts first).
+    grin_lockstep: GRIN segments run the reference's exact lock-step loop with its
+    bundle-summed energy test (pyr_grin_lockstep, material_grin.py:139, :164-176) instead
+    of integrating every ray independently -- for small bundles."""
     lib = require_cuda()
     device = torch.device("cuda", torch.cuda.current_device()) if device is None \
         else torch.device(device)
     if gen is not None and (gen.materialised or
-                            not _gen_fusable(lowered, record_e, grin_history, wave_end)):
+                            not _gen_fusable(lowered, record_e, grin_history or grin_lockstep,
+                                             wave_end)):
         (x0, k0, e0) = gen.materialise(device)
         gen = None
     nsteps = len(lowered)
@@ -335,6 +369,10 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
     # with an auxiliary record (kernel parameter block, csrc/pyr_device.cuh) and
     # MAX_SPLITS_PER_LAUNCH doubling steps; longer sequences continue from the last
     # recorded state in a further launch
+    if grin_lockstep:
+        # the lock-step integrator is a kernel of its own in front of every GRIN segment
+        cuts += [i for (i, ls) in enumerate(lowered)
+                 if i > 0 and ls.st.before.kind == nat.MEDIUM_ISO_GRIN]
     cuts = sorted(set(cuts)) + [nsteps]
     bounded = [0]
     for hi in cuts[1:]:
@@ -395,6 +433,24 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                     nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
                     nx[:, :n_x] = cur_x[:, :n_x]
                     (cur_x, ld_x) = (nx, ld_k)
+            launch_steps = steps
+            if grin_lockstep and not seg_complex and steps[lo].before.kind == nat.MEDIUM_ISO_GRIN:
+                # reference-exact GRIN segment: integrate in lock-step, then let the trace
+                # kernel start from the frozen state in front of the surface
+                ld_s = max(cur_x.stride(0), 1)
+                (gx, gk, ga, hist) = _grin_lockstep(
+                    lib, steps[lo], cur_x, cur_k, cur_e if steps[lo].dir_mode == nat.DIR_POYNTING else None,
+                    cur_alive, n, ld_s, device, stream_ptr, grin_history)
+                (cur_x, cur_k, cur_alive, ld_x, ld_k, cur_e) = (gx, gk, ga, ld_s, ld_s, None)
+                if hist is not None:
+                    rec.grin_hist[lo] = hist
+                patched = nat.PyrStep.from_buffer_copy(steps[lo])
+                patched.before = _probe_medium()          # homogeneous: nothing left to integrate
+                patched.dir_mode = nat.DIR_K
+                patched.k_norm_hint = 0.0
+                patched._grid = getattr(steps[lo], "_grid", None)
+                launch_steps = list(steps)
+                launch_steps[lo] = patched
             want_e = record_e or seg_complex or \
                 (first_aniso is not None and hi == first_aniso)
             rows = hi - lo
@@ -427,7 +483,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                                  w, w_out, ld, ld2))
                     w = w_out
             for i in range(lo, hi):
-                st = steps[i]
+                st = launch_steps[i]
                 (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[i - lo]
                 (st.grin_hist_x, st.grin_hist_k, st.grin_hist_valid, st.grin_hist_count) = \
                     (None, None, None, None)
@@ -462,7 +518,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                 cur_e_arg = None            # engine substitutes (0, 1, 0)
             else:
                 cur_e_arg = cur_e
-            _launch(lib, steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
+            _launch(lib, launch_steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
                     ld_k, flags, stream_ptr, events, wave_end=wave_end,
                     gen=gen_desc if ci == 0 else None, device=device)
             for i in range(lo, hi):
@@ -490,13 +546,13 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                     nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
                     nx[:, :n_x] = cur_x[:, :n_x]
                     (cur_x, ld_x) = (nx, ld_k)
-    if grin_history and _hist_rows is None and rec.grin_hist:
+    if grin_history and _hist_rows is None and any("x" not in h for h in rec.grin_hist.values()):
         # first pass gave the step counts; second pass records the rows
         rows = {i: int(h["count"].max().item()) if h["count"].numel() else 0
                 for (i, h) in rec.grin_hist.items()}
         return trace(lowered, rec.x0, rec.k0, rec.e0, wave, record_e=record_e, device=device,
                      stream=stream, pool=pool, events=events, grin_history=True,
-                     _hist_rows=rows)
+                     _hist_rows=rows, grin_lockstep=grin_lockstep)
     return rec
 
 
@@ -689,14 +745,14 @@ def paths_from_record(rec, splitup=False):
 # entry used by OpticalSystem.seqtrace
 # ---------------------------------------------------------------------------
 def seqtrace(system, initialbundle, elementsequence, splitup=False,
-             record_e=False, grin_history=False):
+             record_e=False, grin_history=False, grin_lockstep=False):
     lowered = lowering.lower(system, elementsequence, initialbundle.wave,
                              splitup=splitup)
     gen = getattr(initialbundle, "generator", None)
     if gen is not None:
         # a generated bundle (OpticalSystemAnalysis.aim): the kernel expands it in registers
         rec = trace(lowered, None, None, None, initialbundle.wave, record_e=record_e,
-                    grin_history=grin_history, gen=gen)
+                    grin_history=grin_history, gen=gen, grin_lockstep=grin_lockstep)
         paths = paths_from_record(rec, splitup=splitup)
         for p in paths:
             p.record = rec
@@ -709,7 +765,7 @@ def seqtrace(system, initialbundle, elementsequence, splitup=False,
         (x0, k0, e0) = (initialbundle.x[0], initialbundle.k[0],
                         initialbundle.Efield[0])
     rec = trace(lowered, x0, k0, e0, initialbundle.wave, record_e=record_e,
-                grin_history=grin_history)
+                grin_history=grin_history, grin_lockstep=grin_lockstep)
     paths = paths_from_record(rec, splitup=splitup)
     for p in paths:
         p.record = rec

@@ -118,7 +118,7 @@ class OpticalSystem(LocalCoordinatesTreeBase):
         return (m_obj_stop, m_stop_img)
 
     def seqtrace(self, initialbundle, elementsequence, splitup=False,
-                 record_efield=False, grin_history=False):
+                 record_efield=False, grin_history=False, grin_lockstep=False):
         """Sequential trace on the GPU.
 
         :param initialbundle: RayBundle (never written)
@@ -133,9 +133,13 @@ class OpticalSystem(LocalCoordinatesTreeBase):
         :param grin_history: record every integrator step of GRIN segments in the
                         bundle rows like the reference does (small bundles only:
                         steps x rays x 49 B)
+        :param grin_lockstep: GRIN segments follow the reference's loop literally --
+                        all rays step until every ray is final, energy test summed
+                        over the bundle (material_grin.py:139, :164-176) -- instead
+                        of the per-ray normalisation; for small bundles
         :return: list[RayPath]
         """
         from .. import engine
         return engine.seqtrace(self, initialbundle, elementsequence,
                                splitup=splitup, record_e=record_efield,
-                               grin_history=grin_history)
+                               grin_history=grin_history, grin_lockstep=grin_lockstep)
