@@ -16,7 +16,8 @@ kernel launch per GPU + the spot-sum kernel; for N > 1 also the one NCCL all-red
   e2e              through the host entry pyr_trace_host_io: descriptor in, image-plane
                    record + spot sums back in pinned host memory (D2H inside the timed
                    region); e2e.host_buffers = the same with x0, k0, E0 uploaded from pinned
-                   host arrays; e2e.all_records = every record of the sequence read back
+                   host arrays; e2e.all_records = every record of the sequence read back;
+                   e2e.metric_only = descriptor in, the 8 spot sums out (MeritTrace)
   config.extra     BASELINE configs 3-5 at their stated total sizes, ray-sharded over the
                    N ranks (strong scaling), each with kernel time, roofline fraction and
                    an in-run parity figure against the oracle on a strided subsample
@@ -583,6 +584,21 @@ def run_gpu(args):
                                "what": "pinned host x0, k0, E0 -> H2D -> trace -> D2H of the image-plane "
                                        "record + spot sums (the round-1 e2e)"}
         del xp, kp, ep
+        # what an optimiser's merit function moves: descriptor in, the 8 spot sums out (nothing
+        # else crosses the bus; only the image-plane entry is recorded)
+        from pyrate_b200.merit import MeritTrace
+        mt = MeritTrace(s, seq, pb.RayBundle(generator=gen, wave=configs.DLINE), device=dev)
+        for _ in range(3):
+            mt()
+        dt_m = wall_region(mt, args.steps, sync, world, dist, dev, torch)
+        e2e["metric_only"] = {"value": world * n * S_COUNTED / dt_m, "ms_per_step": 1e3 * dt_m,
+                              "h2d_bytes_per_step": ht.h2d_bytes, "d2h_bytes_per_step": 64,
+                              "spot_rms": mt(refresh=False),
+                              "what": "pyrate_b200.merit.MeritTrace (pyr_trace_spot): parameters re-read from "
+                                      "the object graph, bundle generated in the kernel, only the last entry "
+                                      "recorded, spot sums read back -- one merit-function evaluation of "
+                                      "optimize/optimize.py:73-91 at full bundle size"}
+        del mt
         if world == 1 and not args.no_extras:
             # every record of the sequence back in host memory (what the S + 2 bundles of the
             # reference's RayPath hold): 13 x 49 B/ray over PCIe
