@@ -116,8 +116,15 @@ enum PyrMediumKind {
 /* closed catalogue of GRIN index profiles, evaluated in the material frame */
 enum PyrGrinProfile {
     PYR_GRIN_GAUSSIAN_XY = 0,   /* n = p0 + p1 exp(-p2 x^2 - p3 y^2)               */
-    PYR_GRIN_POLY_RZ = 1        /* n = p0 + p1 r^2 + p2 r^4 + p3 r^6
+    PYR_GRIN_POLY_RZ = 1,       /* n = p0 + p1 r^2 + p2 r^4 + p3 r^6
                                        + p4 z + p5 z^2 + p6 z^3,  r^2 = x^2+y^2    */
+    PYR_GRIN_USER = 100         /* index function given as CUDA source by the user
+                                   (core/functionobject.py:99-119 of the reference
+                                   takes Python source): such a medium is integrated
+                                   by a kernel compiled at run time (NVRTC,
+                                   pyrate_b200/grin_jit.py); this library refuses it
+                                   as `before` (PYR_E_UNSUPPORTED) and, as `after`,
+                                   needs the per-ray index in PyrStep.after_n_rays    */
 };
 
 enum PyrGrinBoundary {
@@ -239,6 +246,11 @@ typedef struct PyrStep {
      * bundles of one system, demos/demo_doublegauss.py:189-213, in ONE launch)         */
     double before_n_w[PYR_MAX_WAVES];
     double after_n_w[PYR_MAX_WAVES];
+    /* optional (DEVICE, n doubles): refractive index of the deflecting medium AT THE HIT
+     * POINT of every ray, evaluated by the caller -- position dependent media whose index
+     * function this library does not know (PYR_GRIN_USER).  NULL = after.n / the catalogue
+     * profile of after.                                                                  */
+    const double *after_n_rays;
 } PyrStep;
 
 /* per-ray flag bits written to out_flags */

@@ -18,7 +18,7 @@ MAX_WAVES = 4
 (AP_BASE, AP_CIRCULAR, AP_RECTANGULAR) = (0, 1, 2)
 (REFRACT, REFLECT) = (0, 1)
 (MEDIUM_ISO_CONST, MEDIUM_ISO_GRIN, MEDIUM_ANISO) = (0, 1, 2)
-(GRIN_GAUSSIAN_XY, GRIN_POLY_RZ) = (0, 1)
+(GRIN_GAUSSIAN_XY, GRIN_POLY_RZ, GRIN_USER) = (0, 1, 100)
 (BND_NONE, BND_CYLINDER, BND_BOX, BND_SPHERE) = (0, 1, 2, 3)
 (DIR_POYNTING, DIR_K) = (0, 1)
 (STEP_FULL, STEP_PROPAGATE_ONLY, STEP_DEFLECT_ONLY) = (0, 1, 2)
@@ -78,7 +78,8 @@ class PyrStep(C.Structure):
                 ("terms", PyrShapeTerm * MAX_TERMS),
                 ("ld_out2", C.c_int64),
                 ("before_n_w", C.c_double * MAX_WAVES),
-                ("after_n_w", C.c_double * MAX_WAVES)]
+                ("after_n_w", C.c_double * MAX_WAVES),
+                ("after_n_rays", C.c_void_p)]
 
 
 (RASTER_HEXAPOLAR, RASTER_RECT, RASTER_HEX, RASTER_CIRCULAR) = (0, 1, 2, 3)

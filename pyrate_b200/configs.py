@@ -344,7 +344,10 @@ def _make_material(api, lc, matspec, name):
         m.annotations["ds"] = kw["ds"]
         m.annotations["energyviolation"] = kw["energyviolation"]
         # ignored by the reference; read by pyrate_b200's lowering
-        m.annotations["device_profile"] = kw["device_profile"]
+        if "device_profile" in kw:
+            m.annotations["device_profile"] = kw["device_profile"]
+        if "device_source" in kw:
+            m.annotations["device_source"] = kw["device_source"]
         return m
     raise ValueError("unknown material kind %r" % (kind,))
 
@@ -618,7 +621,61 @@ X16_CYLINDER = {   # cylinder lenses (conic sections in y extruded along x), til
     "s_counted": 2,
 }
 
-CONFIGS.update({c["name"]: c for c in (X16_CYLINDER, X13_TIRGLASS, X14_DISPERSIVE, X15_DISPERSIVE_ASPHERE, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
+# A GRIN rod with an index profile OUTSIDE the device catalogue (hyperbolic-secant "selfoc"
+# profile with an axial taper): Python source for the reference, CUDA expressions for the
+# device (compiled at run time, pyrate_b200/grin_jit.py).
+SECH_SOURCE = r"""
+import numpy as np
+
+
+def nfunc(x, **kw):
+    return 1.55 / np.cosh(0.12 * np.sqrt(x[0]**2 + x[1]**2)) * (1.0 + 0.002 * x[2])
+
+
+def dndx(x, **kw):
+    r = np.sqrt(x[0]**2 + x[1]**2) + 1e-300
+    return -1.55 * 0.12 * np.tanh(0.12 * r) / np.cosh(0.12 * r) * (1.0 + 0.002 * x[2]) * x[0] / r
+
+
+def dndy(x, **kw):
+    r = np.sqrt(x[0]**2 + x[1]**2) + 1e-300
+    return -1.55 * 0.12 * np.tanh(0.12 * r) / np.cosh(0.12 * r) * (1.0 + 0.002 * x[2]) * x[1] / r
+
+
+def dndz(x, **kw):
+    return 1.55 / np.cosh(0.12 * np.sqrt(x[0]**2 + x[1]**2)) * 0.002
+
+
+def bnd(x):
+    return x[0]**2 + x[1]**2 < 6.0**2
+"""
+
+X17_USER_GRIN = {
+    "name": "x17_user_grin",
+    "surfaces": [
+        _conic("object", 0.0, opt={"is_stop": True}),
+        _conic("front", 8.0, curv=1. / 40.0, mat="rod", aperture=_circ(4.5)),
+        _conic("back", 15.0, curv=-1. / 60.0, mat=None, tiltx=3. * math.pi / 180.0),
+        _conic("image", 12.0),
+    ],
+    "materials": {"rod": ("IsotropicGrinMaterial", {
+        "source": SECH_SOURCE,
+        "names": ("nfunc", "dndx", "dndy", "dndz", "bnd"),
+        "parameterlist": [],
+        "ds": 0.05, "energyviolation": 0.01,
+        "device_source": {
+            "n": "p[0] / cosh(p[1] * sqrt(x * x + y * y)) * (1.0 + p[2] * z)",
+            "dndx": "-p[0] * p[1] * tanh(p[1] * (sqrt(x * x + y * y) + 1e-300)) / cosh(p[1] * (sqrt(x * x + y * y) + 1e-300)) * (1.0 + p[2] * z) * x / (sqrt(x * x + y * y) + 1e-300)",
+            "dndy": "-p[0] * p[1] * tanh(p[1] * (sqrt(x * x + y * y) + 1e-300)) / cosh(p[1] * (sqrt(x * x + y * y) + 1e-300)) * (1.0 + p[2] * z) * y / (sqrt(x * x + y * y) + 1e-300)",
+            "dndz": "p[0] / cosh(p[1] * sqrt(x * x + y * y)) * p[2]",
+            "inside": "x * x + y * y < 36.0",
+            "params": [1.55, 0.12, 0.002]},
+    })},
+    "bundle": {"rings": 6, "radius": 3.5, "z0": -4.0},
+    "s_counted": 2,
+}
+
+CONFIGS.update({c["name"]: c for c in (X17_USER_GRIN, X16_CYLINDER, X13_TIRGLASS, X14_DISPERSIVE, X15_DISPERSIVE_ASPHERE, X1_TILTED, X2_XYPOLY, X3_VIGNETTE, X4_BIAXIAL,
                                        X5_DEGENERATE, X6_BICONIC, X7_TWO_ELEMENTS,
                                        X8_CRYSTAL_MIRROR, X9_ZERNIKE, X10_ZERNIKE_GENERAL,
                                        X11_GRIDSAG, X12_COMBINATION)})

@@ -72,6 +72,7 @@ struct DAux {
     // the device: the kernel parameter block has no room for them)
     int32_t uniaxial, pad1;
     double eps_o, eps_e, axis[3];
+    const double *after_n_rays;    // per-ray index of the deflecting medium at the hit point (user GRIN)
 };
 
 struct DStep {

@@ -224,7 +224,11 @@ __device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep
     if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
     else rot_t(st.frame.r, r.k, kl);
     double n2sq = st.n2sq[w];
-    if (grin_media && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
+    if (aux && aux->after_n_rays) {
+        // index of a position-dependent medium the caller evaluated at the hit points
+        const double nn = ray_index >= 0 ? aux->after_n_rays[ray_index] : qnan();
+        n2sq = nn * nn;
+    } else if (grin_media && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
         double q[3], g[3];
         g2l_point(aux->after.frame, hit_g, q);
         const double nn = grin_index(aux->after, q, g, false, etab);
@@ -1051,6 +1055,14 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         out.extended = out.extended || grid || comb;
         if (u.shape_kind == PYR_SHAPE_BICONIC && u.n_coeff > 16) return PYR_E_BADARG;
         if (u.aperture_kind < PYR_AP_BASE || u.aperture_kind > PYR_AP_RECTANGULAR) return PYR_E_UNSUPPORTED;
+        // position-dependent media: catalogue profiles only; a user profile is integrated by the
+        // caller's own kernel and may only appear as the deflecting medium with its per-ray index
+        if (u.before.kind == PYR_MEDIUM_ISO_GRIN && u.mode != PYR_STEP_DEFLECT_ONLY &&
+            u.before.grin_profile != PYR_GRIN_GAUSSIAN_XY && u.before.grin_profile != PYR_GRIN_POLY_RZ)
+            return PYR_E_UNSUPPORTED;
+        if (u.after.kind == PYR_MEDIUM_ISO_GRIN && u.mode != PYR_STEP_PROPAGATE_ONLY && !u.after_n_rays &&
+            u.after.grin_profile != PYR_GRIN_GAUSSIAN_XY && u.after.grin_profile != PYR_GRIN_POLY_RZ)
+            return PYR_E_UNSUPPORTED;
         if (u.n_coeff < 0 || u.n_coeff > PYR_MAX_COEFF) return PYR_E_BADARG;
         if (u.split && s != n_steps - 1 && !(flags & PYR_F_COMPLEX)) return PYR_E_BADARG;
         pack_frame(u.shape_frame, d.frame);
@@ -1131,6 +1143,7 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
             if (u.after.kind == PYR_MEDIUM_ANISO) pack_crystal(a.after.eps, a);
             a.grid_tx = u.grid_tx; a.grid_ty = u.grid_ty; a.grid_c = u.grid_c;
             a.grid_nx = u.grid_nx; a.grid_ny = u.grid_ny;
+            a.after_n_rays = u.after_n_rays;
             a.n_terms = 0;
             if (comb) {
                 // one auxiliary record per term, consecutive; record 0 also carries the

@@ -283,6 +283,34 @@ def _grin_lockstep(lib, st, x, k, e, alive, n, ld, device, stream, want_history)
     return xo, ko, ao, hist
 
 
+_USER_GRIN = {}     # (id(material), device index) -> grin_jit.UserGrin (compiled + verified)
+
+
+def _is_user_grin(medium):
+    return medium.kind == nat.MEDIUM_ISO_GRIN and medium.grin_profile == nat.GRIN_USER
+
+
+def _user_grin(material, medium, device):
+    """The NVRTC-compiled kernels of a user-defined GRIN material (compiled once per source,
+    checked against the material's Python functions once per material and device)."""
+    from . import grin_jit
+    key = (id(material), device.index)
+    ug = _USER_GRIN.get(key)
+    if ug is None or ug[0] is not material:
+        u = grin_jit.UserGrin(material.annotations["device_source"], device)
+        u.verify(material, medium.frame)
+        ug = _USER_GRIN[key] = (material, u)
+    return ug[1]
+
+
+def _compose_to_shape(mat_frame, shape_frame):
+    """Frame mapping material-local -> shape-local coordinates: x_s = Rs^T (Rm x_m + om - os)."""
+    rm = np.asarray(list(mat_frame.r)).reshape(3, 3)
+    rs = np.asarray(list(shape_frame.r)).reshape(3, 3)
+    (om, os_) = (np.asarray(list(mat_frame.o)), np.asarray(list(shape_frame.o)))
+    return ((rs.T @ rm).reshape(-1), rs.T @ (om - os_))
+
+
 def _gen_fusable(lowered, record_e, grin_history, wave_end):
     """Can the trace kernel generate the rays itself (PyrRaysIn.gen)?  Real-valued,
     non-splitting sequences without E recording, grid-sag / combination shapes,
@@ -293,6 +321,8 @@ def _gen_fusable(lowered, record_e, grin_history, wave_end):
     for (i, ls) in enumerate(lowered):
         st = ls.st
         if nat.MEDIUM_ANISO in (st.before.kind, st.after.kind) or st.split:
+            return False
+        if _is_user_grin(st.before) or _is_user_grin(st.after):
             return False
         if st.shape_kind in (nat.SHAPE_GRIDSAG, nat.SHAPE_COMBINATION):
             return False
@@ -373,6 +403,19 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         # the lock-step integrator is a kernel of its own in front of every GRIN segment
         cuts += [i for (i, ls) in enumerate(lowered)
                  if i > 0 and ls.st.before.kind == nat.MEDIUM_ISO_GRIN]
+    user_grin = any(_is_user_grin(ls.st.before) or _is_user_grin(ls.st.after) for ls in lowered)
+    if user_grin:
+        # user-written index functions (NVRTC): the segment is integrated by its own kernel in
+        # front of the exit step; the entrance step runs alone, in two phases, because the
+        # refraction into the medium needs n at every ray's hit point
+        if grin_history or grin_lockstep:
+            raise lowering.LoweringError("grin_history / grin_lockstep: catalogue GRIN profiles only")
+        for (i, ls) in enumerate(lowered):
+            if _is_user_grin(ls.st.before) and i > 0:
+                cuts.append(i)
+            if _is_user_grin(ls.st.after):
+                cuts += [i, i + 1] if i > 0 else [i + 1]
+        cuts = [c for c in cuts if c < nsteps]
     cuts = sorted(set(cuts)) + [nsteps]
     bounded = [0]
     for hi in cuts[1:]:
@@ -451,6 +494,23 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                 patched._grid = getattr(steps[lo], "_grid", None)
                 launch_steps = list(steps)
                 launch_steps[lo] = patched
+            if user_grin and _is_user_grin(steps[lo].before):
+                if seg_complex or steps[lo].shape_kind != nat.SHAPE_CONIC:
+                    raise lowering.LoweringError("a user-defined GRIN medium must end at a conic surface "
+                                                 "(real-valued sequences)")
+                ug = _user_grin(lowered[lo].before_obj, steps[lo].before, device)
+                ld_s = max(cur_x.stride(0), 1)
+                (gx, gk, ga) = ug.propagate(steps[lo].before,
+                                            _compose_to_shape(steps[lo].before.frame, steps[lo].shape_frame),
+                                            steps[lo].curv, steps[lo].cc, cur_x, cur_k, cur_alive, n, ld_s)
+                (cur_x, cur_k, cur_alive, ld_x, ld_k, cur_e) = (gx, gk, ga, ld_s, ld_s, None)
+                patched = nat.PyrStep.from_buffer_copy(launch_steps[lo])
+                patched.before = _probe_medium()
+                patched.dir_mode = nat.DIR_K
+                patched.k_norm_hint = 0.0
+                patched._grid = None
+                launch_steps = list(launch_steps)
+                launch_steps[lo] = patched
             want_e = record_e or seg_complex or \
                 (first_aniso is not None and hi == first_aniso)
             rows = hi - lo
@@ -518,9 +578,32 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                 cur_e_arg = None            # engine substitutes (0, 1, 0)
             else:
                 cur_e_arg = cur_e
-            _launch(lib, launch_steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
-                    ld_k, flags, stream_ptr, events, wave_end=wave_end,
-                    gen=gen_desc if ci == 0 else None, device=device)
+            if user_grin and _is_user_grin(steps[lo].after):
+                # entrance into a user-defined GRIN medium (this stretch is the one step):
+                # (A) propagate + intersect + aperture, (B) n at the hit points from the user's
+                # kernel, (C) refraction with the per-ray index -- all into the same record
+                assert hi == lo + 1 and not seg_complex
+                (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[0]
+                phase_a = nat.PyrStep.from_buffer_copy(launch_steps[lo])
+                phase_a.mode = nat.STEP_PROPAGATE_ONLY
+                phase_a._grid = getattr(launch_steps[lo], "_grid", None)
+                _launch(lib, [phase_a], 0, 1, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
+                        ld_k, flags, stream_ptr, events, device=device)
+                ug = _user_grin(lowered[lo].after_obj, steps[lo].after, device)
+                n_hit = ug.index_at(steps[lo].after.frame, bx, n, ld)
+                phase_c = nat.PyrStep.from_buffer_copy(launch_steps[lo])
+                phase_c.mode = nat.STEP_DEFLECT_ONLY
+                phase_c.dir_mode = nat.DIR_K
+                phase_c.k_norm_hint = 0.0
+                phase_c.after_n_rays = n_hit.data_ptr()
+                phase_c._grid = getattr(launch_steps[lo], "_grid", None)
+                kin = bk.clone()                       # phase A left k unchanged in the record
+                _launch(lib, [phase_c], 0, 1, bx, kin, None, bf, n, n, ld, flags & ~nat.F_RECORD_E,
+                        stream_ptr, events, device=device)
+            else:
+                _launch(lib, launch_steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
+                        ld_k, flags, stream_ptr, events, wave_end=wave_end,
+                        gen=gen_desc if ci == 0 else None, device=device)
             for i in range(lo, hi):
                 (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[i - lo]
                 rec.hit.append(bx[:, :w_in])

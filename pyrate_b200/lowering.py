@@ -133,11 +133,21 @@ def _lower_medium_uncached(mat, wave):
     elif "IsotropicGrinMaterial" in names:
         m.kind = nat.MEDIUM_ISO_GRIN
         prof = mat.annotations.get("device_profile")
+        if prof is None and mat.annotations.get("device_source") is not None:
+            # user-written index function (CUDA source, compiled at run time by NVRTC:
+            # pyrate_b200/grin_jit.py); the engine runs such segments through its own kernels
+            m.grin_profile = nat.GRIN_USER
+            m.grin_boundary = nat.BND_NONE
+            m.grin_ds = float(mat.annotations["ds"])
+            m.grin_energy_tol = float(mat.annotations["energyviolation"])
+            m.grin_max_steps = int(mat.annotations.get("max_steps", 0))
+            m.n = 0.0
+            return m
         if prof is None:
             raise LoweringError(
-                "GRIN material %r needs annotations['device_profile'] "
-                "(catalogue: %s)" % (getattr(mat, "name", "?"),
-                                     ", ".join(sorted(PROFILE_KINDS))))
+                "GRIN material %r needs annotations['device_profile'] (catalogue: %s) or "
+                "annotations['device_source'] (CUDA expressions, compiled at run time)"
+                % (getattr(mat, "name", "?"), ", ".join(sorted(PROFILE_KINDS))))
         _verify_grin_profile(mat, prof)
         m.grin_profile = PROFILE_KINDS[prof["kind"]]
         for (i, v) in enumerate(prof["params"]):

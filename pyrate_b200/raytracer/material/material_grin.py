@@ -89,7 +89,7 @@ class IsotropicGrinMaterial(IsotropicMaterial):
     @classmethod
     def p(cls, lc, mysource=None, nfun_name="nfunc", dndx_name="dndx",
           dndy_name="dndy", dndz_name="dndz", bnd_name="bnd",
-          parameterlist=None, name="", comment="", device_profile=None):
+          parameterlist=None, name="", comment="", device_profile=None, device_source=None):
         params = {}
         for (pname, value) in (parameterlist or []):
             params[pname] = FloatOptimizableVariable(value, name=pname)
@@ -99,6 +99,11 @@ class IsotropicGrinMaterial(IsotropicMaterial):
                "bnd_name": bnd_name, "source": mysource}
         if device_profile is not None:
             ann["device_profile"] = device_profile
+        if device_source is not None:
+            # {"n": ..., "dndx": ..., "dndy": ..., "dndz": ..., "inside": ..., "params": [...]}:
+            # CUDA C++ expressions in x, y, z (material frame) and p[] -- the device
+            # counterpart of the Python source above, compiled by pyrate_b200/grin_jit.py
+            ann["device_source"] = device_source
         return cls(ann, {"lc": lc, "params": params}, name=name)
 
     def initialize_from_annotations(self):
@@ -125,6 +130,8 @@ class IsotropicGrinMaterial(IsotropicMaterial):
 
     def device_profile(self):
         prof = self.annotations.get("device_profile")
+        if prof is None and self.annotations.get("device_source") is not None:
+            return None
         if prof is None:
             raise NotImplementedError(
                 "IsotropicGrinMaterial %r has no annotations['device_profile']: the "
@@ -134,7 +141,13 @@ class IsotropicGrinMaterial(IsotropicMaterial):
         return prof
 
     def get_optical_index(self, x, wave=standard_wavelength):
-        return profile_functions(self.device_profile())[0](np.asarray(x))
+        prof = self.device_profile()
+        if prof is None:                          # user profile: the Python source itself
+            return self.user_functions()[0](np.asarray(x))
+        return profile_functions(prof)[0](np.asarray(x))
 
     def in_boundary(self, pos):
-        return profile_functions(self.device_profile())[4](np.asarray(pos))
+        prof = self.device_profile()
+        if prof is None:
+            return self.user_functions()[4](np.asarray(pos))
+        return profile_functions(prof)[4](np.asarray(pos))
