@@ -3,7 +3,7 @@ NVCC ?= nvcc
 ARCH := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS := -O3 -std=c++17 $(ARCH) -lineinfo -Xcompiler -fPIC -Xptxas -v
 SRC := pyrate_b200/csrc/pyr_trace.cu pyrate_b200/csrc/pyr_aniso.cu pyrate_b200/csrc/pyr_host.cu \
-       pyrate_b200/csrc/pyr_grin_lockstep.cu
+       pyrate_b200/csrc/pyr_grin_lockstep.cu pyrate_b200/csrc/pyr_host_crystal.cu
 HDR := $(wildcard pyrate_b200/csrc/*.cuh) include/pyrate_b200.h
 OUT := pyrate_b200/_lib/libpyrate_b200.so
 

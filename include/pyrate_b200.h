@@ -477,8 +477,12 @@ int pyr_trace_host(const PyrStep *steps, int32_t n_steps, const double *x0,
  * record of the sequence like the S + 2 bundles OpticalSystem.seqtrace returns
  * (raytracer/optical_system.py:73-94, ray.py:207-260): x_all / k_all as
  * (n_steps, 3, n_rays), flags_all as (n_steps, n_rays), and the spot sums.  Sequences
- * longer than one launch are continued internally.  Real-valued, non-splitting
- * sequences (crystals go through pyr_trace with PYR_F_COMPLEX on device arrays).
+ * longer than one launch are continued internally.
+ * Sequences with birefringent media: real x0, k0, e0 in; the last record is that of the
+ * doubled bundle (reference hstack order, material_anisotropic.py:89-100): x_last
+ * (3, n m_x) and flags_last (n m_x), k_last and e_last (3, n m_k) complex128 interleaved,
+ * m_x / m_k from pyr_trace_host_crystal_workspace(), which also sizes the workspace; no
+ * `*_all` outputs there.
  */
 typedef struct PyrHostIO {
     const double *x0, *k0, *e0;     /* e0 NULL = (0, 1, 0), ray.py:71-73                */
@@ -488,9 +492,12 @@ typedef struct PyrHostIO {
     double *x_all, *k_all;
     uint8_t *flags_all;
     double *spot8;
+    double *e_last;                 /* E of the last record (crystal sequences; complex128)     */
 } PyrHostIO;
 
 int64_t pyr_trace_host_io_workspace(int32_t n_steps, int64_t chunk_rays, int32_t all_records);
+int64_t pyr_trace_host_crystal_workspace(const PyrStep *steps, int32_t n_steps, int64_t chunk_rays,
+                                         int64_t *mult_x, int64_t *mult_k);
 int pyr_trace_host_io(const PyrStep *steps, int32_t n_steps, const PyrHostIO *io,
                       int64_t n_rays, void *workspace, int64_t workspace_bytes,
                       int64_t chunk_rays);

@@ -110,7 +110,7 @@ class PyrHostIO(C.Structure):
                 ("gen", C.POINTER(PyrBundleGen)),
                 ("x_last", C.c_void_p), ("k_last", C.c_void_p), ("flags_last", C.c_void_p),
                 ("x_all", C.c_void_p), ("k_all", C.c_void_p), ("flags_all", C.c_void_p),
-                ("spot8", C.c_void_p)]
+                ("spot8", C.c_void_p), ("e_last", C.c_void_p)]
 
 
 LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_lib",
@@ -120,7 +120,8 @@ EXPORTS = ("pyr_version", "pyr_strerror", "pyr_sizeof_step",
            "pyr_sizeof_rays_in", "pyr_sizeof_bundle_gen", "pyr_device_count", "pyr_trace",
            "pyr_spot_sums", "pyr_spot_points", "pyr_trace_spot", "pyr_generate_bundle",
            "pyr_grin_lockstep", "pyr_grin_lockstep_scratch", "pyr_trace_host_workspace",
-           "pyr_trace_host", "pyr_trace_host_io_workspace", "pyr_trace_host_io")
+           "pyr_trace_host", "pyr_trace_host_io_workspace", "pyr_trace_host_io",
+           "pyr_trace_host_crystal_workspace")
 
 _lib = None
 
@@ -187,6 +188,9 @@ def load():
                                         C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.pyr_trace_host_io_workspace.restype = C.c_int64
     lib.pyr_trace_host_io_workspace.argtypes = [C.c_int32, C.c_int64, C.c_int32]
+    lib.pyr_trace_host_crystal_workspace.restype = C.c_int64
+    lib.pyr_trace_host_crystal_workspace.argtypes = [C.POINTER(PyrStep), C.c_int32, C.c_int64,
+                                                     C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     lib.pyr_trace_host_io.restype = C.c_int
     lib.pyr_trace_host_io.argtypes = [C.POINTER(PyrStep), C.c_int32, C.POINTER(PyrHostIO),
                                       C.c_int64, C.c_void_p, C.c_int64, C.c_int64]

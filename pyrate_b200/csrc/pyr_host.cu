@@ -23,6 +23,9 @@ int trace_entry(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
 int step_aux_records(const PyrStep &u);     // pyr_trace.cu: auxiliary records pack() will use
 }
 
+int pyr_trace_host_crystal(const PyrStep *steps, int32_t n_steps, const PyrHostIO *io, int64_t n_rays,
+                           void *workspace, int64_t workspace_bytes, int64_t chunk_rays, cudaStream_t *st);
+
 namespace {
 constexpr int kSlots = 4;
 
@@ -124,11 +127,16 @@ int pyr_trace_host_io(const PyrStep *steps, int32_t n_steps, const PyrHostIO *io
         return PYR_E_BADARG;
     if (!io->gen && (!io->x0 || !io->k0)) return PYR_E_BADARG;
     const bool all = io->x_all || io->k_all || io->flags_all;
-    if (workspace_bytes < pyr_trace_host_io_workspace(n_steps, chunk_rays, all ? 1 : 0)) return PYR_E_BADARG;
     if ((reinterpret_cast<uintptr_t>(workspace) & 255u) != 0) return PYR_E_BADARG;
     for (int i = 0; i < n_steps; ++i)
-        if (steps[i].before.kind == PYR_MEDIUM_ANISO || steps[i].after.kind == PYR_MEDIUM_ANISO || steps[i].split)
-            return PYR_E_UNSUPPORTED;       // crystals: pyr_trace with PYR_F_COMPLEX on device arrays
+        if (steps[i].before.kind == PYR_MEDIUM_ANISO || steps[i].after.kind == PYR_MEDIUM_ANISO) {
+            // birefringent media: the complex-valued pipeline (pyr_host_crystal.cu)
+            cudaStream_t *cst = nullptr;
+            const int crc = get_streams(&cst);
+            if (crc != PYR_OK) return crc;
+            return pyr_trace_host_crystal(steps, n_steps, io, n_rays, workspace, workspace_bytes, chunk_rays, cst);
+        }
+    if (workspace_bytes < pyr_trace_host_io_workspace(n_steps, chunk_rays, all ? 1 : 0)) return PYR_E_BADARG;
     const SlotLayout L = layout(chunk_rays, all ? n_steps : 2);
     char *ws = static_cast<char *>(workspace);
     double *spot_dev = reinterpret_cast<double *>(ws + kSlots * L.slot_bytes);

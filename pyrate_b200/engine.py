@@ -1063,15 +1063,30 @@ class HostTracer(object):
         self.chunk = int(min(chunk_rays, max(self.n, 1)))
         self.all_records = bool(all_records)
         ns = len(lowered)
-        nbytes = self.lib.pyr_trace_host_io_workspace(ns, self.chunk, int(self.all_records))
+        self.crystal = any(nat.MEDIUM_ANISO in (ls.st.before.kind, ls.st.after.kind) for ls in lowered)
+        (self.mult_x, self.mult_k) = (1, 1)
+        if self.crystal:
+            # birefringent media: the last record is that of the doubled bundle, k / E complex
+            if self.all_records:
+                raise ValueError("all_records: real-valued sequences only")
+            (mx, mk) = (C.c_int64(1), C.c_int64(1))
+            nbytes = self.lib.pyr_trace_host_crystal_workspace(self.steps, ns, self.chunk,
+                                                               C.byref(mx), C.byref(mk))
+            if nbytes <= 0:
+                raise nat.NativeError("pyr_trace_host_crystal_workspace: sequence not supported")
+            (self.mult_x, self.mult_k) = (int(mx.value), int(mk.value))
+        else:
+            nbytes = self.lib.pyr_trace_host_io_workspace(ns, self.chunk, int(self.all_records))
         self.workspace = torch.empty((nbytes + 256,), dtype=torch.uint8,
                                      device=self.device)
         off = (-self.workspace.data_ptr()) % 256
         self.ws_ptr = self.workspace.data_ptr() + off
         self.ws_bytes = nbytes
-        self.x_last = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
-        self.k_last = torch.empty((3, self.n), dtype=torch.float64).pin_memory()
-        self.flags_last = torch.empty((self.n,), dtype=torch.uint8).pin_memory()
+        kdt = torch.complex128 if self.crystal else torch.float64
+        self.x_last = torch.empty((3, self.n * self.mult_x), dtype=torch.float64).pin_memory()
+        self.k_last = torch.empty((3, self.n * self.mult_k), dtype=kdt).pin_memory()
+        self.e_last = torch.empty((3, self.n * self.mult_k), dtype=kdt).pin_memory() if self.crystal else None
+        self.flags_last = torch.empty((self.n * self.mult_x,), dtype=torch.uint8).pin_memory()
         self.spot8 = torch.zeros((8,), dtype=torch.float64).pin_memory()
         self.x_all = self.k_all = self.flags_all = None
         if self.all_records:
@@ -1108,6 +1123,9 @@ class HostTracer(object):
         io.flags_last = self.flags_last.data_ptr()
         io.spot8 = self.spot8.data_ptr()
         self.d2h_bytes = 49 * self.n + 64
+        if self.crystal:
+            io.e_last = self.e_last.data_ptr()
+            self.d2h_bytes = (25 * self.mult_x + 96 * self.mult_k) * self.n + 64
         if self.all_records:
             io.x_all = self.x_all.data_ptr()
             io.k_all = self.k_all.data_ptr()

@@ -246,3 +246,32 @@ def test_spot_points_compaction_on_device():
         (xy4, c4) = engine.spot_points(hit[:, :n])
         assert int(c4) == n
         assert np.array_equal(as_set(xy4[:, :n].cpu().numpy()), as_set(hit[:2, :n].cpu().numpy()))
+
+
+@pytest.mark.parametrize("name,chunk", [("c4_anisotropic", 1 << 20), ("c4_anisotropic", 1000),
+                                        ("x8_crystal_mirror", 777), ("x4_biaxial", 512)])
+def test_host_entry_traces_crystal_sequences(name, chunk):
+    """pyr_trace_host_io with birefringent media: real host arrays (or a generator) in, the
+    last record of the DOUBLED bundle back (x, complex k and E, flags in the reference's
+    hstack order) -- equal to the device-resident trace, chunked or not."""
+    import torch
+    from pyrate_b200 import engine, lowering
+    spec = configs.CONFIGS[name]
+    (x0, k0, e0) = configs.config_bundle(spec, 20, (0.0, np.sin(0.01), np.cos(0.01)), (1.0, 0.0, 0.0))
+    n = x0.shape[1]                                            # 1261 rays
+    (s, seq) = configs.build_system(spec, pb.api())
+    lowered = lowering.lower(s, seq, configs.DLINE)
+    rec = engine.trace(lowered, x0, k0, e0, configs.DLINE)
+    ht = engine.HostTracer(lowered, n, chunk_rays=chunk)
+    assert ht.crystal and ht.mult_k == rec.k[-1].shape[1] // n and ht.mult_x == rec.hit[-1].shape[1] // n
+    (xp, kp, ep) = (torch.from_numpy(a).pin_memory() for a in (x0, k0, e0))
+    (xl, kl, fl, spot8) = ht(xp, kp, ep)
+    assert np.array_equal(fl.numpy(), rec.flags[-1].cpu().numpy())
+    assert np.array_equal(np.nan_to_num(xl.numpy()), np.nan_to_num(rec.hit[-1].cpu().numpy()))
+    assert np.array_equal(np.nan_to_num(kl.numpy()), np.nan_to_num(rec.k[-1].cpu().numpy()))
+    assert np.array_equal(np.nan_to_num(ht.e_last.numpy()), np.nan_to_num(rec.e[-1].cpu().numpy()))
+    assert spot8[3] == int(((rec.flags[-1] & 2) != 0).sum())
+    gen = bundlegen.config_generator(spec, 20, (0.0, np.sin(0.01), np.cos(0.01)), (1.0, 0.0, 0.0))
+    (xg, kg, fg, _) = ht(gen=gen)
+    assert np.array_equal(fg.numpy(), rec.flags[-1].cpu().numpy())
+    assert util.relerr(np.nan_to_num(xg.numpy()), np.nan_to_num(rec.hit[-1].cpu().numpy())) < 1e-13
