@@ -44,7 +44,7 @@ CPU_BLOCK = 1000      # rays per reference seqtrace call: temporaries stay below
 WORKLOAD = ("double-Gauss (Rudolph 1897) 10 refracting conic surfaces / 13 sequence entries, "
             "%d-ray hexapolar bundle per GPU, single wavelength (BASELINE configs[1])")
 # BASELINE configs 3-5: total rays (strong scaling over the ranks), entries, counted surfaces
-EXTRAS = {"c3_asphere": {"total": 9997351, "label": "c3", "gather": False},
+EXTRAS = {"c3_asphere": {"total": 9997351, "label": "c3", "gather": True},
           "c4_anisotropic": {"total": 1000519, "label": "c4", "gather": False},
           "c5_grin": {"total": 99999907, "label": "c5", "gather": True}}
 

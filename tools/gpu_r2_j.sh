@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+date
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -15 > gpurun_out/pytest_gpu.log; tail -15 gpurun_out/pytest_gpu.log
+date
