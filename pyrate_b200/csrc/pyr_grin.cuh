@@ -243,9 +243,19 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
             const bool e_ok = fabs(dot3(p[j], p[j]) - nq[j] * nq[j]) <= m.energy_tol;      // NaN -> false
             double xs[3];
             l2g_point(m.to_shape, q[j], xs);
-            const double gap = xs[2] - conic_sag(curv, cc, xs[0], xs[1]);
-            const bool crossed = gap > 0.0;
-            const bool v = valid[j] & e_ok & grin_inside_nb(m, q[j]) & (gap == gap);
+            // "z > sag(x, y)" (material_grin.py:181) without the square root and the division of
+            // the sag: z1 = sag is the vertex-branch root of F(z) = A z^2 - 2 z + c r^2, A = c (1 + cc);
+            // z > z1  <=>  F < 0 (or beyond the far root, A z > 1) for A >= 0,  F < 0 and A z < 1 for
+            // A < 0.  The sag is undefined (NaN in the reference, conic_function :214-216: the ray
+            // can neither finish nor stay valid) where 1 - (1 + cc) c^2 r^2 <= 0.
+            const double r2 = fma(xs[0], xs[0], xs[1] * xs[1]);
+            const double A = curv * (1.0 + cc);
+            const bool defined = fma(-A * curv, r2, 1.0) > 0.0;
+            const double F = fma(A * xs[2] - 2.0, xs[2], curv * r2);
+            const double t = A * xs[2];
+            const bool beyond = (A > 0.0) ? ((F < 0.0) | (t > 1.0)) : ((F < 0.0) & (t < 1.0));
+            const bool crossed = defined & beyond;
+            const bool v = valid[j] & e_ok & grin_inside_nb(m, q[j]) & defined & (xs[2] == xs[2]);
             const bool stop = crossed | !v;
             const bool live = !done[j];
             const bool advance = live & !stop;

@@ -15,6 +15,7 @@ from pyrate_b200 import configs, engine, lowering  # noqa: E402
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_doublegauss"
 rays = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 launches = int(sys.argv[3]) if len(sys.argv) > 3 else 5
+generated = len(sys.argv) > 4 and sys.argv[4] == "gen"      # bundle generated in the kernel prologue
 spec = configs.CONFIGS[name]
 rings = configs.rings_for(rays) if rays else spec["bundle"]["rings"]
 (x0, k0, e0) = configs.config_bundle(spec, rings)
@@ -22,7 +23,14 @@ rings = configs.rings_for(rays) if rays else spec["bundle"]["rings"]
 lowered = lowering.lower(s, seq, configs.DLINE)
 dev = torch.device("cuda", 0)
 (x0, k0, e0) = engine.device_bundle(x0, k0, e0, dev)
+gen = None
+if generated:
+    from pyrate_b200 import bundlegen
+    gen = bundlegen.config_generator(spec, rings)
 for _ in range(launches):
-    rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev)
+    if gen is not None:
+        rec = engine.trace(lowered, None, None, None, configs.DLINE, device=dev, gen=gen)
+    else:
+        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev)
 torch.cuda.synchronize()
 print(name, x0.shape[1], "rays", launches, "launches ok")
