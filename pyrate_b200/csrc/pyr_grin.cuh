@@ -14,20 +14,20 @@
 namespace pyr {
 
 // index n and gradient at material-frame position q
-// etab: the 2^(j/32) table of pyr_exp.cuh in shared memory
+// etab: the 2^(j/128) table of pyr_exp.cuh in shared memory
 __device__ __forceinline__ double grin_index(const DMedium &m, const double q[3], double g[3],
                                              bool want_grad, const double *etab) {
     if (m.profile == PYR_GRIN_GAUSSIAN_XY) {
-        // (argument clamped to the range of exp_tab: e^-700 = 1e-304 stands for 0, e^700
-        // for overflow -- either way far outside any index profile)
-        const double arg = fmin(fmax(-fma(m.p[2] * q[0], q[0], m.p[3] * q[1] * q[1]), -700.0), 700.0);
-        const double ex = m.p[1] * exp_tab(arg, etab);
+        // n = p0 + p1 E, E = exp(-(p2 x^2 + p3 y^2)); grad n = -2 p1 E (p2 x, p3 y, 0)
+        const double w0 = m.p[2] * q[0], w1 = m.p[3] * q[1];
+        const double ex = exp_tab_any(-fma(w0, q[0], w1 * q[1]), etab);
         if (want_grad) {
-            g[0] = -2.0 * m.p[2] * q[0] * ex;
-            g[1] = -2.0 * m.p[3] * q[1] * ex;
+            const double h = -2.0 * m.p[1] * ex;
+            g[0] = h * w0;
+            g[1] = h * w1;
             g[2] = 0.0;
         }
-        return m.p[0] + ex;
+        return fma(m.p[1], ex, m.p[0]);
     }
     // PYR_GRIN_POLY_RZ
     const double r2 = fma(q[0], q[0], q[1] * q[1]);
@@ -132,24 +132,20 @@ __device__ __forceinline__ bool grin_propagate(const DMedium &m, int shape_kind,
     return valid;
 }
 
-// ---- straight-line building blocks of the interleaved integrator ----
-// index and gradient of N positions, operation by operation over the N rays
+// ---- straight-line building blocks of the specialised integrator ----
+// index (and gradient) of N positions, operation by operation over the N rays.
+// Gaussian profile: E = exp(-(p2 x^2 + p3 y^2)) and w = (p2 x, p3 y) are returned instead of
+// the gradient -- grad n = -2 p1 E (w0, w1, 0); the kick folds the constant factors.
 template <int PROFILE, int N>
 __device__ __forceinline__ void grin_index_n(const DMedium &m, const double (*q)[3], double *nn,
                                              double (*g)[3], const double *etab) {
     if (PROFILE == PYR_GRIN_GAUSSIAN_XY) {
-        double arg[N], ex[N];
-#pragma unroll
-        for (int j = 0; j < N; ++j)
-            arg[j] = fmin(fmax(-fma(m.p[2] * q[j][0], q[j][0], m.p[3] * q[j][1] * q[j][1]), -700.0), 700.0);
-        exp_tab_n<N>(arg, ex, etab);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
-            ex[j] *= m.p[1];
-            g[j][0] = -2.0 * m.p[2] * q[j][0] * ex[j];
-            g[j][1] = -2.0 * m.p[3] * q[j][1] * ex[j];
-            g[j][2] = 0.0;
-            nn[j] = m.p[0] + ex[j];
+            const double w0 = m.p[2] * q[j][0], w1 = m.p[3] * q[j][1];
+            const double ex = exp_tab_any(-fma(w0, q[j][0], w1 * q[j][1]), etab);
+            g[j][0] = w0; g[j][1] = w1; g[j][2] = ex;
+            nn[j] = fma(m.p[1], ex, m.p[0]);
         }
         return;
     }
@@ -215,6 +211,7 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
         done[j] = !enter[j];          // dead / out-of-range rays (NaN state) never enter
     }
     const double tau2 = 2.0 * m.ds;
+    const double kgrad = -2.0 * m.p[1];                  // Gaussian profile: grad n = kgrad E w
     const int cap = m.max_steps > 0 ? m.max_steps : 1000000;
     for (int it = 0; it < cap; ++it) {
         bool all_done = true;
@@ -231,10 +228,17 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
             if (s < 3) {
 #pragma unroll
                 for (int j = 0; j < N; ++j) {
-                    const double f = tau2 * ds[s] * nq[j];
-                    p[j][0] = fma(f, g[j][0], p[j][0]);
-                    p[j][1] = fma(f, g[j][1], p[j][1]);
-                    p[j][2] = fma(f, g[j][2], p[j][2]);
+                    if (PROFILE == PYR_GRIN_GAUSSIAN_XY) {
+                        // p += tau2 d_s n grad n = (tau2 d_s (-2 p1) n E) (w0, w1, 0)
+                        const double h = (tau2 * ds[s] * kgrad) * nq[j] * g[j][2];
+                        p[j][0] = fma(h, g[j][0], p[j][0]);
+                        p[j][1] = fma(h, g[j][1], p[j][1]);
+                    } else {
+                        const double f = tau2 * ds[s] * nq[j];
+                        p[j][0] = fma(f, g[j][0], p[j][0]);
+                        p[j][1] = fma(f, g[j][1], p[j][1]);
+                        p[j][2] = fma(f, g[j][2], p[j][2]);
+                    }
                 }
             }
         }

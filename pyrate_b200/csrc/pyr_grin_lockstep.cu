@@ -45,10 +45,10 @@ grin_lockstep_kernel(const __grid_constant__ LaunchParams P, const double *__res
     const DStep &st = P.steps[0];
     const DAux *ax = &P.aux[st.aux];
     const DMedium &m = ax->before;
-    __shared__ double etab[32];
+    __shared__ double etab[kExpTabSize];
     __shared__ double red[kLockThreads / 32];
     __shared__ int all_invalid;
-    if (threadIdx.x < 32) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    if (threadIdx.x < kExpTabSize) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
     if (threadIdx.x == 0) all_invalid = 0;
     double *pos = scratch, *vel = scratch + 3 * ld, *upos = scratch + 6 * ld, *uvel = scratch + 9 * ld;
     uint8_t *flag = reinterpret_cast<uint8_t *>(scratch + 12 * ld);

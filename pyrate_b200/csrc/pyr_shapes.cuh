@@ -254,109 +254,169 @@ __device__ __forceinline__ double shape_sag(int kind, const DAux *a, double curv
 }
 
 // Newton iteration on f(t) = z0 + t dz - F(x0 + t dx, y0 + t dy), seeded with the
-// base-conic hit (plane for XY polynomials).  The warp leaves the loop together
-// (__all_sync vote on the step size), capped at `maxit`.  On return (gx, gy) hold
-// dF/dx, dF/dy of the last evaluation and `grad_ok` tells whether that evaluation
-// was within the convergence tolerance of the returned point -- then the surface
-// normal can reuse it instead of evaluating the shape once more.
+// base-conic hit (plane for XY polynomials), for the N rays a thread owns TOGETHER: one
+// loop, N independent dependency chains inside its body (the iteration is a long serial
+// FP64 chain; at 16 resident warps per SM a single chain per thread leaves the pipe idle).
+// The warp leaves the loop together (__all_sync vote on the step sizes), capped at
+// `maxit`.  On return (gx, gy) hold dF/dx, dF/dy of the last evaluation and `grad_ok` tells
+// whether that evaluation was within the convergence tolerance of the returned point --
+// then the surface normal can reuse it instead of evaluating the shape once more.
+template <bool EXT, int N>
+__device__ __forceinline__ void explicit_t_n(int kind, const DAux &a, double curv, double cc,
+                                             const double (&r0)[N][3], const double (&d)[N][3],
+                                             const bool (&active)[N], double (&t)[N],
+                                             double (&gx)[N], double (&gy)[N], bool (&grad_ok)[N]) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        bool ok;
+        if (kind == PYR_SHAPE_ASPHERE) t[j] = conic_t(curv, cc, r0[j], d[j], ok);
+        else if (kind == PYR_SHAPE_BICONIC) t[j] = conic_t(0.5 * (curv + a.curv2), 0.5 * (cc + a.cc2), r0[j], d[j], ok);
+        else if (EXT && kind == PYR_SHAPE_COMBINATION && a.term_kind == PYR_SHAPE_ASPHERE &&
+                 a.term_dx == 0.0 && a.term_dy == 0.0)
+            t[j] = conic_t(a.term_w * a.term_curv, a.term_cc, r0[j], d[j], ok);   // leading base conic
+        else t[j] = -r0[j][2] * fast_rcp(d[j][2]);
+        if (!isfinite(t[j])) t[j] = 0.0;
+        grad_ok[j] = false;
+        gx[j] = gy[j] = 0.0;
+    }
+    for (int it = 0; it < a.newton_maxit; ++it) {
+        bool done = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double x = fma(t[j], d[j][0], r0[j][0]);
+            const double y = fma(t[j], d[j][1], r0[j][1]);
+            double F;
+            explicit_eval<EXT>(kind, a, curv, cc, x, y, F, gx[j], gy[j]);
+            const double res = fma(t[j], d[j][2], r0[j][2]) - F;
+            const double dres = d[j][2] - fma(gx[j], d[j][0], gy[j] * d[j][1]);
+            double step = fast_div(res, dres);
+            const bool bad = !isfinite(step);
+            if (bad) step = 0.0;
+            t[j] -= step;
+            const bool conv = fabs(step) <= a.newton_tol * (1.0 + fabs(t[j]));
+            grad_ok[j] = conv && !bad;
+            done = done && (bad || !active[j] || conv);
+        }
+        if (__all_sync(__activemask(), done)) break;
+    }
+}
+
+// one ray (the crystal kernel's explicit-shape path)
 template <bool EXT>
 __device__ __forceinline__ double explicit_t(int kind, const DAux &a, double curv, double cc,
                                              const double r0[3], const double d[3],
                                              bool active, double &gx, double &gy, bool &grad_ok) {
-    bool ok;
-    double t;
-    if (kind == PYR_SHAPE_ASPHERE) t = conic_t(curv, cc, r0, d, ok);
-    else if (kind == PYR_SHAPE_BICONIC) t = conic_t(0.5 * (curv + a.curv2), 0.5 * (cc + a.cc2), r0, d, ok);
-    else if (EXT && kind == PYR_SHAPE_COMBINATION && a.term_kind == PYR_SHAPE_ASPHERE &&
-             a.term_dx == 0.0 && a.term_dy == 0.0)
-        t = conic_t(a.term_w * a.term_curv, a.term_cc, r0, d, ok);   // leading base conic
-    else t = -r0[2] * fast_rcp(d[2]);
-    if (!isfinite(t)) t = 0.0;
-    grad_ok = false;
-    gx = gy = 0.0;
-    for (int it = 0; it < a.newton_maxit; ++it) {
-        const double x = fma(t, d[0], r0[0]);
-        const double y = fma(t, d[1], r0[1]);
-        double F;
-        explicit_eval<EXT>(kind, a, curv, cc, x, y, F, gx, gy);
-        const double res = fma(t, d[2], r0[2]) - F;
-        const double dres = d[2] - fma(gx, d[0], gy * d[1]);
-        double step = fast_div(res, dres);
-        const bool bad = !isfinite(step);
-        if (bad) step = 0.0;
-        t -= step;
-        const bool conv = fabs(step) <= a.newton_tol * (1.0 + fabs(t));
-        grad_ok = conv && !bad;
-        const bool done = bad || !active || conv;
-        if (__all_sync(__activemask(), done)) break;
-    }
-    return t;
+    const double r0n[1][3] = {{r0[0], r0[1], r0[2]}}, dn[1][3] = {{d[0], d[1], d[2]}};
+    const bool act[1] = {active};
+    double t[1], gxn[1], gyn[1];
+    bool gok[1];
+    explicit_t_n<EXT, 1>(kind, a, curv, cc, r0n, dn, act, t, gxn, gyn, gok);
+    gx = gxn[0]; gy = gyn[0]; grad_ok = gok[0];
+    return t[0];
 }
 
-// Even asphere (the common explicit shape): value, gradient factor dr (dF/dx = x dr,
-// dF/dy = y dr) and its derivative ddr = d(dr)/d(r^2) in one Horner pass.
-__device__ __forceinline__ void asphere_eval2(const DAux &a, double curv, double cc, double r2,
-                                              double &F, double &dr, double &ddr) {
-    const double K = curv * curv * (1.0 + cc);
-    double rsq;
-    const double sq = fast_sqrt_r(fma(-K, r2, 1.0), rsq);            // NaN outside
-    double p = 0.0, dp = 0.0, hp = 0.0;                              // p, p', p''/2
-    for (int i = a.n_coeff - 1; i >= 0; --i) {
-        hp = fma(hp, r2, dp);
-        dp = fma(dp, r2, p);
-        p = fma(p, r2, a.coeff[i]);
-    }
-    F = fma(curv * r2, fast_rcp(1.0 + sq), r2 * p);
-    dr = fma(curv, rsq, 2.0 * fma(r2, dp, p));
-    // d/dr2 [c / sq] = c K / (2 sq^3);  d/dr2 [2 (p + r2 p')] = 2 (2 p' + r2 p'')
-    ddr = fma(0.5 * curv * K, rsq * rsq * rsq, 4.0 * fma(r2, hp, dp));
+// 1 / a to ~2^-40 (MUFU seed + one Newton step): enough for a Newton step whose own error is
+// corrected by the next iteration (the last step of a converged iteration is < 1e-6 |t|)
+__device__ __forceinline__ double rcp_nr1(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    return fma(y, fma(-a, y, 1.0), y);
 }
 
-// Newton for the even asphere, seeded with the base-conic hit.  Newton converges
-// quadratically: step_(k+1) ~ C step_k^2 with C estimated from the last two steps, so
-// once the PREDICTED next step is below the tolerance the iteration stops without the
-// confirming evaluation (two shape evaluations instead of three for a typical asphere)
-// and the gradient at the final point is obtained from the last evaluation to first order
-// in the (tiny) last step -- the omitted terms are O(step^2) ~ 1e-16.
-__device__ __forceinline__ double asphere_t(const DAux &a, double curv, double cc,
-                                            const double r0[3], const double d[3], bool active,
-                                            double &gx, double &gy, bool &grad_ok) {
-    bool ok;
-    double t = conic_t(curv, cc, r0, d, ok);
-    if (!isfinite(t)) t = 0.0;
-    grad_ok = false;
-    gx = gy = 0.0;
-    double prev = 0.0;                                   // |previous step|, 0 = none yet
+// Even asphere (the common explicit shape), N rays of a thread together, WITHOUT a square
+// root or a full-precision division inside the iteration: with q(r^2) = sum a_i r^(2i+2) the
+// hit satisfies  w = z - q(r^2) = conic sag(r^2), and on the vertex branch of the conic that
+// is the root of the conic's implicit function
+//     g(t) = c r^2 + c (1 + cc) w^2 - 2 w,      r^2, z along the ray,
+// (same root as z - F = 0 of surface_shape.py:448-465: near it g = -2 sq (w - sag) with
+// sq = sqrt(1 - (1+cc) c^2 r^2) > 0).  Newton on g, seeded with the base-conic hit, costs one
+// Horner pass for q, q' and ~20 FP64 operations per iteration.  It converges quadratically:
+// step_(k+1) ~ C step_k^2 with C estimated from the last two steps, so once the PREDICTED
+// next step is two orders below the tolerance the iteration stops without the confirming
+// evaluation.  The gradient (dF/dx, dF/dy) = (x, y) dr is then evaluated AT the returned point;
+// there sq = 1 - c (1 + cc) w (surface equation), so no square root is needed either, and a
+// point on the far branch (sq <= 0: the explicit sag is undefined) returns NaN like F does.
+template <int N>
+__device__ __forceinline__ void asphere_t_n(const DAux &a, double curv, double cc,
+                                            const double (&r0)[N][3], const double (&d)[N][3],
+                                            const bool (&active)[N], double (&t)[N],
+                                            double (&gx)[N], double (&gy)[N]) {
+    const double cK1 = curv * (1.0 + cc);
+    double prev[N];                                      // |previous step|, 0 = none yet
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        bool ok;
+        t[j] = conic_t(curv, cc, r0[j], d[j], ok);
+        if (!isfinite(t[j])) t[j] = 0.0;
+        prev[j] = 0.0;
+    }
+    const int nc = a.n_coeff;
     for (int it = 0; it < a.newton_maxit; ++it) {
-        const double x = fma(t, d[0], r0[0]);
-        const double y = fma(t, d[1], r0[1]);
-        const double r2 = fma(x, x, y * y);
-        double F, dr, ddr;
-        asphere_eval2(a, curv, cc, r2, F, dr, ddr);
-        const double res = fma(t, d[2], r0[2]) - F;
-        const double xy = fma(x, d[0], y * d[1]);
-        const double dres = fma(-dr, xy, d[2]);
-        double step = fast_div(res, dres);
-        const bool bad = !isfinite(step);
-        if (bad) step = 0.0;
-        t -= step;
-        const double as = fabs(step), lim = a.newton_tol * (1.0 + fabs(t));
-        const bool conv = as <= lim;
-        // predicted next step |step|^2 C, C = |step| / prev^2; two orders of safety
-        const bool early = !conv && prev > 0.0 && as * as * as <= 0.01 * lim * prev * prev;
-        if (conv) {
-            gx = x * dr; gy = y * dr;                    // within tol of the returned point
-        } else if (early) {
-            const double xn = fma(-step, d[0], x), yn = fma(-step, d[1], y);
-            const double drn = fma(ddr, fma(xn, xn, yn * yn) - r2, dr);
-            gx = xn * drn; gy = yn * drn;
+        double x[N], y[N], r2[N], p[N], dp[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            x[j] = fma(t[j], d[j][0], r0[j][0]);
+            y[j] = fma(t[j], d[j][1], r0[j][1]);
+            r2[j] = fma(x[j], x[j], y[j] * y[j]);
+            p[j] = 0.0; dp[j] = 0.0;
         }
-        grad_ok = (conv || early) && !bad;
-        prev = as;
-        const bool done = bad || !active || conv || early;
+        for (int i = nc - 1; i >= 0; --i) {              // p = sum a_i r2^i and p' by Horner
+            const double ci = a.coeff[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                dp[j] = fma(dp[j], r2[j], p[j]);
+                p[j] = fma(p[j], r2[j], ci);
+            }
+        }
+        bool done = true;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double z = fma(t[j], d[j][2], r0[j][2]);
+            const double w = fma(-r2[j], p[j], z);                         // z - q
+            const double g = fma(curv, r2[j], w * fma(cK1, w, -2.0));
+            const double xy = fma(x[j], d[j][0], y[j] * d[j][1]);          // (d r^2 / dt) / 2
+            const double wp = fma(-2.0 * fma(r2[j], dp[j], p[j]), xy, d[j][2]);   // dw/dt
+            const double hg = fma(curv, xy, fma(cK1, w, -1.0) * wp);       // g' / 2
+            double step = 0.5 * g * rcp_nr1(hg);
+            const bool bad = !isfinite(step);
+            if (bad) step = 0.0;
+            t[j] -= step;
+            const double as = fabs(step), lim = a.newton_tol * (1.0 + fabs(t[j]));
+            const bool conv = as <= lim;
+            // predicted next step |step|^2 C, C = |step| / prev^2; two orders of safety
+            const bool early = prev[j] > 0.0 && as * as * as <= 0.01 * lim * prev[j] * prev[j];
+            prev[j] = as;
+            done = done && (bad || !active[j] || conv || early);
+        }
         if (__all_sync(__activemask(), done)) break;
     }
-    return t;
+    // gradient factor at the returned point: dr = c / sq + 2 (p + r^2 p')
+    {
+        double x[N], y[N], r2[N], p[N], dp[N];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            x[j] = fma(t[j], d[j][0], r0[j][0]);
+            y[j] = fma(t[j], d[j][1], r0[j][1]);
+            r2[j] = fma(x[j], x[j], y[j] * y[j]);
+            p[j] = 0.0; dp[j] = 0.0;
+        }
+        for (int i = nc - 1; i >= 0; --i) {
+            const double ci = a.coeff[i];
+#pragma unroll
+            for (int j = 0; j < N; ++j) {
+                dp[j] = fma(dp[j], r2[j], p[j]);
+                p[j] = fma(p[j], r2[j], ci);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const double w = fma(-r2[j], p[j], fma(t[j], d[j][2], r0[j][2]));
+            const double sq = fma(-cK1, w, 1.0);
+            const double dr = fma(curv, fast_rcp(sq), 2.0 * fma(r2[j], dp[j], p[j]));
+            gx[j] = x[j] * dr; gy[j] = y[j] * dr;
+            if (!(sq > 0.0)) { t[j] = qnan(); gx[j] = gy[j] = qnan(); }
+        }
+    }
 }
 
 // unit normal of an explicit shape: grad = (-Fx, -Fy, 1)/|.|  (FreeShape.getGrad :420-423)

@@ -128,142 +128,159 @@ __device__ __forceinline__ void reproject_e(const double k[3], double e[3]) {
     e[0] = t[0] * inv; e[1] = t[1] * inv; e[2] = t[2] * inv;
 }
 
-// One sequence entry for one ray (real k, E).  Returns the flag byte.
+// One sequence entry for the N rays a thread owns (real k, E); fl[j] = flag byte of ray j.
+// The rays go through every phase together, so the straight-line parts interleave N
+// independent dependency chains and the Newton iteration of an explicit shape is ONE loop
+// over all of them (csrc/pyr_shapes.cuh).
 // ASPH: the only explicit shape of the sequence is the even asphere -- the instantiation
 // carries neither the XY-polynomial / biconic evaluators nor the generic Newton loop (small
-// enough to stay resident in the instruction cache) and uses asphere_t
-template <bool WITH_E, bool HAS_GRIN, bool EXT, bool ASPH = false>
-__device__ __forceinline__ uint32_t step_real(const LaunchParams &P, const DStep &st,
-                                              Ray<WITH_E> &r, double d[3], double hit_g[3],
-                                              int64_t ray_index, int w = 0,
-                                              const double *etab = nullptr,
-                                              bool grin_media = HAS_GRIN) {
+// enough to stay resident in the instruction cache) and uses asphere_t_n
+template <int N, bool WITH_E, bool HAS_GRIN, bool EXT, bool ASPH = false>
+__device__ __forceinline__ void step_real_n(const LaunchParams &P, const DStep &st,
+                                            Ray<WITH_E> (&r)[N], double (&d)[N][3], double (&hit_g)[N][3],
+                                            const int64_t (&ray_index)[N], const int (&w)[N],
+                                            const double *etab, bool grin_media, uint32_t (&fl)[N]) {
     constexpr bool GENERAL = true;
     const DAux *aux = (st.aux >= 0) ? &P.aux[st.aux] : nullptr;
-    bool ok = r.alive;
+    const bool ident = (st.bits & kRotIdentity) != 0;
+    bool ok[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) ok[j] = r[j].alive;
 
     // ---- propagate through a GRIN medium (material_grin.py:215-220) ----
     if (HAS_GRIN && st.before_kind == PYR_MEDIUM_ISO_GRIN) {
-        const bool v = grin_propagate<EXT>(aux->before, st.shape_kind, aux, st.curv, st.cc, r.x, d, r.k,
-                                      ok ? ray_index : -1, st.ld_out, etab);
-        ok = ok && v;
-        const double inv = fast_rsqrt(dot3(r.k, r.k));
-        d[0] = r.k[0] * inv; d[1] = r.k[1] * inv; d[2] = r.k[2] * inv;
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            const bool v = grin_propagate<EXT>(aux->before, st.shape_kind, aux, st.curv, st.cc, r[j].x, d[j], r[j].k,
+                                               ok[j] ? ray_index[j] : -1, st.ld_out, etab);
+            ok[j] = ok[j] && v;
+            const double inv = fast_rsqrt(dot3(r[j].k, r[j].k));
+            d[j][0] = r[j].k[0] * inv; d[j][1] = r[j].k[1] * inv; d[j][2] = r[j].k[2] * inv;
+        }
     }
 
     // ---- into the shape frame (surface_shape.py:151-155) ----
-    double r0[3], dl[3];
-    if (st.bits & kRotIdentity) {
-        r0[0] = r.x[0] - st.frame.o[0]; r0[1] = r.x[1] - st.frame.o[1]; r0[2] = r.x[2] - st.frame.o[2];
-        dl[0] = d[0]; dl[1] = d[1]; dl[2] = d[2];
-    } else {
-        g2l_point(st.frame, r.x, r0);
-        rot_t(st.frame.r, d, dl);
+    double r0[N][3], dl[N][3];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        if (ident) {
+            r0[j][0] = r[j].x[0] - st.frame.o[0]; r0[j][1] = r[j].x[1] - st.frame.o[1];
+            r0[j][2] = r[j].x[2] - st.frame.o[2];
+            dl[j][0] = d[j][0]; dl[j][1] = d[j][1]; dl[j][2] = d[j][2];
+        } else {
+            g2l_point(st.frame, r[j].x, r0[j]);
+            rot_t(st.frame.r, d[j], dl[j]);
+        }
     }
 
     // ---- intersect ----
-    double t;
-    bool hit_ok = true;
-    double gfx = 0.0, gfy = 0.0;
-    bool grad_ok = false;
+    double t[N], gfx[N], gfy[N];
+    bool hit_ok[N], grad_ok[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) { hit_ok[j] = true; grad_ok[j] = false; gfx[j] = gfy[j] = 0.0; t[j] = 0.0; }
     if (GENERAL && (st.bits & kNoIntersect)) {
-        t = 0.0;
+        // t = 0
     } else if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
-        t = conic_t(st.curv, st.cc, r0, dl, hit_ok);
+#pragma unroll
+        for (int j = 0; j < N; ++j) t[j] = conic_t(st.curv, st.cc, r0[j], dl[j], hit_ok[j]);
     } else if (!ASPH && st.shape_kind == PYR_SHAPE_CYLINDER) {
-        t = cylinder_t(st.curv, st.cc, r0, dl, hit_ok);
+#pragma unroll
+        for (int j = 0; j < N; ++j) t[j] = cylinder_t(st.curv, st.cc, r0[j], dl[j], hit_ok[j]);
     } else if (ASPH) {
-        t = asphere_t(*aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
+        asphere_t_n<N>(*aux, st.curv, st.cc, r0, dl, ok, t, gfx, gfy);
+#pragma unroll
+        for (int j = 0; j < N; ++j) grad_ok[j] = true;     // gradient of the returned point itself
     } else {
-        t = explicit_t<EXT>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, gfx, gfy, grad_ok);
-    }
-    const double h[3] = {fma(dl[0], t, r0[0]), fma(dl[1], t, r0[1]), fma(dl[2], t, r0[2])};
-    if (st.bits & kRotIdentity) {
-        hit_g[0] = h[0] + st.frame.o[0]; hit_g[1] = h[1] + st.frame.o[1]; hit_g[2] = h[2] + st.frame.o[2];
-    } else {
-        l2g_point(st.frame, h, hit_g);
+        explicit_t_n<EXT, N>(st.shape_kind, *aux, st.curv, st.cc, r0, dl, ok, t, gfx, gfy, grad_ok);
     }
 
-    // ---- aperture (surface.py:127-135) ----
-    bool ap_ok = true;
-    if (st.aperture_kind != PYR_AP_BASE) {
-        double ax = h[0], ay = h[1];
-        if (GENERAL && !(st.bits & kApSameFrame)) {
-            double a[3];
-            g2l_point(aux->aperture_frame, hit_g, a);
-            ax = a[0]; ay = a[1];
-        }
-        if (st.aperture_kind == PYR_AP_CIRCULAR) {
-            const double rr = fma(ax, ax, ay * ay);
-            ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const double h[3] = {fma(dl[j][0], t[j], r0[j][0]), fma(dl[j][1], t[j], r0[j][1]),
+                             fma(dl[j][2], t[j], r0[j][2])};
+        if (ident) {
+            hit_g[j][0] = h[0] + st.frame.o[0]; hit_g[j][1] = h[1] + st.frame.o[1]; hit_g[j][2] = h[2] + st.frame.o[2];
         } else {
-            ap_ok = (ax >= -st.ap0) && (ax <= st.ap0) && (ay >= -st.ap1) && (ay <= st.ap1);
+            l2g_point(st.frame, h, hit_g[j]);
         }
-    }
-    const bool hit = ok && hit_ok && ap_ok;
 
-    // ---- surface normal in the shape frame (ray.py:156-161) ----
-    double nrm[3];
-    if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
-        conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
-    } else if (!ASPH && st.shape_kind == PYR_SHAPE_CYLINDER) {
-        cylinder_normal(st.curv, st.cc, h[1], nrm);
-    } else if (grad_ok) {
-        // gradient of the converged Newton iterate: within tol of the hit point
-        normal_from_gradient(gfx, gfy, nrm);
-    } else if (ASPH) {
-        double F, dr, ddr;
-        asphere_eval2(*aux, st.curv, st.cc, fma(h[0], h[0], h[1] * h[1]), F, dr, ddr);
-        normal_from_gradient(h[0] * dr, h[1] * dr, nrm);
-    } else {
-        explicit_normal<EXT>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
-    }
+        // ---- aperture (surface.py:127-135) ----
+        bool ap_ok = true;
+        if (st.aperture_kind != PYR_AP_BASE) {
+            double ax = h[0], ay = h[1];
+            if (GENERAL && !(st.bits & kApSameFrame)) {
+                double a[3];
+                g2l_point(aux->aperture_frame, hit_g[j], a);
+                ax = a[0]; ay = a[1];
+            }
+            if (st.aperture_kind == PYR_AP_CIRCULAR) {
+                const double rr = fma(ax, ax, ay * ay);
+                ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
+            } else {
+                ap_ok = (ax >= -st.ap0) && (ax <= st.ap0) && (ay >= -st.ap1) && (ay <= st.ap1);
+            }
+        }
+        const bool hit = ok[j] && hit_ok[j] && ap_ok;
 
-    // ---- deflection (material_isotropic.py:163-236), done in the shape frame ----
-    double kl[3];
-    if (st.bits & kRotIdentity) { kl[0] = r.k[0]; kl[1] = r.k[1]; kl[2] = r.k[2]; }
-    else rot_t(st.frame.r, r.k, kl);
-    double n2sq = st.n2sq[w];
-    if (aux && aux->after_n_rays) {
-        // index of a position-dependent medium the caller evaluated at the hit points
-        const double nn = ray_index >= 0 ? aux->after_n_rays[ray_index] : qnan();
-        n2sq = nn * nn;
-    } else if (grin_media && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
-        double q[3], g[3];
-        g2l_point(aux->after.frame, hit_g, q);
-        const double nn = grin_index(aux->after, q, g, false, etab);
-        n2sq = nn * nn;
+        // ---- surface normal in the shape frame (ray.py:156-161) ----
+        double nrm[3];
+        if (!GENERAL || st.shape_kind == PYR_SHAPE_CONIC) {
+            conic_normal(st.curv, st.cc, (st.bits & kSphere) != 0, h[0], h[1], nrm);
+        } else if (!ASPH && st.shape_kind == PYR_SHAPE_CYLINDER) {
+            cylinder_normal(st.curv, st.cc, h[1], nrm);
+        } else if (ASPH || grad_ok[j]) {
+            // gradient of the converged Newton iterate: within tol of the hit point
+            normal_from_gradient(gfx[j], gfy[j], nrm);
+        } else {
+            explicit_normal<EXT>(st.shape_kind, *aux, st.curv, st.cc, h[0], h[1], nrm);
+        }
+
+        // ---- deflection (material_isotropic.py:163-236), done in the shape frame ----
+        double kl[3];
+        if (ident) { kl[0] = r[j].k[0]; kl[1] = r[j].k[1]; kl[2] = r[j].k[2]; }
+        else rot_t(st.frame.r, r[j].k, kl);
+        double n2sq = st.n2sq[w[j]];
+        if (aux && aux->after_n_rays) {
+            // index of a position-dependent medium the caller evaluated at the hit points
+            const double nn = ray_index[j] >= 0 ? aux->after_n_rays[ray_index[j]] : qnan();
+            n2sq = nn * nn;
+        } else if (grin_media && st.after_kind == PYR_MEDIUM_ISO_GRIN) {
+            double q[3], g[3];
+            g2l_point(aux->after.frame, hit_g[j], q);
+            const double nn = grin_index(aux->after, q, g, false, etab);
+            n2sq = nn * nn;
+        }
+        const double kn = dot3(kl, nrm);
+        // k_inplane = k - (k.n) n ; square = n^2 - k_inplane.k_inplane
+        const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
+        const double square = n2sq - dot3(kin, kin);
+        const double xi = fast_sqrt(square);
+        const bool refr_ok = (square > 0.0) && finite3(nrm);
+        double k2[3];
+        if (st.interaction == PYR_REFLECT) {
+            k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
+        } else {
+            k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
+        }
+        bool alive = hit && refr_ok;
+        if (GENERAL && (st.bits & kNoDeflect)) {
+            alive = hit;                       // k unchanged
+        } else if (ident) { r[j].k[0] = k2[0]; r[j].k[1] = k2[1]; r[j].k[2] = k2[2]; }
+        else rot(st.frame.r, k2, r[j].k);
+        r[j].x[0] = hit_g[j][0]; r[j].x[1] = hit_g[j][1]; r[j].x[2] = hit_g[j][2];
+        if (!ok[j]) { hit_g[j][0] = hit_g[j][1] = hit_g[j][2] = qnan(); }
+        if (!alive) {
+            const double q = qnan();
+            r[j].x[0] = r[j].x[1] = r[j].x[2] = q;
+            r[j].k[0] = r[j].k[1] = r[j].k[2] = q;
+        }
+        if (WITH_E) {
+            if (!alive) r[j].e[0] = r[j].e[1] = r[j].e[2] = qnan();
+            else if (!(GENERAL && (st.bits & kNoDeflect))) reproject_e(r[j].k, r[j].e);
+        }
+        r[j].alive = alive;
+        fl[j] = (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
     }
-    const double kn = dot3(kl, nrm);
-    // k_inplane = k - (k.n) n ; square = n^2 - k_inplane.k_inplane
-    const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
-    const double square = n2sq - dot3(kin, kin);
-    const double xi = fast_sqrt(square);
-    const bool refr_ok = (square > 0.0) && finite3(nrm);
-    double k2[3];
-    if (st.interaction == PYR_REFLECT) {
-        k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
-    } else {
-        k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
-    }
-    bool alive = hit && refr_ok;
-    if (GENERAL && (st.bits & kNoDeflect)) {
-        alive = hit;                       // k unchanged
-    } else if (st.bits & kRotIdentity) { r.k[0] = k2[0]; r.k[1] = k2[1]; r.k[2] = k2[2]; }
-    else rot(st.frame.r, k2, r.k);
-    r.x[0] = hit_g[0]; r.x[1] = hit_g[1]; r.x[2] = hit_g[2];
-    if (!ok) { hit_g[0] = hit_g[1] = hit_g[2] = qnan(); }
-    if (!alive) {
-        const double q = qnan();
-        r.x[0] = r.x[1] = r.x[2] = q;
-        r.k[0] = r.k[1] = r.k[2] = q;
-    }
-    if (WITH_E) {
-        if (!alive) r.e[0] = r.e[1] = r.e[2] = qnan();
-        else if (!(GENERAL && (st.bits & kNoDeflect))) reproject_e(r.k, r.e);
-    }
-    r.alive = alive;
-    return (hit ? PYR_RAY_HIT : 0u) | (alive ? PYR_RAY_ALIVE : 0u);
 }
 
 // Tuned step for the common case (conic shape, homogeneous isotropic media,
@@ -385,8 +402,8 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
     // register-indexed constant loads.
     __shared__ DStep sst[kMaxSteps];
-    __shared__ double etab[(FEAT & 2) ? 32 : 1];          // 2^(j/32) of pyr_exp.cuh (GRIN profiles)
-    if ((FEAT & 2) && threadIdx.x < 32) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __shared__ double etab[(FEAT & 2) ? kExpTabSize : 1];          // 2^(j/128) of pyr_exp.cuh (GRIN profiles)
+    if ((FEAT & 2) && threadIdx.x < kExpTabSize) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
     {
         const uint64_t *src = reinterpret_cast<const uint64_t *>(P.steps);
         uint64_t *dst = reinterpret_cast<uint64_t *>(sst);
@@ -564,15 +581,19 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                     dd[j][0] = ray[j].k[0] * inv; dd[j][1] = ray[j].k[1] * inv; dd[j][2] = ray[j].k[2] * inv;
                 }
             }
+            // steps without an auxiliary record (conic shape, homogeneous isotropic
+            // media, aperture in the shape frame) always take the tuned path
+            if (GENERAL && st.aux >= 0) {
+                int64_t ridx[RPT];
+                int wj[RPT];
 #pragma unroll
-            for (int j = 0; j < RPT; ++j) {
-                // steps without an auxiliary record (conic shape, homogeneous isotropic
-                // media, aperture in the shape frame) always take the tuned path
-                fl[j] = (GENERAL && st.aux >= 0) ? step_real<WITH_E, (FEAT & 2) != 0 && !GRIN_N, (FEAT & 4) != 0, (FEAT & 8) != 0>(P, st, ray[j], dd[j], hit[j],
-                                                                                   in_range[j] ? base + j : -1,
-                                                                                   MULTI ? wsel[j] : 0, etab,
-                                                                                   (FEAT & 2) != 0)
-                                                 : step_lean<WITH_E>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
+                for (int j = 0; j < RPT; ++j) { ridx[j] = in_range[j] ? base + j : -1; wj[j] = MULTI ? wsel[j] : 0; }
+                step_real_n<RPT, WITH_E, (FEAT & 2) != 0 && !GRIN_N, (FEAT & 4) != 0, (FEAT & 8) != 0>(
+                    P, st, ray, dd, hit, ridx, wj, etab, (FEAT & 2) != 0, fl);
+            } else {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j)
+                    fl[j] = step_lean<WITH_E>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
             }
 
             // ---- record the step ----

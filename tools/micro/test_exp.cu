@@ -33,6 +33,13 @@ int main() {
         const double e = ulp_err(pyr::exp_tab(x, pyr::kExp2Tab), expl((long double)x));
         if (e > worst) { worst = e; worst_x = x; }
     }
+    // arguments outside the table range: 0 below, NaN above and for NaN
+    const bool range_ok = pyr::exp_tab_any(-700.5, pyr::kExp2Tab) == 0.0 && pyr::exp_tab_any(-1e300, pyr::kExp2Tab) == 0.0 &&
+                          pyr::exp_tab_any(-INFINITY, pyr::kExp2Tab) == 0.0 && std::isnan(pyr::exp_tab_any(701.0, pyr::kExp2Tab)) &&
+                          std::isnan(pyr::exp_tab_any(INFINITY, pyr::kExp2Tab)) && std::isnan(pyr::exp_tab_any(NAN, pyr::kExp2Tab)) &&
+                          std::isnan(pyr::exp_tab_any(-NAN, pyr::kExp2Tab)) &&
+                          pyr::exp_tab_any(-3.25, pyr::kExp2Tab) == pyr::exp_tab(-3.25, pyr::kExp2Tab);
+    if (!range_ok) { printf("range handling of exp_tab_any failed\n"); return 2; }
     printf("samples %ld max_ulp_err %.4f at x = %.17g\n", count, worst, worst_x);
     return worst <= 1.0 ? 0 : 1;
 }
