@@ -51,16 +51,22 @@ __device__ __forceinline__ cplx operator*(double s, cplx a) { return {s * a.re, 
 __device__ __forceinline__ cplx conj(cplx a) { return {a.re, -a.im}; }
 __device__ __forceinline__ double abs2(cplx a) { return fma(a.re, a.re, a.im * a.im); }
 __device__ __forceinline__ cplx operator/(cplx a, cplx b) {
-    const double d = 1.0 / abs2(b);
+    const double d = fast_rcp(abs2(b));                // b == 0: NaN (callers test cfinite)
     return {(a.re * b.re + a.im * b.im) * d, (a.im * b.re - a.re * b.im) * d};
 }
+// Square roots / reciprocals in this file are the branch-free MUFU + Newton forms of
+// pyr_device.cuh (~1 ulp): the C library's sqrt / hypot / rsqrt / division each carry a range
+// check and an out-of-line slow path -- 14 calls per warp and 7 % of the instructions of the
+// C4 trace (profiles/r02_c4.md) -- and the arguments here are O(1) optical quantities.
 __device__ __forceinline__ cplx csqrt_(cplx z) {       // principal branch, like numpy
-    const double m = hypot(z.re, z.im);
-    if (m == 0.0) return {0.0, 0.0};
-    double a = sqrt(0.5 * (m + fabs(z.re)));
-    double b = 0.5 * z.im / a;
-    if (z.re >= 0.0) return {a, b};
-    return {fabs(b), copysign(a, z.im)};
+    const double m2 = abs2(z);
+    const double m = fast_sqrt(m2);                    // z == 0: NaN, replaced below
+    const double a = fast_sqrt(0.5 * (m + fabs(z.re)));
+    const double b = fast_div(0.5 * z.im, a);
+    cplx r = {a, b};
+    if (!(z.re >= 0.0)) r = {fabs(b), copysign(a, z.im)};
+    if (m2 == 0.0) r = {0.0, 0.0};
+    return r;
 }
 __device__ __forceinline__ bool cfinite(cplx a) { return isfinite(a.re) && isfinite(a.im); }
 
@@ -145,7 +151,7 @@ __device__ __forceinline__ bool quartic_roots(const cplx c[5], const cplx z0[4],
             cplx step = w / (C(1.0) - w * rep);
             if (!cfinite(step)) step = w;
             z[i] = z[i] - step;
-            worst = fmax(worst, abs2(step) / (abs2(z[i]) + 1e-6 * scale * scale));
+            worst = fmax(worst, fast_div(abs2(step), abs2(z[i]) + 1e-6 * scale * scale));
         }
         if (!(worst == worst)) return false;                  // NaN
         if (last) break;
@@ -172,7 +178,7 @@ __device__ __forceinline__ void null_vector(const cplx eps[9], const cplx k[3], 
     const double best = fmax(n01, fmax(n02, n12));
     const cplx *pick = (n01 >= n02 && n01 >= n12) ? c01 : (n02 >= n12 ? c02 : c12);
     if (best > 1e-18 * scale * scale) {
-        const double inv = rsqrt(best);
+        const double inv = fast_rsqrt(best);
         for (int i = 0; i < 3; ++i) e[i] = inv * pick[i];
         return;
     }
@@ -186,7 +192,7 @@ __device__ __forceinline__ void null_vector(const cplx eps[9], const cplx k[3], 
     ccross(r, axis, e1);
     ccross(r, e1, e2);
     const cplx *out = second ? e2 : e1;
-    const double inv = rsqrt(herm2(out));
+    const double inv = fast_rsqrt(herm2(out));
     for (int i = 0; i < 3; ++i) e[i] = inv * out[i];
 }
 
@@ -223,10 +229,10 @@ __device__ __forceinline__ double mode_key(const DAux &ax, const cplx p[3], cons
             if (extraordinary) {
                 const cplx ka = cdotr(k, a);
                 for (int i = 0; i < 3; ++i) e[i] = C(ax.eps_o * a[i]) - ka * k[i];
-                const double inv = rsqrt(herm2(e));
+                const double inv = fast_rsqrt(herm2(e));
                 for (int i = 0; i < 3; ++i) e[i] = inv * e[i];
             } else {
-                const double inv = rsqrt(cross2);
+                const double inv = fast_rsqrt(cross2);
                 for (int i = 0; i < 3; ++i) e[i] = inv * ko[i];
             }
         }
@@ -240,7 +246,7 @@ __device__ __forceinline__ double mode_key(const DAux &ax, const cplx p[3], cons
             null_vector(eps, k, second, e);
         }
     }
-    wgt = 1.0 / (1.0 + abs2(xi));
+    wgt = fast_rcp(1.0 + abs2(xi));
     double s[3];
     poynting_vec(k, e, s);
     return wgt * dot3(s, nrm);
@@ -261,7 +267,7 @@ __device__ __forceinline__ double uni_key(const DAux &ax, const cplx p[3], const
     const double c2r = k[0].re * a[1] - k[1].re * a[0], c2i = k[0].im * a[1] - k[1].im * a[0];
     const double cross2 = c0r * c0r + c0i * c0i + c1r * c1r + c1i * c1i + c2r * c2r + c2i * c2i;
     closed = closed && ax.eps_e != ax.eps_o && cross2 > 1e-8 * herm2(k);
-    const double wgt = 1.0 / (1.0 + abs2(xi));
+    const double wgt = fast_rcp(1.0 + abs2(xi));
     const cplx kn = cdotr(k, nrm);
     if (!extraordinary) return wgt * kn.re;
     const cplx ka = cdotr(k, a);
@@ -270,7 +276,7 @@ __device__ __forceinline__ double uni_key(const DAux &ax, const cplx p[3], const
     for (int i = 0; i < 3; ++i) e[i] = C(ax.eps_o * a[i]) - ka * k[i];
     const cplx ek = ka * (C(ax.eps_o) - kk);
     const cplx en = C(ax.eps_o * dot3(a, nrm)) - ka * kn;
-    return wgt * (kn.re - (ek * conj(en)).re / herm2(e));
+    return wgt * (kn.re - fast_div((ek * conj(en)).re, herm2(e)));
 }
 
 // Anisotropic deflection in the shape frame.  kl: incoming k (shape frame), nrm: unit
@@ -299,7 +305,7 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
         const cplx qb = (de * na) * pa;                          // half the linear coefficient
         const cplx qc = eo * kk + de * (pa * pa) - C(eo * ax.eps_e);
         const cplx disc = csqrt_(qb * qb - qa * qc);
-        const double iqa = 1.0 / qa;
+        const double iqa = fast_rcp(qa);
         xi0 = xo; xi1 = -xo;
         xi2 = iqa * (disc - qb); xi3 = iqa * (-disc - qb);
         ok = ok && cfinite(xi0) && cfinite(xi2) && cfinite(xi3);
@@ -342,7 +348,7 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
             const cplx third = {1.0 / 3.0, 0.0};
             const cplx xi2s = third * (eps[0] + eps[4] + eps[8]) - s0;
             cplx r = csqrt_(xi2s);
-            double scale = sqrt(abs2(r));
+            double scale = fast_sqrt(abs2(r));          // r == 0: NaN, replaced below
             if (!(scale > 1e-3)) { scale = 1.0; r = C(1.0); }
             const cplx z0[4] = {r * cplx{1.03, 0.02}, r * cplx{0.97, -0.02},
                                 r * cplx{-1.03, 0.02}, r * cplx{-0.97, -0.02}};
@@ -408,7 +414,7 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
         }
     }
     const double sgn = mirror ? -1.0 : 1.0;
-    const double sa = sgn * sqrt(wa), sb = sgn * sqrt(wb);
+    const double sa = sgn * fast_sqrt(wa), sb = sgn * fast_sqrt(wb);
     for (int i = 0; i < 3; ++i) {
         ka[i] = sgn * ka[i]; kb[i] = sgn * kb[i];
         ea[i] = sa * ea[i]; eb[i] = sb * eb[i];
@@ -501,7 +507,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 {
                     double sv[3];
                     poynting_vec(k, e, sv);
-                    const double inv = rsqrt(dot3(sv, sv));
+                    const double inv = fast_rsqrt(dot3(sv, sv));
                     d[0] = sv[0] * inv; d[1] = sv[1] * inv; d[2] = sv[2] * inv;
                 }
                 const bool ident = (st.bits & kRotIdentity) != 0;   // chain systems without tilts
@@ -592,7 +598,7 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                         for (int c = 0; c < 3; ++c) tv[c] = a[c] - cc * k2a[c];
                         t2 = herm2(tv);
                     }
-                    const double inv = rsqrt(t2);
+                    const double inv = fast_rsqrt(t2);
                     for (int c = 0; c < 3; ++c) e2a[c] = inv * tv[c];
                 }
 

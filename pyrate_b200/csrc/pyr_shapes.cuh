@@ -25,6 +25,22 @@ __device__ __forceinline__ double conic_t(double curv, double cc, const double r
     return fast_div(G, F + fast_sqrt(square));
 }
 
+// The same hit from the raw MUFU approximations (~2^-20 relative): a Newton SEED for shapes
+// whose base conic is only the leading term (no refinement steps, no slow paths).
+__device__ __forceinline__ double conic_t_seed(double curv, double cc, const double r0[3],
+                                               const double d[3]) {
+    const double cc1 = 1.0 + cc;
+    const double F = d[2] - curv * fma(d[0], r0[0], fma(d[1], r0[1], d[2] * r0[2] * cc1));
+    const double G = curv * fma(r0[0], r0[0], fma(r0[1], r0[1], r0[2] * r0[2] * cc1)) - 2.0 * r0[2];
+    const double H = -curv - cc * curv * d[2] * d[2];
+    const double square = fma(F, F, H * G);
+    double y, ry;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(square));
+    const double den = fma(square, y, F);
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ry) : "d"(den));
+    return G * ry;
+}
+
 // Unit normal of a conic at (x, y) on the vertex branch.
 //   reference: z = sag(x, y); grad = (-c x, -c y, 1 - c z (1 + cc)); n = grad/|grad|
 //   with s = 1 - (1 + cc) c^2 r^2 one has 1 - c z (1 + cc) = sqrt(s) and
@@ -330,7 +346,9 @@ __device__ __forceinline__ double rcp_nr1(double a) {
 //     g(t) = c r^2 + c (1 + cc) w^2 - 2 w,      r^2, z along the ray,
 // (same root as z - F = 0 of surface_shape.py:448-465: near it g = -2 sq (w - sag) with
 // sq = sqrt(1 - (1+cc) c^2 r^2) > 0).  Newton on g, seeded with the base-conic hit, costs one
-// Horner pass for q, q' and ~20 FP64 operations per iteration.  It converges quadratically:
+// Horner pass for q, q' and ~20 FP64 operations per iteration (the seed only needs the MUFU
+// approximations: its distance to the asphere's root is the polynomial term anyway).  It
+// converges quadratically:
 // step_(k+1) ~ C step_k^2 with C estimated from the last two steps, so once the PREDICTED
 // next step is two orders below the tolerance the iteration stops without the confirming
 // evaluation.  The gradient (dF/dx, dF/dy) = (x, y) dr is then evaluated AT the returned point;
@@ -345,8 +363,7 @@ __device__ __forceinline__ void asphere_t_n(const DAux &a, double curv, double c
     double prev[N];                                      // |previous step|, 0 = none yet
 #pragma unroll
     for (int j = 0; j < N; ++j) {
-        bool ok;
-        t[j] = conic_t(curv, cc, r0[j], d[j], ok);
+        t[j] = conic_t_seed(curv, cc, r0[j], d[j]);
         if (!isfinite(t[j])) t[j] = 0.0;
         prev[j] = 0.0;
     }

@@ -1263,6 +1263,13 @@ int trace_complex(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, 
 #define PYR_GRIN_MINB 2
 #endif
 constexpr int kGrinPolicy = PYR_GRIN_RPT == 2 ? 3 : 0;       // TMA record stores need two rays per thread
+// asphere-only kernel: CTA size and resident CTAs per SM (tools builds vary them)
+#ifndef PYR_ASPH_BLOCK
+#define PYR_ASPH_BLOCK 256
+#endif
+#ifndef PYR_ASPH_MINB
+#define PYR_ASPH_MINB 2
+#endif
 
 static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                       uint32_t flags, cudaStream_t stream) {
@@ -1292,7 +1299,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             return launch(trace_real_kernel<PYR_GRIN_RPT, false, 19, PYR_GRIN_MINB, kGrinPolicy | 16>, pk.P,
                           PYR_GRIN_RPT, stream, PYR_GRIN_RPT == 2, false, 256, true);
         if (grin) return launch(trace_real_kernel<1, false, 3, 2, 16>, pk.P, 1, stream, false, false, 256, true);
-        if (asph_only) return launch(trace_real_kernel<2, false, 9, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+        if (asph_only)
+            return launch(trace_real_kernel<2, false, 9, PYR_ASPH_MINB, 19, PYR_ASPH_BLOCK>, pk.P, 2, stream, true, false,
+                          PYR_ASPH_BLOCK, true);
         return launch(trace_real_kernel<2, false, 1, 2, 19>, pk.P, 2, stream, true, false, 256, true);
     }
     if (pk.P.n_waves > 1) {
@@ -1332,7 +1341,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     if (has_grin)   // history / E recording: one ray per thread
         return with_e ? launch(trace_real_kernel<1, true, 3, 2>, pk.P, 1, stream)
                       : launch(trace_real_kernel<1, false, 3, 2>, pk.P, 1, stream);
-    if (asph_only && !with_e) return launch(trace_real_kernel<2, false, 9, 2, 3>, pk.P, 2, stream, true);
+    if (asph_only && !with_e)
+        return launch(trace_real_kernel<2, false, 9, PYR_ASPH_MINB, 3, PYR_ASPH_BLOCK>, pk.P, 2, stream, true, false,
+                      PYR_ASPH_BLOCK);
     return with_e ? launch(trace_real_kernel<2, true, 1, 2, 3>, pk.P, 2, stream, true, true)
                   : launch(trace_real_kernel<2, false, 1, 2, 3>, pk.P, 2, stream, true);
 }
