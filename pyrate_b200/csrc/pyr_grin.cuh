@@ -14,7 +14,7 @@
 namespace pyr {
 
 // index n and gradient at material-frame position q
-// etab: the 2^(j/128) table of pyr_exp.cuh in shared memory
+// etab: the 2^(j/512) table of pyr_exp.cuh in shared memory
 __device__ __forceinline__ double grin_index(const DMedium &m, const double q[3], double g[3],
                                              bool want_grad, const double *etab) {
     if (m.profile == PYR_GRIN_GAUSSIAN_XY) {
@@ -163,9 +163,11 @@ __device__ __forceinline__ void grin_index_n(const DMedium &m, const double (*q)
     }
 }
 
-// boundary test without a branch on the boundary kind
+// boundary test without a branch on the boundary kind; BND >= 0: kind fixed at compile time
+template <int BND>
 __device__ __forceinline__ bool grin_inside_nb(const DMedium &m, const double q[3]) {
     const double r2 = fma(q[0], q[0], q[1] * q[1]);
+    if (BND == PYR_BND_CYLINDER) return r2 < m.b[0] * m.b[0];
     const bool cyl = r2 < m.b[0] * m.b[0];
     const bool box = (fabs(q[0]) < m.b[0]) & (fabs(q[1]) < m.b[1]);
     const bool sph = fma(q[2], q[2], r2) < m.b[0] * m.b[0];
@@ -183,7 +185,7 @@ __device__ __forceinline__ bool grin_inside_nb(const DMedium &m, const double q[
 // lock-step loop (material_grin.py:139) but its frozen state (uq, up) and validity no longer
 // change, so every ray's result is bit-identical to grin_propagate's.  No integrator history
 // (the history mode runs the single-ray function).
-template <int PROFILE, int N>
+template <int PROFILE, int BND, int N>
 __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, double cc,
                                                  double (*x)[3], const double (*d)[3], double (*k)[3],
                                                  const bool *enter, bool *valid_out,
@@ -222,7 +224,10 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
             for (int j = 0; j < N; ++j) {
                 q[j][0] = fma(tau2 * cs[s], p[j][0], q[j][0]);
                 q[j][1] = fma(tau2 * cs[s], p[j][1], q[j][1]);
-                q[j][2] = fma(tau2 * cs[s], p[j][2], q[j][2]);
+                // the Gaussian-xy profile has no z gradient: p_z is constant, the profile does
+                // not read z, and the four drifts add up to tau2 p_z (c0 + c1 + c1 + c0 = 1)
+                if (PROFILE != PYR_GRIN_GAUSSIAN_XY) q[j][2] = fma(tau2 * cs[s], p[j][2], q[j][2]);
+                else if (s == 3) q[j][2] = fma(tau2, p[j][2], q[j][2]);
             }
             grin_index_n<PROFILE, N>(m, q, nq, g, etab);
             if (s < 3) {
@@ -259,7 +264,7 @@ __device__ __forceinline__ void grin_propagate_n(const DMedium &m, double curv, 
             const double t = A * xs[2];
             const bool beyond = (A > 0.0) ? ((F < 0.0) | (t > 1.0)) : ((F < 0.0) & (t < 1.0));
             const bool crossed = defined & beyond;
-            const bool v = valid[j] & e_ok & grin_inside_nb(m, q[j]) & defined & (xs[2] == xs[2]);
+            const bool v = valid[j] & e_ok & grin_inside_nb<BND>(m, q[j]) & defined & (xs[2] == xs[2]);
             const bool stop = crossed | !v;
             const bool live = !done[j];
             const bool advance = live & !stop;
@@ -296,9 +301,13 @@ __device__ __forceinline__ void grin_propagate_rays(const DMedium &m, int shape_
                                                     const bool *enter, bool *valid_out,
                                                     const double *etab) {
     if (shape_kind == PYR_SHAPE_CONIC && m.profile == PYR_GRIN_GAUSSIAN_XY) {
-        grin_propagate_n<PYR_GRIN_GAUSSIAN_XY, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
+        // (the cylinder boundary of demos/demo_grin.py has its own copy of the loop)
+        if (m.boundary == PYR_BND_CYLINDER)
+            grin_propagate_n<PYR_GRIN_GAUSSIAN_XY, PYR_BND_CYLINDER, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
+        else
+            grin_propagate_n<PYR_GRIN_GAUSSIAN_XY, -1, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
     } else if (shape_kind == PYR_SHAPE_CONIC && m.profile == PYR_GRIN_POLY_RZ) {
-        grin_propagate_n<PYR_GRIN_POLY_RZ, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
+        grin_propagate_n<PYR_GRIN_POLY_RZ, -1, N>(m, curv, cc, x, d, k, enter, valid_out, etab);
     } else {
 #pragma unroll 1
         for (int j = 0; j < N; ++j)

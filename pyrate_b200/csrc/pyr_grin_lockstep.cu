@@ -48,7 +48,7 @@ grin_lockstep_kernel(const __grid_constant__ LaunchParams P, const double *__res
     __shared__ double etab[kExpTabSize];
     __shared__ double red[kLockThreads / 32];
     __shared__ int all_invalid;
-    if (threadIdx.x < kExpTabSize) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    for (int i = threadIdx.x; i < kExpTabSize; i += kLockThreads) etab[i] = kExp2Tab[i];
     if (threadIdx.x == 0) all_invalid = 0;
     double *pos = scratch, *vel = scratch + 3 * ld, *upos = scratch + 6 * ld, *uvel = scratch + 9 * ld;
     uint8_t *flag = reinterpret_cast<uint8_t *>(scratch + 12 * ld);

@@ -402,8 +402,9 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // per-step constants are then broadcast LDS reads (short, fixed latency) instead of
     // register-indexed constant loads.
     __shared__ DStep sst[kMaxSteps];
-    __shared__ double etab[(FEAT & 2) ? kExpTabSize : 1];          // 2^(j/128) of pyr_exp.cuh (GRIN profiles)
-    if ((FEAT & 2) && threadIdx.x < kExpTabSize) etab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __shared__ double etab[(FEAT & 2) ? kExpTabSize : 1];          // 2^(j/512) of pyr_exp.cuh (GRIN profiles)
+    if (FEAT & 2)
+        for (int i = threadIdx.x; i < kExpTabSize; i += blockDim.x) etab[i] = kExp2Tab[i];
     {
         const uint64_t *src = reinterpret_cast<const uint64_t *>(P.steps);
         uint64_t *dst = reinterpret_cast<uint64_t *>(sst);
