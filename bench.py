@@ -448,6 +448,23 @@ def run_leg(name, info, args, world, rank, dev, peak, torch, dist):
         dist.all_reduce(kms, op=dist.ReduceOp.MAX)
         dist.all_reduce(entries)
     (kms, entries) = (float(kms.item()), float(entries.item()))
+    # C3 is the HBM-bound leg: also time it from resident input arrays (the layout SURVEY 8d's
+    # 67 B per ray-entry refers to)
+    res_ms = None
+    if fused and name == "c3_asphere":
+        (xa, ka, ea) = gen.materialise(dev)
+        for _ in range(3):
+            engine.trace(lowered, xa, ka, ea, configs.DLINE, device=dev, pool=pool)
+        ev2 = []
+        for _ in range(steps):
+            engine.trace(lowered, xa, ka, ea, configs.DLINE, device=dev, pool=pool, events=ev2)
+        torch.cuda.synchronize(dev)
+        rt = torch.tensor([sum(a.elapsed_time(b) for (a, b) in ev2) / steps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(rt, op=dist.ReduceOp.MAX)
+        res_ms = float(rt.item())
+        del xa, ka, ea
+        gen._cache = None                    # release the 72 B/ray arrays
     out = None
     if rank == 0:
         (c, rms) = engine.spot_from_sums(spot.cpu(), origin)
@@ -474,6 +491,15 @@ def run_leg(name, info, args, world, rank, dev, peak, torch, dist):
             out["gathered_points"] = int(g.counts.sum().item())
             out["gather"] = ("pyr_spot_points (device compaction, count stays on the device) + one "
                              "fixed-width NCCL gather of (2, %d) doubles per rank to rank 0" % width)
+        if out is not None and res_ms is not None:
+            rbytes = entries * per_entry + 72.0 * total
+            out["resident_arrays"] = {
+                "what": "the same trace with x0, k0, E0 read from device arrays (72 B/ray: SURVEY 8d's "
+                        "49 + 72/S_seq = 67 B per ray-entry), kernel only",
+                "trace_kernels_ms": res_ms,
+                "roofline": {"bound": "hbm", "algorithmic_bytes_all_ranks": rbytes,
+                             "achieved": rbytes / (res_ms * 1e-3) / 1e9 / world, "peak": peak, "unit": "GB/s",
+                             "frac": rbytes / (res_ms * 1e-3) / 1e9 / world / peak}}
         try:
             out["parity"] = parity_sample(name, spec, lowered, rec, gen, n)
         except Exception as err:                                # report, never hide
@@ -566,6 +592,7 @@ def run_gpu(args):
             ht(gen=gen)
         dt = wall_region(lambda: ht(gen=gen), args.steps, sync, world, dist, dev, torch)
         (_, rms2) = engine.spot_from_sums(ht.spot8, origin)
+        desc_bytes = ht.h2d_bytes             # descriptor + step table: what a described bundle sends
         e2e = {"value": world * n * S_COUNTED / dt, "unit": "ray-surfaces/s",
                "h2d_bytes_per_step": ht.h2d_bytes, "d2h_bytes_per_step": ht.d2h_bytes,
                "ms_per_step": 1e3 * dt, "spot_rms": rms2, "spot_count": float(ht.spot8[3]),
@@ -592,7 +619,7 @@ def run_gpu(args):
             mt()
         dt_m = wall_region(mt, args.steps, sync, world, dist, dev, torch)
         e2e["metric_only"] = {"value": world * n * S_COUNTED / dt_m, "ms_per_step": 1e3 * dt_m,
-                              "h2d_bytes_per_step": ht.h2d_bytes, "d2h_bytes_per_step": 64,
+                              "h2d_bytes_per_step": desc_bytes, "d2h_bytes_per_step": 64,
                               "spot_rms": mt(refresh=False),
                               "what": "pyrate_b200.merit.MeritTrace (pyr_trace_spot): parameters re-read from "
                                       "the object graph, bundle generated in the kernel, only the last entry "
