@@ -421,6 +421,116 @@ __device__ __forceinline__ void aniso_modes(const DAux &ax, const cplx kl[3], co
     }
 }
 
+// ---------------------------------------------------------------------------
+// Real-valued fast path.  In a transparent uniaxial crystal below every critical angle --
+// BASELINE config 4, and what birefringent systems normally are -- k and E of every mode
+// stay REAL: the complex arithmetic above then multiplies by zero imaginary parts in three
+// of four products.  A warp whose rays all carry real (k, E) runs the functions below (the
+// same formulas, real); a negative radicand (evanescent mode) or a degenerate mode in any
+// lane sends the whole warp through the complex code for that step.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3]) {
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// ray.py:140-152 for real k, E
+__device__ __forceinline__ void poynting_vec_r(const double k[3], const double e[3], double s[3]) {
+    const double ee = dot3(e, e), ek = dot3(e, k);
+    for (int i = 0; i < 3; ++i) s[i] = ee * k[i] - ek * e[i];
+}
+
+// uni_key for a real root: `closed` as there
+__device__ __forceinline__ double uni_key_r(const DAux &ax, const double p[3], const double nrm[3], double xi,
+                                            bool extraordinary, bool &closed) {
+    double k[3], ko[3];
+    for (int i = 0; i < 3; ++i) k[i] = p[i] + nrm[i] * xi;
+    const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+    cross3(k, a, ko);
+    const double kk = dot3(k, k);
+    closed = closed && ax.eps_e != ax.eps_o && dot3(ko, ko) > 1e-8 * kk;
+    const double wgt = fast_rcp(1.0 + xi * xi);
+    const double kn = dot3(k, nrm);
+    if (!extraordinary) return wgt * kn;
+    const double ka = dot3(k, a);
+    double e[3];
+    for (int i = 0; i < 3; ++i) e[i] = ax.eps_o * a[i] - ka * k[i];
+    const double ek = ka * (ax.eps_o - kk);
+    const double en = ax.eps_o * dot3(a, nrm) - ka * kn;
+    return wgt * (kn - fast_div(ek * en, dot3(e, e)));
+}
+
+// one selected mode (closed forms of mode_key<true>), field scaled like aniso_modes does
+__device__ __forceinline__ void uni_mode_r(const DAux &ax, const double p[3], const double nrm[3], double xi,
+                                           bool extraordinary, double sgn, double k[3], double e[3]) {
+    for (int i = 0; i < 3; ++i) k[i] = p[i] + nrm[i] * xi;
+    const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+    if (extraordinary) {
+        const double ka = dot3(k, a);
+        for (int i = 0; i < 3; ++i) e[i] = ax.eps_o * a[i] - ka * k[i];
+    } else {
+        cross3(k, a, e);
+    }
+    // unit field times sqrt(weight), weight = 1 / (1 + xi^2)
+    const double sc = sgn * fast_rsqrt(dot3(e, e) * (1.0 + xi * xi));
+    for (int i = 0; i < 3; ++i) { k[i] = sgn * k[i]; e[i] = sc * e[i]; }
+}
+
+// aniso_modes<false> for real k: returns false where the complex code is needed (evanescent
+// or degenerate mode); NaN outputs for non-finite input like there
+__device__ __forceinline__ bool aniso_modes_r(const DAux &ax, const double kl[3], const double nrm[3],
+                                              bool mirror, double ka[3], double ea[3], double kb[3],
+                                              double eb[3]) {
+    const double kn = dot3(kl, nrm);
+    double p[3];
+    for (int i = 0; i < 3; ++i) p[i] = kl[i] - nrm[i] * kn;
+    const double eo = ax.eps_o, de = ax.eps_e - ax.eps_o;
+    const double a[3] = {ax.axis[0], ax.axis[1], ax.axis[2]};
+    const double kk = dot3(p, p), pa = dot3(p, a), na = dot3(nrm, a);
+    const double r1 = eo - kk;                                   // xi_o^2
+    const double qa = fma(de * na, na, eo);
+    const double qb = (de * na) * pa;
+    const double qc = eo * kk + de * (pa * pa) - eo * ax.eps_e;
+    const double r2 = qb * qb - qa * qc;
+    const bool finite = isfinite(r1) && isfinite(r2) && finite3(nrm);
+    if (!finite) {
+        for (int i = 0; i < 3; ++i) ka[i] = kb[i] = ea[i] = eb[i] = qnan();
+        return true;
+    }
+    if (r1 < 0.0 || r2 < 0.0) return false;                      // evanescent: complex roots
+    const double xo = r1 > 0.0 ? fast_sqrt(r1) : 0.0;
+    const double disc = r2 > 0.0 ? fast_sqrt(r2) : 0.0;
+    const double iqa = fast_rcp(qa);
+    const double xi0 = xo, xi1 = -xo, xi2 = iqa * (disc - qb), xi3 = iqa * (-disc - qb);
+    if (!(isfinite(xi2) && isfinite(xi3))) {
+        for (int i = 0; i < 3; ++i) ka[i] = kb[i] = ea[i] = eb[i] = qnan();
+        return true;
+    }
+    bool closed = true;
+    const double key0 = uni_key_r(ax, p, nrm, xi0, false, closed);
+    const double key1 = uni_key_r(ax, p, nrm, xi1, false, closed);
+    const double key2 = uni_key_r(ax, p, nrm, xi2, true, closed);
+    const double key3 = uni_key_r(ax, p, nrm, xi3, true, closed);
+    if (!closed) return false;                                   // degenerate: general null vectors
+    // stable ascending rank of every key (what the reference's argsort gives)
+    const int r0 = (key1 < key0) + (key2 < key0) + (key3 < key0);
+    const int r1k = (key0 <= key1) + (key2 < key1) + (key3 < key1);
+    const int r2k = (key0 <= key2) + (key1 <= key2) + (key3 < key2);
+    const int r3 = (key0 <= key3) + (key1 <= key3) + (key2 <= key3);
+    const int ra = mirror ? 0 : 2, rb = mirror ? 1 : 3;      // material_anisotropic.py:89-91 / :133-134
+    double xa = xi2, xb = xi3;
+    bool exa = true, exb = true;
+    if (r0 == ra) { xa = xi0; exa = false; } else if (r1k == ra) { xa = xi1; exa = false; }
+    else if (r3 == ra) { xa = xi3; }
+    if (r0 == rb) { xb = xi0; exb = false; } else if (r1k == rb) { xb = xi1; exb = false; }
+    else if (r2k == rb) { xb = xi2; }
+    const double sgn = mirror ? -1.0 : 1.0;
+    uni_mode_r(ax, p, nrm, xa, exa, sgn, ka, ea);
+    uni_mode_r(ax, p, nrm, xb, exb, sgn, kb, eb);
+    return true;
+}
+
 __device__ __forceinline__ void cstore(double *base, int64_t idx, cplx v) {
     __stcs(reinterpret_cast<double2 *>(base) + idx, make_double2(v.re, v.im));
 }
@@ -502,11 +612,21 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 const DAux *aux = st.aux >= 0 ? &P.aux[st.aux] : nullptr;
                 const bool ok = alive;
 
+                // real-valued fast path of this step: every lane of the warp carries real k, E
+                // (dead lanes hold NaN and follow along)
+                const bool lane_real = !ok || (k[0].im == 0.0 && k[1].im == 0.0 && k[2].im == 0.0 &&
+                                               e[0].im == 0.0 && e[1].im == 0.0 && e[2].im == 0.0);
+                const bool warp_real = __all_sync(__activemask(), lane_real);
                 // direction of energy transport: always the Poynting vector here
                 double d[3];
                 {
                     double sv[3];
-                    poynting_vec(k, e, sv);
+                    if (warp_real) {
+                        const double kr[3] = {k[0].re, k[1].re, k[2].re}, er[3] = {e[0].re, e[1].re, e[2].re};
+                        poynting_vec_r(kr, er, sv);
+                    } else {
+                        poynting_vec(k, e, sv);
+                    }
                     const double inv = fast_rsqrt(dot3(sv, sv));
                     d[0] = sv[0] * inv; d[1] = sv[1] * inv; d[2] = sv[2] * inv;
                 }
@@ -564,7 +684,56 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 cplx k2a[3], e2a[3], k2b[3], e2b[3];
                 const bool no_deflect = (st.bits & kNoDeflect) != 0;   // stand-alone propagate
                 const bool aniso = st.after_kind == PYR_MEDIUM_ANISO && !no_deflect;
-                if (no_deflect) {
+                bool done_real = false;
+                if (warp_real && !no_deflect) {
+                    const double klr[3] = {kl[0].re, kl[1].re, kl[2].re};
+                    if (aniso) {
+                        if (!GENERAL_EPS) {
+                            double ka_[3], ea_[3], kb_[3], eb_[3];
+                            const bool fine = aniso_modes_r(*aux, klr, nrm, mirror, ka_, ea_, kb_, eb_);
+                            if (__all_sync(__activemask(), fine)) {
+                                for (int c = 0; c < 3; ++c) {
+                                    k2a[c] = C(ka_[c]); e2a[c] = C(ea_[c]); k2b[c] = C(kb_[c]); e2b[c] = C(eb_[c]);
+                                }
+                                alive = ok;
+                                done_real = true;
+                            }
+                        }
+                    } else {
+                        // isotropic deflection, real k (material_isotropic.py:163-236); total
+                        // reflection invalidates the ray (its complex k is never used)
+                        const double kn = dot3(klr, nrm);
+                        double kin[3];
+                        for (int c = 0; c < 3; ++c) kin[c] = klr[c] - nrm[c] * kn;
+                        const double square = st.n2sq[0] - dot3(kin, kin);
+                        const bool refr_ok = square > 0.0 && finite3(nrm);
+                        const double xi = fast_sqrt(square);
+                        double k2[3];
+                        for (int c = 0; c < 3; ++c) k2[c] = (mirror ? -kin[c] : kin[c]) + nrm[c] * xi;
+                        alive = hit && refr_ok;
+                        double el[3];
+                        if (ident) { for (int c = 0; c < 3; ++c) el[c] = e[c].re; }
+                        else { const double er[3] = {e[0].re, e[1].re, e[2].re}; rot_t(st.frame.r, er, el); }
+                        const double kk = dot3(k2, k2);
+                        double cc = fast_div(dot3(el, k2), kk);
+                        double tv[3] = {el[0] - cc * k2[0], el[1] - cc * k2[1], el[2] - cc * k2[2]};
+                        double t2 = dot3(tv, tv);
+                        if (!(t2 > 1e-24 * dot3(el, el))) {
+                            const double ax = k2[0] * k2[0], ay = k2[1] * k2[1], az = k2[2] * k2[2];
+                            double a[3] = {0.0, 0.0, 0.0};
+                            if (ax <= ay && ax <= az) a[0] = 1.0; else if (ay <= az) a[1] = 1.0; else a[2] = 1.0;
+                            cc = fast_div(dot3(a, k2), kk);
+                            for (int c = 0; c < 3; ++c) tv[c] = a[c] - cc * k2[c];
+                            t2 = dot3(tv, tv);
+                        }
+                        const double inv = fast_rsqrt(t2);
+                        for (int c = 0; c < 3; ++c) { k2a[c] = C(k2[c]); e2a[c] = C(inv * tv[c]); }
+                        done_real = true;
+                    }
+                }
+                if (done_real) {
+                    // (deflected in real arithmetic)
+                } else if (no_deflect) {
                     for (int c = 0; c < 3; ++c) { k2a[c] = kl[c]; }
                     alive = hit;                 // k, E unchanged (material_anisotropic.py:58-68)
                 } else if (aniso) {
