@@ -198,11 +198,19 @@ __device__ __forceinline__ void null_vector(const cplx eps[9], const cplx k[3], 
 
 // general null vector behind a call: the uniaxial kernel needs it only for degenerate
 // modes (propagation along the optic axis, isotropic tensors) and must not pay its
-// registers on the fast path
-__device__ __noinline__ void null_vector_call(const double *eps18, const cplx k[3], bool second, cplx e[3]) {
+// registers on the fast path.  Arguments and result travel BY VALUE (registers): a pointer
+// to the caller's k / e arrays would pin those arrays -- the outputs of every deflection --
+// in local memory for the whole kernel (it did: ~300 local stores per ray, profiles/r02_c4.md)
+struct cvec3 {
+    cplx v[3];
+};
+__device__ __noinline__ cvec3 null_vector_call(const double *eps18, cplx k0, cplx k1, cplx k2, bool second) {
     cplx eps[9];
     for (int i = 0; i < 9; ++i) eps[i] = {eps18[2 * i], eps18[2 * i + 1]};
-    null_vector(eps, k, second, e);
+    const cplx k[3] = {k0, k1, k2};
+    cvec3 r;
+    null_vector(eps, k, second, r.v);
+    return r;
 }
 
 // One mode k = p + xi n: unit null vector e of the propagator, weight of the reference's
@@ -239,7 +247,8 @@ __device__ __forceinline__ double mode_key(const DAux &ax, const cplx p[3], cons
     }
     if (!closed) {
         if (UNI) {
-            null_vector_call(ax.after.eps, k, second, e);
+            const cvec3 nv = null_vector_call(ax.after.eps, k[0], k[1], k[2], second);
+            for (int i = 0; i < 3; ++i) e[i] = nv.v[i];
         } else {
             cplx eps[9];
             for (int i = 0; i < 9; ++i) eps[i] = {ax.after.eps[2 * i], ax.after.eps[2 * i + 1]};
