@@ -781,19 +781,26 @@ trace_complex_kernel(const __grid_constant__ LaunchParams P) {
                 }
 
                 // ---- back to the global frame, record ----
-                cplx kga[3], ega[3], kgb[3], egb[3];
-                if (ident) { for (int c = 0; c < 3; ++c) { kga[c] = k2a[c]; ega[c] = e2a[c]; } }
-                else { crot(st.frame.r, k2a, kga); crot(st.frame.r, e2a, ega); }
-                if (no_deflect) { for (int c = 0; c < 3; ++c) { kga[c] = k[c]; ega[c] = e[c]; } }
+                // (in place: the common cases -- untilted frames, every lane alive -- move nothing)
+                if (no_deflect) {
+                    for (int c = 0; c < 3; ++c) { k2a[c] = k[c]; e2a[c] = e[c]; }
+                } else if (!ident) {
+                    cplx t[3];
+                    crot(st.frame.r, k2a, t); for (int c = 0; c < 3; ++c) k2a[c] = t[c];
+                    crot(st.frame.r, e2a, t); for (int c = 0; c < 3; ++c) e2a[c] = t[c];
+                    if (aniso) {
+                        crot(st.frame.r, k2b, t); for (int c = 0; c < 3; ++c) k2b[c] = t[c];
+                        crot(st.frame.r, e2b, t); for (int c = 0; c < 3; ++c) e2b[c] = t[c];
+                    }
+                }
                 const bool split = aniso && (st.bits & kSplit);
-                if (aniso) {
-                    if (ident) { for (int c = 0; c < 3; ++c) { kgb[c] = k2b[c]; egb[c] = e2b[c]; } }
-                    else { crot(st.frame.r, k2b, kgb); crot(st.frame.r, e2b, egb); }
+                if (__any_sync(__activemask(), !alive)) {
+                    const cplx qn = {qnan(), qnan()};
+                    if (!alive) {
+                        for (int c = 0; c < 3; ++c) { k2a[c] = e2a[c] = k2b[c] = e2b[c] = qn; }
+                    }
                 }
-                const cplx qn = {qnan(), qnan()};
-                if (!alive) {
-                    for (int c = 0; c < 3; ++c) { kga[c] = ega[c] = kgb[c] = egb[c] = qn; }
-                }
+                cplx (&kga)[3] = k2a, (&ega)[3] = e2a, (&kgb)[3] = k2b, (&egb)[3] = e2b;
                 const int64_t ld = st.ld_out;
                 if (st.out_x)
                     for (int c = 0; c < 3; ++c) __stcs(st.out_x + c * ld + col, ok ? hit_g[c] : qnan());
