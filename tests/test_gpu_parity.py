@@ -830,3 +830,62 @@ def test_grin_lockstep_cross_ray_semantics_match_the_oracle(case):
         assert 0 < n_lock < n_free                              # early finishers were invalidated
     else:
         assert n_lock == n_free == x0.shape[1]
+
+
+def _evanescent_spec():
+    """Dense glass -> tilted calcite-like crystal: the in-plane wave vector of a ray fan
+    straddles both critical angles (n_glass sin(theta) from 1.1 to 1.8 against n_o = 1.658,
+    n_e = 1.486), so one or both crystal modes are evanescent for part of the bundle."""
+    eps = np.diag([1.658 ** 2, 1.486 ** 2, 1.658 ** 2]).tolist()
+    return {"name": "evanescent",
+            "surfaces": [configs._conic("stop", 0.0, opt={"is_stop": True}),
+                         configs._conic("glass", 2.0, mat="dense"),
+                         configs._conic("crystal", 6.0, mat="crystal", tiltx=38.0 * np.pi / 180.0),
+                         configs._conic("exit", 4.0, mat="dense"),
+                         configs._conic("image", 6.0, mat="dense")],
+            "materials": {"dense": ("ConstantIndexGlass", {"n": 2.4}),
+                          "crystal": ("AnisotropicMaterial", {"epstensor": eps})},
+            "bundle": {"rings": 5, "radius": 1.0, "z0": -3.0}}
+
+
+@pytest.mark.parametrize("name", ["c4_anisotropic", "x8_crystal_mirror", "evanescent"])
+def test_crystal_real_fast_path_equals_the_complex_code(name):
+    """The crystal kernel runs a warp in real arithmetic while all its rays carry real k, E
+    (csrc/pyr_aniso.cu: aniso_modes_r) and falls back to the complex code per warp and step
+    for evanescent or degenerate modes.  A bundle whose E carries a 1e-30 imaginary part
+    takes the complex code everywhere: both runs must agree -- also where the two kinds of
+    warps sit side by side (the `evanescent` fan: propagating, half and fully evanescent
+    rays in one bundle)."""
+    if name == "evanescent":
+        spec = _evanescent_spec()
+        n = 4099
+        rng = np.random.default_rng(5)
+        ang = np.linspace(-0.43, 0.43, n)
+        tx = rng.uniform(-0.02, 0.02, n)
+        k0 = np.stack((np.sin(tx), np.cos(tx) * np.sin(ang), np.cos(tx) * np.cos(ang)))
+        x0 = np.stack((rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n), np.full(n, -3.0)))
+        e0 = np.cross(k0.T, np.array([0.0, 1.0, 0.3])).T
+        e0 /= np.linalg.norm(e0, axis=0)
+    else:
+        spec = configs.CONFIGS[name]
+        (x0, k0, e0) = configs.config_bundle(spec, 21, (0.0, np.sin(0.03), np.cos(0.03)), (1.0, 0.0, 0.0))
+    (s, seq) = configs.build_system(spec, pb.api())
+    real = s.seqtrace(pb.RayBundle(x0, k0, e0, wave=configs.DLINE), seq)[0].raybundles
+    cplx = s.seqtrace(pb.RayBundle(x0, k0, e0 * (1.0 + 1e-30j), wave=configs.DLINE), seq)[0].raybundles
+    assert len(real) == len(cplx)
+    evanescent = 0
+    for (ib, (a, b)) in enumerate(zip(real, cplx)):
+        (da, db) = (a.numpy(), b.numpy())
+        assert np.array_equal(da["valid"], db["valid"]), ib
+        assert np.array_equal(da["rayID"], db["rayID"]), ib
+        for key in ("x", "k"):
+            (u, v) = (np.asarray(da[key]), np.asarray(db[key]))
+            assert u.shape == v.shape
+            assert np.array_equal(np.isnan(u.real), np.isnan(v.real)), (ib, key)
+            m = ~np.isnan(u.real)
+            scale = max(np.max(np.abs(v[m])), 1e-300) if m.any() else 1.0
+            assert np.max(np.abs(u[m] - v[m])) <= 1e-11 * scale if m.any() else True, (ib, key)
+            if key == "k" and np.iscomplexobj(u):
+                evanescent += int(np.sum(np.abs(u[m].imag) > 1e-6))
+    if name == "evanescent":
+        assert evanescent > 100          # the fan really has evanescent modes
