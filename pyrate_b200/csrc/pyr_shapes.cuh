@@ -339,6 +339,36 @@ __device__ __forceinline__ double rcp_nr1(double a) {
     return fma(y, fma(-a, y, 1.0), y);
 }
 
+// p = sum a_i r2^i and p' = dp / d(r2) by Horner for N rays.  Up to four coefficients (the usual
+// even asphere: A2 .. A8) run as a fixed four-step chain -- the record is zero-padded beyond
+// n_coeff, and a leading zero coefficient leaves the exact value -- without the loop's branches.
+template <int N>
+__device__ __forceinline__ void asphere_horner(const DAux &a, int nc, const double (&r2)[N], double (&p)[N],
+                                               double (&dp)[N]) {
+    if (nc <= 4) {
+        const double c3 = a.coeff[3], c2 = a.coeff[2], c1 = a.coeff[1], c0 = a.coeff[0];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            double pj = c3, dj = 0.0;
+            dj = fma(dj, r2[j], pj); pj = fma(pj, r2[j], c2);
+            dj = fma(dj, r2[j], pj); pj = fma(pj, r2[j], c1);
+            dj = fma(dj, r2[j], pj); pj = fma(pj, r2[j], c0);
+            p[j] = pj; dp[j] = dj;
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < N; ++j) { p[j] = 0.0; dp[j] = 0.0; }
+    for (int i = nc - 1; i >= 0; --i) {
+        const double ci = a.coeff[i];
+#pragma unroll
+        for (int j = 0; j < N; ++j) {
+            dp[j] = fma(dp[j], r2[j], p[j]);
+            p[j] = fma(p[j], r2[j], ci);
+        }
+    }
+}
+
 // Even asphere (the common explicit shape), N rays of a thread together, WITHOUT a square
 // root or a full-precision division inside the iteration: with q(r^2) = sum a_i r^(2i+2) the
 // hit satisfies  w = z - q(r^2) = conic sag(r^2), and on the vertex branch of the conic that
@@ -377,14 +407,7 @@ __device__ __forceinline__ void asphere_t_n(const DAux &a, double curv, double c
             r2[j] = fma(x[j], x[j], y[j] * y[j]);
             p[j] = 0.0; dp[j] = 0.0;
         }
-        for (int i = nc - 1; i >= 0; --i) {              // p = sum a_i r2^i and p' by Horner
-            const double ci = a.coeff[i];
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                dp[j] = fma(dp[j], r2[j], p[j]);
-                p[j] = fma(p[j], r2[j], ci);
-            }
-        }
+        asphere_horner<N>(a, nc, r2, p, dp);
         bool done = true;
 #pragma unroll
         for (int j = 0; j < N; ++j) {
@@ -417,14 +440,7 @@ __device__ __forceinline__ void asphere_t_n(const DAux &a, double curv, double c
             r2[j] = fma(x[j], x[j], y[j] * y[j]);
             p[j] = 0.0; dp[j] = 0.0;
         }
-        for (int i = nc - 1; i >= 0; --i) {
-            const double ci = a.coeff[i];
-#pragma unroll
-            for (int j = 0; j < N; ++j) {
-                dp[j] = fma(dp[j], r2[j], p[j]);
-                p[j] = fma(p[j], r2[j], ci);
-            }
-        }
+        asphere_horner<N>(a, nc, r2, p, dp);
 #pragma unroll
         for (int j = 0; j < N; ++j) {
             const double w = fma(-r2[j], p[j], fma(t[j], d[j][2], r0[j][2]));
