@@ -29,6 +29,8 @@ constexpr uint32_t kPlane = 16u;           // curv == 0 (and conic shape)
 constexpr uint32_t kOutVec2 = 32u;         // outputs allow 128-bit stores
 constexpr uint32_t kNoDeflect = 64u;       // PYR_STEP_PROPAGATE_ONLY
 constexpr uint32_t kNoIntersect = 128u;    // PYR_STEP_DEFLECT_ONLY
+constexpr uint32_t kRecorded = 256u;       // the step has at least one output pointer
+constexpr uint32_t kPlain = 512u;          // untilted frame, no aperture, refraction, cc == 0: step_lean<.., PLAIN>
 
 struct DFrame {
     double r[9];
@@ -113,6 +115,7 @@ struct LaunchParams {
     int32_t in_vec2;               // inputs allow 128-bit loads
     int32_t n_waves;               // > 1: wavelength batch, ray i is in segment #{j: i >= wave_end[j]}
     int64_t wave_end[kMaxWaves];
+    unsigned long long *tile_ctr;  // in-order tile hand-out (csrc/pyr_trace.cu launch()); nullptr: static schedule
     DGen gen;
     DStep steps[kMaxSteps];
     DAux aux[kMaxAux];

@@ -23,6 +23,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "pyr_device.cuh"
 #include "pyr_gen.cuh"
@@ -104,7 +105,7 @@ __device__ __forceinline__ void store_stream2(double *p, double a, double b) {
 __device__ __forceinline__ void poynting_dir(const double k[3], const double e[3], double d[3]) {
     const double ee = dot3(e, e), ek = dot3(e, k);
     double s[3] = {fma(ee, k[0], -ek * e[0]), fma(ee, k[1], -ek * e[1]), fma(ee, k[2], -ek * e[2])};
-    const double inv = rsqrt(dot3(s, s));
+    const double inv = fast_rsqrt(dot3(s, s));
     d[0] = s[0] * inv; d[1] = s[1] * inv; d[2] = s[2] * inv;
 }
 
@@ -255,7 +256,8 @@ __device__ __forceinline__ void step_real_n(const LaunchParams &P, const DStep &
         const double kin[3] = {fma(-kn, nrm[0], kl[0]), fma(-kn, nrm[1], kl[1]), fma(-kn, nrm[2], kl[2])};
         const double square = n2sq - dot3(kin, kin);
         const double xi = fast_sqrt(square);
-        const bool refr_ok = (square > 0.0) && finite3(nrm);
+        // (a non-finite normal makes `square` NaN or -inf: no separate finite check)
+        const bool refr_ok = square > 0.0;
         double k2[3];
         if (st.interaction == PYR_REFLECT) {
             k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
@@ -268,11 +270,13 @@ __device__ __forceinline__ void step_real_n(const LaunchParams &P, const DStep &
         } else if (ident) { r[j].k[0] = k2[0]; r[j].k[1] = k2[1]; r[j].k[2] = k2[2]; }
         else rot(st.frame.r, k2, r[j].k);
         r[j].x[0] = hit_g[j][0]; r[j].x[1] = hit_g[j][1]; r[j].x[2] = hit_g[j][2];
-        if (!ok[j]) { hit_g[j][0] = hit_g[j][1] = hit_g[j][2] = qnan(); }
-        if (!alive) {
-            const double q = qnan();
-            r[j].x[0] = r[j].x[1] = r[j].x[2] = q;
-            r[j].k[0] = r[j].k[1] = r[j].k[2] = q;
+        if (__any_sync(__activemask(), !alive)) {          // (nothing to fill while every lane lives)
+            if (!ok[j]) { hit_g[j][0] = hit_g[j][1] = hit_g[j][2] = qnan(); }
+            if (!alive) {
+                const double q = qnan();
+                r[j].x[0] = r[j].x[1] = r[j].x[2] = q;
+                r[j].k[0] = r[j].k[1] = r[j].k[2] = q;
+            }
         }
         if (WITH_E) {
             if (!alive) r[j].e[0] = r[j].e[1] = r[j].e[2] = qnan();
@@ -290,11 +294,13 @@ __device__ __forceinline__ void step_real_n(const LaunchParams &P, const DStep &
 //   * validity rides on NaN propagation: a ray that dies gets k = NaN once, every
 //     later hit point and wave vector is NaN by arithmetic, and `square > 0`
 //     already rejects NaN normals (no separate finite check).
-template <bool WITH_E>
+// PLAIN (DStep bit kPlain): untilted frame, no aperture, refraction, sphere or plane -- the
+// thirteen entries of the double-Gauss -- without the branches that decide those properties
+template <bool WITH_E, bool PLAIN = false>
 __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, const double d[3],
                                               double hit_g[3], int w = 0) {
     const bool ok = r.alive;
-    const bool ident = (st.bits & kRotIdentity) != 0;
+    const bool ident = PLAIN || (st.bits & kRotIdentity) != 0;
     double r0[3], dl[3], kl[3];
     if (ident) {
         r0[0] = r.x[0] - st.frame.o[0]; r0[1] = r.x[1] - st.frame.o[1]; r0[2] = r.x[2] - st.frame.o[2];
@@ -315,7 +321,7 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
         t = -r0[2] * fast_rcp(dl[2]);
         h[0] = fma(dl[0], t, r0[0]); h[1] = fma(dl[1], t, r0[1]); h[2] = fma(dl[2], t, r0[2]);
         nrm[0] = 0.0; nrm[1] = 0.0; nrm[2] = 1.0;
-    } else if (st.bits & kSphere) {
+    } else if (PLAIN || (st.bits & kSphere)) {
         // cc = 0:  F = d_z - c (d.r0),  G = c (r0.r0) - 2 z0,  H = -c
         const double F = fma(-curv, dot3(dl, r0), dl[2]);
         const double G = fma(curv, dot3(r0, r0), -2.0 * r0[2]);
@@ -352,7 +358,9 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
         l2g_point(st.frame, h, hit_g);
     }
     bool ap_ok = true;
-    if (st.aperture_kind == PYR_AP_CIRCULAR) {
+    if (PLAIN) {
+        // no aperture
+    } else if (st.aperture_kind == PYR_AP_CIRCULAR) {
         const double rr = fma(h[0], h[0], h[1] * h[1]);
         ap_ok = (rr >= st.ap0) && (rr <= st.ap1);
     } else if (st.aperture_kind == PYR_AP_RECTANGULAR) {
@@ -367,7 +375,7 @@ __device__ __forceinline__ uint32_t step_lean(const DStep &st, Ray<WITH_E> &r, c
     const double xi = fast_sqrt(square2);
     const bool alive = hit && (square2 > 0.0);
     double k2[3];
-    if (st.interaction == PYR_REFLECT) {
+    if (!PLAIN && st.interaction == PYR_REFLECT) {
         k2[0] = fma(xi, nrm[0], -kin[0]); k2[1] = fma(xi, nrm[1], -kin[1]); k2[2] = fma(xi, nrm[2], -kin[2]);
     } else {
         k2[0] = fma(xi, nrm[0], kin[0]); k2[1] = fma(xi, nrm[1], kin[1]); k2[2] = fma(xi, nrm[2], kin[2]);
@@ -450,18 +458,33 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             if (load_e) tma_load_1d(dst + (6 + c) * TILE, P.e + c * P.ld_in + t0, bytes, &full_bar[stage]);
         }
     };
+    // In-order tile hand-out (P.tile_ctr != nullptr: large launches of the lean kernels): the CTAs
+    // take their tiles from an atomic cursor instead of the static cyclic schedule, so the set of
+    // tiles in flight stays a compact window however the CTAs drift.  The record streams of a
+    // memory-bound launch then keep their DRAM page locality: C2 1.33 -> 1.15 ms with the same
+    // instruction stream, records bit-identical (profiles/r02_c2_dynamic_tiles.md).
+    const bool DYN = IN_STAGES <= 1 && P.tile_ctr != nullptr;
+    __shared__ long long dyn_tile[2];                    // DYN: current and next tile of the CTA
+    if (DYN && threadIdx.x == 0) {
+        dyn_tile[0] = (long long)atomicAdd(P.tile_ctr, 1ull);
+        dyn_tile[1] = (long long)atomicAdd(P.tile_ctr, 1ull);
+    }
+    if (DYN) __syncthreads();
     if (staged && threadIdx.x == 0) {
         mbar_init(&full_bar[0], 1);
         mbar_init(&full_bar[1], 1);
         fence_mbar_init();
-        if ((int64_t)blockIdx.x * TILE < n) issue_tile(blockIdx.x, 0);
+        const int64_t first = DYN ? dyn_tile[0] : (int64_t)blockIdx.x;
+        if (first * TILE < n) issue_tile(first, 0);
         if (IN_STAGES == 2 && ((int64_t)blockIdx.x + gridDim.x) * TILE < n)
             issue_tile((int64_t)blockIdx.x + gridDim.x, 1);
     }
     __syncthreads();
 
     int it = 0;
-    for (int64_t tile = blockIdx.x; tile * TILE < n; tile += gridDim.x, ++it) {
+    int64_t dyn_next = DYN ? dyn_tile[1] : 0;
+    for (int64_t tile = DYN ? dyn_tile[0] : (int64_t)blockIdx.x; tile * TILE < n;
+         tile = DYN ? dyn_next : tile + gridDim.x, dyn_next = DYN ? dyn_tile[it & 1] : 0, ++it) {
         const int64_t base = tile * TILE + (int64_t)threadIdx.x * RPT;
         const int stage = GEN ? 0 : it % (IN_STAGES > 0 ? IN_STAGES : 1);
         // WITH_E == false still needs E for the first segment's Poynting direction
@@ -494,7 +517,7 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             }
             __syncthreads();                       // every thread has drained this stage
             if (threadIdx.x == 0) {
-                const int64_t next = tile + IN_STAGES * (int64_t)gridDim.x;
+                const int64_t next = DYN ? dyn_next : tile + IN_STAGES * (int64_t)gridDim.x;
                 if (next * TILE < n) issue_tile(next, stage);
             }
         } else {
@@ -592,14 +615,20 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 step_real_n<RPT, WITH_E, (FEAT & 2) != 0 && !GRIN_N, (FEAT & 4) != 0, (FEAT & 8) != 0>(
                     P, st, ray, dd, hit, ridx, wj, etab, (FEAT & 2) != 0, fl);
             } else {
+                if (st.bits & kPlain) {
 #pragma unroll
-                for (int j = 0; j < RPT; ++j)
-                    fl[j] = step_lean<WITH_E>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
+                    for (int j = 0; j < RPT; ++j)
+                        fl[j] = step_lean<WITH_E, true>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < RPT; ++j)
+                        fl[j] = step_lean<WITH_E>(st, ray[j], dd[j], hit[j], MULTI ? wsel[j] : 0);
+                }
             }
 
             // ---- record the step ----
             const int64_t ld = st.ld_out;
-            if (!st.out_x && !st.out_k && !st.out_flags && !(WITH_E && st.out_e)) continue;   // not recorded
+            if (!(st.bits & kRecorded)) continue;                 // no output pointer at all
             if (TMA_OUT && (st.bits & kOutVec2)) {
                 // The CTA's slice of the record goes through shared memory and leaves
                 // as TMA bulk stores issued by one thread: no per-thread global stores,
@@ -688,6 +717,12 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                         if (in_range[j]) st.out_flags[base + j] = (uint8_t)fl[j];
                 }
             }
+        }
+        if (DYN) {
+            // slot it & 1 held this tile: it receives the tile after next
+            __syncthreads();
+            if (threadIdx.x == 0) dyn_tile[it & 1] = (long long)atomicAdd(P.tile_ctr, 1ull);
+            __syncthreads();
         }
     }
     if (TMA_OUT && threadIdx.x == 0) tma_store_wait_read<0>();      // smem must outlive the reads
@@ -1134,6 +1169,11 @@ static int pack(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, in
         else if (u.mode != PYR_STEP_FULL) return PYR_E_BADARG;
         // rows padded to 16 elements: the vector / TMA record path may write up to the
         // next multiple of 2 doubles (16 flag bytes) past the last ray of a row
+        if (d.out_x || d.out_k || d.out_e || d.out_flags) bits |= kRecorded;
+        // the double-Gauss's kind of entry: nothing to decide inside the step (step_lean<.., PLAIN>)
+        if ((bits & kRotIdentity) && u.aperture_kind == PYR_AP_BASE && u.interaction != PYR_REFLECT &&
+            u.shape_kind == PYR_SHAPE_CONIC && u.cc == 0.0 && u.mode == PYR_STEP_FULL)
+            bits |= kPlain;
         if ((d.ld_out % 16 == 0) && (!d.out_x || aligned16(d.out_x)) && (!d.out_k || aligned16(d.out_k)) &&
             (!d.out_e || aligned16(d.out_e)) &&
             (!d.out_flags || aligned16(d.out_flags)))
@@ -1223,9 +1263,38 @@ int sm_count() {
     return g_sm_count;
 }
 
+// one private memory pool per device for the tile cursors (created on first use, kept for the
+// life of the process: it never holds more than a few bytes)
+static cudaMemPool_t tile_cursor_pool() {
+    static std::mutex mu;
+    static cudaMemPool_t pools[64] = {};
+    static bool tried[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tried[dev]) {
+        tried[dev] = true;
+        cudaMemPoolProps props;
+        std::memset(&props, 0, sizeof(props));
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&pools[dev], &props) == cudaSuccess) {
+            unsigned long long keep = ~0ull;                     // never trim: the next launch reuses the bytes
+            cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            pools[dev] = nullptr;
+            cudaGetLastError();
+        }
+    }
+    return pools[dev];
+}
+
 template <typename K>
-static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream, bool tma_out = false,
-                  bool with_e = false, int threads = 256, bool gen = false) {   // threads == kernel's BLOCK
+static int launch(K kernel, LaunchParams &P, int rpt, cudaStream_t stream, bool tma_out = false,
+                  bool with_e = false, int threads = 256, bool gen = false,
+                  bool dynamic_tiles = false) {   // threads == kernel's BLOCK
     // dynamic shared memory: input stages of rpt x 9 doubles per thread (two, or one plus
     // two output stages of rpt x 6 doubles + flag bytes when records leave through the TMA)
     const size_t tile = (size_t)threads * rpt;
@@ -1244,8 +1313,28 @@ static int launch(K kernel, const LaunchParams &P, int rpt, cudaStream_t stream,
     int64_t grid = (int64_t)sm_count() * per_sm;
     if (work < grid) grid = work;
     if (grid < 1) return PYR_OK;
+    // tile cursor of the in-order hand-out: 8 bytes from a private stream-ordered pool, zeroed,
+    // used by this launch and released, all in stream order (re-entrant per stream; nothing
+    // persists but the pool itself).  Any failure falls back to the static schedule.
+    unsigned long long *ctr = nullptr;
+    if (dynamic_tiles && work >= 8 * grid) {
+        cudaMemPool_t pool = tile_cursor_pool();
+        if (pool && cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ctr), sizeof(unsigned long long), pool,
+                                            stream) == cudaSuccess) {
+            if (cudaMemsetAsync(ctr, 0, sizeof(unsigned long long), stream) != cudaSuccess) {
+                cudaFreeAsync(ctr, stream);
+                ctr = nullptr;
+            }
+        } else {
+            ctr = nullptr;
+        }
+        if (!ctr) cudaGetLastError();
+    }
+    P.tile_ctr = ctr;
     kernel<<<(unsigned)grid, threads, smem, stream>>>(P);
     e = cudaGetLastError();
+    if (ctr) cudaFreeAsync(ctr, stream);
+    P.tile_ctr = nullptr;
     return e == cudaSuccess ? PYR_OK : (int)e;
 }
 
@@ -1295,7 +1384,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         for (int s = 0; s < n_steps; ++s)
             grin = grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
         if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
-        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true);
+        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true, true);
         if (grin && !hist)
             return launch(trace_real_kernel<PYR_GRIN_RPT, false, 19, PYR_GRIN_MINB, kGrinPolicy | 16>, pk.P,
                           PYR_GRIN_RPT, stream, PYR_GRIN_RPT == 2, false, 256, true);
@@ -1312,11 +1401,11 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
             grin_or_ext = grin_or_ext || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN ||
                           steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
         if (with_e || grin_or_ext) return PYR_E_UNSUPPORTED;
-        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 11>, pk.P, 2, stream, true);
+        if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 11>, pk.P, 2, stream, true, false, 256, false, true);
         return launch(trace_real_kernel<2, false, 1, 2, 11>, pk.P, 2, stream, true);
     }
     if (!pk.general) {
-        if (with_e) return launch(trace_real_kernel<2, true, 0, 2, 3>, pk.P, 2, stream, true, true);
+        if (with_e) return launch(trace_real_kernel<2, true, 0, 2, 3>, pk.P, 2, stream, true, true, 256, false, true);
 #ifdef PYR_TOOLS
         // PYR_LEAN_VARIANT=50 selects per-thread STG records instead of the TMA record
         // path (A/B knob of tools/ builds only).  Other configurations that were measured
@@ -1327,7 +1416,7 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         }();
         if (variant == 50) return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
 #endif
-        return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true);
+        return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true, false, 256, false, true);
     }
     bool has_grin = false;
     for (int s = 0; s < n_steps; ++s)

@@ -11,6 +11,9 @@ sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
 import pyrate_b200 as pb  # noqa: E402
+from pyrate_b200 import _native as _nat_for_variant  # noqa: E402
+if os.environ.get('PYR_TOOLS_LIB'):
+    _nat_for_variant.use_tools_library(os.environ['PYR_TOOLS_LIB'])
 from pyrate_b200 import bundlegen, configs, engine, lowering  # noqa: E402
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c2_doublegauss"
