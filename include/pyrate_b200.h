@@ -20,8 +20,13 @@
  *     elements).  Anything else still works through plain loads / stores.
  *   - complex arrays are interleaved (re, im) doubles = numpy/torch complex128;
  *     element (c, i) at base[2 * (c * ld + i)].
- *   - every device pointer is caller-owned (the engine allocates nothing
- *     persistent and frees nothing); calls are asynchronous on `stream`.
+ *   - every device pointer is caller-owned; calls are asynchronous on `stream`.
+ *     The only device memory the library itself touches is the 8-byte tile
+ *     cursor of a large launch (>= 8 tiles per resident CTA of the conic-only
+ *     kernels): borrowed from a private stream-ordered pool
+ *     (cudaMallocFromPoolAsync), zeroed, used and released in stream order
+ *     -- calls stay re-entrant per stream and per host thread; if the pool is
+ *     unavailable the launch uses the static tile schedule instead.
  *   - return value: 0 = ok, < 0 = PYR_E_* (see pyr_strerror), > 0 = cudaError_t.
  *   - per-ray failures are never errors: they are reported through the flag
  *     byte (and NaN coordinates), like the reference's `valid` rows.

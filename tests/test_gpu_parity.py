@@ -889,3 +889,34 @@ def test_crystal_real_fast_path_equals_the_complex_code(name):
                 evanescent += int(np.sum(np.abs(u[m].imag) > 1e-6))
     if name == "evanescent":
         assert evanescent > 100          # the fan really has evanescent modes
+
+
+def test_large_launches_on_concurrent_streams_are_independent():
+    """Large launches of the conic-only kernels take their tiles in order from an atomic cursor
+    (8 bytes from the library's stream-ordered pool, csrc/pyr_trace.cu launch()).  Two such traces
+    in flight at the same time on different streams -- and a third one right behind on the first
+    stream -- must each see every tile exactly once: all records equal a lone run's."""
+    import torch
+    from pyrate_b200 import engine, lowering
+    spec = configs.CONFIGS["c2_doublegauss"]
+    (x0, k0, e0) = configs.config_bundle(spec, 1020)            # 3 124 261 rays: 6 103 tiles
+    (s, seq) = configs.build_system(spec, pb.api())
+    low = lowering.lower(s, seq, configs.DLINE)
+    dev = torch.device("cuda", 0)
+    (x0, k0, e0) = engine.device_bundle(x0, k0, e0, dev)
+    ref = engine.trace(low, x0, k0, e0, configs.DLINE, device=dev)
+    torch.cuda.synchronize()
+    (s1, s2) = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+    recs = []
+    for rep in range(3):
+        with torch.cuda.stream(s1):
+            recs.append(engine.trace(low, x0, k0, e0, configs.DLINE, device=dev))
+        with torch.cuda.stream(s2):
+            recs.append(engine.trace(low, x0, k0, e0, configs.DLINE, device=dev))
+    torch.cuda.synchronize()
+    for rec in recs:
+        for key in ("hit", "k", "flags"):
+            for (a, b) in zip(getattr(rec, key), getattr(ref, key)):
+                assert torch.equal(torch.nan_to_num(a) if a.dtype.is_floating_point else a,
+                                   torch.nan_to_num(b) if b.dtype.is_floating_point else b), key
+        assert int((rec.flags[-1] & 2).ne(0).sum()) == x0.shape[1]
