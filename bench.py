@@ -544,18 +544,16 @@ def run_gpu(args):
     ev = []                         # (start, end) CUDA events around each native trace launch
 
     def step_resident():
-        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool, events=ev)
-        spot.zero_()
-        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
+        # trace + spot sums of the image plane in ONE launch (pyr_trace_spot, asynchronous form)
+        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool, events=ev,
+                           spot=(spot, origin))
         if world > 1:
             dist.all_reduce(spot)
         return rec
 
     def step_generated():
         rec = engine.trace(lowered, None, None, None, configs.DLINE, device=dev, pool=pool,
-                           events=ev, gen=gen)
-        spot.zero_()
-        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
+                           events=ev, gen=gen, spot=(spot, origin))
         if world > 1:
             dist.all_reduce(spot)
         return rec
@@ -714,7 +712,7 @@ def run_gpu(args):
                              "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": algo_bytes},
                 "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": 2 * args.steps,
+                "gpu_launches": args.steps,
                 "clocks": clocks.summary()}
         print(json.dumps(line))
     if world > 1:

@@ -403,11 +403,15 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags,
 /*
  * One merit-function evaluation of an optimiser loop (the caller right above the path:
  * optimize/optimize.py:73-91 calls seqtrace + RayBundleAnalysis.get_rms_spot_size once
- * per function evaluation): pyr_trace, then pyr_spot_sums over the record of the LAST step
- * (out_x / out_flags of steps[n_steps - 1], which must be set) about `shift`, then the 8
- * sums are copied to HOST memory `spot8_host` (pinned for speed) and the stream is
- * synchronised -- one call, three launches, one 64-byte read-back.  `spot8_dev`: DEVICE
- * scratch of 8 doubles.
+ * per function evaluation): pyr_trace plus the sums of pyr_spot_sums over the record of the
+ * LAST step (out_x / out_flags of steps[n_steps - 1], which must be set; no ray doubling in
+ * the call) about `shift`, left in `spot8_dev` (DEVICE memory of 8 doubles, overwritten).
+ * Where the call is one launch of the conic-only kernels the trace kernel accumulates the
+ * sums itself (registers over the CTA's tiles, one reduction at the end: no second pass over
+ * the record); otherwise a pyr_spot_sums launch follows.
+ * spot8_host != NULL: the 8 sums are also copied to HOST memory (pinned for speed) and the
+ * stream is synchronised -- one call, one 64-byte read-back.  spot8_host == NULL: the call
+ * stays asynchronous like pyr_trace.
  */
 int pyr_trace_spot(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays,
                    int64_t n_rays, uint32_t flags, const double *shift, double *spot8_dev,

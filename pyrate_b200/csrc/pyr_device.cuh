@@ -116,6 +116,8 @@ struct LaunchParams {
     int32_t n_waves;               // > 1: wavelength batch, ray i is in segment #{j: i >= wave_end[j]}
     int64_t wave_end[kMaxWaves];
     unsigned long long *tile_ctr;  // in-order tile hand-out (csrc/pyr_trace.cu launch()); nullptr: static schedule
+    double *spot8;                 // POLICY bit 32: spot sums of the last entry accumulated by the trace kernel
+    double spot_shift[3];
     DGen gen;
     DStep steps[kMaxSteps];
     DAux aux[kMaxAux];

@@ -435,6 +435,15 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
     // POLICY bit 8: wavelength batch -- per-ray segment index selects the media indices
     // (own instantiations: the plain kernels keep their code)
     constexpr bool MULTI = (POLICY & 8) != 0;
+    // POLICY bit 32: the spot sums of the LAST entry (analysis/ray_analysis.py:44-86: sum x, count,
+    // sum x^2 of the rays that survive it) are accumulated in registers over the CTA's tiles and
+    // reduced once at the end -- pyr_trace_spot without the second pass over the record
+    constexpr bool SPOT = (POLICY & 32) != 0;
+    double sacc[SPOT ? 7 : 1];
+    if (SPOT) {
+#pragma unroll
+        for (int q = 0; q < 7; ++q) sacc[q] = 0.0;
+    }
     constexpr int IN_STAGES = GEN ? 0 : (TMA_OUT ? 1 : 2);
     // record stages: x, k (and E) rows; E recording has room for one stage only
     constexpr int OUT_ROWS = WITH_E ? 9 : 6;
@@ -626,6 +635,17 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
                 }
             }
 
+            if (SPOT && s == P.n_steps - 1) {
+#pragma unroll
+                for (int j = 0; j < RPT; ++j) {
+                    if (fl[j] & PYR_RAY_ALIVE) {
+                        const double a = hit[j][0] - P.spot_shift[0], b = hit[j][1] - P.spot_shift[1],
+                                     c = hit[j][2] - P.spot_shift[2];
+                        sacc[0] += a; sacc[1] += b; sacc[2] += c; sacc[3] += 1.0;
+                        sacc[4] = fma(a, a, sacc[4]); sacc[5] = fma(b, b, sacc[5]); sacc[6] = fma(c, c, sacc[6]);
+                    }
+                }
+            }
             // ---- record the step ----
             const int64_t ld = st.ld_out;
             if (!(st.bits & kRecorded)) continue;                 // no output pointer at all
@@ -723,6 +743,22 @@ trace_real_kernel(const __grid_constant__ LaunchParams P) {
             __syncthreads();
             if (threadIdx.x == 0) dyn_tile[it & 1] = (long long)atomicAdd(P.tile_ctr, 1ull);
             __syncthreads();
+        }
+    }
+    if (SPOT) {
+        __shared__ double spot_sm[BLOCK / 32][7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            double v = sacc[q];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) spot_sm[threadIdx.x >> 5][q] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x < 7) {
+            double v = 0.0;
+            for (int w = 0; w < BLOCK / 32; ++w) v += spot_sm[w][threadIdx.x];
+            atomicAdd(P.spot8 + threadIdx.x, v);
         }
     }
     if (TMA_OUT && threadIdx.x == 0) tma_store_wait_read<0>();      // smem must outlive the reads
@@ -1361,12 +1397,23 @@ constexpr int kGrinPolicy = PYR_GRIN_RPT == 2 ? 3 : 0;       // TMA record store
 #define PYR_ASPH_MINB 2
 #endif
 
+// spot8 / spot_shift / fused: pyr_trace_spot -- where the launch is ONE lean kernel that records the
+// last entry, the kernel accumulates the spot sums itself (*fused = true); otherwise nothing changes
 static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
-                      uint32_t flags, cudaStream_t stream) {
+                      uint32_t flags, cudaStream_t stream, double *spot8 = nullptr,
+                      const double *spot_shift = nullptr, bool *fused = nullptr) {
+    if (fused) *fused = false;
     if (flags & PYR_F_COMPLEX) return trace_complex(steps, n_steps, rays, n_rays, flags, stream);
     static thread_local Packed pk;
     int rc = pack(steps, n_steps, rays, n_rays, flags, pk);
     if (rc != PYR_OK) return rc;
+    pk.P.spot8 = nullptr;
+    const bool want_spot = spot8 != nullptr && fused != nullptr && !pk.general && !pk.any_aniso && n_rays > 0 &&
+                           !(flags & PYR_F_RECORD_E) && pk.P.n_waves <= 1;
+    if (want_spot) {
+        pk.P.spot8 = spot8;
+        for (int c = 0; c < 3; ++c) pk.P.spot_shift[c] = spot_shift ? spot_shift[c] : 0.0;
+    }
     if (pk.any_aniso) return PYR_E_UNSUPPORTED;      // needs PYR_F_COMPLEX
     if (n_rays == 0) return PYR_OK;
     bool with_e = (flags & PYR_F_RECORD_E) != 0;
@@ -1384,6 +1431,10 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         for (int s = 0; s < n_steps; ++s)
             grin = grin || steps[s].before.kind == PYR_MEDIUM_ISO_GRIN || steps[s].after.kind == PYR_MEDIUM_ISO_GRIN;
         if (with_e || pk.extended || pk.P.n_waves > 1) return PYR_E_UNSUPPORTED;
+        if (!pk.general && want_spot) {
+            *fused = true;
+            return launch(trace_real_kernel<2, false, 0, 2, 19 | 32>, pk.P, 2, stream, true, false, 256, true, true);
+        }
         if (!pk.general) return launch(trace_real_kernel<2, false, 0, 2, 19>, pk.P, 2, stream, true, false, 256, true, true);
         if (grin && !hist)
             return launch(trace_real_kernel<PYR_GRIN_RPT, false, 19, PYR_GRIN_MINB, kGrinPolicy | 16>, pk.P,
@@ -1416,6 +1467,10 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
         }();
         if (variant == 50) return launch(trace_real_kernel<2, false, 0, 2>, pk.P, 2, stream);
 #endif
+        if (want_spot && !with_e) {
+            *fused = true;
+            return launch(trace_real_kernel<2, false, 0, 2, 3 | 32>, pk.P, 2, stream, true, false, 256, false, true);
+        }
         return launch(trace_real_kernel<2, false, 0, 2, 3>, pk.P, 2, stream, true, false, 256, false, true);
     }
     bool has_grin = false;
@@ -1524,17 +1579,22 @@ int pyr_spot_sums(const double *x, int64_t ld, const uint8_t *flags, uint32_t ma
 int pyr_trace_spot(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *rays, int64_t n_rays,
                    uint32_t flags, const double *shift, double *spot8_dev, double *spot8_host,
                    void *stream) {
-    if (!steps || n_steps <= 0 || !rays || !spot8_dev || !spot8_host || n_rays < 0) return PYR_E_BADARG;
+    if (!steps || n_steps <= 0 || !rays || !spot8_dev || n_rays < 0) return PYR_E_BADARG;
     const PyrStep &last = steps[n_steps - 1];
     if (!last.out_x || last.split) return PYR_E_BADARG;
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = pyr_trace(steps, n_steps, rays, n_rays, flags, stream);
-    if (rc != PYR_OK) return rc;
     cudaError_t e = cudaMemsetAsync(spot8_dev, 0, 64, st);
     if (e != cudaSuccess) return (int)e;
-    rc = pyr_spot_sums(last.out_x, last.ld_out > 0 ? last.ld_out : n_rays, last.out_flags, PYR_RAY_ALIVE,
-                       n_rays, shift, spot8_dev, stream);
+    bool fused = false;
+    int rc = PYR_OK;
+    if (n_rays > 0) rc = pyr::trace_impl(steps, n_steps, rays, n_rays, flags, st, spot8_dev, shift, &fused);
     if (rc != PYR_OK) return rc;
+    if (!fused) {
+        rc = pyr_spot_sums(last.out_x, last.ld_out > 0 ? last.ld_out : n_rays, last.out_flags, PYR_RAY_ALIVE,
+                           n_rays, shift, spot8_dev, stream);
+        if (rc != PYR_OK) return rc;
+    }
+    if (!spot8_host) return PYR_OK;              // asynchronous form: the sums stay on the device
     e = cudaMemcpyAsync(spot8_host, spot8_dev, 64, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     return e == cudaSuccess ? PYR_OK : (int)e;

@@ -126,8 +126,13 @@ def _alloc_rows(rows, n, device, complex_=False, pool=None):
 
 
 def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
-            events=None, wave_end=None, gen=None, device=None):
+            events=None, wave_end=None, gen=None, device=None, spot=None):
+    """spot = (out8 tensor, shift ctypes array or None): the launch also leaves the spot sums of its
+    last entry in out8 (pyr_trace_spot, asynchronous form: fused into the trace kernel where the
+    launch is a single conic-only kernel, a second kernel otherwise)."""
     if n == 0:
+        if spot is not None:
+            spot[0].zero_()
         return                      # empty bundle: nothing to trace
     arr = (nat.PyrStep * (hi - lo))()
     for i in range(lo, hi):
@@ -156,9 +161,17 @@ def _launch(lib, steps, lo, hi, x, k, e, alive, n, n_x, ld_in, flags, stream,
             torch.cuda.current_stream()
         (a, b) = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         a.record(ext)
-        nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
+        if spot is not None:
+            nat.check(lib.pyr_trace_spot(arr, hi - lo, C.byref(rin), n, flags, spot[1], spot[0].data_ptr(),
+                                         None, stream))
+        else:
+            nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
         b.record(ext)
         events.append((a, b))
+        return
+    if spot is not None:
+        nat.check(lib.pyr_trace_spot(arr, hi - lo, C.byref(rin), n, flags, spot[1], spot[0].data_ptr(),
+                                     None, stream))
         return
     nat.check(lib.pyr_trace(arr, hi - lo, C.byref(rin), n, flags, stream))
 
@@ -333,8 +346,12 @@ def _gen_fusable(lowered, record_e, grin_history, wave_end):
 
 def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
           pool=None, events=None, grin_history=False, _hist_rows=None, wave_end=None,
-          gen=None, grin_lockstep=False):
+          gen=None, grin_lockstep=False, spot=None):
     """Run the lowered sequence on the device.  Returns a TraceRecord.
+
+    spot: (out8, shift) -- also leave the spot sums of the last entry about `shift` (3 floats or
+    None) in the float64 CUDA tensor out8 (overwritten; what `spot_sums` of the last record gives):
+    one C call with the last launch (pyr_trace_spot), fused into the trace kernel where it can be.
 
     events: optional list; a (start, end) pair of CUDA timing events is appended
     per native launch (kernel-only timing for benchmarks).
@@ -461,6 +478,7 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
         n = n0
         n_x = n0
         is_complex = complex_in
+        spot_done = False
         for ci in range(len(cuts) - 1):
             (lo, hi) = (cuts[ci], cuts[ci + 1])
             seg_complex = is_complex or (first_aniso is not None and lo >= first_aniso)
@@ -601,9 +619,14 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                 _launch(lib, [phase_c], 0, 1, bx, kin, None, bf, n, n, ld, flags & ~nat.F_RECORD_E,
                         stream_ptr, events, device=device)
             else:
+                spot_arg = None
+                if spot is not None and hi == nsteps and not seg_complex and not launch_steps[hi - 1].split:
+                    sh = None if spot[1] is None else (C.c_double * 3)(*[float(v) for v in spot[1]])
+                    spot_arg = (spot[0], sh)
+                    spot_done = True
                 _launch(lib, launch_steps, lo, hi, cur_x, cur_k, cur_e_arg, cur_alive, n, n_x,
                         ld_k, flags, stream_ptr, events, wave_end=wave_end,
-                        gen=gen_desc if ci == 0 else None, device=device)
+                        gen=gen_desc if ci == 0 else None, device=device, spot=spot_arg)
             for i in range(lo, hi):
                 (bx, bf, bk, be, w_in, w_out, ld, ld2) = bufs[i - lo]
                 rec.hit.append(bx[:, :w_in])
@@ -629,6 +652,11 @@ def trace(lowered, x0, k0, e0, wave, record_e=False, device=None, stream=None,
                     nx = torch.zeros((3, ld_k), dtype=torch.float64, device=device)
                     nx[:, :n_x] = cur_x[:, :n_x]
                     (cur_x, ld_x) = (nx, ld_k)
+    if spot is not None and not spot_done:
+        # the last launch could not carry the sums (split step, GRIN lock-step / user GRIN phases, ...)
+        spot[0].zero_()
+        if rec.hit:
+            spot_sums(rec.hit[-1], rec.flags[-1], out=spot[0], shift=spot[1])
     if grin_history and _hist_rows is None and any("x" not in h for h in rec.grin_hist.values()):
         # first pass gave the step counts; second pass records the rows
         rows = {i: int(h["count"].max().item()) if h["count"].numel() else 0

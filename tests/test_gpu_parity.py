@@ -920,3 +920,42 @@ def test_large_launches_on_concurrent_streams_are_independent():
                 assert torch.equal(torch.nan_to_num(a) if a.dtype.is_floating_point else a,
                                    torch.nan_to_num(b) if b.dtype.is_floating_point else b), key
         assert int((rec.flags[-1] & 2).ne(0).sum()) == x0.shape[1]
+
+
+@pytest.mark.parametrize("name,rings,odd", [("c2_doublegauss", 120, False), ("c2_doublegauss", 1020, False),
+                                            ("x3_vignette", 150, False), ("c1_doublet", 77, True),
+                                            ("c3_asphere", 120, False), ("c5_grin", 30, False)])
+def test_trace_with_spot_sums_equals_the_separate_reduction(name, rings, odd):
+    """engine.trace(..., spot=...) = pyr_trace_spot without read-back: the conic-only kernels
+    accumulate the spot sums of the last entry themselves (POLICY bit 32), everything else falls
+    back to a pyr_spot_sums launch behind the trace.  Either way the sums equal the separate
+    reduction over the last record -- with dead rays (x3), a generated bundle, rows that are not
+    16-byte aligned (odd ray count: plain loads) and large launches (in-order tiles)."""
+    import torch
+    from pyrate_b200 import bundlegen, engine, lowering
+    spec = configs.CONFIGS[name]
+    (x0, k0, e0) = configs.config_bundle(spec, rings)
+    if odd and x0.shape[1] % 2 == 0:
+        (x0, k0, e0) = (x0[:, :-1], k0[:, :-1], e0[:, :-1])
+    (s, seq) = configs.build_system(spec, pb.api())
+    low = lowering.lower(s, seq, configs.DLINE)
+    dev = torch.device("cuda", 0)
+    origin = engine.last_surface_origin(low)
+    if odd:
+        (xd, kd, ed) = (torch.as_tensor(np.ascontiguousarray(a), device=dev) for a in (x0, k0, e0))
+    else:
+        (xd, kd, ed) = engine.device_bundle(x0, k0, e0, dev)
+    fused = torch.full((8,), 7.0, dtype=torch.float64, device=dev)          # overwritten, not accumulated
+    rec = engine.trace(low, xd, kd, ed, configs.DLINE, device=dev, spot=(fused, origin))
+    ref = torch.zeros(8, dtype=torch.float64, device=dev)
+    engine.spot_sums(rec.hit[-1], rec.flags[-1], out=ref, shift=origin)
+    (a, b) = (fused.cpu().numpy(), ref.cpu().numpy())
+    assert a[3] == b[3] and b[3] > 0
+    assert np.allclose(a, b, rtol=1e-11, atol=1e-9 * b[3])
+    if name == "c2_doublegauss":
+        gen = bundlegen.config_generator(spec, rings)
+        g = torch.zeros(8, dtype=torch.float64, device=dev)
+        grec = engine.trace(low, None, None, None, configs.DLINE, device=dev, gen=gen, spot=(g, origin))
+        gref = torch.zeros(8, dtype=torch.float64, device=dev)
+        engine.spot_sums(grec.hit[-1], grec.flags[-1], out=gref, shift=origin)
+        assert np.allclose(g.cpu().numpy(), gref.cpu().numpy(), rtol=1e-11, atol=1e-9 * b[3])
