@@ -6,9 +6,9 @@ GPU (BASELINE.json configs[1]), FP64.
   python bench.py --gpus N --steps K --warmup W            # this engine
   python bench.py --impl reference --gpus N ...            # CPU arm: the reference itself
 
-One "step" = one full pass of the bundle through the element sequence (one persistent
-kernel launch per GPU + the spot-sum kernel; for N > 1 also the one NCCL all-reduce of the
-8 spot sums).  Prints ONE JSON line on rank 0:
+One "step" = one full pass of the bundle through the element sequence including the spot
+sums of the image plane: ONE persistent kernel launch per GPU (pyr_trace_spot, asynchronous
+form); for N > 1 also the one NCCL all-reduce of the 8 spot sums.  Prints ONE JSON line on rank 0:
 
   value            device-timed, bundle resident in HBM (x0, k0, E0 arrays)
   config.generated the same step with the bundle GENERATED in the kernel's prologue

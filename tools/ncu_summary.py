@@ -12,6 +12,7 @@ src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out"
 prefix = sys.argv[2] if len(sys.argv) > 2 else "prof_r02b_"
 TITLES = OrderedDict([
     ("c2", "C2 double-Gauss, 9 997 351 rays x 13 entries, resident inputs (the headline kernel)"),
+    ("c2spot", "C2, the bench step: trace + spot sums of the image plane in ONE launch (POLICY bit 32)"),
     ("c2gen", "C2, bundle generated in the kernel prologue (no input arrays)"),
     ("c3", "C3 even asphere, 9 997 351 rays x 4 entries (asphere-only instantiation), resident inputs"),
     ("c4", "C4 birefringent doublet, 1 000 519 -> 4 002 076 rays, the ONE complex-stretch launch"),
