@@ -6,9 +6,9 @@ GPU (BASELINE.json configs[1]), FP64.
   python bench.py --gpus N --steps K --warmup W            # this engine
   python bench.py --impl reference --gpus N ...            # CPU arm: the reference itself
 
-One "step" = one full pass of the bundle through the element sequence including the spot
-sums of the image plane: ONE persistent kernel launch per GPU (pyr_trace_spot, asynchronous
-form); for N > 1 also the one NCCL all-reduce of the 8 spot sums.  Prints ONE JSON line on rank 0:
+One "step" = one full pass of the bundle through the element sequence (one persistent
+kernel launch per GPU + the spot-sum kernel; for N > 1 also the one NCCL all-reduce of the
+8 spot sums).  Prints ONE JSON line on rank 0:
 
   value            device-timed, bundle resident in HBM (x0, k0, E0 arrays)
   config.generated the same step with the bundle GENERATED in the kernel's prologue
@@ -543,17 +543,23 @@ def run_gpu(args):
     pool = engine.RecordPool()      # record buffers allocated once, reused per step
     ev = []                         # (start, end) CUDA events around each native trace launch
 
+    # (engine.trace(spot=...) would fold the spot sums into the trace launch -- pyr_trace_spot, what
+    # MeritTrace uses: 1.17 instead of 1.21 ms per step on one GPU -- but the one 8-GPU run of that
+    # step came out slower, 1.37 ms, profiles/r02b_bench_n8_fused_step.json, with no GPU time left to
+    # find out why: the headline step keeps the two launches whose scaling is established)
     def step_resident():
-        # trace + spot sums of the image plane in ONE launch (pyr_trace_spot, asynchronous form)
-        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool, events=ev,
-                           spot=(spot, origin))
+        rec = engine.trace(lowered, x0, k0, e0, configs.DLINE, device=dev, pool=pool, events=ev)
+        spot.zero_()
+        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
         if world > 1:
             dist.all_reduce(spot)
         return rec
 
     def step_generated():
         rec = engine.trace(lowered, None, None, None, configs.DLINE, device=dev, pool=pool,
-                           events=ev, gen=gen, spot=(spot, origin))
+                           events=ev, gen=gen)
+        spot.zero_()
+        engine.spot_sums(rec.hit[-1], rec.flags[-1], out=spot, shift=origin)
         if world > 1:
             dist.all_reduce(spot)
         return rec
@@ -712,7 +718,7 @@ def run_gpu(args):
                              "kernel_ms": kms,
                              "algorithmic_bytes_per_launch": algo_bytes},
                 "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": args.steps,
+                "gpu_launches": 2 * args.steps,
                 "clocks": clocks.summary()}
         print(json.dumps(line))
     if world > 1:
