@@ -1408,8 +1408,9 @@ static int trace_impl(const PyrStep *steps, int32_t n_steps, const PyrRaysIn *ra
     int rc = pack(steps, n_steps, rays, n_rays, flags, pk);
     if (rc != PYR_OK) return rc;
     pk.P.spot8 = nullptr;
+    // (only with a flag record on the last step: without one pyr_spot_sums counts EVERY ray)
     const bool want_spot = spot8 != nullptr && fused != nullptr && !pk.general && !pk.any_aniso && n_rays > 0 &&
-                           !(flags & PYR_F_RECORD_E) && pk.P.n_waves <= 1;
+                           !(flags & PYR_F_RECORD_E) && pk.P.n_waves <= 1 && steps[n_steps - 1].out_flags != nullptr;
     if (want_spot) {
         pk.P.spot8 = spot8;
         for (int c = 0; c < 3; ++c) pk.P.spot_shift[c] = spot_shift ? spot_shift[c] : 0.0;
