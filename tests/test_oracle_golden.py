@@ -237,3 +237,48 @@ def test_uniaxial_closed_form_roots_match_reference_eigenvalues():
             kj = k[:, j]
             m = eps - np.dot(kj, kj) * np.eye(3) + np.outer(kj, kj)      # (eps - k.k 1 + k k^T) E = 0
             assert abs(np.linalg.det(m)) < 1e-10, (r, j)
+
+
+def test_oracle_matches_live_reference_below_the_critical_angles_of_a_crystal():
+    """A ray fan through a dense glass -> tilted calcite-like interface that straddles both
+    critical angles (the bundle of the GPU test of the crystal kernel's real / complex paths).
+    Rays whose four modes propagate agree with the UNMODIFIED reference to rounding.  Rays with
+    evanescent modes cannot be pinned: their Poynting sort keys S.n vanish, so WHICH two of the
+    four complex roots material.py:122-153 keeps is decided by LAPACK's rounding (the selection
+    differs between the reference and any other solver, including this oracle); what both
+    engines agree on there is that the ray stays in the bundle (anisotropic refract has no
+    validity filter, material_anisotropic.py:87-100)."""
+    api = _live_reference_api()
+    import warnings
+    import test_gpu_parity as tg
+    spec = tg._evanescent_spec()
+    n = 61
+    rng = np.random.default_rng(5)
+    ang = np.linspace(-0.43, 0.43, n)
+    tx = rng.uniform(-0.02, 0.02, n)
+    k0 = np.stack((np.sin(tx), np.cos(tx) * np.sin(ang), np.cos(tx) * np.cos(ang)))
+    x0 = np.stack((rng.uniform(-0.5, 0.5, n), rng.uniform(-0.5, 0.5, n), np.full(n, -3.0)))
+    e0 = np.cross(k0.T, np.array([0.0, 1.0, 0.3])).T
+    e0 /= np.linalg.norm(e0, axis=0)
+    (s, seq) = configs.build_system(spec, api)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = s.seqtrace(api.RayBundle(x0.copy(), k0.copy(), e0.copy(), wave=configs.DLINE), seq)[0].raybundles
+        got = onp.seqtrace(onp.system_from_spec(spec), x0, k0, e0, wave=configs.DLINE)[0]
+    assert len(got) == len(ref)
+    (b, rb) = (got[4], ref[4])                       # the bundle born at the crystal surface
+    (gk, rk) = (np.asarray(b["k"])[-1], np.asarray(rb.k)[-1])
+    (gid, rid) = (np.asarray(b["rayID"]), np.asarray(rb.rayID))
+    assert gk.shape == rk.shape == (3, 2 * n) and np.iscomplexobj(rk)
+    assert np.asarray(rb.valid).all() and np.asarray(b["valid"]).all()      # nobody is dropped here
+    (propagating, evanescent) = (0, 0)
+    for ray in range(n):
+        (ko, kr) = (gk[:, gid == ray], rk[:, rid == ray])
+        if np.abs(kr.imag).max() > 1e-9 or np.abs(ko.imag).max() > 1e-9:
+            evanescent += 1
+            continue
+        propagating += 1
+        d = min(max(np.abs(ko[:, 0] - kr[:, 0]).max(), np.abs(ko[:, 1] - kr[:, 1]).max()),
+                max(np.abs(ko[:, 0] - kr[:, 1]).max(), np.abs(ko[:, 1] - kr[:, 0]).max()))
+        assert d < 1e-12, (ray, d)
+    assert propagating >= 40 and evanescent >= 10
